@@ -1,0 +1,244 @@
+/*
+ * occ_b200.h -- C ABI of libocc_b200.so: the B200 (sm_100a) point -> occupancy hot path.
+ *
+ * Drop-in boundary for the hot path of Ghostish/ObjectCentricOccCompletion.  Every entry
+ * point cites the reference interface it replaces (paths relative to the reference repo).
+ * Plain pointers and sizes only; no torch types.  Unless stated otherwise:
+ *   - all data pointers are DEVICE pointers on the current CUDA device;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - calls are asynchronous on `stream`; nothing synchronises unless documented;
+ *   - return value 0 = success, non-zero = error (see occb200_last_error()).
+ */
+#ifndef OCC_B200_H_
+#define OCC_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- library -------------------------------------------------------------------------- */
+
+/* ABI version; bumped on any layout change of the structs below. */
+int occb200_abi_version(void);
+/* Message of the last failing call on this host thread (never NULL). */
+const char *occb200_last_error(void);
+/* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
+int64_t occb200_launch_count(void);
+
+/* reduce_t of mmdet3d/ops/voxel/src/scatter_points_cuda.cu:7 */
+enum { OCCB200_SUM = 0, OCCB200_MEAN = 1, OCCB200_MAX = 2 };
+
+/* per-tracklet status of occb200_annotate_batch (what the reference does in that case) */
+enum {
+  OCCB200_OK = 0,
+  OCCB200_SKIP_SHORT = 1,         /* len(trk) < 10: returns silently     (tools/occ/occ_annotate.py:344)  */
+  OCCB200_NO_POINTS = 2,          /* AssertionError "no points"          (occ_annotate.py:129, 356-359)   */
+  OCCB200_EMPTY_AFTER_FILTER = 3, /* max() of an empty tensor raises     (occ_annotate.py:433-435)        */
+  OCCB200_INDEX_ERROR = 4         /* quantised coord < -dims: IndexError (occ_annotate.py:436)            */
+};
+
+/* ---- A1: points in boxes -------------------------------------------------------------- */
+
+/*
+ * Replaces roiaware_pool3d_ext.points_in_boxes_gpu
+ *   (mmdet3d/ops/roiaware_pool3d/src/roiaware_pool3d.cpp:125-135, kernel
+ *    src/points_in_boxes_cuda.cu:51-77; python wrapper points_in_boxes.py:6-50).
+ * boxes f32 [B,T,7] (x,y,z_bottom,w,l,h,rz), pts f32 [B,M,3] -> out int32 [B,M]:
+ * index of the first box containing the point, else -1 (the kernel writes every element;
+ * the reference wrapper's -1 pre-fill is not needed).
+ * trig: optional f32 [B,T,2] = cosf/sinf(float(rz + pi/2)) computed by the caller (host libm
+ * values make the result bit-identical to points_in_boxes_cpu); NULL = computed on device.
+ */
+int occb200_points_in_boxes_gpu(const float *boxes, const float *pts, const float *trig, int32_t *out,
+                                int B, int T, int M, void *stream);
+
+/* Replaces roiaware_pool3d_ext.points_in_boxes_batch (roiaware_pool3d.cpp:125-135,
+ * points_in_boxes_cuda.cu:79-105): out int32 [B,M,T] multi-hot, every element written. */
+int occb200_points_in_boxes_batch(const float *boxes, const float *pts, const float *trig, int32_t *out,
+                                  int B, int T, int M, void *stream);
+
+/* HOST helper: trig[i] = {cosf(a), sinf(a)}, a = float(double(rz_i) + M_PI/2), with the host libm,
+ * exactly as points_in_boxes_cpu.cpp:16-23 evaluates it.  boxes7 / trig are HOST pointers. */
+void occb200_host_box_trig(const float *boxes7, int64_t n, float *trig);
+
+/* ---- A7 / A8: Voxelization ------------------------------------------------------------ */
+
+/*
+ * Replaces voxel_layer.dynamic_voxelize (mmdet3d/ops/voxel/src/voxelization.cpp:8,
+ * voxelization.h:71-83, voxelization_cuda.cu:24-65,332-375).
+ * points [N, num_features] (dtype 0 = f32, 1 = f64), only columns 0..2 are read;
+ * voxel_size[3], coors_range[6] are HOST arrays; coors int32 [N,3] in z,y,x order,
+ * out-of-range points CLAMPED into the edge voxels (this fork's behaviour).
+ */
+int occb200_dynamic_voxelize(const void *points, int dtype, int64_t N, int num_features,
+                             const float *voxel_size, const float *coors_range, int32_t *coors,
+                             void *stream);
+
+/*
+ * Replaces voxel_layer.hard_voxelize (voxelization.cpp:7, voxelization.h:51-69,
+ * voxelization_cuda.cu:67-184,188-330; CPU semantics voxelization_cpu.cpp:43-142).
+ * points f32 [N,C]; caller allocates and ZERO-fills voxels f32 [max_voxels,max_points,C],
+ * coors int32 [max_voxels,3], num_points_per_voxel int32 [max_voxels] (voxelize.py:46-50).
+ * workspace: device scratch of occb200_hard_voxelize_workspace_bytes(N) bytes.
+ * *voxel_num_host (HOST int) receives the voxel count; this call synchronises `stream`
+ * (the reference returns the count, too).
+ */
+int64_t occb200_hard_voxelize_workspace_bytes(int64_t N);
+int occb200_hard_voxelize(const float *points, int64_t N, int C, const float *voxel_size,
+                          const float *coors_range, int max_points, int max_voxels, float *voxels,
+                          int32_t *coors, int32_t *num_points_per_voxel, void *workspace,
+                          int64_t workspace_bytes, int *voxel_num_host, void *stream);
+
+/* ---- A6 / A9: unique voxels + scatter reductions -------------------------------------- */
+
+/*
+ * Sorted-unique of integer coordinate rows (at::unique_dim(..., sorted, inverse, counts) in
+ * scatter_points_cuda.cu:204-205; torch.unique(coors, dim=0, ...) in ops/sst/sst_ops.py:156-158).
+ * coors: int32 (coor_dtype 0) or int64 (coor_dtype 1) [N,K], 1 <= K <= 8.
+ * mode 0 (scatter_v2): plain lexicographic unique.
+ * mode 1 (DynamicScatter): rows with any negative coordinate are invalid (inverse -1); the first
+ *         unique row is then dropped unconditionally -- the invalid group when there is one, else
+ *         the lexicographically smallest valid voxel (scatter_points_cuda.cu:202-210).
+ * mode 2 (DynamicScatter with 4-column batched coords, scatter_points.py:83-99): as mode 1 applied
+ *         per value of column 0 (batch index in [0, coors[N-1,0]]); output rows keep column 0.
+ * Outputs, caller-allocated for N rows: uniq [<=N,K] (dtype of coors), inverse int32 [N] (-1 = no
+ * voxel), counts int32 [<=N], and the reduction plan: order int32 [N] (point indices grouped by
+ * voxel, ascending inside a voxel) and gstart int32 [<=N] (first position of voxel m in order).
+ * *m_host (HOST) receives the number of unique rows; the call synchronises `stream` (output
+ * shapes depend on it, exactly as in the reference).  The packed sort key must fit 63 bits.
+ */
+int64_t occb200_unique_workspace_bytes(int64_t N, int K);
+int occb200_unique_rows(const void *coors, int coor_dtype, int64_t N, int K, int mode, void *uniq,
+                        int32_t *inverse, int32_t *counts, int32_t *order, int32_t *gstart,
+                        void *workspace, int64_t workspace_bytes, int64_t *m_host, void *stream);
+
+/* Reduction plan (order, gstart, counts) from an existing inverse map int32 [N] with values in
+ * [-1, M): what scatter_v2 needs when the caller passes unq_inv (sst_ops.py:159-160). No sync. */
+int64_t occb200_plan_workspace_bytes(int64_t N);
+int occb200_plan_from_inverse(const int32_t *inverse, int64_t N, int64_t M, int32_t *order,
+                              int32_t *gstart, int32_t *counts, void *workspace,
+                              int64_t workspace_bytes, void *stream);
+
+/*
+ * Segmented reduction of feats f32 [N,C] into out f32 [M,C] following a plan
+ * (feats_reduce_kernel scatter_points_cuda.cu:80-103 + mean division :228-229;
+ *  torch_scatter scatter / scatter_max in sst_ops.py:171-176).
+ * Deterministic: each voxel's points are combined in ascending point index by one (sub-)warp.
+ * reduce: OCCB200_SUM / MEAN / MAX; mean divides by max(count,1); max of an empty voxel is -inf.
+ * argmax (optional, int32 [M,C]): smallest point index attaining the max (:135-160), N if none.
+ */
+int occb200_segment_reduce(const float *feats, int64_t N, int C, const int32_t *order,
+                           const int32_t *gstart, const int32_t *counts, int64_t M, int reduce,
+                           float *out, int32_t *argmax, void *stream);
+
+/*
+ * Replaces voxel_layer.dynamic_point_to_voxel_backward (voxelization.cpp:10,
+ * scatter_points_cuda.cu:236-303).  grad_feats f32 [N,C] is fully written (zero where no
+ * gradient flows).  MAX: the gradient goes to the smallest point index whose feature equals the
+ * voxel max; pass the forward's argmax, or NULL to recompute it from feats / reduced_feats
+ * (stream-ordered scratch allocation inside the call).
+ */
+int occb200_segment_reduce_backward(float *grad_feats, const float *grad_reduced, const float *feats,
+                                    const float *reduced_feats, const int32_t *inverse,
+                                    const int32_t *counts, const int32_t *argmax, int64_t N,
+                                    int64_t M, int C, int reduce, void *stream);
+
+/* ---- A10: occ_ops --------------------------------------------------------------------- */
+
+/* mmdet3d/ops/occ/occ_ops.py:53-93 quantize_points: rois f32 [R,roi_dim] (sizes in columns 4..6),
+ * roi_idx int64 [N]; writes out_coor int64 [N,3] (to_center == 0) or out_center f32 [N,3]. */
+int occb200_quantize_points(const float *points, int64_t N, const float *rois, int roi_dim,
+                            const int64_t *roi_idx, float voxel_size, const float *scale_wlh,
+                            const float *offset_wlh, int to_center, int64_t *out_coor,
+                            float *out_center, void *stream);
+
+/* occ_ops.py:5-50 generate_dense_voxel_centers for R boxes: sizes f32 [R,3] (DEVICE),
+ * dims int32 [R,3] and center_off int64 [R+1] (DEVICE, computed by the caller with
+ * ceil(size*scale+offset / vs) in f32), centers f32 [center_off[R],3], ij-meshgrid order. */
+int occb200_dense_voxel_centers(const float *sizes, const int32_t *dims, const int64_t *center_off,
+                                int R, int64_t total, float voxel_size, const float *scale_wlh,
+                                const float *offset_wlh, float *centers, void *stream);
+
+/* ---- A2-A5: batched tracklet annotation (the "ray-cast") ------------------------------ */
+
+/* One box pose per tracklet-frame: box7 plus the yaw trigonometry the reference evaluates on
+ * the host side of its tensor code (see occb200_host_pose_pack).  64 bytes. */
+typedef struct occb200_pose {
+  float box[7];           /* x, y, z_bottom, x_size, y_size, z_size, yaw  (tools/ctrl/utils.py:42) */
+  float cos_pib, sin_pib; /* cosf/sinf(float(yaw + pi/2)), host libm  (points_in_boxes_cpu.cpp:19-20) */
+  float cos_m, sin_m;     /* torch f32 cos/sin(-yaw)                  (lidar_box3d.py:163-164)       */
+  float cos_p, sin_p;     /* torch f32 cos/sin(+yaw)                  (occ_annotate.py:490-491)      */
+  float pad[3];
+} occb200_pose_t;
+
+/* One LiDAR of one sensor frame.  80 bytes. */
+typedef struct occb200_sensor {
+  int64_t ri_off;    /* offset (floats) of the H x W f32 range image in ri_pool (0 = no return)     */
+  int64_t incl_off;  /* offset (floats) of the FLIPPED inclination table in incl_pool (occ_annotate.py:528) */
+  int32_t H, W;
+  float v2l[12];     /* rows 0..2 of inv(extrinsic) evaluated in f32 on the host (occ_annotate.py:158-160) */
+  float azc;         /* f32 atan2(E[1,0], E[0,0]) evaluated on the host (occ_annotate.py:175)        */
+  int32_t incl_mono; /* +1 table ascending, -1 descending, 0 unknown (linear scan)                   */
+} occb200_sensor_t;
+
+typedef struct occb200_annotate_args {
+  int32_t T;                      /* tracklets                                                */
+  int32_t L;                      /* LiDARs per sensor frame, reference order (occ_annotate.py:235) */
+  int64_t F;                      /* tracklet-frames = trk_frame_off[T]                       */
+  const int64_t *trk_frame_off;   /* [T+1]                                                    */
+  const occb200_pose_t *poses;    /* [F]                                                      */
+  const int32_t *frame_sf;        /* [F] sensor-frame index of each tracklet-frame            */
+  const float *points;            /* [P, point_stride] candidate returns, ego frame of their frame */
+  int32_t point_stride;           /* floats per point (>= 3; 6 for KITTI-format .bin rows)    */
+  int32_t pad0;
+  const int64_t *frame_pt_off;    /* [F+1] point range of each tracklet-frame                 */
+  const occb200_sensor_t *sensors;/* [SF, L]                                                  */
+  const float *incl_pool;
+  const float *ri_pool;
+  double voxel_size;              /* python float of --voxel-size (occ_annotate.py:215)       */
+  const int64_t *label_off;       /* [T+1] slot of each tracklet in labels; slot size >= prod(ceil(max_frames(size)/vs)) */
+  /* outputs */
+  int32_t *labels;                /* [label_off[T]] 0 unknown / 1 occupied / 2 free, (x*Y+y)*Z+z inside the slot */
+  int32_t *dims;                  /* [T,3]  X,Y,Z                                             */
+  float *sizes;                   /* [T,3]  max box size over frames that have in-box points  */
+  int32_t *status;                /* [T]    OCCB200_OK ...                                    */
+  int64_t *n_unknown;             /* [T]    voxels tested for visibility (U)                  */
+  int64_t *n_steps;               /* [T]    visibility tests actually evaluated (<= U*B*L; early exit) ; may be NULL */
+  void *workspace;
+  int64_t workspace_bytes;        /* >= occb200_annotate_workspace_bytes(T, F, label_off[T])  */
+  int32_t flags;                  /* bit 0: force the all-f64 visibility kernel               */
+  int32_t pad1;
+} occb200_annotate_args_t;
+
+int64_t occb200_annotate_workspace_bytes(int32_t T, int64_t F, int64_t total_label_slots);
+
+/*
+ * What tools/occ/occ_annotate.py does per tracklet (get_local_point_list :91-138 and
+ * OccAnnotator.annotate_trk :344-568), for T tracklets in one call: crop the candidate points
+ * to the frame's box, move them to the box frame, voxelise, and label every voxel without a
+ * point free/unknown by the reference's range-image visibility test over all frames and LiDARs.
+ * No host synchronisation.  total_label_slots (= label_off[T]) is passed by value so that the
+ * call needs no device->host read.
+ */
+int occb200_annotate_batch(const occb200_annotate_args_t *args, int64_t total_label_slots, void *stream);
+
+/* HOST helper: fills poses[i] from boxes7 f32 [n,7] and torch-evaluated trig f32 [n,4]
+ * (cos(-yaw), sin(-yaw), cos(yaw), sin(yaw)); cos_pib/sin_pib come from the host libm. */
+void occb200_host_pose_pack(const float *boxes7, const float *trig4, int64_t n, occb200_pose_t *poses);
+
+/*
+ * The reference's point_cloud_to_range_image_idx (tools/occ/occ_annotate.py:141-201) as an
+ * operator: points f64 [B,N,3]; v2l f32 [B,12] and azc f32 [B] host-evaluated as in
+ * occb200_sensor_t; incl f32 [B,H] already flipped -> ri_idx int64 [B,N,2] (row, col; col may be
+ * negative exactly as in the reference), ri_range f64 [B,N].
+ */
+int occb200_point_cloud_to_range_image_idx(const double *points, int B, int64_t N, const float *v2l,
+                                           const float *azc, const float *incl, int H, int W,
+                                           int64_t *ri_idx, double *ri_range, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OCC_B200_H_ */

@@ -1,0 +1,82 @@
+// occ_ops.cu -- A10: mmdet3d/ops/occ/occ_ops.py quantize_points / generate_dense_voxel_centers.
+// The reference evaluates these with ~8 elementwise torch kernels (and a python loop over ROIs for
+// the dense grids); here each is one fused kernel with the same f32 operation order.
+#include "common.cuh"
+
+namespace occb200 {
+
+struct Wlh {
+  float scale[3];
+  float offset[3];
+};
+
+__global__ void k_quantize_points(const float *__restrict__ points, int64_t N, const float *__restrict__ rois,
+                                  int roi_dim, const int64_t *__restrict__ roi_idx, float vs, Wlh w, int to_center,
+                                  int64_t *__restrict__ out_coor, float *__restrict__ out_center) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= N * 3) return;
+  const int64_t i = e / 3;
+  const int j = (int)(e % 3);
+  const float *roi = rois + roi_idx[i] * roi_dim;
+  const float size = __fadd_rn(__fmul_rn(roi[4 + j], w.scale[j]), w.offset[j]);   // occ_ops.py:76-78
+  const float mn = __fdiv_rn(-size, 2.0f);                                          // :80
+  const float q = floorf(__fdiv_rn(__fsub_rn(points[e], mn), vs));                  // :82
+  const long long qi = (long long)q;
+  if (to_center)
+    out_center[e] = __fadd_rn(__fadd_rn(__fmul_rn((float)qi, vs), mn), __fdiv_rn(vs, 2.0f));   // :86-90
+  else
+    out_coor[e] = qi;
+}
+
+__global__ void k_dense_centers(const float *__restrict__ sizes, const int32_t *__restrict__ dims,
+                                const int64_t *__restrict__ center_off, int R, int64_t total, float vs, Wlh w,
+                                float *__restrict__ centers) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= total) return;
+  int lo = 0, hi = R;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (center_off[mid] <= e) lo = mid; else hi = mid;
+  }
+  const int r = lo;
+  const int64_t f = e - center_off[r];
+  const int Y = dims[3 * r + 1], Z = dims[3 * r + 2];
+  const int q[3] = {(int)(f / ((int64_t)Y * Z)), (int)((f / Z) % Y), (int)(f % Z)};   // ij meshgrid (:26-36)
+  for (int j = 0; j < 3; ++j) {
+    const float size = __fadd_rn(__fmul_rn(sizes[3 * r + j], w.scale[j]), w.offset[j]);   // :21
+    const float mn = __fdiv_rn(-size, 2.0f);                                               // :39
+    centers[e * 3 + j] = __fadd_rn(__fadd_rn(__fmul_rn((float)q[j], vs), mn), __fdiv_rn(vs, 2.0f));   // :41-43
+  }
+}
+
+}  // namespace occb200
+
+using namespace occb200;
+
+extern "C" int occb200_quantize_points(const float *points, int64_t N, const float *rois, int roi_dim,
+                                       const int64_t *roi_idx, float voxel_size, const float *scale_wlh,
+                                       const float *offset_wlh, int to_center, int64_t *out_coor, float *out_center,
+                                       void *stream) {
+  OCC_REQUIRE(N >= 0 && roi_dim >= 7, "bad sizes");
+  OCC_REQUIRE(to_center ? out_center != nullptr : out_coor != nullptr, "output pointer is NULL");
+  if (N == 0) return 0;
+  Wlh w;
+  for (int j = 0; j < 3; ++j) { w.scale[j] = scale_wlh[j]; w.offset[j] = offset_wlh[j]; }
+  k_quantize_points<<<(unsigned)ceil_div(N * 3, 256), 256, 0, (cudaStream_t)stream>>>(
+      points, N, rois, roi_dim, roi_idx, voxel_size, w, to_center, out_coor, out_center);
+  OCC_KERNEL_OK("k_quantize_points");
+  return 0;
+}
+
+extern "C" int occb200_dense_voxel_centers(const float *sizes, const int32_t *dims, const int64_t *center_off, int R,
+                                           int64_t total, float voxel_size, const float *scale_wlh,
+                                           const float *offset_wlh, float *centers, void *stream) {
+  OCC_REQUIRE(R >= 0 && total >= 0, "bad sizes");
+  if (R == 0 || total == 0) return 0;
+  Wlh w;
+  for (int j = 0; j < 3; ++j) { w.scale[j] = scale_wlh[j]; w.offset[j] = offset_wlh[j]; }
+  k_dense_centers<<<(unsigned)ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(sizes, dims, center_off, R, total,
+                                                                                    voxel_size, w, centers);
+  OCC_KERNEL_OK("k_dense_centers");
+  return 0;
+}

@@ -1,0 +1,364 @@
+"""Host side of the batched tracklet annotation -- mirrors ``tools/occ/occ_annotate.py``.
+
+The reference annotates one tracklet at a time with ~500 small torch launches
+(``OccAnnotator.annotate_trk``, occ_annotate.py:319-647).  Here the same result
+for a whole batch of tracklets comes from ONE call into libocc_b200.so
+(``occb200_annotate_batch``): the host only *packs* -- it evaluates the handful
+of scalar operations the reference itself performs on the host side of its
+tensor code, with the same torch-CPU / libm calls, so that the device never has
+to guess their bits:
+
+* ``torch.sin/cos(+-yaw)`` f32 per frame  (lidar_box3d.py:163-164, occ_annotate.py:490-491)
+* ``cosf/sinf(yaw + pi/2)`` per frame     (points_in_boxes_cpu.cpp:19-20)
+* ``torch.linalg.inv(extrinsic)`` f32 and ``torch.atan2(E[1,0], E[0,0])`` per (frame, LiDAR)
+  (occ_annotate.py:158-160, 175)
+* the inclination flip                     (occ_annotate.py:528)
+
+Everything per point / per voxel runs in the CUDA kernels (csrc/annotate.cu).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+
+LiDAR_NAME_LIST = ["TOP", "FRONT", "SIDE_LEFT", "SIDE_RIGHT", "REAR"]     # occ_annotate.py:235
+STATUS_NAMES = {0: "ok", 1: "skip_short", 2: "no_points", 3: "empty_after_filter", 4: "index_error", -1: "slot_too_small"}
+FLAG_FORCE_F64 = 1
+
+
+# ------------------------------------------------------------------------------------------------
+# packing (host)
+# ------------------------------------------------------------------------------------------------
+def _host_trig(rz: np.ndarray) -> np.ndarray:
+    r = torch.from_numpy(np.ascontiguousarray(rz, np.float32))
+    m = -r
+    return torch.stack([torch.cos(m), torch.sin(m), torch.cos(r), torch.sin(r)], -1).numpy()
+
+
+def _host_calib(extrinsics: np.ndarray):
+    E = torch.from_numpy(np.ascontiguousarray(extrinsics, np.float32)).reshape(-1, 4, 4)
+    inv = torch.linalg.inv(E)                       # same call as occ_annotate.py:158-160 (on CPU, f32)
+    azc = torch.atan2(E[:, 1, 0], E[:, 0, 0])       # occ_annotate.py:175
+    return inv[:, :3, :].reshape(-1, 12).numpy(), azc.numpy()
+
+
+def _mono(table: np.ndarray) -> int:
+    d = np.diff(table.astype(np.float64))
+    if d.size == 0 or (d >= 0).all():
+        return 1
+    if (d <= 0).all():
+        return -1
+    return 0
+
+
+@dataclass
+class PackedTracklets:
+    """Flat host arrays in the layout of ``occb200_annotate_args_t`` (include/occ_b200.h)."""
+
+    T: int
+    L: int
+    F: int
+    voxel_size: float
+    trk_frame_off: np.ndarray      # i64 [T+1]
+    poses: np.ndarray              # POSE_DTYPE [F]
+    frame_sf: np.ndarray           # i32 [F]
+    points: np.ndarray             # f32 [P, stride]
+    frame_pt_off: np.ndarray       # i64 [F+1]
+    sensors: np.ndarray            # SENSOR_DTYPE [SF, L]
+    incl_pool: np.ndarray          # f32
+    ri_pool: np.ndarray            # f32
+    label_off: np.ndarray          # i64 [T+1]
+
+    @property
+    def total_slots(self) -> int:
+        return int(self.label_off[-1])
+
+    def input_bytes(self) -> int:
+        return sum(a.nbytes for a in (self.trk_frame_off, self.poses, self.frame_sf, self.points, self.frame_pt_off,
+                                      self.sensors, self.incl_pool, self.ri_pool, self.label_off))
+
+
+def pack_tracklets(batch, pack_override: Optional[dict] = None) -> PackedTracklets:
+    """Pack a batch (``segments`` + ``tracklets``; see synth.TrackletBatch) for the device.
+
+    ``pack_override`` may carry host-derived values (``trig`` [F,4], ``pib`` [F,2], ``v2l``, ``azc``)
+    recorded with a golden fixture so a different host libm/torch cannot perturb a parity check.
+    """
+    segs, trks = batch.segments, batch.tracklets
+    L = len(segs[0].inclinations) if segs else len(LiDAR_NAME_LIST)
+    T = len(trks)
+    sf_base = np.cumsum([0] + [s.num_frames for s in segs]).astype(np.int64)
+    SF = int(sf_base[-1])
+    sensors = np.zeros((SF, L), _lib.SENSOR_DTYPE)
+    incl_parts, ri_parts = [], []
+    incl_off = ri_off = 0
+    for si, s in enumerate(segs):
+        v2l, azc = _host_calib(s.extrinsics)
+        v2l = v2l.reshape(s.num_frames, L, 12)
+        azc = azc.reshape(s.num_frames, L)
+        sl = slice(int(sf_base[si]), int(sf_base[si + 1]))
+        for c in range(L):
+            table = np.ascontiguousarray(s.inclinations[c][::-1], np.float32)      # flip (:528)
+            img = np.ascontiguousarray(s.range_images[c], np.float32)
+            nb, H, W = img.shape
+            assert table.shape[0] == H and nb == s.num_frames
+            sensors["incl_off"][sl, c] = incl_off
+            sensors["incl_mono"][sl, c] = _mono(table)
+            sensors["ri_off"][sl, c] = ri_off + np.arange(nb, dtype=np.int64) * H * W
+            sensors["H"][sl, c] = H
+            sensors["W"][sl, c] = W
+            sensors["v2l"][sl, c] = v2l[:, c]
+            sensors["azc"][sl, c] = azc[:, c]
+            incl_parts.append(table)
+            ri_parts.append(img.reshape(-1))
+            incl_off += H
+            ri_off += nb * H * W
+    nfr = [len(t) for t in trks]
+    trk_frame_off = np.cumsum([0] + nfr).astype(np.int64)
+    F = int(trk_frame_off[-1])
+    boxes = np.concatenate([t.boxes for t in trks], 0).astype(np.float32) if F else np.zeros((0, 7), np.float32)
+    frame_sf = (np.concatenate([sf_base[t.segment] + np.asarray(t.frame_ids, np.int64) for t in trks]).astype(np.int32)
+                if F else np.zeros(0, np.int32))
+    per_frame = [p for t in trks for p in t.points]
+    frame_pt_off = np.cumsum([0] + [len(p) for p in per_frame]).astype(np.int64)
+    stride = per_frame[0].shape[1] if per_frame else 3
+    points = (np.concatenate(per_frame, 0).astype(np.float32) if frame_pt_off[-1] > 0
+              else np.zeros((0, stride), np.float32))
+    trig = _host_trig(boxes[:, 6]) if F else np.zeros((0, 4), np.float32)
+    if pack_override and "trig" in pack_override:
+        trig = np.ascontiguousarray(pack_override["trig"], np.float32)
+    poses = np.zeros(F, _lib.POSE_DTYPE)
+    if F:
+        boxes = np.ascontiguousarray(boxes)
+        trig = np.ascontiguousarray(trig, np.float32)
+        _lib.lib().occb200_host_pose_pack(boxes.ctypes.data, trig.ctypes.data, F, poses.ctypes.data)
+    if pack_override:
+        if "pib" in pack_override:
+            poses["cos_pib"] = pack_override["pib"][:, 0]
+            poses["sin_pib"] = pack_override["pib"][:, 1]
+        if "v2l" in pack_override:
+            sensors["v2l"] = np.asarray(pack_override["v2l"], np.float32).reshape(SF, L, 12)
+        if "azc" in pack_override:
+            sensors["azc"] = np.asarray(pack_override["azc"], np.float32).reshape(SF, L)
+    # label slots: upper bound of the grid = ceil(max over ALL frames of the box size / vs) in f32
+    vsf = np.float32(batch.voxel_size)
+    caps = []
+    for t in trks:
+        if len(t) == 0:
+            caps.append(0)
+            continue
+        d = np.ceil(t.boxes[:, 3:6].astype(np.float32).max(0) / vsf).astype(np.int64)
+        caps.append(int(max(d[0], 0) * max(d[1], 0) * max(d[2], 0)))
+    label_off = np.cumsum([0] + caps).astype(np.int64)
+    return PackedTracklets(
+        T=T, L=L, F=F, voxel_size=float(batch.voxel_size), trk_frame_off=trk_frame_off, poses=poses,
+        frame_sf=frame_sf, points=points, frame_pt_off=frame_pt_off, sensors=sensors,
+        incl_pool=np.concatenate(incl_parts) if incl_parts else np.zeros(0, np.float32),
+        ri_pool=np.concatenate(ri_parts) if ri_parts else np.zeros(0, np.float32), label_off=label_off)
+
+
+# ------------------------------------------------------------------------------------------------
+# device side
+# ------------------------------------------------------------------------------------------------
+_FIELDS = ("trk_frame_off", "poses", "frame_sf", "points", "frame_pt_off", "sensors", "incl_pool", "ri_pool",
+           "label_off")
+
+
+def _as_bytes(a: np.ndarray) -> torch.Tensor:
+    a = np.ascontiguousarray(a)
+    return torch.from_numpy(a.view(np.uint8).reshape(-1)) if a.size else torch.zeros(0, dtype=torch.uint8)
+
+
+class HostBuffers:
+    """Pinned host copies of a PackedTracklets, ready for asynchronous H2D."""
+
+    def __init__(self, pk: PackedTracklets, pin: bool = True):
+        self.pk = pk
+        self.bufs = {}
+        for name in _FIELDS:
+            t = _as_bytes(getattr(pk, name))
+            self.bufs[name] = t.pin_memory() if (pin and t.numel()) else t
+
+    def nbytes(self) -> int:
+        return sum(t.numel() for t in self.bufs.values())
+
+
+class DeviceTracklets:
+    """Device-resident inputs + outputs + workspace of one batch; reusable across calls."""
+
+    def __init__(self, pk: PackedTracklets, device=None):
+        _lib.require_cuda()
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.pk = pk
+        self.bufs = {name: torch.empty(max(getattr(pk, name).nbytes, 16), dtype=torch.uint8, device=self.device)
+                     for name in _FIELDS}
+        T, total = pk.T, pk.total_slots
+        dev = self.device
+        self.labels = torch.zeros(max(total, 1), dtype=torch.int32, device=dev)
+        self.dims = torch.zeros((max(T, 1), 3), dtype=torch.int32, device=dev)
+        self.sizes = torch.zeros((max(T, 1), 3), dtype=torch.float32, device=dev)
+        self.status = torch.zeros(max(T, 1), dtype=torch.int32, device=dev)
+        self.n_unknown = torch.zeros(max(T, 1), dtype=torch.int64, device=dev)
+        self.n_steps = torch.zeros(max(T, 1), dtype=torch.int64, device=dev)
+        ws = _lib.lib().occb200_annotate_workspace_bytes(T, pk.F, total)
+        self.workspace = torch.empty(max(ws, 16), dtype=torch.uint8, device=dev)
+
+    def upload(self, host: HostBuffers):
+        """Asynchronous H2D of every input on the current stream; returns the bytes copied."""
+        n = 0
+        for name in _FIELDS:
+            src = host.bufs[name]
+            if src.numel():
+                self.bufs[name][: src.numel()].copy_(src, non_blocking=True)
+                n += src.numel()
+        return n
+
+    def args(self, flags: int = 0) -> _lib.AnnotateArgs:
+        pk, b = self.pk, self.bufs
+        a = _lib.AnnotateArgs()
+        a.T, a.L, a.F = pk.T, pk.L, pk.F
+        a.trk_frame_off = b["trk_frame_off"].data_ptr()
+        a.poses = b["poses"].data_ptr()
+        a.frame_sf = b["frame_sf"].data_ptr()
+        a.points = b["points"].data_ptr()
+        a.point_stride = pk.points.shape[1] if pk.points.ndim == 2 else 3
+        a.frame_pt_off = b["frame_pt_off"].data_ptr()
+        a.sensors = b["sensors"].data_ptr()
+        a.incl_pool = b["incl_pool"].data_ptr()
+        a.ri_pool = b["ri_pool"].data_ptr()
+        a.voxel_size = pk.voxel_size
+        a.label_off = b["label_off"].data_ptr()
+        a.labels = self.labels.data_ptr()
+        a.dims = self.dims.data_ptr()
+        a.sizes = self.sizes.data_ptr()
+        a.status = self.status.data_ptr()
+        a.n_unknown = self.n_unknown.data_ptr()
+        a.n_steps = self.n_steps.data_ptr()
+        a.workspace = self.workspace.data_ptr()
+        a.workspace_bytes = self.workspace.numel()
+        a.flags = flags
+        return a
+
+    def run(self, flags: int = 0):
+        """Launch the whole annotate pipeline on the current stream (no synchronisation)."""
+        a = self.args(flags)
+        with torch.cuda.device(self.device):
+            rc = _lib.lib().occb200_annotate_batch(C.byref(a), self.pk.total_slots, _lib.stream_ptr(self.device))
+        _lib.check(rc, "occb200_annotate_batch")
+
+    def results(self) -> List[dict]:
+        """D2H of labels / dims / status and per-tracklet reshape (synchronises)."""
+        pk = self.pk
+        labels = self.labels.cpu().numpy()
+        dims = self.dims.cpu().numpy()
+        sizes = self.sizes.cpu().numpy()
+        status = self.status.cpu().numpy()
+        nunk = self.n_unknown.cpu().numpy()
+        nsteps = self.n_steps.cpu().numpy()
+        out = []
+        for t in range(pk.T):
+            st = int(status[t])
+            if st != 0:
+                out.append(dict(status=STATUS_NAMES.get(st, str(st)), occ=None, dims=dims[t].copy(),
+                                size=sizes[t].copy(), n_unknown=0, n_steps=0))
+                continue
+            X, Y, Z = (int(v) for v in dims[t])
+            o = int(pk.label_off[t])
+            out.append(dict(status="ok", occ=labels[o:o + X * Y * Z].reshape(X, Y, Z).copy(), dims=dims[t].copy(),
+                            size=sizes[t].copy(), n_unknown=int(nunk[t]), n_steps=int(nsteps[t])))
+        return out
+
+
+def annotate_batch(batch, flags: int = 0, pack_override: Optional[dict] = None, device=None) -> List[dict]:
+    """Annotate every tracklet of ``batch``: the batched equivalent of ``OccAnnotator.annotate_trk``.
+
+    Returns one dict per tracklet: ``status`` (``ok`` or the reason the reference produces no file),
+    ``occ`` int32 [X,Y,Z] with 0 unknown / 1 occupied / 2 free (occ_annotate.py:558-563, 581), ``dims``,
+    ``size``, ``n_unknown`` (U) and ``n_steps`` (visibility tests evaluated).
+    """
+    pk = pack_tracklets(batch, pack_override)
+    host = HostBuffers(pk)
+    dev = DeviceTracklets(pk, device)
+    dev.upload(host)
+    dev.run(flags)
+    return dev.results()
+
+
+def point_cloud_to_range_image_idx(points, extrinsics, inclinations, range_image_size):
+    """Drop-in for occ_annotate.py:141-201 on CUDA tensors.
+
+    points f64 [B,N,3]; extrinsics f32 [B,4,4]; inclinations f32 [B,H] (already flipped);
+    returns (ri_indices int64 [B,N,2], ri_range f64 [B,N]).  As in the reference the extrinsic
+    inverse and the azimuth correction are evaluated on the CPU (occ_annotate.py:158-160).
+    """
+    _lib.require_cuda(points)
+    H, W = range_image_size
+    B, N, _ = points.shape
+    v2l, azc = _host_calib(extrinsics.detach().cpu().numpy())
+    dev = points.device
+    v2l_d = torch.from_numpy(np.ascontiguousarray(v2l)).to(dev)
+    azc_d = torch.from_numpy(np.ascontiguousarray(azc)).to(dev)
+    pts = points.to(torch.float64).contiguous()
+    incl = inclinations.to(device=dev, dtype=torch.float32).contiguous()
+    assert incl.shape == (B, H)
+    idx = torch.empty((B, N, 2), dtype=torch.int64, device=dev)
+    rng = torch.empty((B, N), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        rc = _lib.lib().occb200_point_cloud_to_range_image_idx(pts.data_ptr(), B, N, v2l_d.data_ptr(), azc_d.data_ptr(),
+                                                                incl.data_ptr(), H, W, idx.data_ptr(), rng.data_ptr(),
+                                                                _lib.stream_ptr(dev))
+    _lib.check(rc, "occb200_point_cloud_to_range_image_idx")
+    return idx, rng
+
+
+class OccAnnotator:
+    """Batched counterpart of the reference's ``OccAnnotator`` (occ_annotate.py:228-671).
+
+    Keeps the reference's knobs that affect the result (``voxel_size``, ``overwrite``, the
+    ``<out_dir>/<split>/<segment>/<trk_id>.npz`` layout with key ``occ``) and replaces the
+    per-tracklet python loop by one device call per batch.
+    """
+
+    def __init__(self, out_dir: Optional[str] = None, split: str = "training", voxel_size: float = 0.2,
+                 overwrite: bool = False, device=None):
+        self.out_dir = out_dir
+        self.split = split
+        self.voxel_size = voxel_size
+        self.overwrite = overwrite
+        self.device = device
+
+    def annotate(self, batch) -> List[dict]:
+        batch.voxel_size = self.voxel_size
+        return annotate_batch(batch, device=self.device)
+
+    def out_name(self, segment_name: str, trk_id: str) -> str:
+        return os.path.join(self.out_dir, self.split, segment_name, f"{trk_id}.npz")      # :330-332
+
+    def annotate_and_save(self, batch, names: Sequence[tuple]) -> List[Optional[str]]:
+        """``names[t] = (segment_name, trk_id)``.  Existing loadable files are skipped unless
+        ``overwrite`` (:335-343); tracklets the reference would not write are skipped as well."""
+        res = self.annotate(batch)
+        written = []
+        for r, (seg, tid) in zip(res, names):
+            path = self.out_name(seg, tid)
+            if r["occ"] is None:
+                written.append(None)
+                continue
+            if os.path.isfile(path) and not self.overwrite:
+                try:
+                    np.load(path)
+                    written.append(path)
+                    continue
+                except Exception:
+                    pass
+            os.makedirs(os.path.dirname(path), exist_ok=True)
+            np.savez(path, occ=r["occ"])                                                   # :647
+            written.append(path)
+        return written

@@ -1,0 +1,36 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def pytest_collection_modifyitems(config, items):
+    import torch
+
+    if torch.cuda.is_available():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _built():
+    """Everything is built in-tree once per session (nvcc cross-compiles without a GPU)."""
+    import __graft_entry__ as g
+
+    if not os.path.exists(os.path.join(ROOT, "objectcentricocccompletion_b200", "csrc", "libocc_b200.so")):
+        g.build()
+    from oracle import build as obuild
+
+    obuild.build_oracle()
+    yield
