@@ -27,6 +27,14 @@ const char *occb200_last_error(void);
 /* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
 int64_t occb200_launch_count(void);
 
+/* Optional per-kernel timing of occb200_annotate_batch for roofline reports: while enabled, CUDA
+ * events are recorded around each pipeline kernel on the caller's stream.  occb200_profile_read
+ * synchronises those events and returns, per kernel kind (0 k_frame_inbox, 1 k_tracklet_setup,
+ * 2 k_scan_chunks, 3 k_frame_voxelize, 4 k_visibility), the summed milliseconds and launch counts
+ * since the last read.  Both arrays have 5 entries (HOST). */
+void occb200_profile_enable(int on);
+int occb200_profile_read(double *ms_per_kind, int64_t *launches_per_kind);
+
 /* reduce_t of mmdet3d/ops/voxel/src/scatter_points_cuda.cu:7 */
 enum { OCCB200_SUM = 0, OCCB200_MEAN = 1, OCCB200_MAX = 2 };
 

@@ -50,6 +50,8 @@ SIGNATURES = {
     "occb200_abi_version": (C.c_int, []),
     "occb200_last_error": (C.c_char_p, []),
     "occb200_launch_count": (i64, []),
+    "occb200_profile_enable": (None, [C.c_int]),
+    "occb200_profile_read": (C.c_int, [vp, vp]),
     "occb200_points_in_boxes_gpu": (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]),
     "occb200_points_in_boxes_batch": (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]),
     "occb200_host_box_trig": (None, [vp, i64, vp]),

@@ -11,6 +11,9 @@
 //   k_visibility      persistent CTAs over 256-voxel chunks: the range-image "ray-cast"       (A4/A5)
 #include <math.h>
 
+#include <mutex>
+#include <vector>
+
 #include "common.cuh"
 #include "geom.cuh"
 
@@ -66,6 +69,34 @@ static int64_t ws_layout(int32_t T, int64_t F, int64_t total, char *base, Worksp
   }
   return off;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Optional per-kernel timing (bench.py's roofline): CUDA events recorded around each kernel of the
+// pipeline on the caller's stream; durations are summed per kernel when the profile is read.
+enum { kProfInbox = 0, kProfSetup, kProfScan, kProfVoxelize, kProfVisibility, kProfKinds };
+struct ProfEntry { int kind; cudaEvent_t a, b; };
+static bool g_prof_on = false;
+static std::vector<ProfEntry> g_prof;
+static std::mutex g_prof_mu;
+
+struct ProfScope {
+  cudaStream_t stream;
+  ProfEntry e;
+  bool on;
+  ProfScope(int kind, cudaStream_t s) : stream(s), on(g_prof_on) {
+    if (!on) return;
+    e.kind = kind;
+    cudaEventCreate(&e.a);
+    cudaEventCreate(&e.b);
+    cudaEventRecord(e.a, stream);
+  }
+  ~ProfScope() {
+    if (!on) return;
+    cudaEventRecord(e.b, stream);
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof.push_back(e);
+  }
+};
 
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kFrameThreads)
@@ -399,28 +430,58 @@ extern "C" int occb200_annotate_batch(const occb200_annotate_args_t *a, int64_t 
   const float vsf = (float)a->voxel_size;
   OCC_CUDA(cudaMemsetAsync(w.bits, 0, 4 * w.bits_words, stream));
   if (a->F > 0) {
+    ProfScope ps(kProfInbox, stream);
     k_frame_inbox<<<(unsigned)a->F, kFrameThreads, 0, stream>>>(a->poses, a->points, a->point_stride,
                                                                  a->frame_pt_off, w.frame_kept);
     OCC_KERNEL_OK("k_frame_inbox");
   }
-  k_tracklet_setup<<<(unsigned)ceil_div(a->T, 128), 128, 0, stream>>>(
-      a->T, a->trk_frame_off, a->poses, w.frame_kept, a->label_off, vsf, w.grids, w.frame_trk, a->dims,
-      a->sizes, a->status, a->n_unknown, a->n_steps);
-  OCC_KERNEL_OK("k_tracklet_setup");
-  k_scan_chunks<<<1, 1024, 0, stream>>>(a->T, w.grids, w.chunk_off, w.counter);
-  OCC_KERNEL_OK("k_scan_chunks");
+  {
+    ProfScope ps(kProfSetup, stream);
+    k_tracklet_setup<<<(unsigned)ceil_div(a->T, 128), 128, 0, stream>>>(
+        a->T, a->trk_frame_off, a->poses, w.frame_kept, a->label_off, vsf, w.grids, w.frame_trk, a->dims,
+        a->sizes, a->status, a->n_unknown, a->n_steps);
+    OCC_KERNEL_OK("k_tracklet_setup");
+  }
+  {
+    ProfScope ps(kProfScan, stream);
+    k_scan_chunks<<<1, 1024, 0, stream>>>(a->T, w.grids, w.chunk_off, w.counter);
+    OCC_KERNEL_OK("k_scan_chunks");
+  }
   if (a->F > 0) {
+    ProfScope ps(kProfVoxelize, stream);
     k_frame_voxelize<<<(unsigned)a->F, kFrameThreads, 0, stream>>>(
         a->poses, a->points, a->point_stride, a->frame_pt_off, w.frame_kept, w.frame_trk, w.grids, w.bits, vsf);
     OCC_KERNEL_OK("k_frame_voxelize");
   }
   const int64_t max_items = ceil_div(total, kChunk) + a->T;
   const int grid = (int)std::min<int64_t>(max_items, (int64_t)kNumSMs * 8);
+  ProfScope ps(kProfVisibility, stream);
   k_visibility_f64<<<grid, kChunk, 0, stream>>>(a->T, a->L, a->trk_frame_off, a->poses, a->frame_sf, a->sensors,
                                                 a->incl_pool, a->ri_pool, a->voxel_size, a->label_off, w.grids,
                                                 w.chunk_off, w.counter, w.bits, a->labels, a->status,
                                                 a->n_unknown, a->n_steps);
   OCC_KERNEL_OK("k_visibility_f64");
+  return 0;
+}
+
+extern "C" void occb200_profile_enable(int on) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof_on = on != 0;
+}
+
+extern "C" int occb200_profile_read(double *ms_per_kind, int64_t *launches_per_kind) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (int k = 0; k < kProfKinds; ++k) { ms_per_kind[k] = 0.0; launches_per_kind[k] = 0; }
+  for (auto &e : g_prof) {
+    float ms = 0.f;
+    OCC_CUDA(cudaEventSynchronize(e.b));
+    OCC_CUDA(cudaEventElapsedTime(&ms, e.a, e.b));
+    ms_per_kind[e.kind] += ms;
+    launches_per_kind[e.kind] += 1;
+    cudaEventDestroy(e.a);
+    cudaEventDestroy(e.b);
+  }
+  g_prof.clear();
   return 0;
 }
 

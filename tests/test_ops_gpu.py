@@ -73,7 +73,7 @@ def test_dynamic_voxelize_vs_oracle(C, N):
     assert (got2.cpu().numpy() == exp).all()
     got64 = occ.voxelization(_t(pts.astype(np.float64)), vs, pcr, -1, -1)
     exp64 = np.clip(np.floor((pts[:, :3].astype(np.float64) - np.array(pcr[:3], np.float32)) / np.array(vs, np.float32)),
-                    0, np.array([4096, 4096, 60]) - 1).astype(np.int32)[:, ::-1]
+                    0, np.array([2048, 2048, 60]) - 1).astype(np.int32)[:, ::-1]
     assert (got64.cpu().numpy() == exp64).all()
 
 
