@@ -204,6 +204,7 @@ def main():
     d.run(flags)
     torch.cuda.synchronize()
     res = d.results()
+    n_recheck, q_cap = d.queue_stats(flags)
     ws = workload_stats(res, B, L)
     n_ok = sum(r["occ"] is not None for r in res)
 
@@ -257,8 +258,9 @@ def main():
     _lib.lib().occb200_profile_enable(1)
     timed(step_resident, args.steps)
     _lib.lib().occb200_profile_enable(0)
-    kms = np.zeros(5, np.float64)
-    kn = np.zeros(5, np.int64)
+    nk = _lib.lib().occb200_profile_kinds()
+    kms = np.zeros(nk, np.float64)
+    kn = np.zeros(nk, np.int64)
     _lib.check(_lib.lib().occb200_profile_read(kms.ctypes.data, kn.ctypes.data), "occb200_profile_read")
 
     # ---- e2e --------------------------------------------------------------------------------------
@@ -324,7 +326,8 @@ def main():
                    "voxel_size": batch.voxel_size, "ok_tracklets": n_ok, "l2": "flushed (256 MiB write) between timed steps",
                    "visibility": "f64" if args.force_f64 else "default"},
         "voxel_steps_per_s": steps_all / sec, "executed_steps_per_s": exec_all / sec,
-        "voxel_steps_per_step": ws["steps"], "unknown_voxels_per_step": ws["U"], "voxels_per_step": ws["V"],
+        "voxel_steps_per_step": ws["steps"], "executed_steps_per_step": ws["executed"],
+        "f64_rechecks_per_step": n_recheck, "unknown_voxels_per_step": ws["U"], "voxels_per_step": ws["V"],
         "e2e": {"value": T_all / sec_e2e, "unit": "tracklets/s", "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": d2h_bytes, "ms_per_step": sec_e2e * 1e3},
         "gpu_launches": int(launches),
@@ -333,7 +336,8 @@ def main():
                      "algorithmic_bytes_per_launch": ws["vis_bytes"], "kernel_ms": vis_ms,
                      "kernel_share_of_step": vis_ms / step_ms_prof if step_ms_prof else None,
                      "kernels_ms": dict(zip(("k_frame_inbox", "k_tracklet_setup", "k_scan_chunks", "k_frame_voxelize",
-                                             "k_visibility"), (kms / np.maximum(kn, 1)).round(5).tolist()))},
+                                             "k_visibility", "k_table_setup+k_pair_setup", "k_visibility_recheck"),
+                                            (kms / np.maximum(kn[4], 1)).round(5).tolist()))},
         "cpu_baseline": cpu, "clocks": clocks,
     }
     if gather_ms is not None:

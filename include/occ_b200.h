@@ -30,10 +30,16 @@ int64_t occb200_launch_count(void);
 /* Optional per-kernel timing of occb200_annotate_batch for roofline reports: while enabled, CUDA
  * events are recorded around each pipeline kernel on the caller's stream.  occb200_profile_read
  * synchronises those events and returns, per kernel kind (0 k_frame_inbox, 1 k_tracklet_setup,
- * 2 k_scan_chunks, 3 k_frame_voxelize, 4 k_visibility), the summed milliseconds and launch counts
- * since the last read.  Both arrays have 5 entries (HOST). */
+ * 2 k_scan_chunks, 3 k_frame_voxelize, 4 k_visibility_{fast,f64}, 5 k_table_setup + k_pair_setup,
+ * 6 k_visibility_recheck), the summed milliseconds and launch counts since the last read.
+ * Both arrays have occb200_profile_kinds() entries (HOST). */
 void occb200_profile_enable(int on);
+int occb200_profile_kinds(void);
 int occb200_profile_read(double *ms_per_kind, int64_t *launches_per_kind);
+/* Self-test: maximum |atan2_fast(y,x) - atan2(y,x)| (radians) of the f32 arctangent used by the fast
+ * visibility kernel over n pseudo-random pairs; must stay below the 2e-6 the kernel's margins assume.
+ * Synchronises `stream`. */
+int occb200_selftest_atan2(int64_t n, uint64_t seed, double *max_err_host, void *stream);
 
 /* reduce_t of mmdet3d/ops/voxel/src/scatter_points_cuda.cu:7 */
 enum { OCCB200_SUM = 0, OCCB200_MEAN = 1, OCCB200_MAX = 2 };
@@ -203,7 +209,9 @@ typedef struct occb200_annotate_args {
   int32_t pad0;
   const int64_t *frame_pt_off;    /* [F+1] point range of each tracklet-frame                 */
   const occb200_sensor_t *sensors;/* [SF, L]                                                  */
+  int64_t SF;                     /* sensor frames in `sensors`                               */
   const float *incl_pool;
+  int64_t incl_len;               /* floats in incl_pool                                      */
   const float *ri_pool;
   double voxel_size;              /* python float of --voxel-size (occ_annotate.py:215)       */
   const int64_t *label_off;       /* [T+1] slot of each tracklet in labels; slot size >= prod(ceil(max_frames(size)/vs)) */
@@ -215,12 +223,13 @@ typedef struct occb200_annotate_args {
   int64_t *n_unknown;             /* [T]    voxels tested for visibility (U)                  */
   int64_t *n_steps;               /* [T]    visibility tests actually evaluated (<= U*B*L; early exit) ; may be NULL */
   void *workspace;
-  int64_t workspace_bytes;        /* >= occb200_annotate_workspace_bytes(T, F, label_off[T])  */
-  int32_t flags;                  /* bit 0: force the all-f64 visibility kernel               */
+  int64_t workspace_bytes;        /* >= occb200_annotate_workspace_bytes(T, F, label_off[T], SF, L, incl_len) */
+  int32_t flags;                  /* bit 0: every visibility test in exact f64 (no f32 fast path) */
   int32_t pad1;
 } occb200_annotate_args_t;
 
-int64_t occb200_annotate_workspace_bytes(int32_t T, int64_t F, int64_t total_label_slots);
+int64_t occb200_annotate_workspace_bytes(int32_t T, int64_t F, int64_t total_label_slots, int64_t SF,
+                                         int32_t L, int64_t incl_len);
 
 /*
  * What tools/occ/occ_annotate.py does per tracklet (get_local_point_list :91-138 and
@@ -231,6 +240,12 @@ int64_t occb200_annotate_workspace_bytes(int32_t T, int64_t F, int64_t total_lab
  * call needs no device->host read.
  */
 int occb200_annotate_batch(const occb200_annotate_args_t *args, int64_t total_label_slots, void *stream);
+
+/* After occb200_annotate_batch with the same args: out_host[0] = visibility tests the f32 fast path could
+ * not decide and handed to the exact f64 recheck, out_host[1] = capacity of that queue (tests beyond it
+ * are decided in place).  Synchronises `stream`. */
+int occb200_annotate_queue_stats(const occb200_annotate_args_t *args, int64_t total_label_slots,
+                                 int64_t *out_host, void *stream);
 
 /* HOST helper: fills poses[i] from boxes7 f32 [n,7] and torch-evaluated trig f32 [n,4]
  * (cos(-yaw), sin(-yaw), cos(yaw), sin(yaw)); cos_pib/sin_pib come from the host libm. */

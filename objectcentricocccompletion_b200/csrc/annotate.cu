@@ -8,7 +8,20 @@
 //   k_tracklet_setup  one thread per tracklet: box size = max over kept frames, dims, bounds  (A2/A3)
 //   k_scan_chunks     one CTA: exclusive scan of per-tracklet work chunks -> work list
 //   k_frame_voxelize  one CTA per tracklet-frame: in-box -> box frame -> quantise -> bitset   (A2/A3)
-//   k_visibility      persistent CTAs over 256-voxel chunks: the range-image "ray-cast"       (A4/A5)
+//   k_table_setup     one CTA per (sensor frame, LiDAR): inclination row boundaries + lookup table
+//   k_pair_setup      one thread per (tracklet-frame, LiDAR): voxel-index -> sensor-frame affine map
+//   k_visibility_fast persistent CTAs over 32-voxel chunks: the range-image "ray-cast" in f32 with
+//                     rigorous error margins; tests whose outcome is not certain are queued    (A4/A5)
+//   k_visibility_recheck  the queued tests, re-evaluated with the reference's exact f64 arithmetic
+//   k_visibility_f64  (flags bit 0) every test in exact f64 -- the slow, margin-free formulation
+//
+// Why the fast kernel is still bit-exact.  Per test the reference takes three discrete decisions from
+// f64 quantities: the range-image row (nearest inclination), the column (rounded azimuth) and
+// `range_image >= range`.  The fast kernel evaluates the same quantities in f32 from a per-(frame,
+// LiDAR) affine map of the voxel index, with an explicit bound on |f32 value - reference f64 value|
+// (derived at each use below).  A decision is accepted only if it stays the same anywhere inside that
+// bound; otherwise the test goes to a queue and k_visibility_recheck redoes it with project_exact().
+// Labels therefore never depend on f32 rounding; only the amount of rechecked work does.
 #include <math.h>
 
 #include <mutex>
@@ -19,7 +32,11 @@
 
 namespace occb200 {
 
-constexpr int kChunk = 256;         // voxels per work item == threads per visibility CTA
+constexpr int kChunk = 256;         // f64 kernel: voxels per work item == threads per CTA
+constexpr int kVPL = 2;             // fast kernel: voxels per lane
+constexpr int kFastChunk = 32 * kVPL;   // fast kernel: voxels per work item
+constexpr int kFastWarps = 8;       // fast kernel: warps per CTA, each takes every 8th (frame, LiDAR) pair
+constexpr int kLutPerRow = 16;      // lookup-table cells reserved per inclination-table entry
 constexpr int kFrameThreads = 256;
 constexpr int kSmemBitWords = 8192; // 32 KB: grids up to 262 144 voxels keep their bitset in shared memory
 
@@ -34,17 +51,54 @@ struct TrkGrid {
   int32_t B;
 };
 
+// Per (sensor frame, LiDAR) constants of the fast path.  64 bytes, 4 x LDG.128.
+// Row lookup happens in "u space": u(inc) = sin/(|sin| + cos), monotone with slope in [1/2, 1] over
+// [-90, 90] degrees, so row boundaries never bunch up (unlike tan or sin).
+struct __align__(16) SensCoef {
+  float azc;
+  float kcol;       // W / (2 pi)
+  float Wf;
+  float c_col;      // evaluation error of the f32 column coordinate (pixels)
+  float u_lo, inv_w;   // lookup cell k covers [u_lo + k/inv_w, u_lo + (k+1)/inv_w)
+  int32_t ncell;
+  int32_t H;
+  int32_t W;
+  int32_t ok;       // 0: no fast path for this sensor (table not strictly descending, H < 2, ...)
+  int32_t tab_off;  // == incl_off: position of the table in incl_pool / ub_pool, x kLutPerRow in lut_pool
+  int32_t pad0;
+  int64_t ri_off;
+  int64_t pad1;
+};
+static_assert(sizeof(SensCoef) == 64, "SensCoef must be 64 bytes");
+
+// One (tracklet-frame, LiDAR) pair: p_sensor = A * (x,y,z voxel index) + b.  64 bytes, 4 x LDG.128.
+struct __align__(16) PairCoef {
+  float A[9];
+  float b[3];
+  float eps;        // bound on |f32 p - reference f64 p| per component (metres); < 0: no fast path
+  int32_t sens;     // index into the SensCoef table
+  float pad[2];
+};
+static_assert(sizeof(PairCoef) == 64, "PairCoef must be 64 bytes");
+
 struct Workspace {
   TrkGrid *grids;        // [T]
   int32_t *frame_kept;   // [F]
   int32_t *frame_trk;    // [F]
   int64_t *chunk_off;    // [T+1]
-  unsigned long long *counter;   // work-queue head
+  unsigned long long *counter;   // [0] work-queue head, [1] recheck-queue length
   uint32_t *bits;        // occupancy bitsets
   int64_t bits_words;
+  SensCoef *sens;        // [SF*L]
+  float *ub_pool;        // [incl_len]   u-space row boundaries, table at incl_off
+  uint16_t *lut_pool;    // [incl_len * kLutPerRow]
+  PairCoef *pairs;       // [F*L]
+  int4 *queue;           // recheck queue: (tracklet, voxel, pair index q = i*L + c, unused)
+  int64_t queue_cap;
 };
 
-static int64_t ws_layout(int32_t T, int64_t F, int64_t total, char *base, Workspace *w) {
+static int64_t ws_layout(int32_t T, int64_t F, int64_t total, int64_t SF, int32_t L, int64_t incl_len, char *base,
+                         Workspace *w) {
   int64_t off = 0;
   auto take = [&](int64_t bytes) {
     int64_t o = off;
@@ -55,9 +109,17 @@ static int64_t ws_layout(int32_t T, int64_t F, int64_t total, char *base, Worksp
   int64_t o_kept = take(4 * F);
   int64_t o_ftrk = take(4 * F);
   int64_t o_choff = take(8 * ((int64_t)T + 1));
-  int64_t o_cnt = take(8);
+  int64_t o_cnt = take(8 * 4);
   int64_t words = total / 32 + T + 1;
   int64_t o_bits = take(4 * words);
+  int64_t o_tab = take(sizeof(SensCoef) * SF * L);
+  int64_t o_ub = take(4 * incl_len);
+  int64_t o_lut = take(2 * incl_len * kLutPerRow);
+  int64_t o_pairs = take(sizeof(PairCoef) * F * L);
+  // recheck queue: ~1% of the tests are expected; room for 1/16 of the nominal tests, bounded
+  const double nominal = (double)total * (T > 0 ? (double)F / T : 0.0) * L;
+  int64_t qcap = (int64_t)std::min(std::max(nominal / 16.0, 65536.0), 64.0 * 1024 * 1024);
+  int64_t o_q = take(16 * qcap);
   if (w) {
     w->grids = (TrkGrid *)(base + o_grid);
     w->frame_kept = (int32_t *)(base + o_kept);
@@ -66,6 +128,12 @@ static int64_t ws_layout(int32_t T, int64_t F, int64_t total, char *base, Worksp
     w->counter = (unsigned long long *)(base + o_cnt);
     w->bits = (uint32_t *)(base + o_bits);
     w->bits_words = words;
+    w->sens = (SensCoef *)(base + o_tab);
+    w->ub_pool = (float *)(base + o_ub);
+    w->lut_pool = (uint16_t *)(base + o_lut);
+    w->pairs = (PairCoef *)(base + o_pairs);
+    w->queue = (int4 *)(base + o_q);
+    w->queue_cap = qcap;
   }
   return off;
 }
@@ -73,7 +141,7 @@ static int64_t ws_layout(int32_t T, int64_t F, int64_t total, char *base, Worksp
 // ---------------------------------------------------------------------------------------------
 // Optional per-kernel timing (bench.py's roofline): CUDA events recorded around each kernel of the
 // pipeline on the caller's stream; durations are summed per kernel when the profile is read.
-enum { kProfInbox = 0, kProfSetup, kProfScan, kProfVoxelize, kProfVisibility, kProfKinds };
+enum { kProfInbox = 0, kProfSetup, kProfScan, kProfVoxelize, kProfVisibility, kProfPairSetup, kProfRecheck, kProfKinds };
 struct ProfEntry { int kind; cudaEvent_t a, b; };
 static bool g_prof_on = false;
 static std::vector<ProfEntry> g_prof;
@@ -119,7 +187,7 @@ k_frame_inbox(const occb200_pose_t *__restrict__ poses, const float *__restrict_
 __global__ void k_tracklet_setup(int T, const int64_t *__restrict__ trk_frame_off,
                                  const occb200_pose_t *__restrict__ poses,
                                  const int32_t *__restrict__ frame_kept, const int64_t *__restrict__ label_off,
-                                 float vsf, TrkGrid *__restrict__ grids, int32_t *__restrict__ frame_trk,
+                                 float vsf, int chunk, TrkGrid *__restrict__ grids, int32_t *__restrict__ frame_trk,
                                  int32_t *__restrict__ dims_out, float *__restrict__ sizes_out,
                                  int32_t *__restrict__ status_out, int64_t *__restrict__ n_unknown,
                                  int64_t *__restrict__ n_steps) {
@@ -161,14 +229,14 @@ __global__ void k_tracklet_setup(int T, const int64_t *__restrict__ trk_frame_of
       g.status = -1;                           // caller's slot too small: reported, nothing written
       g.V = 0;
     }
-    g.nchunks = (int)((g.V + kChunk - 1) / kChunk);
+    g.nchunks = (int)((g.V + chunk - 1) / chunk);
   }
   grids[t] = g;
   for (int k = 0; k < 3; ++k) {
     dims_out[3 * t + k] = g.dims[k];
     sizes_out[3 * t + k] = (g.status == OCCB200_OK) ? sz[k] : 0.f;
   }
-  status_out[t] = g.status;                    // refined by k_visibility (flags)
+  status_out[t] = g.status;                    // refined by the visibility kernel (flags)
   n_unknown[t] = 0;
   if (n_steps) n_steps[t] = 0;
 }
@@ -197,7 +265,7 @@ k_scan_chunks(int T, const TrkGrid *__restrict__ grids, int64_t *__restrict__ ch
     run += grids[t].nchunks;
   }
   if (tid == 1023) chunk_off[T] = s_part[1023];
-  if (tid == 0) *counter = 0ull;
+  if (tid < 4) counter[tid] = 0ull;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -284,9 +352,7 @@ k_frame_voxelize(const occb200_pose_t *__restrict__ poses, const float *__restri
 }
 
 // ---------------------------------------------------------------------------------------------
-// Visibility: label every voxel without a point as free (2) if, for ANY frame and ANY LiDAR, the
-// range image holds a return at least as far as the voxel centre along the pixel the centre
-// projects to; otherwise unknown (0).  Occupied voxels are 1.  (occ_annotate.py:466-563)
+// Exact visibility test of one voxel centre against one (frame, LiDAR): occ_annotate.py:490-547.
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ SensorView load_sensor(const occb200_sensor_t *__restrict__ sn,
                                                   const float *__restrict__ incl_pool) {
@@ -299,6 +365,33 @@ __device__ __forceinline__ SensorView load_sensor(const occb200_sensor_t *__rest
   s.mono = __ldg(&sn->incl_mono);
   s.incl = incl_pool + __ldg(&sn->incl_off);
   return s;
+}
+
+// centre = coord.f64 * vs + min_bound + vs/2, left to right (:467-471)
+__device__ __forceinline__ void voxel_centre(const TrkGrid &g, int64_t f, double vs, double &cx, double &cy,
+                                             double &cz) {
+  const int YZ = g.dims[1] * g.dims[2];
+  const int x = (int)(f / YZ), y = (int)((f / g.dims[2]) % g.dims[1]), z = (int)(f % g.dims[2]);
+  cx = __dadd_rn(__dadd_rn(__dmul_rn((double)x, vs), (double)g.mb[0]), vs / 2);
+  cy = __dadd_rn(__dadd_rn(__dmul_rn((double)y, vs), (double)g.mb[1]), vs / 2);
+  cz = __dadd_rn(__dadd_rn(__dmul_rn((double)z, vs), (double)g.mb[2]), vs / 2);
+}
+
+__device__ __noinline__ bool exact_test(double cx, double cy, double cz, const occb200_pose_t *__restrict__ ps,
+                                        const occb200_sensor_t *__restrict__ sn, const float *__restrict__ incl_pool,
+                                        const float *__restrict__ ri_pool) {
+  const double rc = (double)__ldg(&ps->cos_p), rs = (double)__ldg(&ps->sin_p);   // :490-496
+  // ego = centre @ [[c,-s,0],[s,c,0],[0,0,1]] + origin (:497-498); the z row is exact
+  const double ex = __dadd_rn(__fma_rn(cy, rs, __dmul_rn(cx, rc)), (double)__ldg(&ps->box[0]));
+  const double ey = __dadd_rn(__fma_rn(cy, rc, __dmul_rn(cx, -rs)), (double)__ldg(&ps->box[1]));
+  const double ez = __dadd_rn(cz, (double)__ldg(&ps->box[2]));
+  const SensorView sv = load_sensor(sn, incl_pool);
+  int row, col;
+  double rng;
+  project_exact(ex, ey, ez, sv, row, col, rng);
+  if (col < 0) col += sv.W;                      // negative index wraps (:543)
+  const float ri = __ldg(ri_pool + __ldg(&sn->ri_off) + (int64_t)row * sv.W + col);
+  return (double)ri >= rng;                      // :547
 }
 
 __global__ void __launch_bounds__(kChunk)
@@ -344,31 +437,15 @@ k_visibility_f64(int T, int L, const int64_t *__restrict__ trk_frame_off,
     bool is_free = false;
     long long steps = 0;
     if (__any_sync(0xffffffffu, need)) {
-      const int YZ = g.dims[1] * g.dims[2];
-      const int x = (int)(f / YZ), y = (int)((f / g.dims[2]) % g.dims[1]), z = (int)(f % g.dims[2]);
-      // centre = coord.f64 * vs + min_bound + vs/2, left to right (:467-471)
-      const double cx = __dadd_rn(__dadd_rn(__dmul_rn((double)x, vs), (double)g.mb[0]), vs / 2);
-      const double cy = __dadd_rn(__dadd_rn(__dmul_rn((double)y, vs), (double)g.mb[1]), vs / 2);
-      const double cz = __dadd_rn(__dadd_rn(__dmul_rn((double)z, vs), (double)g.mb[2]), vs / 2);
+      double cx, cy, cz;
+      voxel_centre(g, active ? f : 0, vs, cx, cy, cz);
       const int64_t f0 = trk_frame_off[t];
       for (int c = 0; c < L; ++c) {              // LiDARs (:525), OR-ed (:552-556)
         for (int i = 0; i < g.B; ++i) {          // frames (:479), OR-ed (:550)
           if (__all_sync(0xffffffffu, !need || is_free)) break;   // warp-uniform early exit
           if (need && !is_free) {
-            const occb200_pose_t &ps = poses[f0 + i];
-            const double rc = (double)__ldg(&ps.cos_p), rs = (double)__ldg(&ps.sin_p);   // :490-496
-            // ego = centre @ [[c,-s,0],[s,c,0],[0,0,1]] + origin (:497-498); z row is exact
-            const double ex = __dadd_rn(__fma_rn(cy, rs, __dmul_rn(cx, rc)), (double)__ldg(&ps.box[0]));
-            const double ey = __dadd_rn(__fma_rn(cy, rc, __dmul_rn(cx, -rs)), (double)__ldg(&ps.box[1]));
-            const double ez = __dadd_rn(cz, (double)__ldg(&ps.box[2]));
             const occb200_sensor_t *sn = sensors + (int64_t)__ldg(frame_sf + f0 + i) * L + c;
-            const SensorView sv = load_sensor(sn, incl_pool);
-            int row, col;
-            double rng;
-            project_exact(ex, ey, ez, sv, row, col, rng);
-            if (col < 0) col += sv.W;            // negative index wraps (:543)
-            const float ri = __ldg(ri_pool + __ldg(&sn->ri_off) + (int64_t)row * sv.W + col);
-            is_free = (double)ri >= rng;         // :547
+            is_free = exact_test(cx, cy, cz, poses + f0 + i, sn, incl_pool, ri_pool);
             ++steps;
           }
         }
@@ -382,6 +459,408 @@ k_visibility_f64(int T, int L, const int64_t *__restrict__ trk_frame_off,
       if (nmask) atomicAdd((unsigned long long *)&n_unknown[t], (unsigned long long)__popc(nmask));
       if (n_steps && steps) atomicAdd((unsigned long long *)&n_steps[t], (unsigned long long)steps);
     }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fast path, part 1: per-table row lookup.  Table t_0 > t_1 > ... (flipped inclinations,
+// occ_annotate.py:528).  argmin_h |inc - t_h| (first index on ties, :168-173) == number of
+// midpoints m_h = (t_h + t_{h+1})/2 that lie above inc.  Boundaries are stored as ub_h = u(m_h).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double u_of_angle(double a) {
+  const double s = sin(a), c = cos(a);
+  return s / (fabs(s) + c);
+}
+
+__global__ void __launch_bounds__(256)
+k_table_setup(int64_t n_sensors, const occb200_sensor_t *__restrict__ sensors, const float *__restrict__ incl_pool,
+              SensCoef *__restrict__ sens, float *__restrict__ ub_pool, uint16_t *__restrict__ lut_pool) {
+  __shared__ float s_min[256];
+  __shared__ SensCoef s_info;
+  const int64_t e = blockIdx.x;
+  if (e >= n_sensors) return;
+  const occb200_sensor_t &sn = sensors[e];
+  const int H = sn.H;
+  const int64_t off = sn.incl_off;
+  const float *tab = incl_pool + off;
+  float *ub = ub_pool + off;
+  uint16_t *lut = lut_pool + off * kLutPerRow;
+  const bool candidate = (sn.incl_mono == -1) && H >= 2 && H < 65535 && off < (1ll << 26);
+  float local_min = INFINITY;
+  if (candidate) {
+    for (int h = threadIdx.x; h < H - 1; h += blockDim.x) {
+      const double m = 0.5 * ((double)tab[h] + (double)tab[h + 1]);
+      ub[h] = (float)u_of_angle(m);
+    }
+    if (threadIdx.x == 0) ub[H - 1] = -2.f;      // sentinel below every u
+  }
+  __syncthreads();
+  if (candidate) {
+    for (int h = threadIdx.x; h < H - 2; h += blockDim.x) local_min = fminf(local_min, ub[h] - ub[h + 1]);
+    // the table must stay inside (-90, 90) degrees for u() to be monotone
+    for (int h = threadIdx.x; h < H; h += blockDim.x)
+      if (!(fabsf(tab[h]) < 1.5707f)) local_min = -1.f;
+  }
+  s_min[threadIdx.x] = local_min;
+  __syncthreads();
+  for (int d = 128; d > 0; d >>= 1) {
+    if (threadIdx.x < d) s_min[threadIdx.x] = fminf(s_min[threadIdx.x], s_min[threadIdx.x + d]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    SensCoef sc;
+    sc.azc = sn.azc;
+    sc.kcol = (float)((double)sn.W / 6.28318530717958647692);
+    sc.Wf = (float)sn.W;
+    // colf = (W - 0.5) - fma(az, kcol, W/2): two roundings at magnitude <= W plus the rounding of kcol
+    sc.c_col = 2.0f * (float)sn.W * 1.1920929e-07f;
+    sc.u_lo = 0.f; sc.inv_w = 0.f; sc.ncell = 0;
+    sc.H = H; sc.W = sn.W; sc.ok = 0;
+    sc.tab_off = (int32_t)off; sc.pad0 = 0; sc.ri_off = sn.ri_off; sc.pad1 = 0;
+    float spacing = s_min[0];
+    if (candidate && H == 2) spacing = 0.25f;
+    if (candidate && spacing > 1e-6f && isfinite(spacing) && sn.W >= 2 && sn.W < (1 << 22)) {
+      // cells half as wide as the closest pair of boundaries: (cell + 4% slack) holds at most ONE boundary
+      const float top = ub[0], bot = ub[H - 2];
+      const float w = 0.5f * spacing;
+      const int ncell = (int)ceilf((top - bot) / w) + 2;
+      if (ncell <= H * kLutPerRow) {
+        sc.u_lo = bot - w;
+        sc.inv_w = 1.0f / w;
+        sc.ncell = ncell;
+        sc.ok = 1;
+      }
+    }
+    s_info = sc;
+    sens[e] = sc;
+  }
+  __syncthreads();
+  const SensCoef sc = s_info;
+  if (!sc.ok) return;
+  // lut[k] = number of boundaries above the (slightly raised) upper end of cell k, i.e. the row of a point
+  // at the top of the cell; a point lower in the cell is in that row or, past the cell's one boundary, the next.
+  const float w = 1.0f / sc.inv_w;
+  for (int k = threadIdx.x; k < sc.ncell; k += blockDim.x) {
+    const float ue = sc.u_lo + (float)(k + 1) * w + 0.02f * w;
+    int lo = 0, hi = H - 1;                       // count of ub_h > ue (ub descending)
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (ub[mid] > ue) lo = mid + 1; else hi = mid;
+    }
+    lut[k] = (uint16_t)lo;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fast path, part 2: per (tracklet-frame, LiDAR) affine map, composed in f64 and stored in f32.
+//   centre = vs*idx + c0,  c0 = min_bound + vs/2                    (:467-471)
+//   ego    = Rm centre + o, Rm = [[c, s, 0], [-s, c, 0], [0, 0, 1]] (:490-498)
+//   p      = V ego + tv                                              (:161-164)
+//   =>  p = A idx + b,  A = vs V Rm,  b = V Rm c0 + V o + tv
+// eps bounds |f32 chain - reference f64 chain| per component: the three FMAs round at most
+// 3 * 2^-24 * M, the f32 coefficients contribute at most 2^-24 * M, M = |b| + sum |A| * max idx; the
+// reference's own f64 roundings (~1e-14 m) vanish in the slack of the factor 6.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_pair_setup(int64_t n_pairs, int L, const occb200_pose_t *__restrict__ poses,
+                             const int32_t *__restrict__ frame_sf, const int32_t *__restrict__ frame_trk,
+                             const occb200_sensor_t *__restrict__ sensors, const TrkGrid *__restrict__ grids,
+                             const SensCoef *__restrict__ sens, double vs, PairCoef *__restrict__ pairs) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_pairs) return;
+  const int64_t f = e / L;
+  const int c = (int)(e % L);
+  const TrkGrid &g = grids[frame_trk[f]];
+  const occb200_pose_t &ps = poses[f];
+  const int64_t se = (int64_t)frame_sf[f] * L + c;
+  const occb200_sensor_t &sn = sensors[se];
+  PairCoef pc;
+  const double rc = (double)ps.cos_p, rs = (double)ps.sin_p;
+  const double Rm[9] = {rc, rs, 0, -rs, rc, 0, 0, 0, 1};
+  double V[12];
+  for (int k = 0; k < 12; ++k) V[k] = (double)sn.v2l[k];
+  double VR[9];
+  for (int r = 0; r < 3; ++r)
+    for (int k = 0; k < 3; ++k) VR[3 * r + k] = V[4 * r] * Rm[k] + V[4 * r + 1] * Rm[3 + k] + V[4 * r + 2] * Rm[6 + k];
+  const double c0[3] = {(double)g.mb[0] + vs / 2, (double)g.mb[1] + vs / 2, (double)g.mb[2] + vs / 2};
+  const double o[3] = {(double)ps.box[0], (double)ps.box[1], (double)ps.box[2]};
+  float eps = 0.f;
+  for (int r = 0; r < 3; ++r) {
+    const double b = VR[3 * r] * c0[0] + VR[3 * r + 1] * c0[1] + VR[3 * r + 2] * c0[2] + V[4 * r] * o[0] +
+                     V[4 * r + 1] * o[1] + V[4 * r + 2] * o[2] + V[4 * r + 3];
+    double M = fabs(b);
+    for (int k = 0; k < 3; ++k) {
+      const double a = vs * VR[3 * r + k];
+      pc.A[3 * r + k] = (float)a;
+      M += fabs(a) * (double)(g.dims[k] > 0 ? g.dims[k] - 1 : 0);
+    }
+    pc.b[r] = (float)b;
+    eps = fmaxf(eps, (float)(6.0 * 5.9604644775390625e-08 * M));
+  }
+  const bool ok = sens[se].ok && isfinite(eps) && se < (1ll << 31);
+  pc.eps = ok ? eps : -1.f;
+  pc.sens = (int32_t)se;
+  pc.pad[0] = pc.pad[1] = 0.f;
+  pairs[e] = pc;
+}
+
+// Approximate f32 primitives (flush-to-zero MUFU forms, <= 2 ulp): their error is part of every margin.
+__device__ __forceinline__ float rsqrt_approx(float x) {
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+// atan2 in f32: a * P(a^2), a = min/max in [0,1], P of degree 6 (|atan(a) - a P(a^2)| <= 2.5e-7 in exact
+// arithmetic, checked on 2e6 points), plus Horner rounding (<= 4e-7), the approximate division
+// (2 ulp of a: <= 2.4e-7) and the quadrant fix-ups (2 roundings at <= pi: 2.4e-7 each).
+// Total < 1.4e-6 rad; kAtanErr = 2e-6 is the bound used for every margin below (occb200_selftest_atan2
+// measures the actual maximum on the device).
+constexpr float kAtanErr = 2.0e-6f;
+__device__ __forceinline__ float atan2_fast(float y, float x) {
+  const float ax = fabsf(x), ay = fabsf(y);
+  const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+  const float a = mn * rcp_approx(mx);
+  const float s = a * a;
+  float p = 0.006811790633946657f;
+  p = fmaf(p, s, -0.0336042158305645f);
+  p = fmaf(p, s, 0.07962366938591003f);
+  p = fmaf(p, s, -0.1323334276676178f);
+  p = fmaf(p, s, 0.19807815551757812f);
+  p = fmaf(p, s, -0.3331736922264099f);
+  p = fmaf(p, s, 0.9999961256980896f);
+  float r = p * a;
+  if (ay > ax) r = 1.57079632679489661923f - r;
+  if (x < 0.f) r = 3.14159265358979323846f - r;
+  return (y < 0.f) ? -r : r;
+}
+
+// One fast test.  Returns 2 = certainly free, 0 = certainly not free, 1 = undecided (recheck in f64).
+__device__ __forceinline__ int fast_test(const PairCoef &pc, const SensCoef &sc, float x, float y, float z,
+                                         const float *__restrict__ ub, const uint16_t *__restrict__ lut,
+                                         const float *__restrict__ ri_img) {
+  const float px = fmaf(z, pc.A[2], fmaf(y, pc.A[1], fmaf(x, pc.A[0], pc.b[0])));
+  const float py = fmaf(z, pc.A[5], fmaf(y, pc.A[4], fmaf(x, pc.A[3], pc.b[1])));
+  const float pz = fmaf(z, pc.A[8], fmaf(y, pc.A[7], fmaf(x, pc.A[6], pc.b[2])));
+  const float s2 = fmaf(py, py, px * px);
+  const float r2 = fmaf(pz, pz, s2);
+  const float inv_rho = rsqrt_approx(s2);
+  const float inv_r = rsqrt_approx(r2);
+  const float rho = s2 * inv_rho;
+  const float eps = pc.eps;
+
+  // ---- row: u = pz / (|pz| + rho);  |u - u_ref| <= 1.42 eps / r  +  evaluation (~6 ulp of 1)
+  const float u = pz * rcp_approx(fabsf(pz) + rho);
+  const float eps_u = fmaf(1.5f * eps, inv_r, 1.5e-6f);
+  int cell = (int)((u - sc.u_lo) * sc.inv_w);
+  cell = max(0, min(cell, sc.ncell - 1));
+  const int last = sc.H - 1;
+  const int row0 = min((int)__ldg(lut + cell), last);        // row at the top of the cell
+  // a cell holds at most one boundary, so the row is row0 or row0 + 1; ub[H-1] is a -2 sentinel
+  const float b_here = __ldg(ub + row0);                     // boundary between row0 and row0 + 1
+  const float b_up = __ldg(ub + max(row0 - 1, 0));           // boundary between row0 - 1 and row0
+  const float b_dn = __ldg(ub + min(row0 + 1, last));        // boundary between row0 + 1 and row0 + 2
+  const bool step = b_here > u;
+  const int row = row0 + (step ? 1 : 0);
+  const float below = step ? b_dn : b_here;
+  const float above = step ? b_here : ((row0 > 0) ? b_up : 2.f);
+  bool sure = (below <= u) && (u - below > eps_u) && (above - u > eps_u) && (row <= last);
+
+  // ---- column: az = atan2(py, px) + azc, wrapped; colf = (W - 0.5) - (az + pi) / (2 pi) * W  (:176-191)
+  float az = atan2_fast(py, px) + sc.azc;
+  if (az > 3.14159265358979323846f) az -= 6.2831855f;
+  else if (az < -3.14159265358979323846f) az += 6.2831855f;
+  const float colf = (sc.Wf - 0.5f) - fmaf(az, sc.kcol, 0.5f * sc.Wf);
+  const float cr = rintf(colf);
+  // |az - az_ref| <= kAtanErr + 1.42 eps / rho (+ the f32 sum and wrap, inside kAtanErr's slack)
+  const float eps_col = fmaf(fmaf(1.5f * eps, inv_rho, kAtanErr + 3.0e-7f), sc.kcol, sc.c_col);
+  sure = sure && (fabsf(colf - cr) < 0.5f - eps_col);
+  int col = (int)cr;
+  if (col >= sc.W) col -= sc.W;                              // fmod(round(colf), W) (:191)
+  if (col < 0) col += sc.W;                                  // negative index wraps (:543)
+  col = max(0, min(col, sc.W - 1));
+
+  // ---- range: free iff ri >= |p_ref|;  | |p| - |p_ref| | <= sqrt(3) eps
+  const float ri = __ldg(ri_img + (min(row, last) * sc.W + col));
+  const float r = r2 * inv_r;
+  const float e = 1.7321f * eps;
+  const float m = fmaf(r, fmaf(r, 6.0e-7f, 2.01f * e), e * e);   // margin on squared ranges
+  const float ri2 = ri * ri;
+  const bool yes = ri2 >= r2 + m, no = ri2 <= r2 - m;
+  if (!sure || !(yes || no)) return 1;
+  return yes ? 2 : 0;
+}
+
+template <typename T16>
+__device__ __forceinline__ T16 load64(const T16 *p) {          // 64-byte record, warp-uniform address
+  T16 v;
+  const float4 *src = reinterpret_cast<const float4 *>(p);
+  float4 *dst = reinterpret_cast<float4 *>(&v);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) dst[k] = __ldg(src + k);
+  return v;
+}
+
+__global__ void __launch_bounds__(32 * kFastWarps, 3)
+k_visibility_fast(int T, int L, const int64_t *__restrict__ trk_frame_off,
+                  const occb200_pose_t *__restrict__ poses, const int32_t *__restrict__ frame_sf,
+                  const occb200_sensor_t *__restrict__ sensors, const float *__restrict__ incl_pool,
+                  const float *__restrict__ ri_pool, double vs, const int64_t *__restrict__ label_off,
+                  const TrkGrid *__restrict__ grids, const int64_t *__restrict__ chunk_off,
+                  unsigned long long *__restrict__ counter, const uint32_t *__restrict__ bits,
+                  const PairCoef *__restrict__ pairs, const SensCoef *__restrict__ sens,
+                  const float *__restrict__ ub_pool, const uint16_t *__restrict__ lut_pool,
+                  int4 *__restrict__ queue, long long queue_cap, int32_t *__restrict__ labels,
+                  int32_t *__restrict__ status_out, int64_t *__restrict__ n_unknown, int64_t *__restrict__ n_steps) {
+  __shared__ long long s_item;
+  __shared__ unsigned s_free[kVPL];
+  __shared__ unsigned long long s_steps;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long total = chunk_off[T];
+  for (;;) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      s_item = (long long)atomicAdd(counter, 1ull);
+      s_steps = 0ull;
+    }
+    if (threadIdx.x < kVPL) s_free[threadIdx.x] = 0u;
+    __syncthreads();
+    const long long item = s_item;
+    if (item >= total) break;
+    int lo = 0, hi = T;
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (chunk_off[mid] <= item) lo = mid; else hi = mid;
+    }
+    const int t = lo;
+    const TrkGrid g = grids[t];
+    const int chunk = (int)(item - chunk_off[t]);
+    int status = g.status;
+    if (status == OCCB200_OK) {
+      if (g.flags & 2) status = OCCB200_INDEX_ERROR;
+      else if (!(g.flags & 1)) status = OCCB200_EMPTY_AFTER_FILTER;
+    }
+    if (chunk == 0 && threadIdx.x == 0) status_out[t] = status;
+    if (status != OCCB200_OK) continue;
+
+    // voxel v of this lane: flat index f0v + 32*v + lane (bitset word chunk*kVPL + v)
+    const int64_t fbase = (int64_t)chunk * kFastChunk;
+    unsigned active_mask[kVPL], occ_word[kVPL], need_mask[kVPL];
+    float vx[kVPL], vy[kVPL], vz[kVPL];
+    unsigned any_need = 0u;
+    const int YZ = g.dims[1] * g.dims[2];
+#pragma unroll
+    for (int v = 0; v < kVPL; ++v) {
+      const int64_t left = g.V - (fbase + 32 * v);
+      active_mask[v] = left >= 32 ? 0xffffffffu : (left <= 0 ? 0u : ((1u << left) - 1u));
+      occ_word[v] = active_mask[v] ? bits[g.bits_off + (int64_t)chunk * kVPL + v] : 0u;
+      need_mask[v] = ~occ_word[v] & active_mask[v];
+      any_need |= need_mask[v];
+      const int64_t fa = ((active_mask[v] >> lane) & 1u) ? fbase + 32 * v + lane : 0;
+      vx[v] = (float)(int)(fa / YZ);
+      vy[v] = (float)(int)((fa / g.dims[2]) % g.dims[1]);
+      vz[v] = (float)(int)(fa % g.dims[2]);
+    }
+    unsigned long long steps = 0;
+    if (any_need) {
+      const int64_t f0 = trk_frame_off[t];
+      const int npairs = g.B * L;
+      const PairCoef *tp = pairs + f0 * L;
+      PairCoef pc_next = load64(tp + min(warp, npairs - 1));
+      for (int q = warp; q < npairs; q += kFastWarps) {
+        const PairCoef pc = pc_next;
+        if (q + kFastWarps < npairs) pc_next = load64(tp + q + kFastWarps);     // prefetch the next pair
+        unsigned done[kVPL];
+        unsigned open = 0u;
+#pragma unroll
+        for (int v = 0; v < kVPL; ++v) {
+          done[v] = *(volatile unsigned *)&s_free[v];
+          open |= need_mask[v] & ~done[v];
+        }
+        if (open == 0u) break;                                   // every voxel of the chunk is already free
+        const SensCoef sc = load64(sens + pc.sens);
+        const float *ub = ub_pool + sc.tab_off;
+        const uint16_t *lut = lut_pool + (int64_t)sc.tab_off * kLutPerRow;
+        const float *ri_img = ri_pool + sc.ri_off;
+        int res[kVPL];
+#pragma unroll
+        for (int v = 0; v < kVPL; ++v) {
+          res[v] = 0;
+          if (((need_mask[v] & ~done[v]) >> lane) & 1u) {
+            res[v] = (pc.eps >= 0.f) ? fast_test(pc, sc, vx[v], vy[v], vz[v], ub, lut, ri_img) : 1;
+            ++steps;
+          }
+        }
+#pragma unroll
+        for (int v = 0; v < kVPL; ++v) {
+          if (res[v] == 2) atomicOr(&s_free[v], 1u << lane);
+          const unsigned umask = __ballot_sync(0xffffffffu, res[v] == 1);
+          if (umask) {                                           // queue the undecided tests (warp-aggregated)
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(counter + 1, (unsigned long long)__popc(umask));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (res[v] == 1) {
+              const int64_t f = fbase + 32 * v + lane;
+              const unsigned long long slot = base + __popc(umask & ((1u << lane) - 1u));
+              if (slot < (unsigned long long)queue_cap) {
+                queue[slot] = make_int4(t, (int)f, q, 0);
+              } else {                                           // queue full: decide right here
+                double cx, cy, cz;
+                voxel_centre(g, f, vs, cx, cy, cz);
+                const int i = q / L, c = q - i * L;
+                const occb200_sensor_t *sn = sensors + (int64_t)__ldg(frame_sf + f0 + i) * L + c;
+                if (exact_test(cx, cy, cz, poses + f0 + i, sn, incl_pool, ri_pool)) atomicOr(&s_free[v], 1u << lane);
+              }
+            }
+          }
+        }
+      }
+    }
+    for (int o = 16; o > 0; o >>= 1) steps += __shfl_xor_sync(0xffffffffu, steps, o);
+    if (lane == 0 && steps) atomicAdd(&s_steps, steps);
+    __syncthreads();
+    if (warp < kVPL) {
+      const int v = warp;
+      const unsigned fr = s_free[v];
+      unsigned am = 0u, ow = 0u, nm = 0u;
+#pragma unroll
+      for (int k = 0; k < kVPL; ++k)
+        if (k == v) { am = active_mask[k]; ow = occ_word[k]; nm = need_mask[k]; }
+      if ((am >> lane) & 1u)
+        labels[label_off[t] + fbase + 32 * v + lane] = ((ow >> lane) & 1u) ? 1 : (((fr >> lane) & 1u) ? 2 : 0);   // :558-563
+      if (lane == 0) {
+        if (nm) atomicAdd((unsigned long long *)&n_unknown[t], (unsigned long long)__popc(nm));
+        if (v == 0 && n_steps && s_steps) atomicAdd((unsigned long long *)&n_steps[t], s_steps);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_visibility_recheck(int L, const int64_t *__restrict__ trk_frame_off, const occb200_pose_t *__restrict__ poses,
+                     const int32_t *__restrict__ frame_sf, const occb200_sensor_t *__restrict__ sensors,
+                     const float *__restrict__ incl_pool, const float *__restrict__ ri_pool, double vs,
+                     const int64_t *__restrict__ label_off, const TrkGrid *__restrict__ grids,
+                     const unsigned long long *__restrict__ counter, const int4 *__restrict__ queue,
+                     long long queue_cap, int32_t *__restrict__ labels, int64_t *__restrict__ n_steps) {
+  const long long n = min((long long)counter[1], queue_cap);
+  for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) {
+    const int4 it = queue[k];
+    const int t = it.x, f = it.y, q = it.z;
+    int32_t *lab = labels + label_off[t] + f;
+    if (*(volatile int32_t *)lab != 0) continue;               // already proven free by another test
+    const TrkGrid &g = grids[t];
+    double cx, cy, cz;
+    voxel_centre(g, f, vs, cx, cy, cz);
+    const int i = q / L, c = q - i * L;
+    const int64_t f0 = trk_frame_off[t];
+    const occb200_sensor_t *sn = sensors + (int64_t)__ldg(frame_sf + f0 + i) * L + c;
+    if (exact_test(cx, cy, cz, poses + f0 + i, sn, incl_pool, ri_pool)) *lab = 2;
+    if (n_steps) atomicAdd((unsigned long long *)&n_steps[t], 1ull);
   }
 }
 
@@ -409,25 +888,47 @@ __global__ void k_project_points(const double *__restrict__ points, int B, int64
   ri_range[(int64_t)b * N + i] = rng;
 }
 
+// self-test hook: max |atan2_fast - atan2| over n pseudo-random f32 pairs (device-side check of kAtanErr)
+__global__ void k_selftest_atan2(long long n, unsigned long long seed, unsigned long long *__restrict__ max_err) {
+  double worst = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    unsigned long long h = (unsigned long long)i * 0x9E3779B97F4A7C15ull + seed;
+    h ^= h >> 31; h *= 0xBF58476D1CE4E5B9ull; h ^= h >> 29;
+    const float mag_x = exp2f((float)((h >> 8) & 31) - 20.f), mag_y = exp2f((float)((h >> 13) & 31) - 20.f);
+    const float x = ((float)((h >> 20) & 0xfffff) / 524288.f - 1.f) * mag_x;
+    const float y = ((float)((h >> 40) & 0xfffff) / 524288.f - 1.f) * mag_y;
+    if (x == 0.f && y == 0.f) continue;
+    const double err = fabs((double)atan2_fast(y, x) - atan2((double)y, (double)x));
+    worst = fmax(worst, err);
+  }
+  for (int o = 16; o > 0; o >>= 1) worst = fmax(worst, __shfl_xor_sync(0xffffffffu, worst, o));
+  // non-negative doubles order like their bit patterns
+  if ((threadIdx.x & 31) == 0) atomicMax(max_err, (unsigned long long)__double_as_longlong(worst));
+}
+
 }  // namespace occb200
 
 using namespace occb200;
 
-extern "C" int64_t occb200_annotate_workspace_bytes(int32_t T, int64_t F, int64_t total_label_slots) {
-  return ws_layout(T, F, total_label_slots, nullptr, nullptr);
+extern "C" int64_t occb200_annotate_workspace_bytes(int32_t T, int64_t F, int64_t total_label_slots, int64_t SF,
+                                                    int32_t L, int64_t incl_len) {
+  return ws_layout(T, F, total_label_slots, SF, L, incl_len, nullptr, nullptr);
 }
 
 extern "C" int occb200_annotate_batch(const occb200_annotate_args_t *a, int64_t total, void *stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   OCC_REQUIRE(a != nullptr, "args is NULL");
   OCC_REQUIRE(a->T >= 0 && a->F >= 0 && a->L >= 1, "bad T/F/L");
+  OCC_REQUIRE(a->SF >= 0 && a->incl_len >= 0, "bad SF / incl_len");
   OCC_REQUIRE(a->point_stride >= 3, "point_stride must be >= 3");
   OCC_REQUIRE(a->voxel_size > 0, "voxel_size must be positive");
   if (a->T == 0) return 0;
   Workspace w;
-  const int64_t need = ws_layout(a->T, a->F, total, (char *)a->workspace, &w);
+  const int64_t need = ws_layout(a->T, a->F, total, a->SF, a->L, a->incl_len, (char *)a->workspace, &w);
   OCC_REQUIRE(a->workspace != nullptr && a->workspace_bytes >= need, "workspace too small");
   const float vsf = (float)a->voxel_size;
+  const bool f64_only = (a->flags & 1) != 0;
+  const int chunk = f64_only ? kChunk : kFastChunk;
   OCC_CUDA(cudaMemsetAsync(w.bits, 0, 4 * w.bits_words, stream));
   if (a->F > 0) {
     ProfScope ps(kProfInbox, stream);
@@ -438,7 +939,7 @@ extern "C" int occb200_annotate_batch(const occb200_annotate_args_t *a, int64_t 
   {
     ProfScope ps(kProfSetup, stream);
     k_tracklet_setup<<<(unsigned)ceil_div(a->T, 128), 128, 0, stream>>>(
-        a->T, a->trk_frame_off, a->poses, w.frame_kept, a->label_off, vsf, w.grids, w.frame_trk, a->dims,
+        a->T, a->trk_frame_off, a->poses, w.frame_kept, a->label_off, vsf, chunk, w.grids, w.frame_trk, a->dims,
         a->sizes, a->status, a->n_unknown, a->n_steps);
     OCC_KERNEL_OK("k_tracklet_setup");
   }
@@ -453,14 +954,58 @@ extern "C" int occb200_annotate_batch(const occb200_annotate_args_t *a, int64_t 
         a->poses, a->points, a->point_stride, a->frame_pt_off, w.frame_kept, w.frame_trk, w.grids, w.bits, vsf);
     OCC_KERNEL_OK("k_frame_voxelize");
   }
-  const int64_t max_items = ceil_div(total, kChunk) + a->T;
-  const int grid = (int)std::min<int64_t>(max_items, (int64_t)kNumSMs * 8);
-  ProfScope ps(kProfVisibility, stream);
-  k_visibility_f64<<<grid, kChunk, 0, stream>>>(a->T, a->L, a->trk_frame_off, a->poses, a->frame_sf, a->sensors,
-                                                a->incl_pool, a->ri_pool, a->voxel_size, a->label_off, w.grids,
-                                                w.chunk_off, w.counter, w.bits, a->labels, a->status,
-                                                a->n_unknown, a->n_steps);
-  OCC_KERNEL_OK("k_visibility_f64");
+  const int64_t max_items = ceil_div(total, chunk) + a->T;
+  if (f64_only) {
+    const int grid = (int)std::min<int64_t>(max_items, (int64_t)kNumSMs * 8);
+    ProfScope ps(kProfVisibility, stream);
+    k_visibility_f64<<<grid, kChunk, 0, stream>>>(a->T, a->L, a->trk_frame_off, a->poses, a->frame_sf, a->sensors,
+                                                  a->incl_pool, a->ri_pool, a->voxel_size, a->label_off, w.grids,
+                                                  w.chunk_off, w.counter, w.bits, a->labels, a->status,
+                                                  a->n_unknown, a->n_steps);
+    OCC_KERNEL_OK("k_visibility_f64");
+    return 0;
+  }
+  if (a->F > 0 && a->SF > 0) {
+    ProfScope ps(kProfPairSetup, stream);
+    k_table_setup<<<(unsigned)(a->SF * a->L), 256, 0, stream>>>(a->SF * a->L, a->sensors, a->incl_pool, w.sens,
+                                                                w.ub_pool, w.lut_pool);
+    OCC_KERNEL_OK("k_table_setup");
+    const int64_t n_pairs = a->F * a->L;
+    k_pair_setup<<<(unsigned)ceil_div(n_pairs, 128), 128, 0, stream>>>(n_pairs, a->L, a->poses, a->frame_sf,
+                                                                       w.frame_trk, a->sensors, w.grids, w.sens,
+                                                                       a->voxel_size, w.pairs);
+    OCC_KERNEL_OK("k_pair_setup");
+  }
+  {
+    const int grid = (int)std::min<int64_t>(max_items, (int64_t)kNumSMs * 3);
+    ProfScope ps(kProfVisibility, stream);
+    k_visibility_fast<<<grid, 32 * kFastWarps, 0, stream>>>(
+        a->T, a->L, a->trk_frame_off, a->poses, a->frame_sf, a->sensors, a->incl_pool, a->ri_pool, a->voxel_size,
+        a->label_off, w.grids, w.chunk_off, w.counter, w.bits, w.pairs, w.sens, w.ub_pool, w.lut_pool, w.queue,
+        (long long)w.queue_cap, a->labels, a->status, a->n_unknown, a->n_steps);
+    OCC_KERNEL_OK("k_visibility_fast");
+  }
+  {
+    ProfScope ps(kProfRecheck, stream);
+    k_visibility_recheck<<<kNumSMs * 4, 256, 0, stream>>>(a->L, a->trk_frame_off, a->poses, a->frame_sf, a->sensors,
+                                                          a->incl_pool, a->ri_pool, a->voxel_size, a->label_off,
+                                                          w.grids, w.counter, w.queue, (long long)w.queue_cap,
+                                                          a->labels, a->n_steps);
+    OCC_KERNEL_OK("k_visibility_recheck");
+  }
+  return 0;
+}
+
+extern "C" int occb200_annotate_queue_stats(const occb200_annotate_args_t *a, int64_t total, int64_t *out_host,
+                                            void *stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  Workspace w;
+  ws_layout(a->T, a->F, total, a->SF, a->L, a->incl_len, (char *)a->workspace, &w);
+  unsigned long long n = 0;
+  OCC_CUDA(cudaMemcpyAsync(&n, w.counter + 1, 8, cudaMemcpyDeviceToHost, stream));
+  OCC_CUDA(cudaStreamSynchronize(stream));
+  out_host[0] = (int64_t)n;
+  out_host[1] = w.queue_cap;
   return 0;
 }
 
@@ -468,6 +1013,8 @@ extern "C" void occb200_profile_enable(int on) {
   std::lock_guard<std::mutex> lk(g_prof_mu);
   g_prof_on = on != 0;
 }
+
+extern "C" int occb200_profile_kinds(void) { return kProfKinds; }
 
 extern "C" int occb200_profile_read(double *ms_per_kind, int64_t *launches_per_kind) {
   std::lock_guard<std::mutex> lk(g_prof_mu);
@@ -482,6 +1029,19 @@ extern "C" int occb200_profile_read(double *ms_per_kind, int64_t *launches_per_k
     cudaEventDestroy(e.b);
   }
   g_prof.clear();
+  return 0;
+}
+
+extern "C" int occb200_selftest_atan2(int64_t n, uint64_t seed, double *max_err_host, void *stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  unsigned long long *d = nullptr;
+  OCC_CUDA(cudaMallocAsync((void **)&d, 8, stream));
+  OCC_CUDA(cudaMemsetAsync(d, 0, 8, stream));
+  k_selftest_atan2<<<kNumSMs * 4, 256, 0, stream>>>(n, seed, d);
+  OCC_KERNEL_OK("k_selftest_atan2");
+  OCC_CUDA(cudaMemcpyAsync(max_err_host, d, 8, cudaMemcpyDeviceToHost, stream));
+  OCC_CUDA(cudaFreeAsync(d, stream));
+  OCC_CUDA(cudaStreamSynchronize(stream));
   return 0;
 }
 

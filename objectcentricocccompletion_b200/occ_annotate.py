@@ -207,7 +207,8 @@ class DeviceTracklets:
         self.status = torch.zeros(max(T, 1), dtype=torch.int32, device=dev)
         self.n_unknown = torch.zeros(max(T, 1), dtype=torch.int64, device=dev)
         self.n_steps = torch.zeros(max(T, 1), dtype=torch.int64, device=dev)
-        ws = _lib.lib().occb200_annotate_workspace_bytes(T, pk.F, total)
+        ws = _lib.lib().occb200_annotate_workspace_bytes(T, pk.F, total, pk.sensors.shape[0], pk.L,
+                                                         pk.incl_pool.size)
         self.workspace = torch.empty(max(ws, 16), dtype=torch.uint8, device=dev)
 
     def upload(self, host: HostBuffers):
@@ -231,7 +232,9 @@ class DeviceTracklets:
         a.point_stride = pk.points.shape[1] if pk.points.ndim == 2 else 3
         a.frame_pt_off = b["frame_pt_off"].data_ptr()
         a.sensors = b["sensors"].data_ptr()
+        a.SF = pk.sensors.shape[0]
         a.incl_pool = b["incl_pool"].data_ptr()
+        a.incl_len = pk.incl_pool.size
         a.ri_pool = b["ri_pool"].data_ptr()
         a.voxel_size = pk.voxel_size
         a.label_off = b["label_off"].data_ptr()
@@ -252,6 +255,16 @@ class DeviceTracklets:
         with torch.cuda.device(self.device):
             rc = _lib.lib().occb200_annotate_batch(C.byref(a), self.pk.total_slots, _lib.stream_ptr(self.device))
         _lib.check(rc, "occb200_annotate_batch")
+
+    def queue_stats(self, flags: int = 0):
+        """(tests sent to the exact f64 recheck, queue capacity) of the last run (synchronises)."""
+        a = self.args(flags)
+        out = (C.c_int64 * 2)()
+        with torch.cuda.device(self.device):
+            rc = _lib.lib().occb200_annotate_queue_stats(C.byref(a), self.pk.total_slots, C.addressof(out),
+                                                         _lib.stream_ptr(self.device))
+        _lib.check(rc, "occb200_annotate_queue_stats")
+        return int(out[0]), int(out[1])
 
     def results(self) -> List[dict]:
         """D2H of labels / dims / status and per-tracklet reshape (synchronises)."""
