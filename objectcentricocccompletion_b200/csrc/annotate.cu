@@ -37,6 +37,7 @@ constexpr int kVPL = 2;             // fast kernel: voxels per lane
 constexpr int kFastChunk = 32 * kVPL;   // fast kernel: voxels per work item
 constexpr int kFastWarps = 8;       // fast kernel: warps per CTA, each takes every 8th (frame, LiDAR) pair
 constexpr int kLutPerRow = 16;      // lookup-table cells reserved per inclination-table entry
+constexpr int kTileR = 8, kTileC = 32;   // range-image max-pyramid tile (rows x columns)
 constexpr int kFrameThreads = 256;
 constexpr int kSmemBitWords = 8192; // 32 KB: grids up to 262 144 voxels keep their bitset in shared memory
 
@@ -77,7 +78,8 @@ struct __align__(16) PairCoef {
   float b[3];
   float eps;        // bound on |f32 p - reference f64 p| per component (metres); < 0: no fast path
   int32_t sens;     // index into the SensCoef table
-  float pad[2];
+  int32_t q;        // pair index inside the tracklet: frame * L + LiDAR
+  int32_t cull;     // 1: no voxel of the tracklet can be free through this pair (see k_pair_setup)
 };
 static_assert(sizeof(PairCoef) == 64, "PairCoef must be 64 bytes");
 
@@ -95,10 +97,15 @@ struct Workspace {
   PairCoef *pairs;       // [F*L]
   int4 *queue;           // recheck queue: (tracklet, voxel, pair index q = i*L + c, unused)
   int64_t queue_cap;
+  PairCoef *pairs_c;     // [F*L] the non-culled pairs of each tracklet, compacted at trk_frame_off[t] * L
+  int32_t *n_active;     // [T]   how many
+  int64_t *pyr_off;      // [SF*L + 1] first tile of each range image in pyr
+  float *pyr;            // [pyr_tiles] max of the range image over tiles of kTileR x kTileC pixels
+  int64_t pyr_tiles;
 };
 
-static int64_t ws_layout(int32_t T, int64_t F, int64_t total, int64_t SF, int32_t L, int64_t incl_len, char *base,
-                         Workspace *w) {
+static int64_t ws_layout(int32_t T, int64_t F, int64_t total, int64_t SF, int32_t L, int64_t incl_len,
+                         int64_t pyr_tiles, char *base, Workspace *w) {
   int64_t off = 0;
   auto take = [&](int64_t bytes) {
     int64_t o = off;
@@ -120,7 +127,16 @@ static int64_t ws_layout(int32_t T, int64_t F, int64_t total, int64_t SF, int32_
   const double nominal = (double)total * (T > 0 ? (double)F / T : 0.0) * L;
   int64_t qcap = (int64_t)std::min(std::max(nominal / 16.0, 65536.0), 64.0 * 1024 * 1024);
   int64_t o_q = take(16 * qcap);
+  int64_t o_pc = take(sizeof(PairCoef) * F * L);
+  int64_t o_na = take(4 * (int64_t)T);
+  int64_t o_po = take(8 * (SF * L + 1));
+  int64_t o_py = take(4 * pyr_tiles);
   if (w) {
+    w->pairs_c = (PairCoef *)(base + o_pc);
+    w->n_active = (int32_t *)(base + o_na);
+    w->pyr_off = (int64_t *)(base + o_po);
+    w->pyr = (float *)(base + o_py);
+    w->pyr_tiles = pyr_tiles;
     w->grids = (TrkGrid *)(base + o_grid);
     w->frame_kept = (int32_t *)(base + o_kept);
     w->frame_trk = (int32_t *)(base + o_ftrk);
@@ -184,28 +200,22 @@ k_frame_inbox(const occb200_pose_t *__restrict__ poses, const float *__restrict_
 }
 
 // ---------------------------------------------------------------------------------------------
-__global__ void k_tracklet_setup(int T, const int64_t *__restrict__ trk_frame_off,
+__global__ void __launch_bounds__(256)
+k_tracklet_setup(int T, const int64_t *__restrict__ trk_frame_off,
                                  const occb200_pose_t *__restrict__ poses,
                                  const int32_t *__restrict__ frame_kept, const int64_t *__restrict__ label_off,
                                  float vsf, int chunk, TrkGrid *__restrict__ grids, int32_t *__restrict__ frame_trk,
                                  int32_t *__restrict__ dims_out, float *__restrict__ sizes_out,
                                  int32_t *__restrict__ status_out, int64_t *__restrict__ n_unknown,
                                  int64_t *__restrict__ n_steps) {
-  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);   // one warp per tracklet
+  const int lane = threadIdx.x & 31;
   if (t >= T) return;
   const int64_t f0 = trk_frame_off[t], f1 = trk_frame_off[t + 1];
   const int B = (int)(f1 - f0);
-  TrkGrid g;
-  g.B = B;
-  g.flags = 0;
-  g.nchunks = 0;
-  g.V = 0;
-  g.bits_off = label_off[t] / 32 + t;
-  g.dims[0] = g.dims[1] = g.dims[2] = 0;
-  g.mb[0] = g.mb[1] = g.mb[2] = 0.f;
   float sz[3] = {-INFINITY, -INFINITY, -INFINITY};
   int kept = 0;
-  for (int64_t f = f0; f < f1; ++f) {
+  for (int64_t f = f0 + lane; f < f1; f += 32) {
     frame_trk[f] = t;
     if (frame_kept[f]) {                       // occ_annotate.py:111-112, :132-133 (box_mode="max")
       ++kept;
@@ -214,6 +224,20 @@ __global__ void k_tracklet_setup(int T, const int64_t *__restrict__ trk_frame_of
       sz[2] = fmaxf(sz[2], poses[f].box[5]);
     }
   }
+  for (int o = 16; o > 0; o >>= 1) {
+    kept += __shfl_xor_sync(0xffffffffu, kept, o);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) sz[k] = fmaxf(sz[k], __shfl_xor_sync(0xffffffffu, sz[k], o));
+  }
+  if (lane != 0) return;
+  TrkGrid g;
+  g.B = B;
+  g.flags = 0;
+  g.nchunks = 0;
+  g.V = 0;
+  g.bits_off = label_off[t] / 32 + t;
+  g.dims[0] = g.dims[1] = g.dims[2] = 0;
+  g.mb[0] = g.mb[1] = g.mb[2] = 0.f;
   if (B < 10) {
     g.status = OCCB200_SKIP_SHORT;             // :344
   } else if (kept == 0) {
@@ -225,7 +249,7 @@ __global__ void k_tracklet_setup(int T, const int64_t *__restrict__ trk_frame_of
     g.mb[1] = __fmul_rn(sz[1], -0.5f);
     g.mb[2] = __fmul_rn(sz[2], 0.0f);
     g.V = (int64_t)g.dims[0] * g.dims[1] * g.dims[2];
-    if (g.V > label_off[t + 1] - label_off[t] || g.V <= 0) {
+    if (g.V > label_off[t + 1] - label_off[t] || g.V <= 0 || g.V >= (1ll << 31)) {
       g.status = -1;                           // caller's slot too small: reported, nothing written
       g.V = 0;
     }
@@ -552,6 +576,74 @@ k_table_setup(int64_t n_sensors, const occb200_sensor_t *__restrict__ sensors, c
 }
 
 // ---------------------------------------------------------------------------------------------
+// Range-image max pyramid: pyr[tile] = max of the image over kTileR x kTileC pixels.  Used only to
+// PROVE that a (frame, LiDAR) pair cannot free any voxel of a tracklet (all returns in the window
+// the tracklet projects to are nearer than its nearest voxel), so that pair is skipped entirely.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+k_pyr_scan(int64_t n, const occb200_sensor_t *__restrict__ sensors, int64_t cap, int64_t *__restrict__ pyr_off,
+           unsigned long long *__restrict__ counter) {
+  __shared__ int64_t s_part[1024];
+  const int tid = threadIdx.x;
+  const int64_t per = (n + 1023) / 1024;
+  const int64_t a = min((int64_t)tid * per, n), b = min(a + per, n);
+  auto tiles = [&](int64_t e) {
+    const int H = sensors[e].H, W = sensors[e].W;
+    return (int64_t)((H + kTileR - 1) / kTileR) * ((W + kTileC - 1) / kTileC);
+  };
+  int64_t sum = 0;
+  for (int64_t e = a; e < b; ++e) sum += tiles(e);
+  s_part[tid] = sum;
+  __syncthreads();
+  for (int d = 1; d < 1024; d <<= 1) {
+    int64_t v = (tid >= d) ? s_part[tid - d] : 0;
+    __syncthreads();
+    s_part[tid] += v;
+    __syncthreads();
+  }
+  int64_t run = s_part[tid] - sum;
+  for (int64_t e = a; e < b; ++e) {
+    pyr_off[e] = run;
+    run += tiles(e);
+  }
+  if (tid == 1023) {
+    pyr_off[n] = s_part[1023];
+    counter[2] = (s_part[1023] <= cap) ? 1ull : 0ull;      // 1: pyramid fits, culling enabled
+  }
+}
+
+constexpr int kPyrRowGroups = 8;
+__global__ void __launch_bounds__(256)
+k_pyr_build(const occb200_sensor_t *__restrict__ sensors, const float *__restrict__ ri_pool,
+            const int64_t *__restrict__ pyr_off, const unsigned long long *__restrict__ counter,
+            float *__restrict__ pyr) {
+  if (counter[2] == 0ull) return;
+  const int e = blockIdx.x;                        // sensor entry; blockIdx.y = row group
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const occb200_sensor_t &sn = sensors[e];
+  const int H = sn.H, W = sn.W;
+  const int ntr = (H + kTileR - 1) / kTileR, ntc = (W + kTileC - 1) / kTileC;
+  const float *img = ri_pool + sn.ri_off;
+  float *out = pyr + pyr_off[e];
+  for (int tr = blockIdx.y; tr < ntr; tr += kPyrRowGroups) {
+    for (int tc = warp; tc < ntc; tc += 8) {
+      const int col = tc * kTileC + lane;
+      float v[kTileR];
+#pragma unroll
+      for (int r = 0; r < kTileR; ++r) {           // range images are >= 0 (0 = no return)
+        const int row = tr * kTileR + r;
+        v[r] = (col < W && row < H) ? ld_stream(img + (int64_t)row * W + col) : 0.f;
+      }
+      float m = 0.f;
+#pragma unroll
+      for (int r = 0; r < kTileR; ++r) m = fmaxf(m, v[r]);
+      for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+      if (lane == 0) out[tr * ntc + tc] = m;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Fast path, part 2: per (tracklet-frame, LiDAR) affine map, composed in f64 and stored in f32.
 //   centre = vs*idx + c0,  c0 = min_bound + vs/2                    (:467-471)
 //   ego    = Rm centre + o, Rm = [[c, s, 0], [-s, c, 0], [0, 0, 1]] (:490-498)
@@ -560,16 +652,27 @@ k_table_setup(int64_t n_sensors, const occb200_sensor_t *__restrict__ sensors, c
 // eps bounds |f32 chain - reference f64 chain| per component: the three FMAs round at most
 // 3 * 2^-24 * M, the f32 coefficients contribute at most 2^-24 * M, M = |b| + sum |A| * max idx; the
 // reference's own f64 roundings (~1e-14 m) vanish in the slack of the factor 6.
+//
+// Culling.  All voxel centres lie in the ball (centre pc = p(grid centre), radius R = half the grid
+// diagonal).  Seen from the sensor the ball spans inclinations inc_c +- asin(R/d) and azimuths
+// az_c +- asin(R/rho_c); the reference's row/column rules are monotone in those angles, so every
+// pixel any centre can map to lies in the row/column window of the interval ends (padded by one).
+// If the largest return in that window (from the tile pyramid) is below d - R, `ri >= range` is
+// false for every voxel of the tracklet through this pair: the pair is dropped from the work list.
 // ---------------------------------------------------------------------------------------------
 __global__ void k_pair_setup(int64_t n_pairs, int L, const occb200_pose_t *__restrict__ poses,
                              const int32_t *__restrict__ frame_sf, const int32_t *__restrict__ frame_trk,
-                             const occb200_sensor_t *__restrict__ sensors, const TrkGrid *__restrict__ grids,
-                             const SensCoef *__restrict__ sens, double vs, PairCoef *__restrict__ pairs) {
+                             const int64_t *__restrict__ trk_frame_off,
+                             const occb200_sensor_t *__restrict__ sensors, const float *__restrict__ incl_pool,
+                             const TrkGrid *__restrict__ grids, const SensCoef *__restrict__ sens, double vs,
+                             const int64_t *__restrict__ pyr_off, const float *__restrict__ pyr,
+                             const unsigned long long *__restrict__ counter, PairCoef *__restrict__ pairs) {
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n_pairs) return;
   const int64_t f = e / L;
   const int c = (int)(e % L);
-  const TrkGrid &g = grids[frame_trk[f]];
+  const int t = frame_trk[f];
+  const TrkGrid &g = grids[t];
   const occb200_pose_t &ps = poses[f];
   const int64_t se = (int64_t)frame_sf[f] * L + c;
   const occb200_sensor_t &sn = sensors[se];
@@ -584,23 +687,110 @@ __global__ void k_pair_setup(int64_t n_pairs, int L, const occb200_pose_t *__res
   const double c0[3] = {(double)g.mb[0] + vs / 2, (double)g.mb[1] + vs / 2, (double)g.mb[2] + vs / 2};
   const double o[3] = {(double)ps.box[0], (double)ps.box[1], (double)ps.box[2]};
   float eps = 0.f;
+  double pcen[3], R2 = 0.0;
   for (int r = 0; r < 3; ++r) {
     const double b = VR[3 * r] * c0[0] + VR[3 * r + 1] * c0[1] + VR[3 * r + 2] * c0[2] + V[4 * r] * o[0] +
                      V[4 * r + 1] * o[1] + V[4 * r + 2] * o[2] + V[4 * r + 3];
     double M = fabs(b);
+    pcen[r] = b;
     for (int k = 0; k < 3; ++k) {
       const double a = vs * VR[3 * r + k];
+      const double span = (double)(g.dims[k] > 0 ? g.dims[k] - 1 : 0);
       pc.A[3 * r + k] = (float)a;
-      M += fabs(a) * (double)(g.dims[k] > 0 ? g.dims[k] - 1 : 0);
+      M += fabs(a) * span;
+      pcen[r] += 0.5 * span * a;
     }
     pc.b[r] = (float)b;
     eps = fmaxf(eps, (float)(6.0 * 5.9604644775390625e-08 * M));
   }
+  for (int k = 0; k < 3; ++k) {                    // half diagonal of the centre grid in the sensor frame
+    double col2 = 0.0;
+    for (int r = 0; r < 3; ++r) col2 += VR[3 * r + k] * VR[3 * r + k];
+    const double span = vs * (double)(g.dims[k] > 0 ? g.dims[k] - 1 : 0);
+    R2 += col2 * span * span;
+  }
   const bool ok = sens[se].ok && isfinite(eps) && se < (1ll << 31);
   pc.eps = ok ? eps : -1.f;
   pc.sens = (int32_t)se;
-  pc.pad[0] = pc.pad[1] = 0.f;
+  pc.q = (int32_t)(e - trk_frame_off[t] * L);
+  pc.cull = 0;
+  // ---- cull test (conservative; any doubt keeps the pair)
+  if (counter[2] != 0ull && g.status == OCCB200_OK && sn.incl_mono == -1 && sn.H >= 1 && sn.W >= 1) {
+    // the columns of VR are orthogonal only up to the f32 inverse: 1.001 covers it, +1 mm absolute
+    const double R = 0.5 * sqrt(R2) * 1.001 + 1e-3;
+    const double rho = sqrt(pcen[0] * pcen[0] + pcen[1] * pcen[1]);
+    const double d = sqrt(rho * rho + pcen[2] * pcen[2]);
+    if (d > 1.25 * R) {
+      const double rmin = d - R;
+      const double delta = asin(R / d) + 1e-6;
+      const double inc_c = atan2(pcen[2], rho);
+      const float *tab = incl_pool + sn.incl_off;
+      int r0 = nearest_row(inc_c + delta, tab, sn.H, -1) - 1;
+      int r1 = nearest_row(inc_c - delta, tab, sn.H, -1) + 1;
+      r0 = max(r0, 0);
+      r1 = min(r1, sn.H - 1);
+      const int W = sn.W;
+      const int ntc = (W + kTileC - 1) / kTileC;
+      long long c_lo = 0, c_hi = W - 1;            // column window, possibly beyond [0, W): taken modulo W
+      if (rho > 1.05 * R) {
+        const double daz = asin(R / rho) + 1e-6;
+        const double az_c = atan2(pcen[1], pcen[0]) + (double)sn.azc;
+        const double kc = (double)W / 6.28318530717958647692;
+        const double cf_lo = ((double)W - 0.5) - (az_c + daz + 3.14159265358979323846) * kc;
+        const double cf_hi = ((double)W - 0.5) - (az_c - daz + 3.14159265358979323846) * kc;
+        if (cf_hi - cf_lo + 4.0 < (double)W) {
+          c_lo = (long long)floor(cf_lo) - 1;
+          c_hi = (long long)ceil(cf_hi) + 1;
+        }
+      }
+      // tile columns covering [c_lo, c_hi] modulo W
+      float m = 0.f;
+      const float *pimg = pyr + pyr_off[se];
+      const int tr0 = r0 / kTileR, tr1 = r1 / kTileR;
+      if (c_hi - c_lo + 1 >= W) {
+        for (int tr = tr0; tr <= tr1; ++tr)
+          for (int tc = 0; tc < ntc; ++tc) m = fmaxf(m, pimg[tr * ntc + tc]);
+      } else {
+        long long a0 = ((c_lo % W) + W) % W;       // first column, in [0, W)
+        const long long len = c_hi - c_lo + 1;
+        // segment 1: [a0, min(a0+len, W)), segment 2 (wrapped): [0, a0+len-W)
+        const long long e1 = min(a0 + len, (long long)W) - 1;
+        for (int tr = tr0; tr <= tr1; ++tr) {
+          for (long long tc = a0 / kTileC; tc <= e1 / kTileC; ++tc) m = fmaxf(m, pimg[tr * ntc + tc]);
+          if (a0 + len > W)
+            for (long long tc = 0; tc <= (a0 + len - W - 1) / kTileC; ++tc) m = fmaxf(m, pimg[tr * ntc + tc]);
+        }
+      }
+      if ((double)m < rmin - 1e-3) pc.cull = 1;
+    }
+  }
   pairs[e] = pc;
+}
+
+// One warp per tracklet: copy the surviving pairs, in order, to the front of the tracklet's slot.
+__global__ void __launch_bounds__(256)
+k_pair_compact(int T, int L, const int64_t *__restrict__ trk_frame_off, const PairCoef *__restrict__ pairs,
+               PairCoef *__restrict__ pairs_c, int32_t *__restrict__ n_active) {
+  const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (t >= T) return;
+  const int64_t base = trk_frame_off[t] * L;
+  const int n = (int)(trk_frame_off[t + 1] - trk_frame_off[t]) * L;
+  int count = 0;
+  for (int q0 = 0; q0 < n; q0 += 32) {
+    const int q = q0 + lane;
+    const bool keep = q < n && pairs[base + q].cull == 0;
+    const unsigned mask = __ballot_sync(0xffffffffu, keep);
+    if (keep) {
+      const int dst = count + __popc(mask & ((1u << lane) - 1u));
+      const float4 *src = reinterpret_cast<const float4 *>(pairs + base + q);
+      float4 *d4 = reinterpret_cast<float4 *>(pairs_c + base + dst);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) d4[k] = src[k];
+    }
+    count += __popc(mask);
+  }
+  if (lane == 0) n_active[t] = count;
 }
 
 // Approximate f32 primitives (flush-to-zero MUFU forms, <= 2 ulp): their error is part of every margin.
@@ -705,6 +895,22 @@ __device__ __forceinline__ T16 load64(const T16 *p) {          // 64-byte record
   return v;
 }
 
+// Rare path of the fast kernel (recheck queue full): decide one test exactly, from global memory only.
+__device__ __noinline__ bool exact_from_ids(int t, int f, int q, int L, double vs, const TrkGrid *__restrict__ grids,
+                                            const int64_t *__restrict__ trk_frame_off,
+                                            const occb200_pose_t *__restrict__ poses,
+                                            const int32_t *__restrict__ frame_sf,
+                                            const occb200_sensor_t *__restrict__ sensors,
+                                            const float *__restrict__ incl_pool, const float *__restrict__ ri_pool) {
+  const TrkGrid g = grids[t];
+  double cx, cy, cz;
+  voxel_centre(g, f, vs, cx, cy, cz);
+  const int i = q / L, c = q - i * L;
+  const int64_t f0 = trk_frame_off[t];
+  const occb200_sensor_t *sn = sensors + (int64_t)__ldg(frame_sf + f0 + i) * L + c;
+  return exact_test(cx, cy, cz, poses + f0 + i, sn, incl_pool, ri_pool);
+}
+
 __global__ void __launch_bounds__(32 * kFastWarps, 3)
 k_visibility_fast(int T, int L, const int64_t *__restrict__ trk_frame_off,
                   const occb200_pose_t *__restrict__ poses, const int32_t *__restrict__ frame_sf,
@@ -712,20 +918,21 @@ k_visibility_fast(int T, int L, const int64_t *__restrict__ trk_frame_off,
                   const float *__restrict__ ri_pool, double vs, const int64_t *__restrict__ label_off,
                   const TrkGrid *__restrict__ grids, const int64_t *__restrict__ chunk_off,
                   unsigned long long *__restrict__ counter, const uint32_t *__restrict__ bits,
-                  const PairCoef *__restrict__ pairs, const SensCoef *__restrict__ sens,
+                  const PairCoef *__restrict__ pairs, const int32_t *__restrict__ n_active,
+                  const SensCoef *__restrict__ sens,
                   const float *__restrict__ ub_pool, const uint16_t *__restrict__ lut_pool,
                   int4 *__restrict__ queue, long long queue_cap, int32_t *__restrict__ labels,
                   int32_t *__restrict__ status_out, int64_t *__restrict__ n_unknown, int64_t *__restrict__ n_steps) {
   __shared__ long long s_item;
   __shared__ unsigned s_free[kVPL];
-  __shared__ unsigned long long s_steps;
+  __shared__ unsigned s_steps;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long total = chunk_off[T];
   for (;;) {
     __syncthreads();
     if (threadIdx.x == 0) {
       s_item = (long long)atomicAdd(counter, 1ull);
-      s_steps = 0ull;
+      s_steps = 0u;
     }
     if (threadIdx.x < kVPL) s_free[threadIdx.x] = 0u;
     __syncthreads();
@@ -737,60 +944,63 @@ k_visibility_fast(int T, int L, const int64_t *__restrict__ trk_frame_off,
       if (chunk_off[mid] <= item) lo = mid; else hi = mid;
     }
     const int t = lo;
-    const TrkGrid g = grids[t];
     const int chunk = (int)(item - chunk_off[t]);
-    int status = g.status;
+    const TrkGrid *gp = grids + t;
+    int status = gp->status;
+    const int gflags = gp->flags;
     if (status == OCCB200_OK) {
-      if (g.flags & 2) status = OCCB200_INDEX_ERROR;
-      else if (!(g.flags & 1)) status = OCCB200_EMPTY_AFTER_FILTER;
+      if (gflags & 2) status = OCCB200_INDEX_ERROR;
+      else if (!(gflags & 1)) status = OCCB200_EMPTY_AFTER_FILTER;
     }
     if (chunk == 0 && threadIdx.x == 0) status_out[t] = status;
     if (status != OCCB200_OK) continue;
 
-    // voxel v of this lane: flat index f0v + 32*v + lane (bitset word chunk*kVPL + v)
-    const int64_t fbase = (int64_t)chunk * kFastChunk;
-    unsigned active_mask[kVPL], occ_word[kVPL], need_mask[kVPL];
+    // voxel v of this lane: flat index fbase + 32*v + lane (bitset word chunk*kVPL + v)
+    const int dY = gp->dims[1], dZ = gp->dims[2];
+    const int V = (int)gp->V;
+    const int fbase = chunk * kFastChunk;
+    const int64_t word0 = gp->bits_off + (int64_t)chunk * kVPL;
     float vx[kVPL], vy[kVPL], vz[kVPL];
-    unsigned any_need = 0u;
-    const int YZ = g.dims[1] * g.dims[2];
+    unsigned mine = 0u;        // bit v: this lane's voxel v exists and holds no point
+    unsigned occ = 0u;         // bit v: it holds a point
 #pragma unroll
     for (int v = 0; v < kVPL; ++v) {
-      const int64_t left = g.V - (fbase + 32 * v);
-      active_mask[v] = left >= 32 ? 0xffffffffu : (left <= 0 ? 0u : ((1u << left) - 1u));
-      occ_word[v] = active_mask[v] ? bits[g.bits_off + (int64_t)chunk * kVPL + v] : 0u;
-      need_mask[v] = ~occ_word[v] & active_mask[v];
-      any_need |= need_mask[v];
-      const int64_t fa = ((active_mask[v] >> lane) & 1u) ? fbase + 32 * v + lane : 0;
-      vx[v] = (float)(int)(fa / YZ);
-      vy[v] = (float)(int)((fa / g.dims[2]) % g.dims[1]);
-      vz[v] = (float)(int)(fa % g.dims[2]);
+      const int f = fbase + 32 * v + lane;
+      const bool active = f < V;
+      const unsigned w = (fbase + 32 * v < V) ? bits[word0 + v] : 0u;
+      const bool o = active && ((w >> lane) & 1u);
+      occ |= (o ? 1u : 0u) << v;
+      mine |= ((active && !o) ? 1u : 0u) << v;
+      const int fa = active ? f : 0;
+      const int yz = dY * dZ;
+      const int ix = fa / yz, rem = fa - ix * yz;
+      const int iy = rem / dZ;
+      vx[v] = (float)ix;
+      vy[v] = (float)iy;
+      vz[v] = (float)(rem - iy * dZ);
     }
-    unsigned long long steps = 0;
-    if (any_need) {
+    unsigned steps = 0;
+    if (__any_sync(0xffffffffu, mine != 0u)) {
       const int64_t f0 = trk_frame_off[t];
-      const int npairs = g.B * L;
+      const int npairs = n_active[t];              // pairs that survived culling, compacted
       const PairCoef *tp = pairs + f0 * L;
-      PairCoef pc_next = load64(tp + min(warp, npairs - 1));
-      for (int q = warp; q < npairs; q += kFastWarps) {
-        const PairCoef pc = pc_next;
-        if (q + kFastWarps < npairs) pc_next = load64(tp + q + kFastWarps);     // prefetch the next pair
-        unsigned done[kVPL];
-        unsigned open = 0u;
+      for (int k = warp; k < npairs; k += kFastWarps) {
+        unsigned todo = mine;
 #pragma unroll
-        for (int v = 0; v < kVPL; ++v) {
-          done[v] = *(volatile unsigned *)&s_free[v];
-          open |= need_mask[v] & ~done[v];
-        }
-        if (open == 0u) break;                                   // every voxel of the chunk is already free
+        for (int v = 0; v < kVPL; ++v) todo &= ~(((*(volatile unsigned *)&s_free[v] >> lane) & 1u) << v);
+        if (!__any_sync(0xffffffffu, todo != 0u)) break;         // every voxel of the chunk is already free
+        const PairCoef pc = load64(tp + k);
+        if (k + kFastWarps < npairs) asm volatile("prefetch.global.L1 [%0];" ::"l"(tp + k + kFastWarps));
+        const int q = pc.q;
         const SensCoef sc = load64(sens + pc.sens);
         const float *ub = ub_pool + sc.tab_off;
-        const uint16_t *lut = lut_pool + (int64_t)sc.tab_off * kLutPerRow;
+        const uint16_t *lut = lut_pool + sc.tab_off * kLutPerRow;
         const float *ri_img = ri_pool + sc.ri_off;
         int res[kVPL];
 #pragma unroll
         for (int v = 0; v < kVPL; ++v) {
           res[v] = 0;
-          if (((need_mask[v] & ~done[v]) >> lane) & 1u) {
+          if ((todo >> v) & 1u) {
             res[v] = (pc.eps >= 0.f) ? fast_test(pc, sc, vx[v], vy[v], vz[v], ub, lut, ri_img) : 1;
             ++steps;
           }
@@ -804,16 +1014,13 @@ k_visibility_fast(int T, int L, const int64_t *__restrict__ trk_frame_off,
             if (lane == 0) base = atomicAdd(counter + 1, (unsigned long long)__popc(umask));
             base = __shfl_sync(0xffffffffu, base, 0);
             if (res[v] == 1) {
-              const int64_t f = fbase + 32 * v + lane;
+              const int f = fbase + 32 * v + lane;
               const unsigned long long slot = base + __popc(umask & ((1u << lane) - 1u));
               if (slot < (unsigned long long)queue_cap) {
-                queue[slot] = make_int4(t, (int)f, q, 0);
-              } else {                                           // queue full: decide right here
-                double cx, cy, cz;
-                voxel_centre(g, f, vs, cx, cy, cz);
-                const int i = q / L, c = q - i * L;
-                const occb200_sensor_t *sn = sensors + (int64_t)__ldg(frame_sf + f0 + i) * L + c;
-                if (exact_test(cx, cy, cz, poses + f0 + i, sn, incl_pool, ri_pool)) atomicOr(&s_free[v], 1u << lane);
+                queue[slot] = make_int4(t, f, q, 0);
+              } else if (exact_from_ids(t, f, q, L, vs, grids, trk_frame_off, poses, frame_sf, sensors, incl_pool,
+                                        ri_pool)) {              // queue full: decide right here
+                atomicOr(&s_free[v], 1u << lane);
               }
             }
           }
@@ -826,15 +1033,12 @@ k_visibility_fast(int T, int L, const int64_t *__restrict__ trk_frame_off,
     if (warp < kVPL) {
       const int v = warp;
       const unsigned fr = s_free[v];
-      unsigned am = 0u, ow = 0u, nm = 0u;
-#pragma unroll
-      for (int k = 0; k < kVPL; ++k)
-        if (k == v) { am = active_mask[k]; ow = occ_word[k]; nm = need_mask[k]; }
-      if ((am >> lane) & 1u)
-        labels[label_off[t] + fbase + 32 * v + lane] = ((ow >> lane) & 1u) ? 1 : (((fr >> lane) & 1u) ? 2 : 0);   // :558-563
+      const int f = fbase + 32 * v + lane;
+      if (f < V) labels[label_off[t] + f] = ((occ >> v) & 1u) ? 1 : (((fr >> lane) & 1u) ? 2 : 0);   // :558-563
+      const unsigned nm = __ballot_sync(0xffffffffu, (mine >> v) & 1u);
       if (lane == 0) {
         if (nm) atomicAdd((unsigned long long *)&n_unknown[t], (unsigned long long)__popc(nm));
-        if (v == 0 && n_steps && s_steps) atomicAdd((unsigned long long *)&n_steps[t], s_steps);
+        if (v == 0 && n_steps && s_steps) atomicAdd((unsigned long long *)&n_steps[t], (unsigned long long)s_steps);
       }
     }
   }
@@ -911,20 +1115,24 @@ __global__ void k_selftest_atan2(long long n, unsigned long long seed, unsigned 
 using namespace occb200;
 
 extern "C" int64_t occb200_annotate_workspace_bytes(int32_t T, int64_t F, int64_t total_label_slots, int64_t SF,
-                                                    int32_t L, int64_t incl_len) {
-  return ws_layout(T, F, total_label_slots, SF, L, incl_len, nullptr, nullptr);
+                                                    int32_t L, int64_t incl_len, int64_t pyr_tiles) {
+  return ws_layout(T, F, total_label_slots, SF, L, incl_len, pyr_tiles, nullptr, nullptr);
+}
+
+extern "C" int64_t occb200_pyramid_tiles(int32_t H, int32_t W) {
+  return (int64_t)((H + kTileR - 1) / kTileR) * ((W + kTileC - 1) / kTileC);
 }
 
 extern "C" int occb200_annotate_batch(const occb200_annotate_args_t *a, int64_t total, void *stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   OCC_REQUIRE(a != nullptr, "args is NULL");
   OCC_REQUIRE(a->T >= 0 && a->F >= 0 && a->L >= 1, "bad T/F/L");
-  OCC_REQUIRE(a->SF >= 0 && a->incl_len >= 0, "bad SF / incl_len");
+  OCC_REQUIRE(a->SF >= 0 && a->incl_len >= 0 && a->pyr_tiles >= 0, "bad SF / incl_len / pyr_tiles");
   OCC_REQUIRE(a->point_stride >= 3, "point_stride must be >= 3");
   OCC_REQUIRE(a->voxel_size > 0, "voxel_size must be positive");
   if (a->T == 0) return 0;
   Workspace w;
-  const int64_t need = ws_layout(a->T, a->F, total, a->SF, a->L, a->incl_len, (char *)a->workspace, &w);
+  const int64_t need = ws_layout(a->T, a->F, total, a->SF, a->L, a->incl_len, a->pyr_tiles, (char *)a->workspace, &w);
   OCC_REQUIRE(a->workspace != nullptr && a->workspace_bytes >= need, "workspace too small");
   const float vsf = (float)a->voxel_size;
   const bool f64_only = (a->flags & 1) != 0;
@@ -938,7 +1146,7 @@ extern "C" int occb200_annotate_batch(const occb200_annotate_args_t *a, int64_t 
   }
   {
     ProfScope ps(kProfSetup, stream);
-    k_tracklet_setup<<<(unsigned)ceil_div(a->T, 128), 128, 0, stream>>>(
+    k_tracklet_setup<<<(unsigned)ceil_div(a->T, 8), 256, 0, stream>>>(
         a->T, a->trk_frame_off, a->poses, w.frame_kept, a->label_off, vsf, chunk, w.grids, w.frame_trk, a->dims,
         a->sizes, a->status, a->n_unknown, a->n_steps);
     OCC_KERNEL_OK("k_tracklet_setup");
@@ -970,18 +1178,31 @@ extern "C" int occb200_annotate_batch(const occb200_annotate_args_t *a, int64_t 
     k_table_setup<<<(unsigned)(a->SF * a->L), 256, 0, stream>>>(a->SF * a->L, a->sensors, a->incl_pool, w.sens,
                                                                 w.ub_pool, w.lut_pool);
     OCC_KERNEL_OK("k_table_setup");
+    const int64_t n_sens = a->SF * a->L;
+    k_pyr_scan<<<1, 1024, 0, stream>>>(n_sens, a->sensors, (a->flags & 2) ? (int64_t)-1 : w.pyr_tiles, w.pyr_off,
+                                       w.counter);
+    OCC_KERNEL_OK("k_pyr_scan");
+    if (w.pyr_tiles > 0 && !(a->flags & 2)) {
+      k_pyr_build<<<dim3((unsigned)n_sens, kPyrRowGroups), 256, 0, stream>>>(a->sensors, a->ri_pool, w.pyr_off,
+                                                                             w.counter, w.pyr);
+      OCC_KERNEL_OK("k_pyr_build");
+    }
     const int64_t n_pairs = a->F * a->L;
-    k_pair_setup<<<(unsigned)ceil_div(n_pairs, 128), 128, 0, stream>>>(n_pairs, a->L, a->poses, a->frame_sf,
-                                                                       w.frame_trk, a->sensors, w.grids, w.sens,
-                                                                       a->voxel_size, w.pairs);
+    k_pair_setup<<<(unsigned)ceil_div(n_pairs, 128), 128, 0, stream>>>(
+        n_pairs, a->L, a->poses, a->frame_sf, w.frame_trk, a->trk_frame_off, a->sensors, a->incl_pool, w.grids,
+        w.sens, a->voxel_size, w.pyr_off, w.pyr, w.counter, w.pairs);
     OCC_KERNEL_OK("k_pair_setup");
+    k_pair_compact<<<(unsigned)ceil_div(a->T, 8), 256, 0, stream>>>(a->T, a->L, a->trk_frame_off, w.pairs, w.pairs_c,
+                                                                    w.n_active);
+    OCC_KERNEL_OK("k_pair_compact");
   }
   {
     const int grid = (int)std::min<int64_t>(max_items, (int64_t)kNumSMs * 3);
     ProfScope ps(kProfVisibility, stream);
     k_visibility_fast<<<grid, 32 * kFastWarps, 0, stream>>>(
         a->T, a->L, a->trk_frame_off, a->poses, a->frame_sf, a->sensors, a->incl_pool, a->ri_pool, a->voxel_size,
-        a->label_off, w.grids, w.chunk_off, w.counter, w.bits, w.pairs, w.sens, w.ub_pool, w.lut_pool, w.queue,
+        a->label_off, w.grids, w.chunk_off, w.counter, w.bits, w.pairs_c, w.n_active, w.sens, w.ub_pool, w.lut_pool,
+        w.queue,
         (long long)w.queue_cap, a->labels, a->status, a->n_unknown, a->n_steps);
     OCC_KERNEL_OK("k_visibility_fast");
   }
@@ -1000,7 +1221,7 @@ extern "C" int occb200_annotate_queue_stats(const occb200_annotate_args_t *a, in
                                             void *stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   Workspace w;
-  ws_layout(a->T, a->F, total, a->SF, a->L, a->incl_len, (char *)a->workspace, &w);
+  ws_layout(a->T, a->F, total, a->SF, a->L, a->incl_len, a->pyr_tiles, (char *)a->workspace, &w);
   unsigned long long n = 0;
   OCC_CUDA(cudaMemcpyAsync(&n, w.counter + 1, 8, cudaMemcpyDeviceToHost, stream));
   OCC_CUDA(cudaStreamSynchronize(stream));

@@ -31,6 +31,7 @@ from . import _lib
 LiDAR_NAME_LIST = ["TOP", "FRONT", "SIDE_LEFT", "SIDE_RIGHT", "REAR"]     # occ_annotate.py:235
 STATUS_NAMES = {0: "ok", 1: "skip_short", 2: "no_points", 3: "empty_after_filter", 4: "index_error", -1: "slot_too_small"}
 FLAG_FORCE_F64 = 1
+FLAG_NO_CULL = 2
 
 
 # ------------------------------------------------------------------------------------------------
@@ -207,8 +208,12 @@ class DeviceTracklets:
         self.status = torch.zeros(max(T, 1), dtype=torch.int32, device=dev)
         self.n_unknown = torch.zeros(max(T, 1), dtype=torch.int64, device=dev)
         self.n_steps = torch.zeros(max(T, 1), dtype=torch.int64, device=dev)
-        ws = _lib.lib().occb200_annotate_workspace_bytes(T, pk.F, total, pk.sensors.shape[0], pk.L,
-                                                         pk.incl_pool.size)
+        L_ = _lib.lib()
+        sn = pk.sensors.reshape(-1)
+        self.pyr_tiles = int(sum(L_.occb200_pyramid_tiles(int(h), int(w_)) * int(n) for (h, w_), n in
+                                 zip(*np.unique(np.stack([sn["H"], sn["W"]], 1), axis=0, return_counts=True)))) if sn.size else 0
+        ws = L_.occb200_annotate_workspace_bytes(T, pk.F, total, pk.sensors.shape[0], pk.L, pk.incl_pool.size,
+                                                 self.pyr_tiles)
         self.workspace = torch.empty(max(ws, 16), dtype=torch.uint8, device=dev)
 
     def upload(self, host: HostBuffers):
@@ -236,6 +241,7 @@ class DeviceTracklets:
         a.incl_pool = b["incl_pool"].data_ptr()
         a.incl_len = pk.incl_pool.size
         a.ri_pool = b["ri_pool"].data_ptr()
+        a.pyr_tiles = self.pyr_tiles
         a.voxel_size = pk.voxel_size
         a.label_off = b["label_off"].data_ptr()
         a.labels = self.labels.data_ptr()
