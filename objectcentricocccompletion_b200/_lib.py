@@ -13,7 +13,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
-LIB_PATH = os.path.join(CSRC, "libocc_b200.so")
+LIB_PATH = os.environ.get("OCCB200_LIB", os.path.join(CSRC, "libocc_b200.so"))
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "occ_b200.h")
 
 vp, i32, i64, f32, f64 = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_double

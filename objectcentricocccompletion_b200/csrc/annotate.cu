@@ -4,10 +4,10 @@
 // OccAnnotator.annotate_trk :344-568 (normative step list: SURVEY.md Appendix A).
 //
 // Kernels (all on the caller's stream, no host synchronisation):
-//   k_frame_inbox     one CTA per tracklet-frame: does any candidate point fall in the box?   (A1)
-//   k_tracklet_setup  one thread per tracklet: box size = max over kept frames, dims, bounds  (A2/A3)
+//   k_tracklet_presetup  one warp per tracklet: optimistic grid (box size = max over all frames)
+//   k_frame_voxelize  one CTA per tracklet-frame: in-box -> box frame -> quantise -> bitset (A1/A2/A3)
+//   k_tracklet_setup  one warp per tracklet: box size = max over KEPT frames; rare re-voxelisation (A2/A3)
 //   k_scan_chunks     one CTA: exclusive scan of per-tracklet work chunks -> work list
-//   k_frame_voxelize  one CTA per tracklet-frame: in-box -> box frame -> quantise -> bitset   (A2/A3)
 //   k_table_setup     one CTA per (sensor frame, LiDAR): inclination row boundaries + lookup table
 //   k_pair_setup      one thread per (tracklet-frame, LiDAR): voxel-index -> sensor-frame affine map
 //   k_visibility_fast persistent CTAs over 32-voxel chunks: the range-image "ray-cast" in f32 with
@@ -33,7 +33,13 @@
 namespace occb200 {
 
 constexpr int kChunk = 256;         // f64 kernel: voxels per work item == threads per CTA
-constexpr int kVPL = 2;             // fast kernel: voxels per lane
+#ifndef OCC_VPL
+#define OCC_VPL 2
+#endif
+#ifndef OCC_MINB
+#define OCC_MINB 4
+#endif
+constexpr int kVPL = OCC_VPL;       // fast kernel: voxels per lane
 constexpr int kFastChunk = 32 * kVPL;   // fast kernel: voxels per work item
 constexpr int kFastWarps = 8;       // fast kernel: warps per CTA, each takes every 8th (frame, LiDAR) pair
 constexpr int kLutPerRow = 16;      // lookup-table cells reserved per inclination-table entry
@@ -50,6 +56,8 @@ struct TrkGrid {
   int64_t bits_off; // word offset of the occupancy bitset
   int32_t nchunks;
   int32_t B;
+  int32_t redo;     // 1: the optimistic grid was wrong, k_frame_voxelize runs again for this tracklet
+  int32_t pad;
 };
 
 // Per (sensor frame, LiDAR) constants of the fast path.  64 bytes, 4 x LDG.128.
@@ -183,86 +191,226 @@ struct ProfScope {
 };
 
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kFrameThreads)
-k_frame_inbox(const occb200_pose_t *__restrict__ poses, const float *__restrict__ points, int stride,
-              const int64_t *__restrict__ frame_pt_off, int32_t *__restrict__ frame_kept) {
-  const int64_t f = blockIdx.x;
-  const occb200_pose_t &ps = poses[f];
-  const BoxTest bt = make_box_test(ps.box, ps.cos_pib, ps.sin_pib);
-  const int64_t n0 = frame_pt_off[f], n1 = frame_pt_off[f + 1];
-  int any = 0;
-  for (int64_t j = n0 + threadIdx.x; j < n1; j += kFrameThreads) {
-    const float *p = points + j * stride;
-    any |= pt_in_box(bt, ld_stream(p), ld_stream(p + 1), ld_stream(p + 2));
+// Crop + voxelise.  The grid of a tracklet depends on its box size = max over the frames that have at
+// least one in-box point (occ_annotate.py:111-112, 132-133), which is only known after every frame has
+// been cropped.  Almost always every frame has such a point, so the pipeline is optimistic:
+//   k_tracklet_presetup  grid from the max over ALL frames
+//   k_frame_voxelize     ONE pass over the points: in-box test, box frame, quantise, set bits; records
+//                        which frames had in-box points
+//   k_tracklet_setup     recomputes the size from the kept frames; if it differs the tracklet's bits are
+//                        cleared and a second k_frame_voxelize pass redoes just that tracklet
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void grid_from_size(TrkGrid &g, const float sz[3], float vsf, int64_t cap, int chunk) {
+  g.status = OCCB200_OK;
+  for (int k = 0; k < 3; ++k) g.dims[k] = (int)ceilf(__fdiv_rn(sz[k], vsf));   // :414-416
+  g.mb[0] = __fmul_rn(sz[0], -0.5f);           // min over corners of [0,0,0,w,l,h,0] (:422-423)
+  g.mb[1] = __fmul_rn(sz[1], -0.5f);
+  g.mb[2] = __fmul_rn(sz[2], 0.0f);
+  g.V = (int64_t)g.dims[0] * g.dims[1] * g.dims[2];
+  if (g.V > cap || g.V <= 0 || g.V >= (1ll << 31)) {
+    g.status = -1;                             // caller's slot too small: reported, nothing written
+    g.V = 0;
   }
-  any = __syncthreads_or(any);
-  if (threadIdx.x == 0) frame_kept[f] = any;
+  g.nchunks = (int)((g.V + chunk - 1) / chunk);
 }
 
-// ---------------------------------------------------------------------------------------------
+// One in-box point -> bit index in the tracklet's occupancy bitset, or -1; flags |= 1 kept, |= 2 index error.
+__device__ __forceinline__ int64_t voxel_of_point(const BoxTest &bt, const occb200_pose_t &ps, const TrkGrid &g,
+                                                  float vsf, float x, float y, float z, int &flags) {
+  if (!pt_in_box(bt, x, y, z)) return -1;
+  flags |= 4;                                   // the frame has an in-box point
+  // local = (p + (-origin)) @ [[c,-s,0],[s,c,0],[0,0,1]]  (:117-122, lidar_box3d.py:165-184):
+  // sgemm accumulates k = 0,1,2 as an FMA chain; the k=2 terms are exact no-ops.
+  const float c = ps.cos_m, s = ps.sin_m;       // torch f32 cos/sin(-yaw)
+  const float tx = __fadd_rn(x, -ps.box[0]), ty = __fadd_rn(y, -ps.box[1]), tz = __fadd_rn(z, -ps.box[2]);
+  const float lx = __fmaf_rn(ty, s, __fmul_rn(tx, c));
+  const float ly = __fmaf_rn(ty, c, __fmul_rn(tx, -s));
+  const float lz = tz;
+  // q = floor((local - min_bound) / vs)  (:425)
+  float qx = floorf(__fdiv_rn(__fsub_rn(lx, g.mb[0]), vsf));
+  float qy = floorf(__fdiv_rn(__fsub_rn(ly, g.mb[1]), vsf));
+  float qz = floorf(__fdiv_rn(__fsub_rn(lz, g.mb[2]), vsf));
+  const float dX = (float)g.dims[0], dY = (float)g.dims[1], dZ = (float)g.dims[2];
+  if (!(qx < dX && qy < dY && qz < dZ)) return -1;   // only the upper bound is filtered (:430-431)
+  flags |= 1;
+  if (qx < 0.f) qx += dX;                       // PyTorch negative-index wrap (:436)
+  if (qy < 0.f) qy += dY;
+  if (qz < 0.f) qz += dZ;
+  if (qx < 0.f || qy < 0.f || qz < 0.f) {
+    flags |= 2;                                 // IndexError in the reference
+    return -1;
+  }
+  return ((int64_t)qx * g.dims[1] + (int64_t)qy) * g.dims[2] + (int64_t)qz;
+}
+
 __global__ void __launch_bounds__(256)
-k_tracklet_setup(int T, const int64_t *__restrict__ trk_frame_off,
-                                 const occb200_pose_t *__restrict__ poses,
-                                 const int32_t *__restrict__ frame_kept, const int64_t *__restrict__ label_off,
-                                 float vsf, int chunk, TrkGrid *__restrict__ grids, int32_t *__restrict__ frame_trk,
-                                 int32_t *__restrict__ dims_out, float *__restrict__ sizes_out,
-                                 int32_t *__restrict__ status_out, int64_t *__restrict__ n_unknown,
-                                 int64_t *__restrict__ n_steps) {
+k_tracklet_presetup(int T, const int64_t *__restrict__ trk_frame_off, const occb200_pose_t *__restrict__ poses,
+                    const int64_t *__restrict__ label_off, float vsf, int chunk, TrkGrid *__restrict__ grids,
+                    int32_t *__restrict__ frame_trk, int64_t *__restrict__ n_unknown, int64_t *__restrict__ n_steps) {
   const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);   // one warp per tracklet
   const int lane = threadIdx.x & 31;
   if (t >= T) return;
   const int64_t f0 = trk_frame_off[t], f1 = trk_frame_off[t + 1];
-  const int B = (int)(f1 - f0);
   float sz[3] = {-INFINITY, -INFINITY, -INFINITY};
-  int kept = 0;
   for (int64_t f = f0 + lane; f < f1; f += 32) {
     frame_trk[f] = t;
-    if (frame_kept[f]) {                       // occ_annotate.py:111-112, :132-133 (box_mode="max")
-      ++kept;
-      sz[0] = fmaxf(sz[0], poses[f].box[3]);
-      sz[1] = fmaxf(sz[1], poses[f].box[4]);
-      sz[2] = fmaxf(sz[2], poses[f].box[5]);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) sz[k] = fmaxf(sz[k], poses[f].box[3 + k]);
+  }
+  for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+    for (int k = 0; k < 3; ++k) sz[k] = fmaxf(sz[k], __shfl_xor_sync(0xffffffffu, sz[k], o));
+  if (lane != 0) return;
+  TrkGrid g;
+  g.B = (int)(f1 - f0);
+  g.flags = 0;
+  g.nchunks = 0;
+  g.V = 0;
+  g.redo = 0;
+  g.pad = 0;
+  g.bits_off = label_off[t] / 32 + t;
+  g.dims[0] = g.dims[1] = g.dims[2] = 0;
+  g.mb[0] = g.mb[1] = g.mb[2] = 0.f;
+  if (g.B < 10) g.status = OCCB200_SKIP_SHORT;  // :344
+  else grid_from_size(g, sz, vsf, label_off[t + 1] - label_off[t], chunk);
+  grids[t] = g;
+  n_unknown[t] = 0;
+  if (n_steps) n_steps[t] = 0;
+}
+
+constexpr int kPtsPerThread = 4;                // independent point loads in flight per thread
+__global__ void __launch_bounds__(kFrameThreads)
+k_frame_voxelize(const occb200_pose_t *__restrict__ poses, const float *__restrict__ points, int stride,
+                 const int64_t *__restrict__ frame_pt_off, int32_t *__restrict__ frame_kept,
+                 const int32_t *__restrict__ frame_trk, TrkGrid *__restrict__ grids,
+                 uint32_t *__restrict__ bits, float vsf, int redo_pass) {
+  __shared__ uint32_t s_bits[kSmemBitWords];
+  __shared__ int s_flags;
+  const int64_t f = blockIdx.x;
+  const int t = frame_trk[f];
+  if (redo_pass && (grids[t].redo == 0 || frame_kept[f] == 0)) return;   // second pass: corrected tracklets only
+  const TrkGrid g = grids[t];
+  if (g.status != OCCB200_OK) {
+    if (threadIdx.x == 0 && !redo_pass) frame_kept[f] = 0;
+    return;
+  }
+  const int words = (int)((g.V + 31) / 32);
+  const bool use_smem = words <= kSmemBitWords;
+  uint32_t *gbits = bits + g.bits_off;
+  if (use_smem)
+    for (int w = threadIdx.x; w < words; w += kFrameThreads) s_bits[w] = 0u;
+  if (threadIdx.x == 0) s_flags = 0;
+  __syncthreads();
+
+  const occb200_pose_t ps = poses[f];
+  const BoxTest bt = make_box_test(ps.box, ps.cos_pib, ps.sin_pib);
+  const int64_t n0 = frame_pt_off[f], n1 = frame_pt_off[f + 1];
+  const int lane = threadIdx.x & 31;
+  int flags = 0;
+  for (int64_t base = n0; base < n1; base += kFrameThreads * kPtsPerThread) {   // warp-uniform trip count
+    float px[kPtsPerThread], py[kPtsPerThread], pz[kPtsPerThread];
+#pragma unroll
+    for (int u = 0; u < kPtsPerThread; ++u) {
+      const int64_t j = base + u * kFrameThreads + threadIdx.x;
+      const float *p = points + j * stride;
+      const bool ok = j < n1;
+      px[u] = ok ? ld_stream(p) : 0.f;
+      py[u] = ok ? ld_stream(p + 1) : 0.f;
+      pz[u] = ok ? ld_stream(p + 2) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < kPtsPerThread; ++u) {
+      const int64_t j = base + u * kFrameThreads + threadIdx.x;
+      int64_t idx = -1;
+      if (j < n1) idx = voxel_of_point(bt, ps, g, vsf, px[u], py[u], pz[u], flags);
+      int word = -1;
+      uint32_t bit = 0u;
+      if (idx >= 0) {
+        word = (int)(idx >> 5);
+        bit = 1u << (idx & 31);
+        // most points land in voxels that are already marked: look before touching an atomic
+        const uint32_t cur = use_smem ? s_bits[word] : __ldg(gbits + word);
+        if (cur & bit) word = -1;
+      }
+      // warp-level dedup of what is left: lanes on the same bitset word merge their bits, one atomic per word
+      if (__any_sync(0xffffffffu, word >= 0)) {
+        const unsigned peers = __match_any_sync(0xffffffffu, word);
+        const uint32_t merged = __reduce_or_sync(peers, word >= 0 ? bit : 0u);
+        if (word >= 0 && lane == __ffs(peers) - 1) {
+          if (use_smem) atomicOr(&s_bits[word], merged);
+          else atomicOr(&gbits[word], merged);
+        }
+      }
+    }
+  }
+  if (flags) atomicOr(&s_flags, flags);
+  __syncthreads();
+  if (use_smem)
+    for (int w = threadIdx.x; w < words; w += kFrameThreads) {
+      const uint32_t v = s_bits[w];
+      if (v) atomicOr(&gbits[w], v);
+    }
+  if (threadIdx.x == 0) {
+    const int fl = s_flags;
+    if (!redo_pass) frame_kept[f] = (fl & 4) ? 1 : 0;
+    if (fl & 3) atomicOr(&grids[t].flags, fl & 3);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_tracklet_setup(int T, const int64_t *__restrict__ trk_frame_off, const occb200_pose_t *__restrict__ poses,
+                 const int32_t *__restrict__ frame_kept, const int64_t *__restrict__ label_off, float vsf, int chunk,
+                 TrkGrid *__restrict__ grids, uint32_t *__restrict__ bits, int32_t *__restrict__ dims_out,
+                 float *__restrict__ sizes_out, int32_t *__restrict__ status_out) {
+  const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);   // one warp per tracklet
+  const int lane = threadIdx.x & 31;
+  if (t >= T) return;
+  const int64_t f0 = trk_frame_off[t], f1 = trk_frame_off[t + 1];
+  TrkGrid g = grids[t];
+  float sz[3] = {-INFINITY, -INFINITY, -INFINITY}, sz_all[3] = {-INFINITY, -INFINITY, -INFINITY};
+  int kept = 0;
+  for (int64_t f = f0 + lane; f < f1; f += 32) {
+    const bool k_ = frame_kept[f] != 0;           // occ_annotate.py:111-112, :132-133 (box_mode="max")
+    kept += k_ ? 1 : 0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const float b = poses[f].box[3 + k];
+      sz_all[k] = fmaxf(sz_all[k], b);
+      if (k_) sz[k] = fmaxf(sz[k], b);
     }
   }
   for (int o = 16; o > 0; o >>= 1) {
     kept += __shfl_xor_sync(0xffffffffu, kept, o);
 #pragma unroll
-    for (int k = 0; k < 3; ++k) sz[k] = fmaxf(sz[k], __shfl_xor_sync(0xffffffffu, sz[k], o));
+    for (int k = 0; k < 3; ++k) {
+      sz[k] = fmaxf(sz[k], __shfl_xor_sync(0xffffffffu, sz[k], o));
+      sz_all[k] = fmaxf(sz_all[k], __shfl_xor_sync(0xffffffffu, sz_all[k], o));
+    }
+  }
+  if (g.status == OCCB200_OK || g.status == -1) {
+    if (kept == 0) {
+      g.status = OCCB200_NO_POINTS;               // :129
+      g.V = 0;
+      g.nchunks = 0;
+      g.dims[0] = g.dims[1] = g.dims[2] = 0;
+    } else if (sz[0] != sz_all[0] || sz[1] != sz_all[1] || sz[2] != sz_all[2]) {
+      // a frame without in-box points carried the largest box: clear the bits set with the optimistic grid
+      // and let the second k_frame_voxelize pass redo this tracklet with the true one.
+      const int old_words = (int)((g.V + 31) / 32);
+      grid_from_size(g, sz, vsf, label_off[t + 1] - label_off[t], chunk);
+      g.flags = 0;
+      g.redo = 1;
+      uint32_t *gbits = bits + g.bits_off;
+      for (int w = lane; w < old_words; w += 32) gbits[w] = 0u;
+    }
   }
   if (lane != 0) return;
-  TrkGrid g;
-  g.B = B;
-  g.flags = 0;
-  g.nchunks = 0;
-  g.V = 0;
-  g.bits_off = label_off[t] / 32 + t;
-  g.dims[0] = g.dims[1] = g.dims[2] = 0;
-  g.mb[0] = g.mb[1] = g.mb[2] = 0.f;
-  if (B < 10) {
-    g.status = OCCB200_SKIP_SHORT;             // :344
-  } else if (kept == 0) {
-    g.status = OCCB200_NO_POINTS;              // :129
-  } else {
-    g.status = OCCB200_OK;
-    for (int k = 0; k < 3; ++k) g.dims[k] = (int)ceilf(__fdiv_rn(sz[k], vsf));   // :414-416
-    g.mb[0] = __fmul_rn(sz[0], -0.5f);         // min over corners of [0,0,0,w,l,h,0] (:422-423)
-    g.mb[1] = __fmul_rn(sz[1], -0.5f);
-    g.mb[2] = __fmul_rn(sz[2], 0.0f);
-    g.V = (int64_t)g.dims[0] * g.dims[1] * g.dims[2];
-    if (g.V > label_off[t + 1] - label_off[t] || g.V <= 0 || g.V >= (1ll << 31)) {
-      g.status = -1;                           // caller's slot too small: reported, nothing written
-      g.V = 0;
-    }
-    g.nchunks = (int)((g.V + chunk - 1) / chunk);
-  }
   grids[t] = g;
   for (int k = 0; k < 3; ++k) {
     dims_out[3 * t + k] = g.dims[k];
     sizes_out[3 * t + k] = (g.status == OCCB200_OK) ? sz[k] : 0.f;
   }
   status_out[t] = g.status;                    // refined by the visibility kernel (flags)
-  n_unknown[t] = 0;
-  if (n_steps) n_steps[t] = 0;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -274,7 +422,7 @@ k_scan_chunks(int T, const TrkGrid *__restrict__ grids, int64_t *__restrict__ ch
   const int per = (T + 1023) / 1024;
   const int a = min(tid * per, T), b = min(a + per, T);
   int64_t sum = 0;
-  for (int t = a; t < b; ++t) sum += grids[t].nchunks;
+  for (int t = a; t < b; ++t) sum += (grids[t].status == OCCB200_OK) ? grids[t].nchunks : 0;
   s_part[tid] = sum;
   __syncthreads();
   for (int d = 1; d < 1024; d <<= 1) {          // Hillis-Steele inclusive scan
@@ -286,93 +434,10 @@ k_scan_chunks(int T, const TrkGrid *__restrict__ grids, int64_t *__restrict__ ch
   int64_t run = s_part[tid] - sum;
   for (int t = a; t < b; ++t) {
     chunk_off[t] = run;
-    run += grids[t].nchunks;
+    run += (grids[t].status == OCCB200_OK) ? grids[t].nchunks : 0;
   }
   if (tid == 1023) chunk_off[T] = s_part[1023];
   if (tid < 4) counter[tid] = 0ull;
-}
-
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kFrameThreads)
-k_frame_voxelize(const occb200_pose_t *__restrict__ poses, const float *__restrict__ points, int stride,
-                 const int64_t *__restrict__ frame_pt_off, const int32_t *__restrict__ frame_kept,
-                 const int32_t *__restrict__ frame_trk, TrkGrid *__restrict__ grids,
-                 uint32_t *__restrict__ bits, float vsf) {
-  __shared__ uint32_t s_bits[kSmemBitWords];
-  __shared__ int s_flags;
-  const int64_t f = blockIdx.x;
-  if (!frame_kept[f]) return;                   // frame contributes no points (:111-112)
-  const int t = frame_trk[f];
-  const TrkGrid g = grids[t];
-  if (g.status != OCCB200_OK) return;
-  const int words = (int)((g.V + 31) / 32);
-  const bool use_smem = words <= kSmemBitWords;
-  uint32_t *gbits = bits + g.bits_off;
-  if (use_smem)
-    for (int w = threadIdx.x; w < words; w += kFrameThreads) s_bits[w] = 0u;
-  if (threadIdx.x == 0) s_flags = 0;
-  __syncthreads();
-
-  const occb200_pose_t &ps = poses[f];
-  const BoxTest bt = make_box_test(ps.box, ps.cos_pib, ps.sin_pib);
-  const float ox = ps.box[0], oy = ps.box[1], oz = ps.box[2];
-  const float c = ps.cos_m, s = ps.sin_m;       // torch f32 cos/sin(-yaw)
-  const float dX = (float)g.dims[0], dY = (float)g.dims[1], dZ = (float)g.dims[2];
-  const int64_t n0 = frame_pt_off[f], n1 = frame_pt_off[f + 1];
-  const int lane = threadIdx.x & 31;
-  int flags = 0;
-  for (int64_t base = n0; base < n1; base += kFrameThreads) {   // warp-uniform trip count
-    const int64_t j = base + threadIdx.x;
-    int word = -1;
-    uint32_t bit = 0u;
-    if (j < n1) {
-      const float *p = points + j * stride;
-      const float x = ld_stream(p), y = ld_stream(p + 1), z = ld_stream(p + 2);
-      if (pt_in_box(bt, x, y, z)) {
-        // local = (p + (-origin)) @ [[c,-s,0],[s,c,0],[0,0,1]]  (:117-122, lidar_box3d.py:165-184):
-        // sgemm accumulates k = 0,1,2 as an FMA chain; the k=2 terms are exact no-ops.
-        const float tx = __fadd_rn(x, -ox), ty = __fadd_rn(y, -oy), tz = __fadd_rn(z, -oz);
-        const float lx = __fmaf_rn(ty, s, __fmul_rn(tx, c));
-        const float ly = __fmaf_rn(ty, c, __fmul_rn(tx, -s));
-        const float lz = tz;
-        // q = floor((local - min_bound) / vs)  (:425)
-        float qx = floorf(__fdiv_rn(__fsub_rn(lx, g.mb[0]), vsf));
-        float qy = floorf(__fdiv_rn(__fsub_rn(ly, g.mb[1]), vsf));
-        float qz = floorf(__fdiv_rn(__fsub_rn(lz, g.mb[2]), vsf));
-        if (qx < dX && qy < dY && qz < dZ) {    // only the upper bound is filtered (:430-431)
-          flags |= 1;
-          if (qx < 0.f) qx += dX;               // PyTorch negative-index wrap (:436)
-          if (qy < 0.f) qy += dY;
-          if (qz < 0.f) qz += dZ;
-          if (qx < 0.f || qy < 0.f || qz < 0.f) {
-            flags |= 2;                         // IndexError in the reference
-          } else {
-            const int64_t idx = ((int64_t)qx * g.dims[1] + (int64_t)qy) * g.dims[2] + (int64_t)qz;
-            word = (int)(idx >> 5);
-            bit = 1u << (idx & 31);
-          }
-        }
-      }
-    }
-    // warp-level dedup: lanes that hit the same bitset word merge their bits, one atomic per word
-    const unsigned peers = __match_any_sync(0xffffffffu, word);
-    const uint32_t merged = __reduce_or_sync(peers, bit);
-    if (word >= 0 && lane == __ffs(peers) - 1) {
-      if (use_smem) {
-        if ((s_bits[word] & merged) != merged) atomicOr(&s_bits[word], merged);
-      } else {
-        atomicOr(&gbits[word], merged);
-      }
-    }
-  }
-  if (flags) atomicOr(&s_flags, flags);
-  __syncthreads();
-  if (use_smem)
-    for (int w = threadIdx.x; w < words; w += kFrameThreads) {
-      const uint32_t v = s_bits[w];
-      if (v) atomicOr(&gbits[w], v);
-    }
-  if (threadIdx.x == 0 && s_flags) atomicOr(&grids[t].flags, s_flags);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -911,7 +976,7 @@ __device__ __noinline__ bool exact_from_ids(int t, int f, int q, int L, double v
   return exact_test(cx, cy, cz, poses + f0 + i, sn, incl_pool, ri_pool);
 }
 
-__global__ void __launch_bounds__(32 * kFastWarps, 3)
+__global__ void __launch_bounds__(32 * kFastWarps, OCC_MINB)
 k_visibility_fast(int T, int L, const int64_t *__restrict__ trk_frame_off,
                   const occb200_pose_t *__restrict__ poses, const int32_t *__restrict__ frame_sf,
                   const occb200_sensor_t *__restrict__ sensors, const float *__restrict__ incl_pool,
@@ -1138,29 +1203,35 @@ extern "C" int occb200_annotate_batch(const occb200_annotate_args_t *a, int64_t 
   const bool f64_only = (a->flags & 1) != 0;
   const int chunk = f64_only ? kChunk : kFastChunk;
   OCC_CUDA(cudaMemsetAsync(w.bits, 0, 4 * w.bits_words, stream));
-  if (a->F > 0) {
+  {
     ProfScope ps(kProfInbox, stream);
-    k_frame_inbox<<<(unsigned)a->F, kFrameThreads, 0, stream>>>(a->poses, a->points, a->point_stride,
-                                                                 a->frame_pt_off, w.frame_kept);
-    OCC_KERNEL_OK("k_frame_inbox");
+    k_tracklet_presetup<<<(unsigned)ceil_div(a->T, 8), 256, 0, stream>>>(a->T, a->trk_frame_off, a->poses, a->label_off,
+                                                                         vsf, chunk, w.grids, w.frame_trk,
+                                                                         a->n_unknown, a->n_steps);
+    OCC_KERNEL_OK("k_tracklet_presetup");
+  }
+  if (a->F > 0) {
+    ProfScope ps(kProfVoxelize, stream);
+    k_frame_voxelize<<<(unsigned)a->F, kFrameThreads, 0, stream>>>(
+        a->poses, a->points, a->point_stride, a->frame_pt_off, w.frame_kept, w.frame_trk, w.grids, w.bits, vsf, 0);
+    OCC_KERNEL_OK("k_frame_voxelize");
   }
   {
     ProfScope ps(kProfSetup, stream);
     k_tracklet_setup<<<(unsigned)ceil_div(a->T, 8), 256, 0, stream>>>(
-        a->T, a->trk_frame_off, a->poses, w.frame_kept, a->label_off, vsf, chunk, w.grids, w.frame_trk, a->dims,
-        a->sizes, a->status, a->n_unknown, a->n_steps);
+        a->T, a->trk_frame_off, a->poses, w.frame_kept, a->label_off, vsf, chunk, w.grids, w.bits, a->dims, a->sizes,
+        a->status);
     OCC_KERNEL_OK("k_tracklet_setup");
+    if (a->F > 0) {   // corrected tracklets only; every other CTA leaves at once
+      k_frame_voxelize<<<(unsigned)a->F, kFrameThreads, 0, stream>>>(
+          a->poses, a->points, a->point_stride, a->frame_pt_off, w.frame_kept, w.frame_trk, w.grids, w.bits, vsf, 1);
+      OCC_KERNEL_OK("k_frame_voxelize(redo)");
+    }
   }
   {
     ProfScope ps(kProfScan, stream);
     k_scan_chunks<<<1, 1024, 0, stream>>>(a->T, w.grids, w.chunk_off, w.counter);
     OCC_KERNEL_OK("k_scan_chunks");
-  }
-  if (a->F > 0) {
-    ProfScope ps(kProfVoxelize, stream);
-    k_frame_voxelize<<<(unsigned)a->F, kFrameThreads, 0, stream>>>(
-        a->poses, a->points, a->point_stride, a->frame_pt_off, w.frame_kept, w.frame_trk, w.grids, w.bits, vsf);
-    OCC_KERNEL_OK("k_frame_voxelize");
   }
   const int64_t max_items = ceil_div(total, chunk) + a->T;
   if (f64_only) {
@@ -1197,7 +1268,7 @@ extern "C" int occb200_annotate_batch(const occb200_annotate_args_t *a, int64_t 
     OCC_KERNEL_OK("k_pair_compact");
   }
   {
-    const int grid = (int)std::min<int64_t>(max_items, (int64_t)kNumSMs * 3);
+    const int grid = (int)std::min<int64_t>(max_items, (int64_t)kNumSMs * OCC_MINB);
     ProfScope ps(kProfVisibility, stream);
     k_visibility_fast<<<grid, 32 * kFastWarps, 0, stream>>>(
         a->T, a->L, a->trk_frame_off, a->poses, a->frame_sf, a->sensors, a->incl_pool, a->ri_pool, a->voxel_size,
