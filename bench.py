@@ -105,6 +105,17 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def ncu_traffic():
+    """DRAM bytes per launch of the ray-cast kernel from the committed ncu capture (profiles/), or None."""
+    p = os.path.join(ROOT, "profiles", "vis_fast_ncu.json")
+    try:
+        m = json.load(open(p))["metrics"]
+        scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        return sum(float(m[k]["value"]) * scale[m[k]["unit"]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+    except Exception:
+        return None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -328,7 +339,7 @@ def main():
                 "d2h_bytes_per_step": d2h_bytes, "ms_per_step": sec_e2e * 1e3},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": "k_visibility", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "frac": achieved / peak, "traffic": ncu_traffic(), "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": ws["vis_bytes"], "kernel_ms": vis_ms,
                      "kernel_share_of_step": vis_ms / step_ms_prof if step_ms_prof else None,
                      "kernels_ms": dict(zip(("k_frame_inbox", "k_tracklet_setup", "k_scan_chunks", "k_frame_voxelize",

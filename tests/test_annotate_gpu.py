@@ -33,7 +33,7 @@ def test_reference_fixture(name, flags):
     dict(n=5, b=25, vs=0.25, kind="vehicle", seed=3, small=True),
     dict(n=4, b=10, vs=0.15, kind="vehicle", seed=4, small=True),
 ])
-@pytest.mark.parametrize("flags", [0, 1])
+@pytest.mark.parametrize("flags", [0, 1, 2])     # default / all-f64 / no pair culling
 def test_vs_oracle(cfg, flags):
     from objectcentricocccompletion_b200 import synth
     from oracle import oracle
@@ -134,6 +134,7 @@ def test_fast_path_margins():
 
     err = ctypes.c_double(0)
     _lib.check(_lib.lib().occb200_selftest_atan2(200_000_000, 12345, ctypes.addressof(err), _lib.stream_ptr()), "selftest")
+    print('max |atan2_fast - atan2| =', err.value)
     assert 0 < err.value < 1.6e-6, err.value
     batch = synth.make_batch(8, 20, 0.2, seed=5)
     pk = occ_annotate.pack_tracklets(batch)
