@@ -292,6 +292,7 @@ def main():
         # the one collective of the job: final gather of per-rank results to rank 0 over NVLink (not per step)
         from objectcentricocccompletion_b200 import dist as occ_dist
 
+        occ_dist.gather_results(res[:1], [rank], world, dst=0)      # opens the NCCL p2p channels (lazy, ~1 s)
         torch.cuda.synchronize()
         dist.barrier()
         t0 = time.perf_counter()
