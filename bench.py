@@ -343,8 +343,9 @@ def main():
                      "frac": achieved / peak, "traffic": ncu_traffic(), "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": ws["vis_bytes"], "kernel_ms": vis_ms,
                      "kernel_share_of_step": vis_ms / step_ms_prof if step_ms_prof else None,
-                     "kernels_ms": dict(zip(("k_frame_inbox", "k_tracklet_setup", "k_scan_chunks", "k_frame_voxelize",
-                                             "k_visibility", "k_table_setup+k_pair_setup", "k_visibility_recheck"),
+                     "kernels_ms": dict(zip(("k_tracklet_presetup", "k_tracklet_setup+redo", "k_scan_chunks", "k_frame_voxelize",
+                                             "k_visibility", "side:k_table_setup+k_pyr_scan+k_pyr_build",
+                                             "k_visibility_recheck", "k_pair_setup+k_pair_compact"),
                                             (kms / np.maximum(kn[4], 1)).round(5).tolist()))},
         "cpu_baseline": cpu, "clocks": clocks,
     }

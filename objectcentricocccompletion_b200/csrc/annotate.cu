@@ -96,6 +96,7 @@ struct Workspace {
   int32_t *frame_kept;   // [F]
   int32_t *frame_trk;    // [F]
   int64_t *chunk_off;    // [T+1]
+  unsigned long long *pyr_flag;  // [0] 1: pyramid built (fits), culling enabled -- written on the side stream
   unsigned long long *counter;   // [0] work-queue head, [1] recheck-queue length
   uint32_t *bits;        // occupancy bitsets
   int64_t bits_words;
@@ -125,6 +126,7 @@ static int64_t ws_layout(int32_t T, int64_t F, int64_t total, int64_t SF, int32_
   int64_t o_ftrk = take(4 * F);
   int64_t o_choff = take(8 * ((int64_t)T + 1));
   int64_t o_cnt = take(8 * 4);
+  int64_t o_pf = take(8);
   int64_t words = total / 32 + T + 1;
   int64_t o_bits = take(4 * words);
   int64_t o_tab = take(sizeof(SensCoef) * SF * L);
@@ -150,6 +152,7 @@ static int64_t ws_layout(int32_t T, int64_t F, int64_t total, int64_t SF, int32_
     w->frame_trk = (int32_t *)(base + o_ftrk);
     w->chunk_off = (int64_t *)(base + o_choff);
     w->counter = (unsigned long long *)(base + o_cnt);
+    w->pyr_flag = (unsigned long long *)(base + o_pf);
     w->bits = (uint32_t *)(base + o_bits);
     w->bits_words = words;
     w->sens = (SensCoef *)(base + o_tab);
@@ -163,9 +166,35 @@ static int64_t ws_layout(int32_t T, int64_t F, int64_t total, int64_t SF, int32_
 }
 
 // ---------------------------------------------------------------------------------------------
+// The sensor-side setup (row tables, range-image pyramid) does not depend on the tracklets, so it runs on
+// a side stream concurrently with the crop/voxelise chain and joins before k_pair_setup (fork/join with
+// events; capturable in a CUDA graph).
+struct SideStream {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+};
+static SideStream g_side[64];
+static std::mutex g_side_mu;
+
+static int side_stream(SideStream **out) {
+  int dev = 0;
+  OCC_CUDA(cudaGetDevice(&dev));
+  OCC_REQUIRE(dev >= 0 && dev < 64, "device index out of range");
+  std::lock_guard<std::mutex> lk(g_side_mu);
+  SideStream &s = g_side[dev];
+  if (!s.stream) {
+    OCC_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    OCC_CUDA(cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming));
+    OCC_CUDA(cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming));
+  }
+  *out = &s;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Optional per-kernel timing (bench.py's roofline): CUDA events recorded around each kernel of the
 // pipeline on the caller's stream; durations are summed per kernel when the profile is read.
-enum { kProfInbox = 0, kProfSetup, kProfScan, kProfVoxelize, kProfVisibility, kProfPairSetup, kProfRecheck, kProfKinds };
+enum { kProfInbox = 0, kProfSetup, kProfScan, kProfVoxelize, kProfVisibility, kProfPairSetup, kProfRecheck, kProfPairCull, kProfKinds };
 struct ProfEntry { int kind; cudaEvent_t a, b; };
 static bool g_prof_on = false;
 static std::vector<ProfEntry> g_prof;
@@ -245,7 +274,7 @@ __device__ __forceinline__ int64_t voxel_of_point(const BoxTest &bt, const occb2
 
 __global__ void __launch_bounds__(256)
 k_tracklet_presetup(int T, const int64_t *__restrict__ trk_frame_off, const occb200_pose_t *__restrict__ poses,
-                    const int64_t *__restrict__ label_off, float vsf, int chunk, TrkGrid *__restrict__ grids,
+                    const int64_t *__restrict__ frame_pt_off, const int64_t *__restrict__ label_off, float vsf, int chunk, TrkGrid *__restrict__ grids,
                     int32_t *__restrict__ frame_trk, int64_t *__restrict__ n_unknown, int64_t *__restrict__ n_steps) {
   const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);   // one warp per tracklet
   const int lane = threadIdx.x & 31;
@@ -254,8 +283,9 @@ k_tracklet_presetup(int T, const int64_t *__restrict__ trk_frame_off, const occb
   float sz[3] = {-INFINITY, -INFINITY, -INFINITY};
   for (int64_t f = f0 + lane; f < f1; f += 32) {
     frame_trk[f] = t;
+    if (frame_pt_off[f + 1] > frame_pt_off[f])     // a frame without candidates cannot be a kept frame
 #pragma unroll
-    for (int k = 0; k < 3; ++k) sz[k] = fmaxf(sz[k], poses[f].box[3 + k]);
+      for (int k = 0; k < 3; ++k) sz[k] = fmaxf(sz[k], poses[f].box[3 + k]);
   }
   for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
@@ -272,6 +302,7 @@ k_tracklet_presetup(int T, const int64_t *__restrict__ trk_frame_off, const occb
   g.dims[0] = g.dims[1] = g.dims[2] = 0;
   g.mb[0] = g.mb[1] = g.mb[2] = 0.f;
   if (g.B < 10) g.status = OCCB200_SKIP_SHORT;  // :344
+  else if (sz[0] == -INFINITY) g.status = OCCB200_NO_POINTS;   // no candidate point at all (:129)
   else grid_from_size(g, sz, vsf, label_off[t + 1] - label_off[t], chunk);
   grids[t] = g;
   n_unknown[t] = 0;
@@ -359,7 +390,8 @@ k_frame_voxelize(const occb200_pose_t *__restrict__ poses, const float *__restri
 
 __global__ void __launch_bounds__(256)
 k_tracklet_setup(int T, const int64_t *__restrict__ trk_frame_off, const occb200_pose_t *__restrict__ poses,
-                 const int32_t *__restrict__ frame_kept, const int64_t *__restrict__ label_off, float vsf, int chunk,
+                 const int64_t *__restrict__ frame_pt_off, const int32_t *__restrict__ frame_kept,
+                 const int64_t *__restrict__ label_off, float vsf, int chunk,
                  TrkGrid *__restrict__ grids, uint32_t *__restrict__ bits, int32_t *__restrict__ dims_out,
                  float *__restrict__ sizes_out, int32_t *__restrict__ status_out) {
   const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);   // one warp per tracklet
@@ -375,7 +407,7 @@ k_tracklet_setup(int T, const int64_t *__restrict__ trk_frame_off, const occb200
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
       const float b = poses[f].box[3 + k];
-      sz_all[k] = fmaxf(sz_all[k], b);
+      if (frame_pt_off[f + 1] > frame_pt_off[f]) sz_all[k] = fmaxf(sz_all[k], b);   // what presetup assumed
       if (k_) sz[k] = fmaxf(sz[k], b);
     }
   }
@@ -673,7 +705,7 @@ k_pyr_scan(int64_t n, const occb200_sensor_t *__restrict__ sensors, int64_t cap,
   }
   if (tid == 1023) {
     pyr_off[n] = s_part[1023];
-    counter[2] = (s_part[1023] <= cap) ? 1ull : 0ull;      // 1: pyramid fits, culling enabled
+    counter[0] = (s_part[1023] <= cap) ? 1ull : 0ull;      // 1: pyramid fits, culling enabled
   }
 }
 
@@ -682,7 +714,7 @@ __global__ void __launch_bounds__(256)
 k_pyr_build(const occb200_sensor_t *__restrict__ sensors, const float *__restrict__ ri_pool,
             const int64_t *__restrict__ pyr_off, const unsigned long long *__restrict__ counter,
             float *__restrict__ pyr) {
-  if (counter[2] == 0ull) return;
+  if (counter[0] == 0ull) return;
   const int e = blockIdx.x;                        // sensor entry; blockIdx.y = row group
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const occb200_sensor_t &sn = sensors[e];
@@ -690,20 +722,27 @@ k_pyr_build(const occb200_sensor_t *__restrict__ sensors, const float *__restric
   const int ntr = (H + kTileR - 1) / kTileR, ntc = (W + kTileC - 1) / kTileC;
   const float *img = ri_pool + sn.ri_off;
   float *out = pyr + pyr_off[e];
+  constexpr int kU = 4;                            // tiles per warp in flight: 32 independent loads per lane
   for (int tr = blockIdx.y; tr < ntr; tr += kPyrRowGroups) {
-    for (int tc = warp; tc < ntc; tc += 8) {
-      const int col = tc * kTileC + lane;
-      float v[kTileR];
+    for (int tc0 = warp * kU; tc0 < ntc; tc0 += 8 * kU) {
+      float v[kU][kTileR];
 #pragma unroll
-      for (int r = 0; r < kTileR; ++r) {           // range images are >= 0 (0 = no return)
-        const int row = tr * kTileR + r;
-        v[r] = (col < W && row < H) ? ld_stream(img + (int64_t)row * W + col) : 0.f;
+      for (int u = 0; u < kU; ++u) {
+        const int col = (tc0 + u) * kTileC + lane;
+#pragma unroll
+        for (int r = 0; r < kTileR; ++r) {         // range images are >= 0 (0 = no return)
+          const int row = tr * kTileR + r;
+          v[u][r] = (tc0 + u < ntc && col < W && row < H) ? ld_stream(img + (int64_t)row * W + col) : 0.f;
+        }
       }
-      float m = 0.f;
 #pragma unroll
-      for (int r = 0; r < kTileR; ++r) m = fmaxf(m, v[r]);
-      for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-      if (lane == 0) out[tr * ntc + tc] = m;
+      for (int u = 0; u < kU; ++u) {
+        float m = 0.f;
+#pragma unroll
+        for (int r = 0; r < kTileR; ++r) m = fmaxf(m, v[u][r]);
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if (lane == 0 && tc0 + u < ntc) out[tr * ntc + tc0 + u] = m;
+      }
     }
   }
 }
@@ -780,7 +819,7 @@ __global__ void k_pair_setup(int64_t n_pairs, int L, const occb200_pose_t *__res
   pc.q = (int32_t)(e - trk_frame_off[t] * L);
   pc.cull = 0;
   // ---- cull test (conservative; any doubt keeps the pair)
-  if (counter[2] != 0ull && g.status == OCCB200_OK && sn.incl_mono == -1 && sn.H >= 1 && sn.W >= 1) {
+  if (counter[0] != 0ull && g.status == OCCB200_OK && sn.incl_mono == -1 && sn.H >= 1 && sn.W >= 1) {
     // the columns of VR are orthogonal only up to the f32 inverse: 1.001 covers it, +1 mm absolute
     const double R = 0.5 * sqrt(R2) * 1.001 + 1e-3;
     const double rho = sqrt(pcen[0] * pcen[0] + pcen[1] * pcen[1]);
@@ -1061,14 +1100,16 @@ k_visibility_fast(int T, int L, const int64_t *__restrict__ trk_frame_off,
         const float *ub = ub_pool + sc.tab_off;
         const uint16_t *lut = lut_pool + sc.tab_off * kLutPerRow;
         const float *ri_img = ri_pool + sc.ri_off;
+        // all kVPL tests are evaluated unconditionally (no divergence, their dependent chains interleave);
+        // results of voxels this lane does not need are discarded
         int res[kVPL];
 #pragma unroll
+        for (int v = 0; v < kVPL; ++v) res[v] = fast_test(pc, sc, vx[v], vy[v], vz[v], ub, lut, ri_img);
+#pragma unroll
         for (int v = 0; v < kVPL; ++v) {
-          res[v] = 0;
-          if ((todo >> v) & 1u) {
-            res[v] = (pc.eps >= 0.f) ? fast_test(pc, sc, vx[v], vy[v], vz[v], ub, lut, ri_img) : 1;
-            ++steps;
-          }
+          const bool need = (todo >> v) & 1u;
+          res[v] = need ? ((pc.eps >= 0.f) ? res[v] : 1) : 0;
+          steps += need ? 1u : 0u;
         }
 #pragma unroll
         for (int v = 0; v < kVPL; ++v) {
@@ -1202,10 +1243,32 @@ extern "C" int occb200_annotate_batch(const occb200_annotate_args_t *a, int64_t 
   const float vsf = (float)a->voxel_size;
   const bool f64_only = (a->flags & 1) != 0;
   const int chunk = f64_only ? kChunk : kFastChunk;
+  SideStream *side = nullptr;
+  const bool fast = !f64_only && a->F > 0 && a->SF > 0;
+  if (fast) {                                       // fork: sensor-side setup on the side stream
+    if (side_stream(&side)) return 1;
+    OCC_CUDA(cudaEventRecord(side->fork, stream));
+    OCC_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
+    ProfScope ps(kProfPairSetup, side->stream);
+    const int64_t n_sens = a->SF * a->L;
+    k_table_setup<<<(unsigned)n_sens, 256, 0, side->stream>>>(n_sens, a->sensors, a->incl_pool, w.sens, w.ub_pool,
+                                                              w.lut_pool);
+    OCC_KERNEL_OK("k_table_setup");
+    k_pyr_scan<<<1, 1024, 0, side->stream>>>(n_sens, a->sensors, (a->flags & 2) ? (int64_t)-1 : w.pyr_tiles,
+                                             w.pyr_off, w.pyr_flag);
+    OCC_KERNEL_OK("k_pyr_scan");
+    if (w.pyr_tiles > 0 && !(a->flags & 2)) {
+      k_pyr_build<<<dim3((unsigned)n_sens, kPyrRowGroups), 256, 0, side->stream>>>(a->sensors, a->ri_pool, w.pyr_off,
+                                                                                   w.pyr_flag, w.pyr);
+      OCC_KERNEL_OK("k_pyr_build");
+    }
+    OCC_CUDA(cudaEventRecord(side->join, side->stream));
+  }
   OCC_CUDA(cudaMemsetAsync(w.bits, 0, 4 * w.bits_words, stream));
   {
     ProfScope ps(kProfInbox, stream);
-    k_tracklet_presetup<<<(unsigned)ceil_div(a->T, 8), 256, 0, stream>>>(a->T, a->trk_frame_off, a->poses, a->label_off,
+    k_tracklet_presetup<<<(unsigned)ceil_div(a->T, 8), 256, 0, stream>>>(a->T, a->trk_frame_off, a->poses,
+                                                                         a->frame_pt_off, a->label_off,
                                                                          vsf, chunk, w.grids, w.frame_trk,
                                                                          a->n_unknown, a->n_steps);
     OCC_KERNEL_OK("k_tracklet_presetup");
@@ -1219,8 +1282,8 @@ extern "C" int occb200_annotate_batch(const occb200_annotate_args_t *a, int64_t 
   {
     ProfScope ps(kProfSetup, stream);
     k_tracklet_setup<<<(unsigned)ceil_div(a->T, 8), 256, 0, stream>>>(
-        a->T, a->trk_frame_off, a->poses, w.frame_kept, a->label_off, vsf, chunk, w.grids, w.bits, a->dims, a->sizes,
-        a->status);
+        a->T, a->trk_frame_off, a->poses, a->frame_pt_off, w.frame_kept, a->label_off, vsf, chunk, w.grids, w.bits,
+        a->dims, a->sizes, a->status);
     OCC_KERNEL_OK("k_tracklet_setup");
     if (a->F > 0) {   // corrected tracklets only; every other CTA leaves at once
       k_frame_voxelize<<<(unsigned)a->F, kFrameThreads, 0, stream>>>(
@@ -1244,24 +1307,13 @@ extern "C" int occb200_annotate_batch(const occb200_annotate_args_t *a, int64_t 
     OCC_KERNEL_OK("k_visibility_f64");
     return 0;
   }
-  if (a->F > 0 && a->SF > 0) {
-    ProfScope ps(kProfPairSetup, stream);
-    k_table_setup<<<(unsigned)(a->SF * a->L), 256, 0, stream>>>(a->SF * a->L, a->sensors, a->incl_pool, w.sens,
-                                                                w.ub_pool, w.lut_pool);
-    OCC_KERNEL_OK("k_table_setup");
-    const int64_t n_sens = a->SF * a->L;
-    k_pyr_scan<<<1, 1024, 0, stream>>>(n_sens, a->sensors, (a->flags & 2) ? (int64_t)-1 : w.pyr_tiles, w.pyr_off,
-                                       w.counter);
-    OCC_KERNEL_OK("k_pyr_scan");
-    if (w.pyr_tiles > 0 && !(a->flags & 2)) {
-      k_pyr_build<<<dim3((unsigned)n_sens, kPyrRowGroups), 256, 0, stream>>>(a->sensors, a->ri_pool, w.pyr_off,
-                                                                             w.counter, w.pyr);
-      OCC_KERNEL_OK("k_pyr_build");
-    }
+  if (fast) {
+    OCC_CUDA(cudaStreamWaitEvent(stream, side->join, 0));   // join
+    ProfScope ps(kProfPairCull, stream);
     const int64_t n_pairs = a->F * a->L;
     k_pair_setup<<<(unsigned)ceil_div(n_pairs, 128), 128, 0, stream>>>(
         n_pairs, a->L, a->poses, a->frame_sf, w.frame_trk, a->trk_frame_off, a->sensors, a->incl_pool, w.grids,
-        w.sens, a->voxel_size, w.pyr_off, w.pyr, w.counter, w.pairs);
+        w.sens, a->voxel_size, w.pyr_off, w.pyr, w.pyr_flag, w.pairs);
     OCC_KERNEL_OK("k_pair_setup");
     k_pair_compact<<<(unsigned)ceil_div(a->T, 8), 256, 0, stream>>>(a->T, a->L, a->trk_frame_off, w.pairs, w.pairs_c,
                                                                     w.n_active);
