@@ -41,6 +41,7 @@ WORKLOADS = {
     "c1": "c1: 1 vehicle tracklet x 20 frames, 0.2 m voxels, 5 LiDARs",
     "c2": "c2: 64 vehicle tracklets x 40 frames, 0.2 m voxels, 5 LiDARs (one shared segment)",
     "c3": "c3: 16 truck/bus tracklets x 40 frames, 0.1 m voxels, 5 LiDARs",
+    "c5s": "c5 (scaled): 1024 vehicle tracklets x 40 frames over 16 segments, 0.2 m voxels, 5 LiDARs",
 }
 
 

@@ -459,6 +459,8 @@ def config_batch(name: str, seed: int = 0, small: bool = False) -> TrackletBatch
         return make_batch(16, 40, 0.1, "large", seed, tracklets_per_segment=16, small=small)
     if name == "c5":      # 10k C2-shaped tracklets
         return make_batch(10000, 40, 0.2, "vehicle", seed, tracklets_per_segment=64, small=small)
+    if name == "c5s":     # 1/10 of C5 for quick scaling checks
+        return make_batch(1024, 40, 0.2, "vehicle", seed, tracklets_per_segment=64, small=small)
     raise ValueError(f"unknown config {name}")
 
 
