@@ -95,6 +95,8 @@ struct Workspace {
   TrkGrid *grids;        // [T]
   int32_t *frame_kept;   // [F]
   int32_t *frame_trk;    // [F]
+  int32_t *redo_list;    // [F] frames of tracklets whose optimistic grid was wrong
+  unsigned long long *redo_count;
   int64_t *chunk_off;    // [T+1]
   unsigned long long *pyr_flag;  // [0] 1: pyramid built (fits), culling enabled -- written on the side stream
   unsigned long long *counter;   // [0] work-queue head, [1] recheck-queue length
@@ -124,6 +126,8 @@ static int64_t ws_layout(int32_t T, int64_t F, int64_t total, int64_t SF, int32_
   int64_t o_grid = take(sizeof(TrkGrid) * (int64_t)T);
   int64_t o_kept = take(4 * F);
   int64_t o_ftrk = take(4 * F);
+  int64_t o_redo = take(4 * F);
+  int64_t o_rc = take(8);
   int64_t o_choff = take(8 * ((int64_t)T + 1));
   int64_t o_cnt = take(8 * 4);
   int64_t o_pf = take(8);
@@ -150,6 +154,8 @@ static int64_t ws_layout(int32_t T, int64_t F, int64_t total, int64_t SF, int32_
     w->grids = (TrkGrid *)(base + o_grid);
     w->frame_kept = (int32_t *)(base + o_kept);
     w->frame_trk = (int32_t *)(base + o_ftrk);
+    w->redo_list = (int32_t *)(base + o_redo);
+    w->redo_count = (unsigned long long *)(base + o_rc);
     w->chunk_off = (int64_t *)(base + o_choff);
     w->counter = (unsigned long long *)(base + o_cnt);
     w->pyr_flag = (unsigned long long *)(base + o_pf);
@@ -275,9 +281,11 @@ __device__ __forceinline__ int64_t voxel_of_point(const BoxTest &bt, const occb2
 __global__ void __launch_bounds__(256)
 k_tracklet_presetup(int T, const int64_t *__restrict__ trk_frame_off, const occb200_pose_t *__restrict__ poses,
                     const int64_t *__restrict__ frame_pt_off, const int64_t *__restrict__ label_off, float vsf, int chunk, TrkGrid *__restrict__ grids,
-                    int32_t *__restrict__ frame_trk, int64_t *__restrict__ n_unknown, int64_t *__restrict__ n_steps) {
+                    int32_t *__restrict__ frame_trk, unsigned long long *__restrict__ redo_count,
+                    int64_t *__restrict__ n_unknown, int64_t *__restrict__ n_steps) {
   const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);   // one warp per tracklet
   const int lane = threadIdx.x & 31;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *redo_count = 0ull;
   if (t >= T) return;
   const int64_t f0 = trk_frame_off[t], f1 = trk_frame_off[t + 1];
   float sz[3] = {-INFINITY, -INFINITY, -INFINITY};
@@ -314,16 +322,22 @@ __global__ void __launch_bounds__(kFrameThreads)
 k_frame_voxelize(const occb200_pose_t *__restrict__ poses, const float *__restrict__ points, int stride,
                  const int64_t *__restrict__ frame_pt_off, int32_t *__restrict__ frame_kept,
                  const int32_t *__restrict__ frame_trk, TrkGrid *__restrict__ grids,
-                 uint32_t *__restrict__ bits, float vsf, int redo_pass) {
+                 uint32_t *__restrict__ bits, float vsf, const int32_t *__restrict__ redo_list,
+                 const unsigned long long *__restrict__ redo_count) {
   __shared__ uint32_t s_bits[kSmemBitWords];
   __shared__ int s_flags;
-  const int64_t f = blockIdx.x;
+  // first pass: CTA b = tracklet-frame b.  second pass (redo_list != NULL): a small grid strides over the
+  // frames of the tracklets whose optimistic grid was wrong -- usually none.
+  const bool redo_pass = redo_list != nullptr;
+  const long long n_work = redo_pass ? (long long)*redo_count : (long long)gridDim.x;
+  for (long long wi = blockIdx.x; wi < n_work; wi += gridDim.x) {
+  __syncthreads();
+  const int64_t f = redo_pass ? (int64_t)redo_list[wi] : (int64_t)wi;
   const int t = frame_trk[f];
-  if (redo_pass && (grids[t].redo == 0 || frame_kept[f] == 0)) return;   // second pass: corrected tracklets only
   const TrkGrid g = grids[t];
   if (g.status != OCCB200_OK) {
     if (threadIdx.x == 0 && !redo_pass) frame_kept[f] = 0;
-    return;
+    continue;
   }
   const int words = (int)((g.V + 31) / 32);
   const bool use_smem = words <= kSmemBitWords;
@@ -386,13 +400,15 @@ k_frame_voxelize(const occb200_pose_t *__restrict__ poses, const float *__restri
     if (!redo_pass) frame_kept[f] = (fl & 4) ? 1 : 0;
     if (fl & 3) atomicOr(&grids[t].flags, fl & 3);
   }
+  }
 }
 
 __global__ void __launch_bounds__(256)
 k_tracklet_setup(int T, const int64_t *__restrict__ trk_frame_off, const occb200_pose_t *__restrict__ poses,
                  const int64_t *__restrict__ frame_pt_off, const int32_t *__restrict__ frame_kept,
                  const int64_t *__restrict__ label_off, float vsf, int chunk,
-                 TrkGrid *__restrict__ grids, uint32_t *__restrict__ bits, int32_t *__restrict__ dims_out,
+                 TrkGrid *__restrict__ grids, uint32_t *__restrict__ bits, int32_t *__restrict__ redo_list,
+                 unsigned long long *__restrict__ redo_count, int32_t *__restrict__ dims_out,
                  float *__restrict__ sizes_out, int32_t *__restrict__ status_out) {
   const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);   // one warp per tracklet
   const int lane = threadIdx.x & 31;
@@ -434,6 +450,15 @@ k_tracklet_setup(int T, const int64_t *__restrict__ trk_frame_off, const occb200
       g.redo = 1;
       uint32_t *gbits = bits + g.bits_off;
       for (int w = lane; w < old_words; w += 32) gbits[w] = 0u;
+      unsigned long long base = 0;
+      if (lane == 0) base = atomicAdd(redo_count, (unsigned long long)kept);
+      base = __shfl_sync(0xffffffffu, base, 0);
+      for (int64_t f = f0 + lane; f - lane < f1; f += 32) {        // kept frames, warp-compacted
+        const bool k_ = f < f1 && frame_kept[f] != 0;
+        const unsigned m = __ballot_sync(0xffffffffu, k_);
+        if (k_) redo_list[base + __popc(m & ((1u << lane) - 1u))] = (int32_t)f;
+        base += __popc(m);
+      }
     }
   }
   if (lane != 0) return;
@@ -1269,25 +1294,27 @@ extern "C" int occb200_annotate_batch(const occb200_annotate_args_t *a, int64_t 
     ProfScope ps(kProfInbox, stream);
     k_tracklet_presetup<<<(unsigned)ceil_div(a->T, 8), 256, 0, stream>>>(a->T, a->trk_frame_off, a->poses,
                                                                          a->frame_pt_off, a->label_off,
-                                                                         vsf, chunk, w.grids, w.frame_trk,
+                                                                         vsf, chunk, w.grids, w.frame_trk, w.redo_count,
                                                                          a->n_unknown, a->n_steps);
     OCC_KERNEL_OK("k_tracklet_presetup");
   }
   if (a->F > 0) {
     ProfScope ps(kProfVoxelize, stream);
     k_frame_voxelize<<<(unsigned)a->F, kFrameThreads, 0, stream>>>(
-        a->poses, a->points, a->point_stride, a->frame_pt_off, w.frame_kept, w.frame_trk, w.grids, w.bits, vsf, 0);
+        a->poses, a->points, a->point_stride, a->frame_pt_off, w.frame_kept, w.frame_trk, w.grids, w.bits, vsf, nullptr,
+        nullptr);
     OCC_KERNEL_OK("k_frame_voxelize");
   }
   {
     ProfScope ps(kProfSetup, stream);
     k_tracklet_setup<<<(unsigned)ceil_div(a->T, 8), 256, 0, stream>>>(
         a->T, a->trk_frame_off, a->poses, a->frame_pt_off, w.frame_kept, a->label_off, vsf, chunk, w.grids, w.bits,
-        a->dims, a->sizes, a->status);
+        w.redo_list, w.redo_count, a->dims, a->sizes, a->status);
     OCC_KERNEL_OK("k_tracklet_setup");
-    if (a->F > 0) {   // corrected tracklets only; every other CTA leaves at once
-      k_frame_voxelize<<<(unsigned)a->F, kFrameThreads, 0, stream>>>(
-          a->poses, a->points, a->point_stride, a->frame_pt_off, w.frame_kept, w.frame_trk, w.grids, w.bits, vsf, 1);
+    if (a->F > 0) {   // frames of corrected tracklets only (device-side list, usually short)
+      k_frame_voxelize<<<(unsigned)std::min<int64_t>(a->F, kNumSMs * 7), kFrameThreads, 0, stream>>>(
+          a->poses, a->points, a->point_stride, a->frame_pt_off, w.frame_kept, w.frame_trk, w.grids, w.bits, vsf,
+          w.redo_list, w.redo_count);
       OCC_KERNEL_OK("k_frame_voxelize(redo)");
     }
   }
