@@ -78,6 +78,46 @@ def build_ref(verbose: bool = False):
     return built
 
 
+_PIB_CUDA_SHIM = r"""
+#include <torch/extension.h>
+int points_in_boxes_gpu(at::Tensor boxes_tensor, at::Tensor pts_tensor, at::Tensor box_idx_of_points_tensor);
+int points_in_boxes_batch(at::Tensor boxes_tensor, at::Tensor pts_tensor, at::Tensor box_idx_of_points_tensor);
+PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
+  m.def("points_in_boxes_gpu", &points_in_boxes_gpu, "points_in_boxes_gpu (reference CUDA source)");
+  m.def("points_in_boxes_batch", &points_in_boxes_batch, "points_in_boxes_batch (reference CUDA source)");
+}
+"""
+
+
+def build_ref_cuda(verbose: bool = False):
+    """The reference's own CUDA kernels, UNMODIFIED, compiled for sm_100a into oracle/_ref:
+    `ref_voxel_layer_cuda` (voxelization_cuda.cu + scatter_points_cuda.cu + the CPU files, -DWITH_CUDA) and
+    `ref_points_in_boxes_cuda` (points_in_boxes_cuda.cu + a shim).  They are the "reference on B200" bar of
+    tools/bench_ops.py and a second oracle for the operators on the GPU box."""
+    if not os.path.isdir(REFERENCE):
+        return None
+    os.makedirs(REF_OUT, exist_ok=True)
+    os.environ["TORCH_CUDA_ARCH_LIST"] = "10.0a"
+    from torch.utils.cpp_extension import load
+
+    vdir = os.path.join(REFERENCE, "mmdet3d/ops/voxel/src")
+    if not _has_ext("ref_voxel_layer_cuda"):
+        load(name="ref_voxel_layer_cuda",
+             sources=[os.path.join(vdir, f) for f in ("voxelization.cpp", "voxelization_cpu.cpp", "scatter_points_cpu.cpp",
+                                                      "voxelization_cuda.cu", "scatter_points_cuda.cu")],
+             build_directory=_mk(os.path.join(REF_OUT, "ref_voxel_layer_cuda")), verbose=verbose,
+             extra_cflags=["-O2", "-DWITH_CUDA"], extra_cuda_cflags=["-O2", "-DWITH_CUDA"], with_cuda=True)
+    if not _has_ext("ref_points_in_boxes_cuda"):
+        d = _mk(os.path.join(REF_OUT, "ref_points_in_boxes_cuda"))
+        shim = os.path.join(d, "pib_cuda_shim.cpp")
+        with open(shim, "w") as f:
+            f.write(_PIB_CUDA_SHIM)
+        load(name="ref_points_in_boxes_cuda",
+             sources=[shim, os.path.join(REFERENCE, "mmdet3d/ops/roiaware_pool3d/src/points_in_boxes_cuda.cu")],
+             build_directory=d, verbose=verbose, extra_cflags=["-O2"], extra_cuda_cflags=["-O2"], with_cuda=True)
+    return True
+
+
 def _mk(d):
     os.makedirs(d, exist_ok=True)
     return d
@@ -105,3 +145,5 @@ def load_ref(name):
 if __name__ == "__main__":
     print(build_oracle(force="--force" in sys.argv))
     print(build_ref(verbose="-v" in sys.argv))
+    if "--cuda" in sys.argv:
+        print(build_ref_cuda(verbose="-v" in sys.argv))
