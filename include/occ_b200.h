@@ -215,6 +215,7 @@ typedef struct occb200_annotate_args {
   int64_t incl_len;               /* floats in incl_pool                                      */
   const float *ri_pool;
   int64_t pyr_tiles;              /* sum of occb200_pyramid_tiles(H, W) over the SF*L sensors; 0 = no pair culling */
+  int64_t items_cap;              /* occb200_annotate_items_cap(T, label_off, trk_frame_off, L) from the host copies */
   double voxel_size;              /* python float of --voxel-size (occ_annotate.py:215)       */
   const int64_t *label_off;       /* [T+1] slot of each tracklet in labels; slot size >= prod(ceil(max_frames(size)/vs)) */
   /* outputs */
@@ -225,14 +226,16 @@ typedef struct occb200_annotate_args {
   int64_t *n_unknown;             /* [T]    voxels tested for visibility (U)                  */
   int64_t *n_steps;               /* [T]    visibility tests actually evaluated (<= U*B*L; early exit) ; may be NULL */
   void *workspace;
-  int64_t workspace_bytes;        /* >= occb200_annotate_workspace_bytes(T, F, label_off[T], SF, L, incl_len, pyr_tiles) */
+  int64_t workspace_bytes;        /* >= occb200_annotate_workspace_bytes(T, F, label_off[T], SF, L, incl_len, pyr_tiles, items_cap) */
   int32_t flags;                  /* bit 0: every visibility test in exact f64 (no f32 fast path);
                                      bit 1: no (frame, LiDAR) pair culling                          */
   int32_t pad1;
 } occb200_annotate_args_t;
 
 int64_t occb200_annotate_workspace_bytes(int32_t T, int64_t F, int64_t total_label_slots, int64_t SF,
-                                         int32_t L, int64_t incl_len, int64_t pyr_tiles);
+                                         int32_t L, int64_t incl_len, int64_t pyr_tiles, int64_t items_cap);
+/* HOST helper: upper bound of the ray-cast kernel's work items (for args.items_cap); HOST arrays. */
+int64_t occb200_annotate_items_cap(int32_t T, const int64_t *label_off, const int64_t *trk_frame_off, int32_t L);
 /* HOST helper: tiles the max-pyramid of one H x W range image needs (for args.pyr_tiles). */
 int64_t occb200_pyramid_tiles(int32_t H, int32_t W);
 

@@ -17,7 +17,7 @@ LIB_PATH = os.environ.get("OCCB200_LIB", os.path.join(CSRC, "libocc_b200.so"))
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "occ_b200.h")
 
 vp, i32, i64, f32, f64 = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_double
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 
 class Pose(C.Structure):
@@ -33,7 +33,7 @@ class Sensor(C.Structure):
 class AnnotateArgs(C.Structure):
     _fields_ = [("T", i32), ("L", i32), ("F", i64), ("trk_frame_off", vp), ("poses", vp), ("frame_sf", vp),
                 ("points", vp), ("point_stride", i32), ("pad0", i32), ("frame_pt_off", vp), ("sensors", vp),
-                ("SF", i64), ("incl_pool", vp), ("incl_len", i64), ("ri_pool", vp), ("pyr_tiles", i64), ("voxel_size", f64), ("label_off", vp), ("labels", vp),
+                ("SF", i64), ("incl_pool", vp), ("incl_len", i64), ("ri_pool", vp), ("pyr_tiles", i64), ("items_cap", i64), ("voxel_size", f64), ("label_off", vp), ("labels", vp),
                 ("dims", vp), ("sizes", vp), ("status", vp), ("n_unknown", vp), ("n_steps", vp), ("workspace", vp),
                 ("workspace_bytes", i64), ("flags", i32), ("pad1", i32)]
 
@@ -68,7 +68,8 @@ SIGNATURES = {
     "occb200_segment_reduce_backward": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, i64, i64, C.c_int, C.c_int, vp]),
     "occb200_quantize_points": (C.c_int, [vp, i64, vp, C.c_int, vp, f32, vp, vp, C.c_int, vp, vp, vp]),
     "occb200_dense_voxel_centers": (C.c_int, [vp, vp, vp, C.c_int, i64, f32, vp, vp, vp, vp]),
-    "occb200_annotate_workspace_bytes": (i64, [i32, i64, i64, i64, i32, i64, i64]),
+    "occb200_annotate_workspace_bytes": (i64, [i32, i64, i64, i64, i32, i64, i64, i64]),
+    "occb200_annotate_items_cap": (i64, [i32, vp, vp, i32]),
     "occb200_pyramid_tiles": (i64, [i32, i32]),
     "occb200_annotate_batch": (C.c_int, [C.POINTER(AnnotateArgs), i64, vp]),
     "occb200_annotate_queue_stats": (C.c_int, [C.POINTER(AnnotateArgs), i64, vp, vp]),

@@ -41,7 +41,11 @@ constexpr int kChunk = 256;         // f64 kernel: voxels per work item == threa
 #endif
 constexpr int kVPL = OCC_VPL;       // fast kernel: voxels per lane
 constexpr int kFastChunk = 32 * kVPL;   // fast kernel: voxels per work item
-constexpr int kFastWarps = 8;       // fast kernel: warps per CTA, each takes every 8th (frame, LiDAR) pair
+constexpr int kFastWarps = 8;       // fast kernel: independent warps per CTA
+#ifndef OCC_PPI
+#define OCC_PPI 16
+#endif
+constexpr int kPairsPerItem = OCC_PPI;   // fast kernel: (frame, LiDAR) pairs one work item covers for its 64 voxels
 constexpr int kLutPerRow = 16;      // lookup-table cells reserved per inclination-table entry
 constexpr int kTileR = 8, kTileC = 32;   // range-image max-pyramid tile (rows x columns)
 constexpr int kFrameThreads = 256;
@@ -91,6 +95,19 @@ struct __align__(16) PairCoef {
 };
 static_assert(sizeof(PairCoef) == 64, "PairCoef must be 64 bytes");
 
+// What the fast visibility kernel needs of a tracklet, in one 64-byte record (4 x LDG.128).
+struct __align__(16) TrkHot {
+  int32_t V, dY, dZ;
+  int32_t status;       // final status (flags of k_frame_voxelize folded in)
+  int32_t nact;         // pairs that survived culling
+  int32_t pad0;
+  int64_t bits_off;
+  int64_t label_off;
+  int64_t pairs_base;   // first PairCoef of the tracklet in pairs_c
+  int64_t pad1[2];
+};
+static_assert(sizeof(TrkHot) == 64, "TrkHot must be 64 bytes");
+
 struct Workspace {
   TrkGrid *grids;        // [T]
   int32_t *frame_kept;   // [F]
@@ -109,14 +126,17 @@ struct Workspace {
   int4 *queue;           // recheck queue: (tracklet, voxel, pair index q = i*L + c, unused)
   int64_t queue_cap;
   PairCoef *pairs_c;     // [F*L] the non-culled pairs of each tracklet, compacted at trk_frame_off[t] * L
-  int32_t *n_active;     // [T]   how many
+  TrkHot *hot;           // [T]
+  uint32_t *free_bits;   // same layout as `bits`: voxels proven free
+  int2 *item_map;        // [items_cap] work items of the fast kernel: (tracklet, chunk | slice << 20)
+  int64_t items_cap;
   int64_t *pyr_off;      // [SF*L + 1] first tile of each range image in pyr
   float *pyr;            // [pyr_tiles] max of the range image over tiles of kTileR x kTileC pixels
   int64_t pyr_tiles;
 };
 
 static int64_t ws_layout(int32_t T, int64_t F, int64_t total, int64_t SF, int32_t L, int64_t incl_len,
-                         int64_t pyr_tiles, char *base, Workspace *w) {
+                         int64_t pyr_tiles, int64_t items_cap, char *base, Workspace *w) {
   int64_t off = 0;
   auto take = [&](int64_t bytes) {
     int64_t o = off;
@@ -133,6 +153,8 @@ static int64_t ws_layout(int32_t T, int64_t F, int64_t total, int64_t SF, int32_
   int64_t o_pf = take(8);
   int64_t words = total / 32 + T + 1;
   int64_t o_bits = take(4 * words);
+  int64_t o_fbits = take(4 * words);
+  int64_t o_imap = take(8 * items_cap);
   int64_t o_tab = take(sizeof(SensCoef) * SF * L);
   int64_t o_ub = take(4 * incl_len);
   int64_t o_lut = take(2 * incl_len * kLutPerRow);
@@ -142,12 +164,12 @@ static int64_t ws_layout(int32_t T, int64_t F, int64_t total, int64_t SF, int32_
   int64_t qcap = (int64_t)std::min(std::max(nominal / 16.0, 65536.0), 64.0 * 1024 * 1024);
   int64_t o_q = take(16 * qcap);
   int64_t o_pc = take(sizeof(PairCoef) * F * L);
-  int64_t o_na = take(4 * (int64_t)T);
+  int64_t o_na = take(sizeof(TrkHot) * (int64_t)T);
   int64_t o_po = take(8 * (SF * L + 1));
   int64_t o_py = take(4 * pyr_tiles);
   if (w) {
     w->pairs_c = (PairCoef *)(base + o_pc);
-    w->n_active = (int32_t *)(base + o_na);
+    w->hot = (TrkHot *)(base + o_na);
     w->pyr_off = (int64_t *)(base + o_po);
     w->pyr = (float *)(base + o_py);
     w->pyr_tiles = pyr_tiles;
@@ -161,6 +183,9 @@ static int64_t ws_layout(int32_t T, int64_t F, int64_t total, int64_t SF, int32_
     w->pyr_flag = (unsigned long long *)(base + o_pf);
     w->bits = (uint32_t *)(base + o_bits);
     w->bits_words = words;
+    w->free_bits = (uint32_t *)(base + o_fbits);
+    w->item_map = (int2 *)(base + o_imap);
+    w->items_cap = items_cap;
     w->sens = (SensCoef *)(base + o_tab);
     w->ub_pool = (float *)(base + o_ub);
     w->lut_pool = (uint16_t *)(base + o_lut);
@@ -282,10 +307,12 @@ __global__ void __launch_bounds__(256)
 k_tracklet_presetup(int T, const int64_t *__restrict__ trk_frame_off, const occb200_pose_t *__restrict__ poses,
                     const int64_t *__restrict__ frame_pt_off, const int64_t *__restrict__ label_off, float vsf, int chunk, TrkGrid *__restrict__ grids,
                     int32_t *__restrict__ frame_trk, unsigned long long *__restrict__ redo_count,
-                    int64_t *__restrict__ n_unknown, int64_t *__restrict__ n_steps) {
+                    unsigned long long *__restrict__ counter, int64_t *__restrict__ n_unknown,
+                    int64_t *__restrict__ n_steps) {
   const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);   // one warp per tracklet
   const int lane = threadIdx.x & 31;
   if (blockIdx.x == 0 && threadIdx.x == 0) *redo_count = 0ull;
+  if (blockIdx.x == 0 && threadIdx.x < 4) counter[threadIdx.x] = 0ull;
   if (t >= T) return;
   const int64_t f0 = trk_frame_off[t], f1 = trk_frame_off[t + 1];
   float sz[3] = {-INFINITY, -INFINITY, -INFINITY};
@@ -896,30 +923,58 @@ __global__ void k_pair_setup(int64_t n_pairs, int L, const occb200_pose_t *__res
   pairs[e] = pc;
 }
 
-// One warp per tracklet: copy the surviving pairs, in order, to the front of the tracklet's slot.
+// One warp per tracklet: copy the surviving pairs, in order, to the front of the tracklet's slot, fix the final
+// status, write the tracklet's hot record and emit its work items (chunk x slice of kPairsPerItem pairs).
+// Item ids come from an atomic counter, so their order across tracklets is arbitrary -- they are independent.
 __global__ void __launch_bounds__(256)
-k_pair_compact(int T, int L, const int64_t *__restrict__ trk_frame_off, const PairCoef *__restrict__ pairs,
-               PairCoef *__restrict__ pairs_c, int32_t *__restrict__ n_active) {
+k_pair_compact(int T, int L, const int64_t *__restrict__ trk_frame_off, const int64_t *__restrict__ label_off,
+               const TrkGrid *__restrict__ grids, const PairCoef *__restrict__ pairs, PairCoef *__restrict__ pairs_c,
+               TrkHot *__restrict__ hot, int2 *__restrict__ item_map, long long items_cap,
+               unsigned long long *__restrict__ counter, int32_t *__restrict__ status_out) {
   const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (t >= T) return;
+  const TrkGrid g = grids[t];
+  int status = g.status;                          // flags are final: k_frame_voxelize has completed
+  if (status == OCCB200_OK) {
+    if (g.flags & 2) status = OCCB200_INDEX_ERROR;
+    else if (!(g.flags & 1)) status = OCCB200_EMPTY_AFTER_FILTER;
+  }
   const int64_t base = trk_frame_off[t] * L;
   const int n = (int)(trk_frame_off[t + 1] - trk_frame_off[t]) * L;
   int count = 0;
-  for (int q0 = 0; q0 < n; q0 += 32) {
-    const int q = q0 + lane;
-    const bool keep = q < n && pairs[base + q].cull == 0;
-    const unsigned mask = __ballot_sync(0xffffffffu, keep);
-    if (keep) {
-      const int dst = count + __popc(mask & ((1u << lane) - 1u));
-      const float4 *src = reinterpret_cast<const float4 *>(pairs + base + q);
-      float4 *d4 = reinterpret_cast<float4 *>(pairs_c + base + dst);
+  if (status == OCCB200_OK)
+    for (int q0 = 0; q0 < n; q0 += 32) {
+      const int q = q0 + lane;
+      const bool keep = q < n && pairs[base + q].cull == 0;
+      const unsigned mask = __ballot_sync(0xffffffffu, keep);
+      if (keep) {
+        const int dst = count + __popc(mask & ((1u << lane) - 1u));
+        const float4 *src = reinterpret_cast<const float4 *>(pairs + base + q);
+        float4 *d4 = reinterpret_cast<float4 *>(pairs_c + base + dst);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) d4[k] = src[k];
+        for (int k = 0; k < 4; ++k) d4[k] = src[k];
+      }
+      count += __popc(mask);
     }
-    count += __popc(mask);
+  const int nslice = (count + kPairsPerItem - 1) / kPairsPerItem;
+  const int nchunk = (status == OCCB200_OK) ? (int)((g.V + kFastChunk - 1) / kFastChunk) : 0;
+  const long long nitems = (long long)nchunk * nslice;
+  unsigned long long i0 = 0;
+  if (lane == 0 && nitems) i0 = atomicAdd(counter + 3, (unsigned long long)nitems);
+  i0 = __shfl_sync(0xffffffffu, i0, 0);
+  for (long long i = lane; i < nitems; i += 32)
+    if ((long long)i0 + i < items_cap)
+      item_map[i0 + i] = make_int2(t, (int)(i / nslice) | ((int)(i % nslice) << 20));
+  if (lane == 0) {
+    TrkHot h;
+    h.V = (int32_t)g.V; h.dY = g.dims[1]; h.dZ = g.dims[2];
+    h.status = status; h.nact = count; h.pad0 = 0;
+    h.bits_off = g.bits_off; h.label_off = label_off[t]; h.pairs_base = base;
+    h.pad1[0] = h.pad1[1] = 0;
+    hot[t] = h;
+    status_out[t] = status;
   }
-  if (lane == 0) n_active[t] = count;
 }
 
 // Approximate f32 primitives (flush-to-zero MUFU forms, <= 2 ulp): their error is part of every margin.
@@ -1040,138 +1095,100 @@ __device__ __noinline__ bool exact_from_ids(int t, int f, int q, int L, double v
   return exact_test(cx, cy, cz, poses + f0 + i, sn, incl_pool, ri_pool);
 }
 
+// Every warp is on its own: it claims a work item (64 voxels x up to kPairsPerItem surviving pairs) from an
+// atomic counter, tests, and ORs the voxels it proved free into the global free bitset.  No shared memory, no
+// barriers.  Labels are written afterwards by k_labels from the occupancy and free bitsets.
 __global__ void __launch_bounds__(32 * kFastWarps, OCC_MINB)
-k_visibility_fast(int T, int L, const int64_t *__restrict__ trk_frame_off,
+k_visibility_fast(int L, const int64_t *__restrict__ trk_frame_off,
                   const occb200_pose_t *__restrict__ poses, const int32_t *__restrict__ frame_sf,
                   const occb200_sensor_t *__restrict__ sensors, const float *__restrict__ incl_pool,
-                  const float *__restrict__ ri_pool, double vs, const int64_t *__restrict__ label_off,
-                  const TrkGrid *__restrict__ grids, const int64_t *__restrict__ chunk_off,
-                  unsigned long long *__restrict__ counter, const uint32_t *__restrict__ bits,
-                  const PairCoef *__restrict__ pairs, const int32_t *__restrict__ n_active,
-                  const SensCoef *__restrict__ sens,
+                  const float *__restrict__ ri_pool, double vs, const TrkGrid *__restrict__ grids,
+                  unsigned long long *__restrict__ counter, long long items_cap,
+                  const uint32_t *__restrict__ bits, uint32_t *__restrict__ free_bits,
+                  const int2 *__restrict__ item_map, const TrkHot *__restrict__ hot,
+                  const PairCoef *__restrict__ pairs, const SensCoef *__restrict__ sens,
                   const float *__restrict__ ub_pool, const uint16_t *__restrict__ lut_pool,
-                  int4 *__restrict__ queue, long long queue_cap, int32_t *__restrict__ labels,
-                  int32_t *__restrict__ status_out, int64_t *__restrict__ n_unknown, int64_t *__restrict__ n_steps) {
-  __shared__ long long s_item;
-  __shared__ unsigned s_free[kVPL];
-  __shared__ unsigned s_steps;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const long long total = chunk_off[T];
+                  int4 *__restrict__ queue, long long queue_cap, int64_t *__restrict__ n_steps) {
+  const int lane = threadIdx.x & 31;
+  const long long total = min((long long)counter[3], items_cap);
   for (;;) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      s_item = (long long)atomicAdd(counter, 1ull);
-      s_steps = 0u;
-    }
-    if (threadIdx.x < kVPL) s_free[threadIdx.x] = 0u;
-    __syncthreads();
-    const long long item = s_item;
+    long long item = 0;
+    if (lane == 0) item = (long long)atomicAdd(counter, 1ull);
+    item = __shfl_sync(0xffffffffu, item, 0);
     if (item >= total) break;
-    int lo = 0, hi = T;
-    while (hi - lo > 1) {
-      const int mid = (lo + hi) >> 1;
-      if (chunk_off[mid] <= item) lo = mid; else hi = mid;
-    }
-    const int t = lo;
-    const int chunk = (int)(item - chunk_off[t]);
-    const TrkGrid *gp = grids + t;
-    int status = gp->status;
-    const int gflags = gp->flags;
-    if (status == OCCB200_OK) {
-      if (gflags & 2) status = OCCB200_INDEX_ERROR;
-      else if (!(gflags & 1)) status = OCCB200_EMPTY_AFTER_FILTER;
-    }
-    if (chunk == 0 && threadIdx.x == 0) status_out[t] = status;
-    if (status != OCCB200_OK) continue;
-
-    // voxel v of this lane: flat index fbase + 32*v + lane (bitset word chunk*kVPL + v)
-    const int dY = gp->dims[1], dZ = gp->dims[2];
-    const int V = (int)gp->V;
+    const int2 m = __ldg(item_map + item);
+    const int t = m.x, chunk = m.y & 0xfffff, slice = m.y >> 20;
+    const TrkHot h = load64(hot + t);
+    const int V = h.V, dZ = h.dZ, yz = h.dY * dZ;
     const int fbase = chunk * kFastChunk;
-    const int64_t word0 = gp->bits_off + (int64_t)chunk * kVPL;
+    const int64_t word0 = h.bits_off + (int64_t)chunk * kVPL;
     float vx[kVPL], vy[kVPL], vz[kVPL];
-    unsigned mine = 0u;        // bit v: this lane's voxel v exists and holds no point
-    unsigned occ = 0u;         // bit v: it holds a point
+    unsigned todo = 0u;        // bit v: this lane's voxel v exists, holds no point and is not known to be free
 #pragma unroll
     for (int v = 0; v < kVPL; ++v) {
       const int f = fbase + 32 * v + lane;
       const bool active = f < V;
-      const unsigned w = (fbase + 32 * v < V) ? bits[word0 + v] : 0u;
-      const bool o = active && ((w >> lane) & 1u);
-      occ |= (o ? 1u : 0u) << v;
-      mine |= ((active && !o) ? 1u : 0u) << v;
+      unsigned w = 0xffffffffu;
+      if (fbase + 32 * v < V) w = __ldg(bits + word0 + v) | *(volatile const uint32_t *)(free_bits + word0 + v);
+      todo |= ((active && !((w >> lane) & 1u)) ? 1u : 0u) << v;
       const int fa = active ? f : 0;
-      const int yz = dY * dZ;
       const int ix = fa / yz, rem = fa - ix * yz;
       const int iy = rem / dZ;
       vx[v] = (float)ix;
       vy[v] = (float)iy;
       vz[v] = (float)(rem - iy * dZ);
     }
-    unsigned steps = 0;
-    if (__any_sync(0xffffffffu, mine != 0u)) {
-      const int64_t f0 = trk_frame_off[t];
-      const int npairs = n_active[t];              // pairs that survived culling, compacted
-      const PairCoef *tp = pairs + f0 * L;
-      for (int k = warp; k < npairs; k += kFastWarps) {
-        unsigned todo = mine;
+    unsigned steps = 0, found = 0u;
+    const int k0 = slice * kPairsPerItem, k1 = min(h.nact, k0 + kPairsPerItem);
+    const PairCoef *tp = pairs + h.pairs_base;
+    for (int k = k0; k < k1; ++k) {
+      if (!__any_sync(0xffffffffu, todo != 0u)) break;           // every voxel of the item is settled
+      const PairCoef pc = load64(tp + k);
+      if (k + 1 < k1) asm volatile("prefetch.global.L1 [%0];" ::"l"(tp + k + 1));
+      const SensCoef sc = load64(sens + pc.sens);
+      const float *ub = ub_pool + sc.tab_off;
+      const uint16_t *lut = lut_pool + sc.tab_off * kLutPerRow;
+      const float *ri_img = ri_pool + sc.ri_off;
+      // all kVPL tests are evaluated unconditionally (no divergence, their dependent chains interleave);
+      // results of voxels this lane does not need are discarded
+      int res[kVPL];
 #pragma unroll
-        for (int v = 0; v < kVPL; ++v) todo &= ~(((*(volatile unsigned *)&s_free[v] >> lane) & 1u) << v);
-        if (!__any_sync(0xffffffffu, todo != 0u)) break;         // every voxel of the chunk is already free
-        const PairCoef pc = load64(tp + k);
-        if (k + kFastWarps < npairs) asm volatile("prefetch.global.L1 [%0];" ::"l"(tp + k + kFastWarps));
-        const int q = pc.q;
-        const SensCoef sc = load64(sens + pc.sens);
-        const float *ub = ub_pool + sc.tab_off;
-        const uint16_t *lut = lut_pool + sc.tab_off * kLutPerRow;
-        const float *ri_img = ri_pool + sc.ri_off;
-        // all kVPL tests are evaluated unconditionally (no divergence, their dependent chains interleave);
-        // results of voxels this lane does not need are discarded
-        int res[kVPL];
+      for (int v = 0; v < kVPL; ++v) res[v] = fast_test(pc, sc, vx[v], vy[v], vz[v], ub, lut, ri_img);
 #pragma unroll
-        for (int v = 0; v < kVPL; ++v) res[v] = fast_test(pc, sc, vx[v], vy[v], vz[v], ub, lut, ri_img);
-#pragma unroll
-        for (int v = 0; v < kVPL; ++v) {
-          const bool need = (todo >> v) & 1u;
-          res[v] = need ? ((pc.eps >= 0.f) ? res[v] : 1) : 0;
-          steps += need ? 1u : 0u;
+      for (int v = 0; v < kVPL; ++v) {
+        const bool need = (todo >> v) & 1u;
+        res[v] = need ? ((pc.eps >= 0.f) ? res[v] : 1) : 0;
+        steps += need ? 1u : 0u;
+        if (res[v] == 2) {
+          found |= 1u << v;
+          todo &= ~(1u << v);
         }
-#pragma unroll
-        for (int v = 0; v < kVPL; ++v) {
-          if (res[v] == 2) atomicOr(&s_free[v], 1u << lane);
-          const unsigned umask = __ballot_sync(0xffffffffu, res[v] == 1);
-          if (umask) {                                           // queue the undecided tests (warp-aggregated)
-            unsigned long long base = 0;
-            if (lane == 0) base = atomicAdd(counter + 1, (unsigned long long)__popc(umask));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (res[v] == 1) {
-              const int f = fbase + 32 * v + lane;
-              const unsigned long long slot = base + __popc(umask & ((1u << lane) - 1u));
-              if (slot < (unsigned long long)queue_cap) {
-                queue[slot] = make_int4(t, f, q, 0);
-              } else if (exact_from_ids(t, f, q, L, vs, grids, trk_frame_off, poses, frame_sf, sensors, incl_pool,
-                                        ri_pool)) {              // queue full: decide right here
-                atomicOr(&s_free[v], 1u << lane);
-              }
+        const unsigned umask = __ballot_sync(0xffffffffu, res[v] == 1);
+        if (umask) {                                             // queue the undecided tests (warp-aggregated)
+          unsigned long long base = 0;
+          if (lane == 0) base = atomicAdd(counter + 1, (unsigned long long)__popc(umask));
+          base = __shfl_sync(0xffffffffu, base, 0);
+          if (res[v] == 1) {
+            const int f = fbase + 32 * v + lane;
+            const unsigned long long slot = base + __popc(umask & ((1u << lane) - 1u));
+            if (slot < (unsigned long long)queue_cap) {
+              queue[slot] = make_int4(t, f, pc.q, 0);
+            } else if (exact_from_ids(t, f, pc.q, L, vs, grids, trk_frame_off, poses, frame_sf, sensors, incl_pool,
+                                      ri_pool)) {                // queue full: decide right here
+              found |= 1u << v;
+              todo &= ~(1u << v);
             }
           }
         }
       }
     }
-    for (int o = 16; o > 0; o >>= 1) steps += __shfl_xor_sync(0xffffffffu, steps, o);
-    if (lane == 0 && steps) atomicAdd(&s_steps, steps);
-    __syncthreads();
-    if (warp < kVPL) {
-      const int v = warp;
-      const unsigned fr = s_free[v];
-      const int f = fbase + 32 * v + lane;
-      if (f < V) labels[label_off[t] + f] = ((occ >> v) & 1u) ? 1 : (((fr >> lane) & 1u) ? 2 : 0);   // :558-563
-      const unsigned nm = __ballot_sync(0xffffffffu, (mine >> v) & 1u);
-      if (lane == 0) {
-        if (nm) atomicAdd((unsigned long long *)&n_unknown[t], (unsigned long long)__popc(nm));
-        if (v == 0 && n_steps && s_steps) atomicAdd((unsigned long long *)&n_steps[t], (unsigned long long)s_steps);
-      }
+#pragma unroll
+    for (int v = 0; v < kVPL; ++v) {
+      const unsigned fw = __ballot_sync(0xffffffffu, (found >> v) & 1u);
+      if (fw && lane == 0) atomicOr(free_bits + word0 + v, fw);
     }
+    for (int o = 16; o > 0; o >>= 1) steps += __shfl_xor_sync(0xffffffffu, steps, o);
+    if (lane == 0 && n_steps && steps) atomicAdd((unsigned long long *)&n_steps[t], (unsigned long long)steps);
   }
 }
 
@@ -1179,24 +1196,43 @@ __global__ void __launch_bounds__(256)
 k_visibility_recheck(int L, const int64_t *__restrict__ trk_frame_off, const occb200_pose_t *__restrict__ poses,
                      const int32_t *__restrict__ frame_sf, const occb200_sensor_t *__restrict__ sensors,
                      const float *__restrict__ incl_pool, const float *__restrict__ ri_pool, double vs,
-                     const int64_t *__restrict__ label_off, const TrkGrid *__restrict__ grids,
-                     const unsigned long long *__restrict__ counter, const int4 *__restrict__ queue,
-                     long long queue_cap, int32_t *__restrict__ labels, int64_t *__restrict__ n_steps) {
+                     const TrkGrid *__restrict__ grids, const unsigned long long *__restrict__ counter,
+                     const int4 *__restrict__ queue, long long queue_cap, uint32_t *__restrict__ free_bits,
+                     int64_t *__restrict__ n_steps) {
   const long long n = min((long long)counter[1], queue_cap);
   for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) {
     const int4 it = queue[k];
     const int t = it.x, f = it.y, q = it.z;
-    int32_t *lab = labels + label_off[t] + f;
-    if (*(volatile int32_t *)lab != 0) continue;               // already proven free by another test
     const TrkGrid &g = grids[t];
+    uint32_t *word = free_bits + g.bits_off + (f >> 5);
+    const uint32_t bit = 1u << (f & 31);
+    if (*(volatile uint32_t *)word & bit) continue;            // already proven free by another test
     double cx, cy, cz;
     voxel_centre(g, f, vs, cx, cy, cz);
     const int i = q / L, c = q - i * L;
     const int64_t f0 = trk_frame_off[t];
     const occb200_sensor_t *sn = sensors + (int64_t)__ldg(frame_sf + f0 + i) * L + c;
-    if (exact_test(cx, cy, cz, poses + f0 + i, sn, incl_pool, ri_pool)) *lab = 2;
+    if (exact_test(cx, cy, cz, poses + f0 + i, sn, incl_pool, ri_pool)) atomicOr(word, bit);
     if (n_steps) atomicAdd((unsigned long long *)&n_steps[t], 1ull);
   }
+}
+
+// labels from the two bitsets: 1 occupied, 2 free, 0 unknown (occ_annotate.py:558-563); one CTA per tracklet
+__global__ void __launch_bounds__(256)
+k_labels(const TrkHot *__restrict__ hot, const uint32_t *__restrict__ bits, const uint32_t *__restrict__ free_bits,
+         int32_t *__restrict__ labels, int64_t *__restrict__ n_unknown) {
+  const int t = blockIdx.x;
+  const TrkHot h = hot[t];
+  if (h.status != OCCB200_OK) return;
+  int unk = 0;
+  for (int f = threadIdx.x; f < h.V; f += blockDim.x) {
+    const uint32_t o = bits[h.bits_off + (f >> 5)], fr = free_bits[h.bits_off + (f >> 5)];
+    const bool occ = (o >> (f & 31)) & 1u;
+    labels[h.label_off + f] = occ ? 1 : (((fr >> (f & 31)) & 1u) ? 2 : 0);
+    unk += occ ? 0 : 1;
+  }
+  for (int o = 16; o > 0; o >>= 1) unk += __shfl_xor_sync(0xffffffffu, unk, o);
+  if ((threadIdx.x & 31) == 0 && unk) atomicAdd((unsigned long long *)&n_unknown[t], (unsigned long long)unk);
 }
 
 // standalone operator: the reference's point_cloud_to_range_image_idx
@@ -1246,8 +1282,20 @@ __global__ void k_selftest_atan2(long long n, unsigned long long seed, unsigned 
 using namespace occb200;
 
 extern "C" int64_t occb200_annotate_workspace_bytes(int32_t T, int64_t F, int64_t total_label_slots, int64_t SF,
-                                                    int32_t L, int64_t incl_len, int64_t pyr_tiles) {
-  return ws_layout(T, F, total_label_slots, SF, L, incl_len, pyr_tiles, nullptr, nullptr);
+                                                    int32_t L, int64_t incl_len, int64_t pyr_tiles, int64_t items_cap) {
+  return ws_layout(T, F, total_label_slots, SF, L, incl_len, pyr_tiles, items_cap, nullptr, nullptr);
+}
+
+// HOST helper: upper bound of the fast kernel's work items, from the host copies of label_off / trk_frame_off.
+extern "C" int64_t occb200_annotate_items_cap(int32_t T, const int64_t *label_off, const int64_t *trk_frame_off,
+                                              int32_t L) {
+  int64_t n = 0;
+  for (int t = 0; t < T; ++t) {
+    const int64_t chunks = ceil_div(label_off[t + 1] - label_off[t], kFastChunk);
+    const int64_t slices = ceil_div((trk_frame_off[t + 1] - trk_frame_off[t]) * L, kPairsPerItem);
+    n += chunks * slices;
+  }
+  return n;
 }
 
 extern "C" int64_t occb200_pyramid_tiles(int32_t H, int32_t W) {
@@ -1258,12 +1306,12 @@ extern "C" int occb200_annotate_batch(const occb200_annotate_args_t *a, int64_t 
   cudaStream_t stream = (cudaStream_t)stream_;
   OCC_REQUIRE(a != nullptr, "args is NULL");
   OCC_REQUIRE(a->T >= 0 && a->F >= 0 && a->L >= 1, "bad T/F/L");
-  OCC_REQUIRE(a->SF >= 0 && a->incl_len >= 0 && a->pyr_tiles >= 0, "bad SF / incl_len / pyr_tiles");
+  OCC_REQUIRE(a->SF >= 0 && a->incl_len >= 0 && a->pyr_tiles >= 0 && a->items_cap >= 0, "bad SF / incl_len / pyr_tiles / items_cap");
   OCC_REQUIRE(a->point_stride >= 3, "point_stride must be >= 3");
   OCC_REQUIRE(a->voxel_size > 0, "voxel_size must be positive");
   if (a->T == 0) return 0;
   Workspace w;
-  const int64_t need = ws_layout(a->T, a->F, total, a->SF, a->L, a->incl_len, a->pyr_tiles, (char *)a->workspace, &w);
+  const int64_t need = ws_layout(a->T, a->F, total, a->SF, a->L, a->incl_len, a->pyr_tiles, a->items_cap, (char *)a->workspace, &w);
   OCC_REQUIRE(a->workspace != nullptr && a->workspace_bytes >= need, "workspace too small");
   const float vsf = (float)a->voxel_size;
   const bool f64_only = (a->flags & 1) != 0;
@@ -1289,13 +1337,13 @@ extern "C" int occb200_annotate_batch(const occb200_annotate_args_t *a, int64_t 
     }
     OCC_CUDA(cudaEventRecord(side->join, side->stream));
   }
-  OCC_CUDA(cudaMemsetAsync(w.bits, 0, 4 * w.bits_words, stream));
+  OCC_CUDA(cudaMemsetAsync(w.bits, 0, (char *)(w.free_bits + w.bits_words) - (char *)w.bits, stream));   // both bitsets
   {
     ProfScope ps(kProfInbox, stream);
     k_tracklet_presetup<<<(unsigned)ceil_div(a->T, 8), 256, 0, stream>>>(a->T, a->trk_frame_off, a->poses,
                                                                          a->frame_pt_off, a->label_off,
                                                                          vsf, chunk, w.grids, w.frame_trk, w.redo_count,
-                                                                         a->n_unknown, a->n_steps);
+                                                                         w.counter, a->n_unknown, a->n_steps);
     OCC_KERNEL_OK("k_tracklet_presetup");
   }
   if (a->F > 0) {
@@ -1311,14 +1359,23 @@ extern "C" int occb200_annotate_batch(const occb200_annotate_args_t *a, int64_t 
         a->T, a->trk_frame_off, a->poses, a->frame_pt_off, w.frame_kept, a->label_off, vsf, chunk, w.grids, w.bits,
         w.redo_list, w.redo_count, a->dims, a->sizes, a->status);
     OCC_KERNEL_OK("k_tracklet_setup");
-    if (a->F > 0) {   // frames of corrected tracklets only (device-side list, usually short)
-      k_frame_voxelize<<<(unsigned)std::min<int64_t>(a->F, kNumSMs * 7), kFrameThreads, 0, stream>>>(
+    if (a->F > 0) {   // frames of corrected tracklets only (device-side list, usually short); in the fast path
+                      // this runs on the side stream, next to k_pair_setup, and joins before the ray-cast
+      cudaStream_t rs = stream;
+      if (fast) {
+        OCC_CUDA(cudaStreamWaitEvent(stream, side->join, 0));      // the side stream is idle from here on
+        OCC_CUDA(cudaEventRecord(side->fork, stream));
+        OCC_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
+        rs = side->stream;
+      }
+      k_frame_voxelize<<<(unsigned)std::min<int64_t>(a->F, kNumSMs * 7), kFrameThreads, 0, rs>>>(
           a->poses, a->points, a->point_stride, a->frame_pt_off, w.frame_kept, w.frame_trk, w.grids, w.bits, vsf,
           w.redo_list, w.redo_count);
       OCC_KERNEL_OK("k_frame_voxelize(redo)");
+      if (fast) OCC_CUDA(cudaEventRecord(side->join, side->stream));
     }
   }
-  {
+  if (f64_only) {
     ProfScope ps(kProfScan, stream);
     k_scan_chunks<<<1, 1024, 0, stream>>>(a->T, w.grids, w.chunk_off, w.counter);
     OCC_KERNEL_OK("k_scan_chunks");
@@ -1335,34 +1392,36 @@ extern "C" int occb200_annotate_batch(const occb200_annotate_args_t *a, int64_t 
     return 0;
   }
   if (fast) {
-    OCC_CUDA(cudaStreamWaitEvent(stream, side->join, 0));   // join
     ProfScope ps(kProfPairCull, stream);
     const int64_t n_pairs = a->F * a->L;
     k_pair_setup<<<(unsigned)ceil_div(n_pairs, 128), 128, 0, stream>>>(
         n_pairs, a->L, a->poses, a->frame_sf, w.frame_trk, a->trk_frame_off, a->sensors, a->incl_pool, w.grids,
         w.sens, a->voxel_size, w.pyr_off, w.pyr, w.pyr_flag, w.pairs);
     OCC_KERNEL_OK("k_pair_setup");
-    k_pair_compact<<<(unsigned)ceil_div(a->T, 8), 256, 0, stream>>>(a->T, a->L, a->trk_frame_off, w.pairs, w.pairs_c,
-                                                                    w.n_active);
+    k_pair_compact<<<(unsigned)ceil_div(a->T, 8), 256, 0, stream>>>(a->T, a->L, a->trk_frame_off, a->label_off, w.grids,
+                                                                    w.pairs, w.pairs_c, w.hot, w.item_map,
+                                                                    (long long)w.items_cap, w.counter, a->status);
     OCC_KERNEL_OK("k_pair_compact");
   }
+  if (fast && a->F > 0) OCC_CUDA(cudaStreamWaitEvent(stream, side->join, 0));   // redo pass done: bits final
   {
-    const int grid = (int)std::min<int64_t>(max_items, (int64_t)kNumSMs * OCC_MINB);
+    const int grid = (int)std::min<int64_t>(ceil_div(std::max<int64_t>(w.items_cap, 1), kFastWarps),
+                                            (int64_t)kNumSMs * OCC_MINB);
     ProfScope ps(kProfVisibility, stream);
     k_visibility_fast<<<grid, 32 * kFastWarps, 0, stream>>>(
-        a->T, a->L, a->trk_frame_off, a->poses, a->frame_sf, a->sensors, a->incl_pool, a->ri_pool, a->voxel_size,
-        a->label_off, w.grids, w.chunk_off, w.counter, w.bits, w.pairs_c, w.n_active, w.sens, w.ub_pool, w.lut_pool,
-        w.queue,
-        (long long)w.queue_cap, a->labels, a->status, a->n_unknown, a->n_steps);
+        a->L, a->trk_frame_off, a->poses, a->frame_sf, a->sensors, a->incl_pool, a->ri_pool, a->voxel_size, w.grids,
+        w.counter, (long long)w.items_cap, w.bits, w.free_bits, w.item_map, w.hot, w.pairs_c, w.sens, w.ub_pool,
+        w.lut_pool, w.queue, (long long)w.queue_cap, a->n_steps);
     OCC_KERNEL_OK("k_visibility_fast");
   }
   {
     ProfScope ps(kProfRecheck, stream);
     k_visibility_recheck<<<kNumSMs * 4, 256, 0, stream>>>(a->L, a->trk_frame_off, a->poses, a->frame_sf, a->sensors,
-                                                          a->incl_pool, a->ri_pool, a->voxel_size, a->label_off,
-                                                          w.grids, w.counter, w.queue, (long long)w.queue_cap,
-                                                          a->labels, a->n_steps);
+                                                          a->incl_pool, a->ri_pool, a->voxel_size, w.grids, w.counter,
+                                                          w.queue, (long long)w.queue_cap, w.free_bits, a->n_steps);
     OCC_KERNEL_OK("k_visibility_recheck");
+    k_labels<<<(unsigned)a->T, 256, 0, stream>>>(w.hot, w.bits, w.free_bits, a->labels, a->n_unknown);
+    OCC_KERNEL_OK("k_labels");
   }
   return 0;
 }
@@ -1371,7 +1430,7 @@ extern "C" int occb200_annotate_queue_stats(const occb200_annotate_args_t *a, in
                                             void *stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   Workspace w;
-  ws_layout(a->T, a->F, total, a->SF, a->L, a->incl_len, a->pyr_tiles, (char *)a->workspace, &w);
+  ws_layout(a->T, a->F, total, a->SF, a->L, a->incl_len, a->pyr_tiles, a->items_cap, (char *)a->workspace, &w);
   unsigned long long n = 0;
   OCC_CUDA(cudaMemcpyAsync(&n, w.counter + 1, 8, cudaMemcpyDeviceToHost, stream));
   OCC_CUDA(cudaStreamSynchronize(stream));

@@ -212,8 +212,10 @@ class DeviceTracklets:
         sn = pk.sensors.reshape(-1)
         self.pyr_tiles = int(sum(L_.occb200_pyramid_tiles(int(h), int(w_)) * int(n) for (h, w_), n in
                                  zip(*np.unique(np.stack([sn["H"], sn["W"]], 1), axis=0, return_counts=True)))) if sn.size else 0
+        self.items_cap = int(L_.occb200_annotate_items_cap(T, pk.label_off.ctypes.data, pk.trk_frame_off.ctypes.data,
+                                                           pk.L)) if T else 0
         ws = L_.occb200_annotate_workspace_bytes(T, pk.F, total, pk.sensors.shape[0], pk.L, pk.incl_pool.size,
-                                                 self.pyr_tiles)
+                                                 self.pyr_tiles, self.items_cap)
         self.workspace = torch.empty(max(ws, 16), dtype=torch.uint8, device=dev)
 
     def upload(self, host: HostBuffers):
@@ -242,6 +244,7 @@ class DeviceTracklets:
         a.incl_len = pk.incl_pool.size
         a.ri_pool = b["ri_pool"].data_ptr()
         a.pyr_tiles = self.pyr_tiles
+        a.items_cap = self.items_cap
         a.voxel_size = pk.voxel_size
         a.label_off = b["label_off"].data_ptr()
         a.labels = self.labels.data_ptr()
