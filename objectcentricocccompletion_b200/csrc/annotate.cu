@@ -822,6 +822,7 @@ __global__ void k_pair_setup(int64_t n_pairs, int L, const occb200_pose_t *__res
                              const occb200_sensor_t *__restrict__ sensors, const float *__restrict__ incl_pool,
                              const TrkGrid *__restrict__ grids, const SensCoef *__restrict__ sens, double vs,
                              const int64_t *__restrict__ pyr_off, const float *__restrict__ pyr,
+                             const uint16_t *__restrict__ lut_pool,
                              const unsigned long long *__restrict__ counter, PairCoef *__restrict__ pairs) {
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n_pairs) return;
@@ -880,11 +881,19 @@ __global__ void k_pair_setup(int64_t n_pairs, int L, const occb200_pose_t *__res
       const double rmin = d - R;
       const double delta = asin(R / d) + 1e-6;
       const double inc_c = atan2(pcen[2], rho);
-      const float *tab = incl_pool + sn.incl_off;
-      int r0 = nearest_row(inc_c + delta, tab, sn.H, -1) - 1;
-      int r1 = nearest_row(inc_c - delta, tab, sn.H, -1) + 1;
-      r0 = max(r0, 0);
-      r1 = min(r1, sn.H - 1);
+      // rows of the interval ends: the table lookup gives the row at the top of a cell (the true row is that
+      // or the next one), which is all a conservative window needs; sensors without a table use every row
+      int r0 = 0, r1 = sn.H - 1;
+      const SensCoef sc = sens[se];
+      if (sc.ok) {
+        const uint16_t *lut = lut_pool + (int64_t)sc.tab_off * kLutPerRow;
+        const float u_hi = (float)u_of_angle(fmin(inc_c + delta, 1.5707)) + 2e-6f;
+        const float u_lo = (float)u_of_angle(fmax(inc_c - delta, -1.5707)) - 2e-6f;
+        const int c_hi = max(0, min((int)((u_hi - sc.u_lo) * sc.inv_w) + 2, sc.ncell - 1));
+        const int c_lo = max(0, min((int)floorf((u_lo - sc.u_lo) * sc.inv_w) - 2, sc.ncell - 1));
+        r0 = max((int)lut[c_hi] - 1, 0);
+        r1 = min((int)lut[c_lo] + 2, sn.H - 1);
+      }
       const int W = sn.W;
       const int ntc = (W + kTileC - 1) / kTileC;
       long long c_lo = 0, c_hi = W - 1;            // column window, possibly beyond [0, W): taken modulo W
@@ -1225,7 +1234,7 @@ k_labels(const TrkHot *__restrict__ hot, const uint32_t *__restrict__ bits, cons
   const TrkHot h = hot[t];
   if (h.status != OCCB200_OK) return;
   int unk = 0;
-  for (int f = threadIdx.x; f < h.V; f += blockDim.x) {
+  for (int f = blockIdx.y * blockDim.x + threadIdx.x; f < h.V; f += gridDim.y * blockDim.x) {
     const uint32_t o = bits[h.bits_off + (f >> 5)], fr = free_bits[h.bits_off + (f >> 5)];
     const bool occ = (o >> (f & 31)) & 1u;
     labels[h.label_off + f] = occ ? 1 : (((fr >> (f & 31)) & 1u) ? 2 : 0);
@@ -1394,9 +1403,9 @@ extern "C" int occb200_annotate_batch(const occb200_annotate_args_t *a, int64_t 
   if (fast) {
     ProfScope ps(kProfPairCull, stream);
     const int64_t n_pairs = a->F * a->L;
-    k_pair_setup<<<(unsigned)ceil_div(n_pairs, 128), 128, 0, stream>>>(
+    k_pair_setup<<<(unsigned)ceil_div(n_pairs, 64), 64, 0, stream>>>(
         n_pairs, a->L, a->poses, a->frame_sf, w.frame_trk, a->trk_frame_off, a->sensors, a->incl_pool, w.grids,
-        w.sens, a->voxel_size, w.pyr_off, w.pyr, w.pyr_flag, w.pairs);
+        w.sens, a->voxel_size, w.pyr_off, w.pyr, w.lut_pool, w.pyr_flag, w.pairs);
     OCC_KERNEL_OK("k_pair_setup");
     k_pair_compact<<<(unsigned)ceil_div(a->T, 8), 256, 0, stream>>>(a->T, a->L, a->trk_frame_off, a->label_off, w.grids,
                                                                     w.pairs, w.pairs_c, w.hot, w.item_map,
@@ -1420,7 +1429,7 @@ extern "C" int occb200_annotate_batch(const occb200_annotate_args_t *a, int64_t 
                                                           a->incl_pool, a->ri_pool, a->voxel_size, w.grids, w.counter,
                                                           w.queue, (long long)w.queue_cap, w.free_bits, a->n_steps);
     OCC_KERNEL_OK("k_visibility_recheck");
-    k_labels<<<(unsigned)a->T, 256, 0, stream>>>(w.hot, w.bits, w.free_bits, a->labels, a->n_unknown);
+    k_labels<<<dim3((unsigned)a->T, 8), 256, 0, stream>>>(w.hot, w.bits, w.free_bits, a->labels, a->n_unknown);
     OCC_KERNEL_OK("k_labels");
   }
   return 0;
