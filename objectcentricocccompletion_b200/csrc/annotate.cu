@@ -46,7 +46,7 @@ constexpr int kFastWarps = 8;       // fast kernel: independent warps per CTA
 #define OCC_PPI 16
 #endif
 constexpr int kPairsPerItem = OCC_PPI;   // fast kernel: (frame, LiDAR) pairs one work item covers for its 64 voxels
-constexpr int kLutPerRow = 16;      // lookup-table cells reserved per inclination-table entry
+constexpr int kLutPerRow = 64;      // lookup-table cells reserved per inclination-table entry
 constexpr int kTileR = 8, kTileC = 32;   // range-image max-pyramid tile (rows x columns)
 constexpr int kFrameThreads = 256;
 constexpr int kSmemBitWords = 8192; // 32 KB: grids up to 262 144 voxels keep their bitset in shared memory
@@ -72,15 +72,17 @@ struct __align__(16) SensCoef {
   float kcol;       // W / (2 pi)
   float Wf;
   float c_col;      // evaluation error of the f32 column coordinate (pixels)
-  float u_lo, inv_w;   // lookup cell k covers [u_lo + k/inv_w, u_lo + (k+1)/inv_w)
+  float u_lo, inv_w;   // lookup cell k covers [u_lo + k/inv_w, u_lo + (k+1)/inv_w); the cells span all of [-1, 1]
   int32_t ncell;
   int32_t H;
   int32_t W;
   int32_t ok;       // 0: no fast path for this sensor (table not strictly descending, H < 2, ...)
-  int32_t tab_off;  // == incl_off: position of the table in incl_pool / ub_pool, x kLutPerRow in lut_pool
-  int32_t pad0;
+  int32_t tab_off;  // == incl_off: the table sits at 2*tab_off+1 in ub_pool (sentinels around it) and at
+                    // kLutPerRow*tab_off in lut_pool
+  float cell0;      // -u_lo * inv_w: cell = int(fma(u, inv_w, cell0))
   int64_t ri_off;
-  int64_t pad1;
+  float col0;       // W/2 - 0.5: colf = fma(az, -kcol, col0)
+  float pad1;
 };
 static_assert(sizeof(SensCoef) == 64, "SensCoef must be 64 bytes");
 
@@ -120,7 +122,7 @@ struct Workspace {
   uint32_t *bits;        // occupancy bitsets
   int64_t bits_words;
   SensCoef *sens;        // [SF*L]
-  float *ub_pool;        // [incl_len]   u-space row boundaries, table at incl_off
+  float *ub_pool;        // [2*incl_len+2] u-space row boundaries, table at 2*incl_off+1 with a sentinel on each side
   uint16_t *lut_pool;    // [incl_len * kLutPerRow]
   PairCoef *pairs;       // [F*L]
   int4 *queue;           // recheck queue: (tracklet, voxel, pair index q = i*L + c, unused)
@@ -156,7 +158,7 @@ static int64_t ws_layout(int32_t T, int64_t F, int64_t total, int64_t SF, int32_
   int64_t o_fbits = take(4 * words);
   int64_t o_imap = take(8 * items_cap);
   int64_t o_tab = take(sizeof(SensCoef) * SF * L);
-  int64_t o_ub = take(4 * incl_len);
+  int64_t o_ub = take(4 * (2 * incl_len + 2));
   int64_t o_lut = take(2 * incl_len * kLutPerRow);
   int64_t o_pairs = take(sizeof(PairCoef) * F * L);
   // recheck queue: ~1% of the tests are expected; room for 1/16 of the nominal tests, bounded
@@ -656,16 +658,19 @@ k_table_setup(int64_t n_sensors, const occb200_sensor_t *__restrict__ sensors, c
   const int H = sn.H;
   const int64_t off = sn.incl_off;
   const float *tab = incl_pool + off;
-  float *ub = ub_pool + off;
+  float *ub = ub_pool + 2 * off + 1;              // ub[-1] = +2 and ub[H-1] = -2 are sentinels
   uint16_t *lut = lut_pool + off * kLutPerRow;
-  const bool candidate = (sn.incl_mono == -1) && H >= 2 && H < 65535 && off < (1ll << 26);
+  const bool candidate = (sn.incl_mono == -1) && H >= 2 && H < 65535 && off < (1ll << 24);
   float local_min = INFINITY;
   if (candidate) {
     for (int h = threadIdx.x; h < H - 1; h += blockDim.x) {
       const double m = 0.5 * ((double)tab[h] + (double)tab[h + 1]);
       ub[h] = (float)u_of_angle(m);
     }
-    if (threadIdx.x == 0) ub[H - 1] = -2.f;      // sentinel below every u
+    if (threadIdx.x == 0) {
+      ub[-1] = 2.f;
+      ub[H - 1] = -2.f;
+    }
   }
   __syncthreads();
   if (candidate) {
@@ -685,21 +690,24 @@ k_table_setup(int64_t n_sensors, const occb200_sensor_t *__restrict__ sensors, c
     sc.azc = sn.azc;
     sc.kcol = (float)((double)sn.W / 6.28318530717958647692);
     sc.Wf = (float)sn.W;
-    // colf = (W - 0.5) - fma(az, kcol, W/2): two roundings at magnitude <= W plus the rounding of kcol
-    sc.c_col = 2.0f * (float)sn.W * 1.1920929e-07f;
-    sc.u_lo = 0.f; sc.inv_w = 0.f; sc.ncell = 0;
+    sc.col0 = 0.5f * (float)sn.W - 0.5f;
+    // colf = fma(az, -kcol, W/2 - 0.5) with |az| <= 2 pi (no wrap: the column is taken modulo W afterwards): one
+    // rounding at magnitude <= 1.5 W, the rounding of kcol (<= 2^-24 * W) and of az's sum (in kAtanErr's slack);
+    // the reference wraps with float32(2 pi), which moves its colf by W * 2.8e-8 relative to an exact wrap
+    sc.c_col = 3.0f * (float)sn.W * 1.1920929e-07f + (float)sn.W * 4e-8f;
+    sc.u_lo = 0.f; sc.inv_w = 0.f; sc.ncell = 0; sc.cell0 = 0.f;
     sc.H = H; sc.W = sn.W; sc.ok = 0;
-    sc.tab_off = (int32_t)off; sc.pad0 = 0; sc.ri_off = sn.ri_off; sc.pad1 = 0;
+    sc.tab_off = (int32_t)off; sc.ri_off = sn.ri_off; sc.pad1 = 0.f;
     float spacing = s_min[0];
     if (candidate && H == 2) spacing = 0.25f;
     if (candidate && spacing > 1e-6f && isfinite(spacing) && sn.W >= 2 && sn.W < (1 << 22)) {
-      // cells half as wide as the closest pair of boundaries: (cell + 4% slack) holds at most ONE boundary
-      const float top = ub[0], bot = ub[H - 2];
+      // cells half as wide as the closest pair of boundaries (so a cell holds at most one), covering [-1, 1]
       const float w = 0.5f * spacing;
-      const int ncell = (int)ceilf((top - bot) / w) + 2;
+      const int ncell = (int)ceilf(2.04f / w) + 1;
       if (ncell <= H * kLutPerRow) {
-        sc.u_lo = bot - w;
+        sc.u_lo = -1.02f;
         sc.inv_w = 1.0f / w;
+        sc.cell0 = 1.02f * sc.inv_w;
         sc.ncell = ncell;
         sc.ok = 1;
       }
@@ -710,8 +718,9 @@ k_table_setup(int64_t n_sensors, const occb200_sensor_t *__restrict__ sensors, c
   __syncthreads();
   const SensCoef sc = s_info;
   if (!sc.ok) return;
-  // lut[k] = number of boundaries above the (slightly raised) upper end of cell k, i.e. the row of a point
-  // at the top of the cell; a point lower in the cell is in that row or, past the cell's one boundary, the next.
+  // lut[k] = number of boundaries above the (slightly raised) upper end of cell k, i.e. the row of a point at
+  // the top of the cell.  It only has to be a good starting guess: the kernel accepts a row only after checking
+  // the two boundaries around it.
   const float w = 1.0f / sc.inv_w;
   for (int k = threadIdx.x; k < sc.ncell; k += blockDim.x) {
     const float ue = sc.u_lo + (float)(k + 1) * w + 0.02f * w;
@@ -889,8 +898,8 @@ __global__ void k_pair_setup(int64_t n_pairs, int L, const occb200_pose_t *__res
         const uint16_t *lut = lut_pool + (int64_t)sc.tab_off * kLutPerRow;
         const float u_hi = (float)u_of_angle(fmin(inc_c + delta, 1.5707)) + 2e-6f;
         const float u_lo = (float)u_of_angle(fmax(inc_c - delta, -1.5707)) - 2e-6f;
-        const int c_hi = max(0, min((int)((u_hi - sc.u_lo) * sc.inv_w) + 2, sc.ncell - 1));
-        const int c_lo = max(0, min((int)floorf((u_lo - sc.u_lo) * sc.inv_w) - 2, sc.ncell - 1));
+        const int c_hi = max(0, min((int)floorf(fmaf(u_hi, sc.inv_w, sc.cell0)) + 2, sc.ncell - 1));
+        const int c_lo = max(0, min((int)floorf(fmaf(u_lo, sc.inv_w, sc.cell0)) - 2, sc.ncell - 1));
         r0 = max((int)lut[c_hi] - 1, 0);
         r1 = min((int)lut[c_lo] + 2, sn.H - 1);
       }
@@ -1022,9 +1031,21 @@ __device__ __forceinline__ float atan2_fast(float y, float x) {
   return (y < 0.f) ? -r : r;
 }
 
+// Per-iteration constants of one (frame, LiDAR) pair, derived once per warp iteration.
+struct PairConst {
+  float e15;        // 1.5 eps
+  float c1, c2;     // range margin: m = r * (r * 6e-7 + c1) + c2,  c1 = 2.01 sqrt(3) eps, c2 = 3 eps^2
+  float ecol;       // (kAtanErr + 3e-7) * kcol + c_col
+  float e15k;       // 1.5 eps * kcol
+  float nkcol;      // -kcol
+  unsigned last;    // H - 1
+  unsigned ncm1;    // ncell - 1
+};
+
 // One fast test.  Returns 2 = certainly free, 0 = certainly not free, 1 = undecided (recheck in f64).
-__device__ __forceinline__ int fast_test(const PairCoef &pc, const SensCoef &sc, float x, float y, float z,
-                                         const float *__restrict__ ub, const uint16_t *__restrict__ lut,
+// `ub` points at the table's boundary 0 (sentinels at ub[-1] = +2 and ub[H-1] = -2).
+__device__ __forceinline__ int fast_test(const PairCoef &pc, const SensCoef &sc, const PairConst &k, float x, float y,
+                                         float z, const float *__restrict__ ub, const uint16_t *__restrict__ lut,
                                          const float *__restrict__ ri_img) {
   const float px = fmaf(z, pc.A[2], fmaf(y, pc.A[1], fmaf(x, pc.A[0], pc.b[0])));
   const float py = fmaf(z, pc.A[5], fmaf(y, pc.A[4], fmaf(x, pc.A[3], pc.b[1])));
@@ -1033,49 +1054,38 @@ __device__ __forceinline__ int fast_test(const PairCoef &pc, const SensCoef &sc,
   const float r2 = fmaf(pz, pz, s2);
   const float inv_rho = rsqrt_approx(s2);
   const float inv_r = rsqrt_approx(r2);
-  const float rho = s2 * inv_rho;
-  const float eps = pc.eps;
 
   // ---- row: u = pz / (|pz| + rho);  |u - u_ref| <= 1.42 eps / r  +  evaluation (~6 ulp of 1)
-  const float u = pz * rcp_approx(fabsf(pz) + rho);
-  const float eps_u = fmaf(1.5f * eps, inv_r, 1.5e-6f);
-  int cell = (int)((u - sc.u_lo) * sc.inv_w);
-  cell = max(0, min(cell, sc.ncell - 1));
-  const int last = sc.H - 1;
-  const int row0 = min((int)__ldg(lut + cell), last);        // row at the top of the cell
-  // a cell holds at most one boundary, so the row is row0 or row0 + 1; ub[H-1] is a -2 sentinel
-  const float b_here = __ldg(ub + row0);                     // boundary between row0 and row0 + 1
-  const float b_up = __ldg(ub + max(row0 - 1, 0));           // boundary between row0 - 1 and row0
-  const float b_dn = __ldg(ub + min(row0 + 1, last));        // boundary between row0 + 1 and row0 + 2
-  const bool step = b_here > u;
-  const int row = row0 + (step ? 1 : 0);
-  const float below = step ? b_dn : b_here;
-  const float above = step ? b_here : ((row0 > 0) ? b_up : 2.f);
-  bool sure = (below <= u) && (u - below > eps_u) && (above - u > eps_u) && (row <= last);
+  const float u = pz * rcp_approx(fmaf(s2, inv_rho, fabsf(pz)));
+  const unsigned cell = min((unsigned)(int)fmaf(u, sc.inv_w, sc.cell0), k.ncm1);   // NaN -> 0
+  const unsigned row0 = min((unsigned)__ldg(lut + cell), k.last);                  // row at the top of the cell
+  const float *ubr = ub + row0;
+  const float b_up = __ldg(ubr - 1), b_here = __ldg(ubr), b_dn = __ldg(ubr + 1);   // ub[H] is never selected
+  const bool step = b_here > u;                               // a cell holds at most one boundary
+  const unsigned row = row0 + (step ? 1u : 0u);
+  const float below = step ? b_dn : b_here;                   // boundary between row and row + 1
+  const float above = step ? b_here : b_up;                   // boundary between row - 1 and row
+  // accepted only if u lies strictly between the two boundaries of `row`, by more than its error
+  const bool ok_row = fminf(u - below, above - u) > fmaf(k.e15, inv_r, 1.5e-6f) && row <= k.last;
 
-  // ---- column: az = atan2(py, px) + azc, wrapped; colf = (W - 0.5) - (az + pi) / (2 pi) * W  (:176-191)
-  float az = atan2_fast(py, px) + sc.azc;
-  if (az > 3.14159265358979323846f) az -= 6.2831855f;
-  else if (az < -3.14159265358979323846f) az += 6.2831855f;
-  const float colf = (sc.Wf - 0.5f) - fmaf(az, sc.kcol, 0.5f * sc.Wf);
+  // ---- column: az = atan2(py, px) + azc (not wrapped: |az| <= 2 pi and the column is taken modulo W);
+  //      colf = (W - 0.5) - (az + pi) / (2 pi) * W  (:176-191);  |az - az_ref| <= kAtanErr + 1.42 eps / rho
+  const float az = atan2_fast(py, px) + sc.azc;
+  const float colf = fmaf(az, k.nkcol, sc.col0);
   const float cr = rintf(colf);
-  // |az - az_ref| <= kAtanErr + 1.42 eps / rho (+ the f32 sum and wrap, inside kAtanErr's slack)
-  const float eps_col = fmaf(fmaf(1.5f * eps, inv_rho, kAtanErr + 3.0e-7f), sc.kcol, sc.c_col);
-  sure = sure && (fabsf(colf - cr) < 0.5f - eps_col);
+  const bool ok_col = fabsf(colf - cr) + fmaf(k.e15k, inv_rho, k.ecol) < 0.5f;
   int col = (int)cr;
-  if (col >= sc.W) col -= sc.W;                              // fmod(round(colf), W) (:191)
-  if (col < 0) col += sc.W;                                  // negative index wraps (:543)
-  col = max(0, min(col, sc.W - 1));
+  col += (col < 0) ? sc.W : 0;                                // fmod(round(colf), W) (:191) and
+  col -= (col >= sc.W) ? sc.W : 0;                            // negative index wrap (:543)
+  col = min((unsigned)col, (unsigned)(sc.W - 1));
 
   // ---- range: free iff ri >= |p_ref|;  | |p| - |p_ref| | <= sqrt(3) eps
-  const float ri = __ldg(ri_img + (min(row, last) * sc.W + col));
+  const float ri = __ldg(ri_img + (min(row, k.last) * (unsigned)sc.W + (unsigned)col));
   const float r = r2 * inv_r;
-  const float e = 1.7321f * eps;
-  const float m = fmaf(r, fmaf(r, 6.0e-7f, 2.01f * e), e * e);   // margin on squared ranges
+  const float m = fmaf(r, fmaf(r, 6.0e-7f, k.c1), k.c2);      // margin on squared ranges
   const float ri2 = ri * ri;
   const bool yes = ri2 >= r2 + m, no = ri2 <= r2 - m;
-  if (!sure || !(yes || no)) return 1;
-  return yes ? 2 : 0;
+  return (ok_row && ok_col && (yes || no)) ? (yes ? 2 : 0) : 1;
 }
 
 template <typename T16>
@@ -1155,14 +1165,23 @@ k_visibility_fast(int L, const int64_t *__restrict__ trk_frame_off,
       const PairCoef pc = load64(tp + k);
       if (k + 1 < k1) asm volatile("prefetch.global.L1 [%0];" ::"l"(tp + k + 1));
       const SensCoef sc = load64(sens + pc.sens);
-      const float *ub = ub_pool + sc.tab_off;
+      const float *ub = ub_pool + 2 * sc.tab_off + 1;
       const uint16_t *lut = lut_pool + sc.tab_off * kLutPerRow;
       const float *ri_img = ri_pool + sc.ri_off;
+      PairConst kc;
+      kc.e15 = 1.5f * pc.eps;
+      kc.c1 = 2.01f * 1.7321f * pc.eps;
+      kc.c2 = 3.0003f * pc.eps * pc.eps;
+      kc.ecol = fmaf(kAtanErr + 3.0e-7f, sc.kcol, sc.c_col);
+      kc.e15k = kc.e15 * sc.kcol;
+      kc.nkcol = -sc.kcol;
+      kc.last = (unsigned)(sc.H - 1);
+      kc.ncm1 = (unsigned)(sc.ncell - 1);
       // all kVPL tests are evaluated unconditionally (no divergence, their dependent chains interleave);
       // results of voxels this lane does not need are discarded
       int res[kVPL];
 #pragma unroll
-      for (int v = 0; v < kVPL; ++v) res[v] = fast_test(pc, sc, vx[v], vy[v], vz[v], ub, lut, ri_img);
+      for (int v = 0; v < kVPL; ++v) res[v] = fast_test(pc, sc, kc, vx[v], vy[v], vz[v], ub, lut, ri_img);
 #pragma unroll
       for (int v = 0; v < kVPL; ++v) {
         const bool need = (todo >> v) & 1u;

@@ -1,0 +1,23 @@
+import sys; sys.path.insert(0,'.')
+import numpy as np, torch
+import objectcentricocccompletion_b200 as occ
+from objectcentricocccompletion_b200 import synth
+from oracle import oracle
+from oracle.make_golden import edge_batch
+b = edge_batch()
+got = occ.annotate_batch(b); exp = oracle.annotate_batch(b)
+assert all((g['occ']==e['occ']).all() for g,e in zip(got,exp) if e['occ'] is not None)
+b = synth.make_batch(2, 10, 0.2, seed=9, small=True)
+for f in (0,1,2): occ.annotate_batch(b, flags=f)
+pts, bidx = synth.scatter_inputs(4, 4, 256, 5, seed=1)
+p = torch.from_numpy(pts).cuda()
+vs, pcr = [0.2]*3, [-204.8,-204.8,-4,204.8,204.8,8]
+c = occ.Voxelization(vs, pcr, -1)(p)
+f = p[:, :3].contiguous().requires_grad_()
+o, oc = occ.DynamicScatter(vs, pcr, False)(f, c); o.sum().backward()
+c4 = torch.cat([torch.from_numpy(bidx).cuda()[:,None].int(), c],1).contiguous()
+occ.DynamicScatter(vs, pcr, True)(p[:, :3].contiguous(), c4)
+occ.scatter_v2(p, c4.long(), 'max')
+occ.voxelization(p, [0.5]*3, [-210,-210,-5,210,210,9], 8, 3000)
+occ.points_in_boxes_gpu(p[None,:,:3].contiguous(), torch.tensor([[[0,0,0,4,4,4,0.3]]],device='cuda'))
+torch.cuda.synchronize(); print('sanitizer workload ok')
