@@ -882,22 +882,27 @@ __global__ void k_pair_setup(int64_t n_pairs, int L, const occb200_pose_t *__res
   pc.cull = 0;
   // ---- cull test (conservative; any doubt keeps the pair)
   if (counter[0] != 0ull && g.status == OCCB200_OK && sn.incl_mono == -1 && sn.H >= 1 && sn.W >= 1) {
+    // f32 geometry: the window is padded by 1e-4 rad (>> f32 error, << a pixel) and one extra row / column
     // the columns of VR are orthogonal only up to the f32 inverse: 1.001 covers it, +1 mm absolute
-    const double R = 0.5 * sqrt(R2) * 1.001 + 1e-3;
-    const double rho = sqrt(pcen[0] * pcen[0] + pcen[1] * pcen[1]);
-    const double d = sqrt(rho * rho + pcen[2] * pcen[2]);
-    if (d > 1.25 * R) {
-      const double rmin = d - R;
-      const double delta = asin(R / d) + 1e-6;
-      const double inc_c = atan2(pcen[2], rho);
+    const float R = 0.5f * sqrtf((float)R2) * 1.001f + 1e-3f;
+    const float cxs = (float)pcen[0], cys = (float)pcen[1], czs = (float)pcen[2];
+    const float rho = sqrtf(cxs * cxs + cys * cys);
+    const float d = sqrtf(rho * rho + czs * czs);
+    if (d > 1.25f * R) {
+      const float rmin = d - R - 1e-3f * (1.f + d * 1e-3f);
+      const float delta = asinf(R / d) + 1e-4f;
+      const float inc_c = atan2f(czs, rho);
       // rows of the interval ends: the table lookup gives the row at the top of a cell (the true row is that
       // or the next one), which is all a conservative window needs; sensors without a table use every row
       int r0 = 0, r1 = sn.H - 1;
       const SensCoef sc = sens[se];
       if (sc.ok) {
         const uint16_t *lut = lut_pool + (int64_t)sc.tab_off * kLutPerRow;
-        const float u_hi = (float)u_of_angle(fmin(inc_c + delta, 1.5707)) + 2e-6f;
-        const float u_lo = (float)u_of_angle(fmax(inc_c - delta, -1.5707)) - 2e-6f;
+        float sh, ch, sl, cl;
+        sincosf(fminf(inc_c + delta, 1.5707f), &sh, &ch);
+        sincosf(fmaxf(inc_c - delta, -1.5707f), &sl, &cl);
+        const float u_hi = sh / (fabsf(sh) + ch) + 1e-5f;
+        const float u_lo = sl / (fabsf(sl) + cl) - 1e-5f;
         const int c_hi = max(0, min((int)floorf(fmaf(u_hi, sc.inv_w, sc.cell0)) + 2, sc.ncell - 1));
         const int c_lo = max(0, min((int)floorf(fmaf(u_lo, sc.inv_w, sc.cell0)) - 2, sc.ncell - 1));
         r0 = max((int)lut[c_hi] - 1, 0);
@@ -906,15 +911,15 @@ __global__ void k_pair_setup(int64_t n_pairs, int L, const occb200_pose_t *__res
       const int W = sn.W;
       const int ntc = (W + kTileC - 1) / kTileC;
       long long c_lo = 0, c_hi = W - 1;            // column window, possibly beyond [0, W): taken modulo W
-      if (rho > 1.05 * R) {
-        const double daz = asin(R / rho) + 1e-6;
-        const double az_c = atan2(pcen[1], pcen[0]) + (double)sn.azc;
-        const double kc = (double)W / 6.28318530717958647692;
-        const double cf_lo = ((double)W - 0.5) - (az_c + daz + 3.14159265358979323846) * kc;
-        const double cf_hi = ((double)W - 0.5) - (az_c - daz + 3.14159265358979323846) * kc;
-        if (cf_hi - cf_lo + 4.0 < (double)W) {
-          c_lo = (long long)floor(cf_lo) - 1;
-          c_hi = (long long)ceil(cf_hi) + 1;
+      if (rho > 1.05f * R) {
+        const float daz = asinf(R / rho) + 1e-4f;
+        const float az_c = atan2f(cys, cxs) + sn.azc;
+        const float kc = (float)W / 6.2831853f;
+        const float cf_lo = ((float)W - 0.5f) - (az_c + daz + 3.14159265f) * kc;
+        const float cf_hi = ((float)W - 0.5f) - (az_c - daz + 3.14159265f) * kc;
+        if (cf_hi - cf_lo + 6.0f < (float)W) {
+          c_lo = (long long)floorf(cf_lo) - 2;
+          c_hi = (long long)ceilf(cf_hi) + 2;
         }
       }
       // tile columns covering [c_lo, c_hi] modulo W
@@ -935,7 +940,7 @@ __global__ void k_pair_setup(int64_t n_pairs, int L, const occb200_pose_t *__res
             for (long long tc = 0; tc <= (a0 + len - W - 1) / kTileC; ++tc) m = fmaxf(m, pimg[tr * ntc + tc]);
         }
       }
-      if ((double)m < rmin - 1e-3) pc.cull = 1;
+      if (m < rmin) pc.cull = 1;
     }
   }
   pairs[e] = pc;
