@@ -1,0 +1,70 @@
+"""On-disk formats: round trip through the reference's file layout."""
+import os
+
+import numpy as np
+import pytest
+
+
+def _dataset(tmp_path):
+    from objectcentricocccompletion_b200 import synth, waymo_io
+
+    batch = synth.make_batch(3, 12, 0.2, seed=21, small=True)
+    # one short tracklet: the reference skips it (occ_annotate.py:344)
+    t = batch.tracklets[2]
+    batch.tracklets[2] = synth.Tracklet(boxes=t.boxes[:8], points=t.points[:8], segment=0, frame_ids=t.frame_ids[:8])
+    recs = waymo_io.write_synthetic_dataset(batch, str(tmp_path / "data"))
+    return batch, recs
+
+
+def test_formats_round_trip_cpu(tmp_path):
+    """Files -> Segment / Tracklet objects -> npz files.  The loaded candidate sets are supersets of the synthetic
+    ones (the frame cloud holds every object's returns, as real data does), so expectations are taken on the
+    loaded batch."""
+    from objectcentricocccompletion_b200 import waymo_io
+    from oracle import oracle
+
+    batch, recs = _dataset(tmp_path)
+    root = str(tmp_path / "data")
+    pc = waymo_io.read_velodyne_bin(os.path.join(root, "kitti_format/training/velodyne/0000000.bin"))
+    assert pc.dtype == np.float32 and pc.shape[1] == 6
+    ts2idx = waymo_io.load_idx2timestamp(os.path.join(root, "kitti_format"))
+    assert len(ts2idx) == 12
+    loaded = waymo_io.build_segment_batch(recs[:2], ts2idx, root, "training", 0.2)
+    seg, seg0 = loaded.segments[0], batch.segments[0]
+    assert (seg.extrinsics == seg0.extrinsics).all()
+    assert all((a == b).all() for a, b in zip(seg.range_images, seg0.range_images))
+    assert all((a == b).all() for a, b in zip(seg.inclinations, seg0.inclinations))
+    for t0, t1 in zip(batch.tracklets[:2], loaded.tracklets):
+        assert (t0.boxes == t1.boxes).all() and (t0.frame_ids == t1.frame_ids).all()
+        assert all(b.shape[1] == 6 and b.dtype == np.float32 for b in t1.points)
+    exp = oracle.annotate_batch(loaded)
+    assert all(e["status"] == "ok" for e in exp)
+    # driver semantics with the oracle as the annotate function (no GPU needed)
+    out = str(tmp_path / "out")
+    paths = waymo_io.annotate_from_disk(recs, root, out, annotate_fn=oracle.annotate_batch)
+    assert paths[2] is None and all(p and os.path.isfile(p) for p in paths[:2])
+    assert paths[0].endswith(os.path.join("training", "segment-0000", "obj0.npz"))
+    z = np.load(paths[0])
+    assert list(z.keys()) == ["occ"] and z["occ"].dtype == np.int32 and (z["occ"] == exp[0]["occ"]).all()
+    # resume: existing files are kept, not recomputed (occ_annotate.py:335-343)
+    calls = []
+    waymo_io.annotate_from_disk(recs, root, out, annotate_fn=lambda b: calls.append(1) or oracle.annotate_batch(b))
+    assert calls == []
+    waymo_io.annotate_from_disk(recs, root, out, overwrite=True,
+                                annotate_fn=lambda b: calls.append(1) or oracle.annotate_batch(b))
+    assert calls == [1]
+
+
+@pytest.mark.gpu
+def test_annotate_from_disk_gpu(tmp_path):
+    from objectcentricocccompletion_b200 import waymo_io
+    from oracle import oracle
+
+    batch, recs = _dataset(tmp_path)
+    root = str(tmp_path / "data")
+    paths = waymo_io.annotate_from_disk(recs, root, str(tmp_path / "out"))
+    ts2idx = waymo_io.load_idx2timestamp(os.path.join(root, "kitti_format"))
+    exp = oracle.annotate_batch(waymo_io.build_segment_batch(recs[:2], ts2idx, root, "training", 0.2))
+    for p, e in zip(paths[:2], exp):
+        assert (np.load(p)["occ"] == e["occ"]).all()
+    assert paths[2] is None
