@@ -367,7 +367,7 @@ def main():
                 "d2h_bytes_per_step": d2h_bytes, "ms_per_step": sec_e2e * 1e3},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": "k_visibility", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": ncu_traffic(), "peak_source": peak_src,
+                     "frac": achieved / peak, "traffic": ncu_traffic() if args.workload == "c2" else None, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": ws["vis_bytes"], "kernel_ms": vis_ms,
                      "kernel_share_of_step": vis_ms / step_ms_prof if step_ms_prof else None,
                      "kernels_ms": dict(zip(("k_tracklet_presetup", "k_tracklet_setup+redo", "k_scan_chunks", "k_frame_voxelize",

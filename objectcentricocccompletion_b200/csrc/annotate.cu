@@ -946,58 +946,63 @@ __global__ void k_pair_setup(int64_t n_pairs, int L, const occb200_pose_t *__res
   pairs[e] = pc;
 }
 
-// One warp per tracklet: copy the surviving pairs, in order, to the front of the tracklet's slot, fix the final
-// status, write the tracklet's hot record and emit its work items (chunk x slice of kPairsPerItem pairs).
-// Item ids come from an atomic counter, so their order across tracklets is arbitrary -- they are independent.
+// One CTA per tracklet: warp 0 copies the surviving pairs, in order, to the front of the tracklet's slot, fixes the
+// final status and writes the tracklet's hot record; all threads then emit the work items (chunk x slice of
+// kPairsPerItem pairs).  Item ids come from an atomic counter, so their order across tracklets is arbitrary.
 __global__ void __launch_bounds__(256)
 k_pair_compact(int T, int L, const int64_t *__restrict__ trk_frame_off, const int64_t *__restrict__ label_off,
                const TrkGrid *__restrict__ grids, const PairCoef *__restrict__ pairs, PairCoef *__restrict__ pairs_c,
                TrkHot *__restrict__ hot, int2 *__restrict__ item_map, long long items_cap,
                unsigned long long *__restrict__ counter, int32_t *__restrict__ status_out) {
-  const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  __shared__ long long s_i0, s_nitems;
+  __shared__ int s_nslice;
+  const int t = blockIdx.x;
   const int lane = threadIdx.x & 31;
-  if (t >= T) return;
-  const TrkGrid g = grids[t];
-  int status = g.status;                          // flags are final: k_frame_voxelize has completed
-  if (status == OCCB200_OK) {
-    if (g.flags & 2) status = OCCB200_INDEX_ERROR;
-    else if (!(g.flags & 1)) status = OCCB200_EMPTY_AFTER_FILTER;
-  }
-  const int64_t base = trk_frame_off[t] * L;
-  const int n = (int)(trk_frame_off[t + 1] - trk_frame_off[t]) * L;
-  int count = 0;
-  if (status == OCCB200_OK)
-    for (int q0 = 0; q0 < n; q0 += 32) {
-      const int q = q0 + lane;
-      const bool keep = q < n && pairs[base + q].cull == 0;
-      const unsigned mask = __ballot_sync(0xffffffffu, keep);
-      if (keep) {
-        const int dst = count + __popc(mask & ((1u << lane) - 1u));
-        const float4 *src = reinterpret_cast<const float4 *>(pairs + base + q);
-        float4 *d4 = reinterpret_cast<float4 *>(pairs_c + base + dst);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) d4[k] = src[k];
-      }
-      count += __popc(mask);
+  if (threadIdx.x < 32) {
+    const TrkGrid g = grids[t];
+    int status = g.status;                          // flags are final: k_frame_voxelize has completed
+    if (status == OCCB200_OK) {
+      if (g.flags & 2) status = OCCB200_INDEX_ERROR;
+      else if (!(g.flags & 1)) status = OCCB200_EMPTY_AFTER_FILTER;
     }
-  const int nslice = (count + kPairsPerItem - 1) / kPairsPerItem;
-  const int nchunk = (status == OCCB200_OK) ? (int)((g.V + kFastChunk - 1) / kFastChunk) : 0;
-  const long long nitems = (long long)nchunk * nslice;
-  unsigned long long i0 = 0;
-  if (lane == 0 && nitems) i0 = atomicAdd(counter + 3, (unsigned long long)nitems);
-  i0 = __shfl_sync(0xffffffffu, i0, 0);
-  for (long long i = lane; i < nitems; i += 32)
-    if ((long long)i0 + i < items_cap)
-      item_map[i0 + i] = make_int2(t, (int)(i / nslice) | ((int)(i % nslice) << 20));
-  if (lane == 0) {
-    TrkHot h;
-    h.V = (int32_t)g.V; h.dY = g.dims[1]; h.dZ = g.dims[2];
-    h.status = status; h.nact = count; h.pad0 = 0;
-    h.bits_off = g.bits_off; h.label_off = label_off[t]; h.pairs_base = base;
-    h.pad1[0] = h.pad1[1] = 0;
-    hot[t] = h;
-    status_out[t] = status;
+    const int64_t base = trk_frame_off[t] * L;
+    const int n = (int)(trk_frame_off[t + 1] - trk_frame_off[t]) * L;
+    int count = 0;
+    if (status == OCCB200_OK)
+      for (int q0 = 0; q0 < n; q0 += 32) {
+        const int q = q0 + lane;
+        const bool keep = q < n && pairs[base + q].cull == 0;
+        const unsigned mask = __ballot_sync(0xffffffffu, keep);
+        if (keep) {
+          const int dst = count + __popc(mask & ((1u << lane) - 1u));
+          const float4 *src = reinterpret_cast<const float4 *>(pairs + base + q);
+          float4 *d4 = reinterpret_cast<float4 *>(pairs_c + base + dst);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) d4[k] = src[k];
+        }
+        count += __popc(mask);
+      }
+    if (lane == 0) {
+      const int nslice = (count + kPairsPerItem - 1) / kPairsPerItem;
+      const int nchunk = (status == OCCB200_OK) ? (int)((g.V + kFastChunk - 1) / kFastChunk) : 0;
+      const long long nitems = (long long)nchunk * nslice;
+      s_nslice = nslice;
+      s_nitems = nitems;
+      s_i0 = nitems ? (long long)atomicAdd(counter + 3, (unsigned long long)nitems) : 0;
+      TrkHot h;
+      h.V = (int32_t)g.V; h.dY = g.dims[1]; h.dZ = g.dims[2];
+      h.status = status; h.nact = count; h.pad0 = 0;
+      h.bits_off = g.bits_off; h.label_off = label_off[t]; h.pairs_base = base;
+      h.pad1[0] = h.pad1[1] = 0;
+      hot[t] = h;
+      status_out[t] = status;
+    }
   }
+  __syncthreads();
+  const long long i0 = s_i0, nitems = s_nitems;
+  const int nslice = s_nslice;
+  for (long long i = threadIdx.x; i < nitems; i += blockDim.x)
+    if (i0 + i < items_cap) item_map[i0 + i] = make_int2(t, (int)(i / nslice) | ((int)(i % nslice) << 20));
 }
 
 // Approximate f32 primitives (flush-to-zero MUFU forms, <= 2 ulp): their error is part of every margin.
@@ -1246,7 +1251,11 @@ k_visibility_recheck(int L, const int64_t *__restrict__ trk_frame_off, const occ
     const int64_t f0 = trk_frame_off[t];
     const occb200_sensor_t *sn = sensors + (int64_t)__ldg(frame_sf + f0 + i) * L + c;
     if (exact_test(cx, cy, cz, poses + f0 + i, sn, incl_pool, ri_pool)) atomicOr(word, bit);
-    if (n_steps) atomicAdd((unsigned long long *)&n_steps[t], 1ull);
+    if (n_steps) {                                             // one atomic per tracklet per warp, not per test
+      const unsigned peers = __match_any_sync(__activemask(), t);
+      if ((threadIdx.x & 31) == __ffs(peers) - 1)
+        atomicAdd((unsigned long long *)&n_steps[t], (unsigned long long)__popc(peers));
+    }
   }
 }
 
@@ -1431,7 +1440,7 @@ extern "C" int occb200_annotate_batch(const occb200_annotate_args_t *a, int64_t 
         n_pairs, a->L, a->poses, a->frame_sf, w.frame_trk, a->trk_frame_off, a->sensors, a->incl_pool, w.grids,
         w.sens, a->voxel_size, w.pyr_off, w.pyr, w.lut_pool, w.pyr_flag, w.pairs);
     OCC_KERNEL_OK("k_pair_setup");
-    k_pair_compact<<<(unsigned)ceil_div(a->T, 8), 256, 0, stream>>>(a->T, a->L, a->trk_frame_off, a->label_off, w.grids,
+    k_pair_compact<<<(unsigned)a->T, 256, 0, stream>>>(a->T, a->L, a->trk_frame_off, a->label_off, w.grids,
                                                                     w.pairs, w.pairs_c, w.hot, w.item_map,
                                                                     (long long)w.items_cap, w.counter, a->status);
     OCC_KERNEL_OK("k_pair_compact");
