@@ -1178,6 +1178,8 @@ k_visibility_fast(int L, const int64_t *__restrict__ trk_frame_off,
       const float *ub = ub_pool + 2 * sc.tab_off + 1;
       const uint16_t *lut = lut_pool + sc.tab_off * kLutPerRow;
       const float *ri_img = ri_pool + sc.ri_off;
+      // materialise the three bases as 64-bit registers: per-test addresses are then ONE imad.wide each
+      asm volatile("" : "+l"(ub), "+l"(lut), "+l"(ri_img));
       PairConst kc;
       kc.e15 = 1.5f * pc.eps;
       kc.c1 = 2.01f * 1.7321f * pc.eps;
@@ -1440,12 +1442,13 @@ extern "C" int occb200_annotate_batch(const occb200_annotate_args_t *a, int64_t 
         n_pairs, a->L, a->poses, a->frame_sf, w.frame_trk, a->trk_frame_off, a->sensors, a->incl_pool, w.grids,
         w.sens, a->voxel_size, w.pyr_off, w.pyr, w.lut_pool, w.pyr_flag, w.pairs);
     OCC_KERNEL_OK("k_pair_setup");
+    // k_pair_compact reads the per-tracklet flags the redo pass may still be updating: join first
+    if (a->F > 0) OCC_CUDA(cudaStreamWaitEvent(stream, side->join, 0));
     k_pair_compact<<<(unsigned)a->T, 256, 0, stream>>>(a->T, a->L, a->trk_frame_off, a->label_off, w.grids,
                                                                     w.pairs, w.pairs_c, w.hot, w.item_map,
                                                                     (long long)w.items_cap, w.counter, a->status);
     OCC_KERNEL_OK("k_pair_compact");
   }
-  if (fast && a->F > 0) OCC_CUDA(cudaStreamWaitEvent(stream, side->join, 0));   // redo pass done: bits final
   {
     const int grid = (int)std::min<int64_t>(ceil_div(std::max<int64_t>(w.items_cap, 1), kFastWarps),
                                             (int64_t)kNumSMs * OCC_MINB);

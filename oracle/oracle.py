@@ -312,7 +312,8 @@ class PackedBatch:
                       else np.zeros((0, 7), np.float32))
         self.frame_sf = (np.concatenate([sf_base[t.segment] + t.frame_ids for t in trks]).astype(np.int32)
                          if trks else np.zeros(0, np.int32))
-        allp = [p for t in trks for p in t.points]
+        # only xyz enters the path (occ_annotate.py:97 slices [:, :3]); KITTI rows carry 3 more columns
+        allp = [np.asarray(p)[:, :3] for t in trks for p in t.points]
         self.pt_off = np.cumsum([0] + [len(p) for p in allp]).astype(np.int64)
         self.points = (np.concatenate(allp, 0).astype(np.float32) if allp and self.pt_off[-1] > 0
                        else np.zeros((0, 3), np.float32))

@@ -146,3 +146,44 @@ def test_fast_path_margins():
     res = d.results()
     executed = sum(r["n_steps"] for r in res if r["occ"] is not None)
     assert n_recheck < cap and n_recheck < 0.05 * executed, (n_recheck, executed)
+
+
+def test_many_tracklets_two_pipes():
+    """1024 tracklets over 16 segments (dozens of them take the size-correction redo pass): the fast path,
+    the fast path without culling and the all-f64 path agree bit for bit, repeated runs on two buffers /
+    two streams (bench.py's e2e pipeline) reproduce them, and a sampled subset matches the oracle."""
+    import torch
+
+    from objectcentricocccompletion_b200 import occ_annotate, synth
+    from oracle import oracle
+
+    batch = synth.config_batch("c5s", seed=0)
+    pk = occ_annotate.pack_tracklets(batch)
+    host = occ_annotate.HostBuffers(pk)
+    keys = ("labels", "dims", "status", "n_unknown")
+    d, d2 = occ_annotate.DeviceTracklets(pk), occ_annotate.DeviceTracklets(pk)
+    d.upload(host)
+    d.run(occ_annotate.FLAG_FORCE_F64)
+    torch.cuda.synchronize()
+    ref = {k: getattr(d, k).cpu().numpy().copy() for k in keys}
+    want = d.results()
+    pipes = [(torch.cuda.Stream(), d), (torch.cuda.Stream(), d2)]
+    for flags in (0, occ_annotate.FLAG_NO_CULL):
+        for rep in range(3):
+            for i in range(6):
+                st, dd = pipes[i % 2]
+                with torch.cuda.stream(st):
+                    dd.upload(host)
+                    dd.run(flags)
+            torch.cuda.synchronize()
+            for _, dd in pipes:
+                for k in keys:
+                    assert (getattr(dd, k).cpu().numpy() == ref[k]).all(), (flags, rep, k)
+    sel = list(range(0, len(batch.tracklets), 37))
+    sub = synth.TrackletBatch(segments=batch.segments, tracklets=[batch.tracklets[i] for i in sel],
+                              voxel_size=batch.voxel_size)
+    exp = oracle.annotate_batch(sub, threads=8)
+    for e, i in zip(exp, sel):
+        assert e["status"] == want[i]["status"]
+        if e["occ"] is not None:
+            assert (e["occ"] == want[i]["occ"]).all()

@@ -150,3 +150,19 @@ def test_ops_fail_loudly_without_cuda():
         occ.scatter_v2(torch.zeros(4, 3), torch.zeros(4, 3, dtype=torch.long), "mean")
     with pytest.raises(RuntimeError):
         occ.points_in_boxes_gpu(torch.zeros(1, 4, 3), torch.zeros(1, 1, 7))
+
+
+def test_oracle_ignores_extra_point_columns():
+    """KITTI-format rows carry 6 columns; only xyz enters the path (occ_annotate.py:97)."""
+    import numpy as np
+
+    from objectcentricocccompletion_b200 import synth
+    from oracle import oracle
+
+    b = synth.make_batch(2, 10, 0.2, seed=9, small=True)
+    exp = oracle.annotate_batch(b)
+    for t in b.tracklets:
+        t.points = [np.concatenate([p, np.full((len(p), 3), 7.0, np.float32)], 1) for p in t.points]
+    got = oracle.annotate_batch(b)
+    for e, g in zip(exp, got):
+        assert e["status"] == g["status"] and (e["occ"] == g["occ"]).all()
