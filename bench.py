@@ -56,6 +56,8 @@ def parse():
     ap.add_argument("--cpu-threads", type=int, default=0, help="0 = all host cores")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--force-f64", action="store_true", help="all-f64 visibility kernel")
+    ap.add_argument("--flags", type=int, default=0, help="extra occb200_annotate_args_t.flags bits (A/B measurements)")
+    ap.add_argument("--no-graph", action="store_true", help="launch the kernels one by one instead of replaying a CUDA graph")
     return ap.parse_args()
 
 
@@ -212,7 +214,7 @@ def main():
     pk = occ_annotate.pack_tracklets(batch)
     host = occ_annotate.HostBuffers(pk, pin=True)
     d = occ_annotate.DeviceTracklets(pk, dev)
-    flags = occ_annotate.FLAG_FORCE_F64 if args.force_f64 else 0
+    flags = (occ_annotate.FLAG_FORCE_F64 if args.force_f64 else 0) | args.flags
     d.upload(host)
     d.run(flags)
     torch.cuda.synchronize()
@@ -244,8 +246,14 @@ def main():
     # pinned result buffers for the e2e leg
     out_host = {k: torch.empty_like(getattr(d, k), device="cpu").pin_memory() for k in ("labels", "dims", "status", "n_unknown")}
 
+    use_graph = not args.no_graph
+    graph_kernels = d.capture(flags) if use_graph else 0
+
     def step_resident():
-        d.run(flags)
+        if use_graph:
+            d.replay(flags)
+        else:
+            d.run(flags)
 
     def step_e2e():
         d.upload(host)
@@ -264,12 +272,12 @@ def main():
         sampler.start()
     l0 = _lib.launch_count()
     ms = timed(step_resident, args.steps)
-    launches = _lib.launch_count() - l0
+    launches = graph_kernels * args.steps if use_graph else _lib.launch_count() - l0
     barrier()
 
     # ---- roofline pass: the same steps with events around each kernel ---------------------------
     _lib.lib().occb200_profile_enable(1)
-    timed(step_resident, args.steps)
+    timed(lambda: d.run(flags), args.steps)           # direct launches: the events sit between the kernels
     _lib.lib().occb200_profile_enable(0)
     nk = _lib.lib().occb200_profile_kinds()
     kms = np.zeros(nk, np.float64)
@@ -279,6 +287,9 @@ def main():
     # ---- e2e: host buffers -> H2D -> kernels -> D2H every step, double-buffered on two streams so the upload
     # of step k+1 overlaps the kernels / download of step k (inputs per step 134 MB > L2: no flush needed) -------
     d2 = occ_annotate.DeviceTracklets(pk, dev)
+    if use_graph:
+        d2.upload(host)
+        d2.capture(flags)
     out_host2 = {k: torch.empty_like(h).pin_memory() for k, h in out_host.items()}
     pipes = [(torch.cuda.Stream(dev), d, out_host), (torch.cuda.Stream(dev), d2, out_host2)]
 
@@ -291,7 +302,10 @@ def main():
             st, dd, oh = pipes[i % 2]
             with torch.cuda.stream(st):
                 dd.upload(host)
-                dd.run(flags)
+                if use_graph:
+                    dd.replay(flags)
+                else:
+                    dd.run(flags)
                 for k, h in oh.items():
                     h.copy_(getattr(dd, k), non_blocking=True)
         ends = []
@@ -359,7 +373,8 @@ def main():
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOADS[args.workload], "tracklets_per_step_per_gpu": T, "frames": B, "lidars": L,
                    "voxel_size": batch.voxel_size, "ok_tracklets": n_ok, "l2": "flushed (256 MiB write) between timed steps",
-                   "visibility": "f64" if args.force_f64 else "default"},
+                   "visibility": "f64" if args.force_f64 else "default",
+                   "launch": "cuda graph replay" if use_graph else "kernel by kernel"},
         "voxel_steps_per_s": steps_all / sec, "executed_steps_per_s": exec_all / sec,
         "voxel_steps_per_step": ws["steps"], "executed_steps_per_step": ws["executed"],
         "f64_rechecks_per_step": n_recheck, "unknown_voxels_per_step": ws["U"], "voxels_per_step": ws["V"],

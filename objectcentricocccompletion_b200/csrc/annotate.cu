@@ -39,13 +39,23 @@ constexpr int kChunk = 256;         // f64 kernel: voxels per work item == threa
 #ifndef OCC_MINB
 #define OCC_MINB 4
 #endif
-constexpr int kVPL = OCC_VPL;       // fast kernel: voxels per lane
+constexpr int kVPL = OCC_VPL;       // fast kernel, phase 2: voxels per lane
+#ifndef OCC_VPL1
+#define OCC_VPL1 2
+#endif
+constexpr int kVPL1 = OCC_VPL1;     // fast kernel, phase 1: voxels per lane
 constexpr int kFastChunk = 32 * kVPL;   // fast kernel: voxels per work item
 constexpr int kFastWarps = 8;       // fast kernel: independent warps per CTA
 #ifndef OCC_PPI
 #define OCC_PPI 16
 #endif
 constexpr int kPairsPerItem = OCC_PPI;   // fast kernel: (frame, LiDAR) pairs one work item covers for its 64 voxels
+#ifndef OCC_P1
+#define OCC_P1 8
+#endif
+constexpr int kPhase1Pairs = OCC_P1;     // pairs tested on EVERY non-occupied voxel before the survivors are compacted
+constexpr float kAtanErr = 2.0e-6f;     // bound on |atan2_fast - atan2| (derivation at atan2_fast)
+constexpr int kFrameStride = 8;          // pair order: frames 0,8,16,.. then 1,9,17,.. (spread viewpoints come first)
 constexpr int kLutPerRow = 64;      // lookup-table cells reserved per inclination-table entry
 constexpr int kTileR = 8, kTileC = 32;   // range-image max-pyramid tile (rows x columns)
 constexpr int kFrameThreads = 256;
@@ -97,6 +107,28 @@ struct __align__(16) PairCoef {
 };
 static_assert(sizeof(PairCoef) == 64, "PairCoef must be 64 bytes");
 
+// What one iteration of the fast visibility kernel needs of a surviving pair, in ONE 128-byte record (one L1 line,
+// 8 x LDG.128, prefetched one iteration ahead): the pair's affine map, the fields of its sensor entry and the
+// per-pair constants of the margins.  Built by k_pair_compact.
+struct __align__(16) PairHot {
+  float A[9];
+  float b[3];
+  float eps;        // < 0: no fast path for this pair (every test goes to the exact recheck)
+  int32_t q;
+  float azc, inv_w, cell0m, col0;   // cell0m = cell0 - 0.5: the cell index is taken by round-to-nearest
+  int32_t W, tab_off;
+  int64_t ri_off;
+  float e15;        // 1.5 eps
+  float c1, c2;     // range margin: m = r * (r * 6e-7 + c1) + c2,  c1 = 2.01 sqrt(3) eps, c2 = 3 eps^2
+  float ecol;       // (kAtanErr + 3e-7) * kcol + c_col
+  float e15k;       // 1.5 eps * kcol
+  float nkcol;      // -kcol
+  uint32_t last;    // H - 1
+  uint32_t ncm1;    // ncell - 1
+  int32_t pad[2];
+};
+static_assert(sizeof(PairHot) == 128, "PairHot must be 128 bytes");
+
 // What the fast visibility kernel needs of a tracklet, in one 64-byte record (4 x LDG.128).
 struct __align__(16) TrkHot {
   int32_t V, dY, dZ;
@@ -118,7 +150,8 @@ struct Workspace {
   unsigned long long *redo_count;
   int64_t *chunk_off;    // [T+1]
   unsigned long long *pyr_flag;  // [0] 1: pyramid built (fits), culling enabled -- written on the side stream
-  unsigned long long *counter;   // [0] work-queue head, [1] recheck-queue length
+  unsigned long long *counter;   // [0] phase-1 ticket, [1] recheck-queue length, [3] phase-1 items,
+                                 // [4] phase-2 ticket, [5] phase-2 items
   uint32_t *bits;        // occupancy bitsets
   int64_t bits_words;
   SensCoef *sens;        // [SF*L]
@@ -127,11 +160,13 @@ struct Workspace {
   PairCoef *pairs;       // [F*L]
   int4 *queue;           // recheck queue: (tracklet, voxel, pair index q = i*L + c, unused)
   int64_t queue_cap;
-  PairCoef *pairs_c;     // [F*L] the non-culled pairs of each tracklet, compacted at trk_frame_off[t] * L
+  PairHot *pairs_c;      // [F*L] the non-culled pairs of each tracklet, compacted at trk_frame_off[t] * L
   TrkHot *hot;           // [T]
   uint32_t *free_bits;   // same layout as `bits`: voxels proven free
   int2 *item_map;        // [items_cap] work items of the fast kernel: (tracklet, chunk | slice << 20)
   int64_t items_cap;
+  int32_t *unk_list;     // [total] per tracklet (at label_off): voxels still undecided after phase 1, any order
+  uint32_t *n_unk;       // [T] length of each tracklet's list
   int64_t *pyr_off;      // [SF*L + 1] first tile of each range image in pyr
   float *pyr;            // [pyr_tiles] max of the range image over tiles of kTileR x kTileC pixels
   int64_t pyr_tiles;
@@ -151,7 +186,7 @@ static int64_t ws_layout(int32_t T, int64_t F, int64_t total, int64_t SF, int32_
   int64_t o_redo = take(4 * F);
   int64_t o_rc = take(8);
   int64_t o_choff = take(8 * ((int64_t)T + 1));
-  int64_t o_cnt = take(8 * 4);
+  int64_t o_cnt = take(8 * 8);
   int64_t o_pf = take(8);
   int64_t words = total / 32 + T + 1;
   int64_t o_bits = take(4 * words);
@@ -165,12 +200,16 @@ static int64_t ws_layout(int32_t T, int64_t F, int64_t total, int64_t SF, int32_
   const double nominal = (double)total * (T > 0 ? (double)F / T : 0.0) * L;
   int64_t qcap = (int64_t)std::min(std::max(nominal / 16.0, 65536.0), 64.0 * 1024 * 1024);
   int64_t o_q = take(16 * qcap);
-  int64_t o_pc = take(sizeof(PairCoef) * F * L);
+  int64_t o_pc = take(sizeof(PairHot) * F * L);
   int64_t o_na = take(sizeof(TrkHot) * (int64_t)T);
   int64_t o_po = take(8 * (SF * L + 1));
   int64_t o_py = take(4 * pyr_tiles);
+  int64_t o_ul = take(4 * total);
+  int64_t o_nu = take(4 * (int64_t)T);
   if (w) {
-    w->pairs_c = (PairCoef *)(base + o_pc);
+    w->unk_list = (int32_t *)(base + o_ul);
+    w->n_unk = (uint32_t *)(base + o_nu);
+    w->pairs_c = (PairHot *)(base + o_pc);
     w->hot = (TrkHot *)(base + o_na);
     w->pyr_off = (int64_t *)(base + o_po);
     w->pyr = (float *)(base + o_py);
@@ -309,12 +348,12 @@ __global__ void __launch_bounds__(256)
 k_tracklet_presetup(int T, const int64_t *__restrict__ trk_frame_off, const occb200_pose_t *__restrict__ poses,
                     const int64_t *__restrict__ frame_pt_off, const int64_t *__restrict__ label_off, float vsf, int chunk, TrkGrid *__restrict__ grids,
                     int32_t *__restrict__ frame_trk, unsigned long long *__restrict__ redo_count,
-                    unsigned long long *__restrict__ counter, int64_t *__restrict__ n_unknown,
-                    int64_t *__restrict__ n_steps) {
+                    unsigned long long *__restrict__ counter, uint32_t *__restrict__ n_unk,
+                    int64_t *__restrict__ n_unknown, int64_t *__restrict__ n_steps) {
   const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);   // one warp per tracklet
   const int lane = threadIdx.x & 31;
   if (blockIdx.x == 0 && threadIdx.x == 0) *redo_count = 0ull;
-  if (blockIdx.x == 0 && threadIdx.x < 4) counter[threadIdx.x] = 0ull;
+  if (blockIdx.x == 0 && threadIdx.x < 8) counter[threadIdx.x] = 0ull;
   if (t >= T) return;
   const int64_t f0 = trk_frame_off[t], f1 = trk_frame_off[t + 1];
   float sz[3] = {-INFINITY, -INFINITY, -INFINITY};
@@ -343,6 +382,7 @@ k_tracklet_presetup(int T, const int64_t *__restrict__ trk_frame_off, const occb
   else grid_from_size(g, sz, vsf, label_off[t + 1] - label_off[t], chunk);
   grids[t] = g;
   n_unknown[t] = 0;
+  n_unk[t] = 0u;
   if (n_steps) n_steps[t] = 0;
 }
 
@@ -523,7 +563,7 @@ k_scan_chunks(int T, const TrkGrid *__restrict__ grids, int64_t *__restrict__ ch
     run += (grids[t].status == OCCB200_OK) ? grids[t].nchunks : 0;
   }
   if (tid == 1023) chunk_off[T] = s_part[1023];
-  if (tid < 4) counter[tid] = 0ull;
+  if (tid < 8) counter[tid] = 0ull;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -922,22 +962,29 @@ __global__ void k_pair_setup(int64_t n_pairs, int L, const occb200_pose_t *__res
           c_hi = (long long)ceilf(cf_hi) + 2;
         }
       }
-      // tile columns covering [c_lo, c_hi] modulo W
-      float m = 0.f;
+      // tile columns covering [c_lo, c_hi] modulo W: segment 1 = tiles [ta, tb], segment 2 (wrapped) = [0, tw]
       const float *pimg = pyr + pyr_off[se];
       const int tr0 = r0 / kTileR, tr1 = r1 / kTileR;
-      if (c_hi - c_lo + 1 >= W) {
-        for (int tr = tr0; tr <= tr1; ++tr)
-          for (int tc = 0; tc < ntc; ++tc) m = fmaxf(m, pimg[tr * ntc + tc]);
-      } else {
-        long long a0 = ((c_lo % W) + W) % W;       // first column, in [0, W)
+      int ta = 0, tb = ntc - 1, tw = -1;
+      if (c_hi - c_lo + 1 < W) {
+        const long long a0 = ((c_lo % W) + W) % W;       // first column, in [0, W)
         const long long len = c_hi - c_lo + 1;
-        // segment 1: [a0, min(a0+len, W)), segment 2 (wrapped): [0, a0+len-W)
-        const long long e1 = min(a0 + len, (long long)W) - 1;
-        for (int tr = tr0; tr <= tr1; ++tr) {
-          for (long long tc = a0 / kTileC; tc <= e1 / kTileC; ++tc) m = fmaxf(m, pimg[tr * ntc + tc]);
-          if (a0 + len > W)
-            for (long long tc = 0; tc <= (a0 + len - W - 1) / kTileC; ++tc) m = fmaxf(m, pimg[tr * ntc + tc]);
+        ta = (int)(a0 / kTileC);
+        tb = (int)((min(a0 + len, (long long)W) - 1) / kTileC);
+        if (a0 + len > W) tw = (int)((a0 + len - W - 1) / kTileC);
+      }
+      // four independent loads in flight per step (a serial max chain would pay one L2 latency per tile); the
+      // scan stops as soon as one tile reaches rmin -- the pair is kept then
+      float m = 0.f;
+      for (int tr = tr0; tr <= tr1 && m < rmin; ++tr) {
+        const float *prow = pimg + (int64_t)tr * ntc;
+        for (int seg = 0; seg < 2; ++seg) {
+          const int s0 = seg ? 0 : ta, s1 = seg ? tw : tb;
+          for (int tc = s0; tc <= s1 && m < rmin; tc += 4) {
+            const float v0 = prow[tc], v1 = prow[min(tc + 1, s1)], v2 = prow[min(tc + 2, s1)],
+                        v3 = prow[min(tc + 3, s1)];
+            m = fmaxf(fmaxf(m, fmaxf(v0, v1)), fmaxf(v2, v3));
+          }
         }
       }
       if (m < rmin) pc.cull = 1;
@@ -946,57 +993,126 @@ __global__ void k_pair_setup(int64_t n_pairs, int L, const occb200_pose_t *__res
   pairs[e] = pc;
 }
 
-// One CTA per tracklet: warp 0 copies the surviving pairs, in order, to the front of the tracklet's slot, fixes the
-// final status and writes the tracklet's hot record; all threads then emit the work items (chunk x slice of
-// kPairsPerItem pairs).  Item ids come from an atomic counter, so their order across tracklets is arbitrary.
+// j-th frame of a tracklet of B frames in the order 0, S, 2S, .., 1, S+1, .. (S = kFrameStride)
+__device__ __forceinline__ int strided_frame(int j, int B) {
+#pragma unroll
+  for (int r = 0; r < kFrameStride; ++r) {
+    const int cnt = (B - r + kFrameStride - 1) / kFrameStride;
+    if (j < cnt) return r + j * kFrameStride;
+    j -= cnt;
+  }
+  return B - 1;                                   // not reached for j < B
+}
+
+// One CTA per tracklet: the surviving pairs are copied (merged with their sensor entry into 128-byte records) to
+// the front of the tracklet's slot -- frames in strided order, so that the first kPhase1Pairs pairs look at the
+// object from spread-out viewpoints; thread 0 fixes the final status and writes the tracklet's hot record; all
+// threads then emit the phase-1 work items (one per chunk of 32 * kVPL1 voxels).  Item ids come from an atomic counter, so their order across tracklets is arbitrary.
 __global__ void __launch_bounds__(256)
 k_pair_compact(int T, int L, const int64_t *__restrict__ trk_frame_off, const int64_t *__restrict__ label_off,
-               const TrkGrid *__restrict__ grids, const PairCoef *__restrict__ pairs, PairCoef *__restrict__ pairs_c,
+               const TrkGrid *__restrict__ grids, const PairCoef *__restrict__ pairs,
+               const SensCoef *__restrict__ sens, PairHot *__restrict__ pairs_c,
                TrkHot *__restrict__ hot, int2 *__restrict__ item_map, long long items_cap,
                unsigned long long *__restrict__ counter, int32_t *__restrict__ status_out) {
   __shared__ long long s_i0, s_nitems;
+  __shared__ int s_cnt[8];
+  const int t = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const TrkGrid g = grids[t];
+  int status = g.status;                            // flags are final: both k_frame_voxelize passes have completed
+  if (status == OCCB200_OK) {
+    if (g.flags & 2) status = OCCB200_INDEX_ERROR;
+    else if (!(g.flags & 1)) status = OCCB200_EMPTY_AFTER_FILTER;
+  }
+  const int64_t base = trk_frame_off[t] * L;
+  const int B = (int)(trk_frame_off[t + 1] - trk_frame_off[t]);
+  const int n = (status == OCCB200_OK) ? B * L : 0;
+  int count = 0;                                    // surviving pairs so far (same value in every thread)
+  for (int j0 = 0; j0 < n; j0 += 256) {             // 256 pairs per pass, one per thread
+    const int j = j0 + threadIdx.x;
+    int q = 0;
+    if (j < n) {
+      const int pf = j / L;
+      q = strided_frame(pf, B) * L + (j - pf * L);
+    }
+    PairCoef pc;
+    bool keep = false;
+    if (j < n) {
+      pc = pairs[base + q];
+      keep = pc.cull == 0;
+    }
+    const unsigned mask = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) s_cnt[warp] = __popc(mask);
+    __syncthreads();
+    int before = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      before += (w < warp) ? s_cnt[w] : 0;
+      total += s_cnt[w];
+    }
+    if (keep) {
+      const int dst = count + before + __popc(mask & ((1u << lane) - 1u));
+      const SensCoef sc = sens[pc.sens];
+      PairHot p;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) p.A[k] = pc.A[k];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) p.b[k] = pc.b[k];
+      p.eps = pc.eps; p.q = pc.q;
+      p.azc = sc.azc; p.inv_w = sc.inv_w; p.cell0m = sc.cell0 - 0.5f; p.col0 = sc.col0;
+      p.W = sc.W; p.tab_off = sc.tab_off; p.ri_off = sc.ri_off;
+      p.e15 = 1.5f * pc.eps;
+      p.c1 = 2.01f * 1.7321f * pc.eps;
+      p.c2 = 3.0003f * pc.eps * pc.eps;
+      p.ecol = fmaf(kAtanErr + 3.0e-7f, sc.kcol, sc.c_col);
+      p.e15k = p.e15 * sc.kcol;
+      p.nkcol = -sc.kcol;
+      p.last = (uint32_t)(sc.H - 1);
+      p.ncm1 = (uint32_t)(sc.ncell - 1);
+      p.pad[0] = p.pad[1] = 0;
+      const float4 *src = reinterpret_cast<const float4 *>(&p);
+      float4 *d4 = reinterpret_cast<float4 *>(pairs_c + base + dst);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) d4[k] = src[k];
+    }
+    count += total;
+    __syncthreads();                                // s_cnt is reused by the next pass
+  }
+  if (threadIdx.x == 0) {
+    const long long nitems =
+        (status == OCCB200_OK && count > 0) ? (long long)((g.V + 32 * kVPL1 - 1) / (32 * kVPL1)) : 0;
+    s_nitems = nitems;
+    s_i0 = nitems ? (long long)atomicAdd(counter + 3, (unsigned long long)nitems) : 0;
+    TrkHot h;
+    h.V = (int32_t)g.V; h.dY = g.dims[1]; h.dZ = g.dims[2];
+    h.status = status; h.nact = count; h.pad0 = 0;
+    h.bits_off = g.bits_off; h.label_off = label_off[t]; h.pairs_base = base;
+    h.pad1[0] = h.pad1[1] = 0;
+    hot[t] = h;
+    status_out[t] = status;
+  }
+  __syncthreads();
+  const long long i0 = s_i0, nitems = s_nitems;
+  for (long long i = threadIdx.x; i < nitems; i += blockDim.x)
+    if (i0 + i < items_cap) item_map[i0 + i] = make_int2(t, (int)i);
+}
+
+// After phase 1: one CTA per tracklet emits the phase-2 work items -- (64 listed voxels) x (slice of kPairsPerItem
+// of the pairs phase 1 did not cover).  item_map is reused: phase 1 has finished with it.
+__global__ void __launch_bounds__(256)
+k_phase2_emit(const TrkHot *__restrict__ hot, const uint32_t *__restrict__ n_unk, int2 *__restrict__ item_map,
+              long long items_cap, unsigned long long *__restrict__ counter) {
+  __shared__ long long s_i0, s_nitems;
   __shared__ int s_nslice;
   const int t = blockIdx.x;
-  const int lane = threadIdx.x & 31;
-  if (threadIdx.x < 32) {
-    const TrkGrid g = grids[t];
-    int status = g.status;                          // flags are final: k_frame_voxelize has completed
-    if (status == OCCB200_OK) {
-      if (g.flags & 2) status = OCCB200_INDEX_ERROR;
-      else if (!(g.flags & 1)) status = OCCB200_EMPTY_AFTER_FILTER;
-    }
-    const int64_t base = trk_frame_off[t] * L;
-    const int n = (int)(trk_frame_off[t + 1] - trk_frame_off[t]) * L;
-    int count = 0;
-    if (status == OCCB200_OK)
-      for (int q0 = 0; q0 < n; q0 += 32) {
-        const int q = q0 + lane;
-        const bool keep = q < n && pairs[base + q].cull == 0;
-        const unsigned mask = __ballot_sync(0xffffffffu, keep);
-        if (keep) {
-          const int dst = count + __popc(mask & ((1u << lane) - 1u));
-          const float4 *src = reinterpret_cast<const float4 *>(pairs + base + q);
-          float4 *d4 = reinterpret_cast<float4 *>(pairs_c + base + dst);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) d4[k] = src[k];
-        }
-        count += __popc(mask);
-      }
-    if (lane == 0) {
-      const int nslice = (count + kPairsPerItem - 1) / kPairsPerItem;
-      const int nchunk = (status == OCCB200_OK) ? (int)((g.V + kFastChunk - 1) / kFastChunk) : 0;
-      const long long nitems = (long long)nchunk * nslice;
-      s_nslice = nslice;
-      s_nitems = nitems;
-      s_i0 = nitems ? (long long)atomicAdd(counter + 3, (unsigned long long)nitems) : 0;
-      TrkHot h;
-      h.V = (int32_t)g.V; h.dY = g.dims[1]; h.dZ = g.dims[2];
-      h.status = status; h.nact = count; h.pad0 = 0;
-      h.bits_off = g.bits_off; h.label_off = label_off[t]; h.pairs_base = base;
-      h.pad1[0] = h.pad1[1] = 0;
-      hot[t] = h;
-      status_out[t] = status;
-    }
+  if (threadIdx.x == 0) {
+    const int nact = hot[t].nact;
+    const long long nchunk = (hot[t].status == OCCB200_OK) ? ((long long)n_unk[t] + kFastChunk - 1) / kFastChunk : 0;
+    const int nslice = nact > kPhase1Pairs ? (nact - kPhase1Pairs + kPairsPerItem - 1) / kPairsPerItem : 0;
+    const long long nitems = nchunk * nslice;
+    s_nslice = nslice;
+    s_nitems = nitems;
+    s_i0 = nitems ? (long long)atomicAdd(counter + 5, (unsigned long long)nitems) : 0;
   }
   __syncthreads();
   const long long i0 = s_i0, nitems = s_nitems;
@@ -1022,7 +1138,6 @@ __device__ __forceinline__ float rcp_approx(float x) {
 // (2 ulp of a: <= 2.4e-7) and the quadrant fix-ups (2 roundings at <= pi: 2.4e-7 each).
 // Total < 1.4e-6 rad; kAtanErr = 2e-6 is the bound used for every margin below (occb200_selftest_atan2
 // measures the actual maximum on the device).
-constexpr float kAtanErr = 2.0e-6f;
 __device__ __forceinline__ float atan2_fast(float y, float x) {
   const float ax = fabsf(x), ay = fabsf(y);
   const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
@@ -1041,25 +1156,18 @@ __device__ __forceinline__ float atan2_fast(float y, float x) {
   return (y < 0.f) ? -r : r;
 }
 
-// Per-iteration constants of one (frame, LiDAR) pair, derived once per warp iteration.
-struct PairConst {
-  float e15;        // 1.5 eps
-  float c1, c2;     // range margin: m = r * (r * 6e-7 + c1) + c2,  c1 = 2.01 sqrt(3) eps, c2 = 3 eps^2
-  float ecol;       // (kAtanErr + 3e-7) * kcol + c_col
-  float e15k;       // 1.5 eps * kcol
-  float nkcol;      // -kcol
-  unsigned last;    // H - 1
-  unsigned ncm1;    // ncell - 1
-};
+// float -> nearest integer (ties to even) without the conversion unit: valid for |x| < 2^22; anything else
+// (NaN included) gives an arbitrary integer, which every caller clamps before using it as an index.
+constexpr float kMagic = 12582912.f;              // 1.5 * 2^23
+__device__ __forceinline__ int magic_int(float biased) { return __float_as_int(biased) - 0x4B400000; }
 
 // One fast test.  Returns 2 = certainly free, 0 = certainly not free, 1 = undecided (recheck in f64).
 // `ub` points at the table's boundary 0 (sentinels at ub[-1] = +2 and ub[H-1] = -2).
-__device__ __forceinline__ int fast_test(const PairCoef &pc, const SensCoef &sc, const PairConst &k, float x, float y,
-                                         float z, const float *__restrict__ ub, const uint16_t *__restrict__ lut,
-                                         const float *__restrict__ ri_img) {
-  const float px = fmaf(z, pc.A[2], fmaf(y, pc.A[1], fmaf(x, pc.A[0], pc.b[0])));
-  const float py = fmaf(z, pc.A[5], fmaf(y, pc.A[4], fmaf(x, pc.A[3], pc.b[1])));
-  const float pz = fmaf(z, pc.A[8], fmaf(y, pc.A[7], fmaf(x, pc.A[6], pc.b[2])));
+__device__ __forceinline__ int fast_test(const PairHot &p, float x, float y, float z, const float *__restrict__ ub,
+                                         const uint16_t *__restrict__ lut, const float *__restrict__ ri_img) {
+  const float px = fmaf(z, p.A[2], fmaf(y, p.A[1], fmaf(x, p.A[0], p.b[0])));
+  const float py = fmaf(z, p.A[5], fmaf(y, p.A[4], fmaf(x, p.A[3], p.b[1])));
+  const float pz = fmaf(z, p.A[8], fmaf(y, p.A[7], fmaf(x, p.A[6], p.b[2])));
   const float s2 = fmaf(py, py, px * px);
   const float r2 = fmaf(pz, pz, s2);
   const float inv_rho = rsqrt_approx(s2);
@@ -1067,8 +1175,9 @@ __device__ __forceinline__ int fast_test(const PairCoef &pc, const SensCoef &sc,
 
   // ---- row: u = pz / (|pz| + rho);  |u - u_ref| <= 1.42 eps / r  +  evaluation (~6 ulp of 1)
   const float u = pz * rcp_approx(fmaf(s2, inv_rho, fabsf(pz)));
-  const unsigned cell = min((unsigned)(int)fmaf(u, sc.inv_w, sc.cell0), k.ncm1);   // NaN -> 0
-  const unsigned row0 = min((unsigned)__ldg(lut + cell), k.last);                  // row at the top of the cell
+  // the lookup cell is only a starting guess (checked against the boundaries below): nearest instead of floor
+  const unsigned cell = min((unsigned)magic_int(fmaf(u, p.inv_w, p.cell0m) + kMagic), p.ncm1);
+  const unsigned row0 = min((unsigned)__ldg(lut + cell), p.last);                  // row at the top of the cell
   const float *ubr = ub + row0;
   const float b_up = __ldg(ubr - 1), b_here = __ldg(ubr), b_dn = __ldg(ubr + 1);   // ub[H] is never selected
   const bool step = b_here > u;                               // a cell holds at most one boundary
@@ -1076,26 +1185,37 @@ __device__ __forceinline__ int fast_test(const PairCoef &pc, const SensCoef &sc,
   const float below = step ? b_dn : b_here;                   // boundary between row and row + 1
   const float above = step ? b_here : b_up;                   // boundary between row - 1 and row
   // accepted only if u lies strictly between the two boundaries of `row`, by more than its error
-  const bool ok_row = fminf(u - below, above - u) > fmaf(k.e15, inv_r, 1.5e-6f) && row <= k.last;
+  const bool ok_row = fminf(u - below, above - u) > fmaf(p.e15, inv_r, 1.5e-6f) && row <= p.last;
 
   // ---- column: az = atan2(py, px) + azc (not wrapped: |az| <= 2 pi and the column is taken modulo W);
   //      colf = (W - 0.5) - (az + pi) / (2 pi) * W  (:176-191);  |az - az_ref| <= kAtanErr + 1.42 eps / rho
-  const float az = atan2_fast(py, px) + sc.azc;
-  const float colf = fmaf(az, k.nkcol, sc.col0);
-  const float cr = rintf(colf);
-  const bool ok_col = fabsf(colf - cr) + fmaf(k.e15k, inv_rho, k.ecol) < 0.5f;
-  int col = (int)cr;
-  col += (col < 0) ? sc.W : 0;                                // fmod(round(colf), W) (:191) and
-  col -= (col >= sc.W) ? sc.W : 0;                            // negative index wrap (:543)
-  col = min((unsigned)col, (unsigned)(sc.W - 1));
+  const float az = atan2_fast(py, px) + p.azc;
+  const float colf = fmaf(az, p.nkcol, p.col0);
+  const float cb = colf + kMagic;                             // |colf| <= 1.5 W < 2^22
+  const float cr = cb - kMagic;                               // == rintf(colf)
+  const bool ok_col = fabsf(colf - cr) + fmaf(p.e15k, inv_rho, p.ecol) < 0.5f;
+  int col = magic_int(cb);
+  col += (col < 0) ? p.W : 0;                                 // fmod(round(colf), W) (:191) and
+  col -= (col >= p.W) ? p.W : 0;                              // negative index wrap (:543)
+  col = min((unsigned)col, (unsigned)(p.W - 1));
 
   // ---- range: free iff ri >= |p_ref|;  | |p| - |p_ref| | <= sqrt(3) eps
-  const float ri = __ldg(ri_img + (min(row, k.last) * (unsigned)sc.W + (unsigned)col));
+  const float ri = __ldg(ri_img + (min(row, p.last) * (unsigned)p.W + (unsigned)col));
   const float r = r2 * inv_r;
-  const float m = fmaf(r, fmaf(r, 6.0e-7f, k.c1), k.c2);      // margin on squared ranges
+  const float m = fmaf(r, fmaf(r, 6.0e-7f, p.c1), p.c2);      // margin on squared ranges
   const float ri2 = ri * ri;
   const bool yes = ri2 >= r2 + m, no = ri2 <= r2 - m;
   return (ok_row && ok_col && (yes || no)) ? (yes ? 2 : 0) : 1;
+}
+
+template <typename T16>
+__device__ __forceinline__ T16 load128(const T16 *p) {         // 128-byte record, warp-uniform address
+  T16 v;
+  const float4 *src = reinterpret_cast<const float4 *>(p);
+  float4 *dst = reinterpret_cast<float4 *>(&v);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) dst[k] = __ldg(src + k);
+  return v;
 }
 
 template <typename T16>
@@ -1124,9 +1244,15 @@ __device__ __noinline__ bool exact_from_ids(int t, int f, int q, int L, double v
   return exact_test(cx, cy, cz, poses + f0 + i, sn, incl_pool, ri_pool);
 }
 
-// Every warp is on its own: it claims a work item (64 voxels x up to kPairsPerItem surviving pairs) from an
-// atomic counter, tests, and ORs the voxels it proved free into the global free bitset.  No shared memory, no
-// barriers.  Labels are written afterwards by k_labels from the occupancy and free bitsets.
+// Every warp is on its own: it claims a work item from an atomic counter, tests, and ORs the voxels it proved
+// free into the global free bitset.  No shared memory, no barriers.  Two launches:
+//   PHASE 1  item = 64 consecutive voxels of a tracklet x its first kPhase1Pairs surviving pairs.  Most voxels that
+//            can be freed at all are freed here; what is left (non-occupied, not free) is appended to the
+//            tracklet's list (warp-aggregated atomics, arbitrary order).
+//   PHASE 2  item = 64 LISTED voxels x a slice of kPairsPerItem of the remaining pairs: every lane holds a voxel
+//            that really needs the tests (dense lanes), and voxels freed in phase 1 are never tested again.
+// Labels are written afterwards by k_labels from the occupancy and free bitsets.
+template <int PHASE, int VPL>
 __global__ void __launch_bounds__(32 * kFastWarps, OCC_MINB)
 k_visibility_fast(int L, const int64_t *__restrict__ trk_frame_off,
                   const occb200_pose_t *__restrict__ poses, const int32_t *__restrict__ frame_sf,
@@ -1135,32 +1261,50 @@ k_visibility_fast(int L, const int64_t *__restrict__ trk_frame_off,
                   unsigned long long *__restrict__ counter, long long items_cap,
                   const uint32_t *__restrict__ bits, uint32_t *__restrict__ free_bits,
                   const int2 *__restrict__ item_map, const TrkHot *__restrict__ hot,
-                  const PairCoef *__restrict__ pairs, const SensCoef *__restrict__ sens,
+                  const PairHot *__restrict__ pairs,
                   const float *__restrict__ ub_pool, const uint16_t *__restrict__ lut_pool,
-                  int4 *__restrict__ queue, long long queue_cap, int64_t *__restrict__ n_steps) {
+                  int4 *__restrict__ queue, long long queue_cap, int32_t *__restrict__ unk_list,
+                  uint32_t *__restrict__ n_unk, int64_t *__restrict__ n_steps) {
   const int lane = threadIdx.x & 31;
-  const long long total = min((long long)counter[3], items_cap);
+  unsigned long long *ticket = counter + (PHASE == 1 ? 0 : 4);
+  const long long total = min((long long)counter[PHASE == 1 ? 3 : 5], items_cap);
   for (;;) {
     long long item = 0;
-    if (lane == 0) item = (long long)atomicAdd(counter, 1ull);
+    if (lane == 0) item = (long long)atomicAdd(ticket, 1ull);
     item = __shfl_sync(0xffffffffu, item, 0);
     if (item >= total) break;
     const int2 m = __ldg(item_map + item);
     const int t = m.x, chunk = m.y & 0xfffff, slice = m.y >> 20;
     const TrkHot h = load64(hot + t);
-    const int V = h.V, dZ = h.dZ, yz = h.dY * dZ;
-    const int fbase = chunk * kFastChunk;
-    const int64_t word0 = h.bits_off + (int64_t)chunk * kVPL;
-    float vx[kVPL], vy[kVPL], vz[kVPL];
+    const int dZ = h.dZ, yz = h.dY * dZ;
+    const int fbase = chunk * (32 * VPL);
+    int32_t *list = unk_list + h.label_off;
+    int vf[VPL];              // flat voxel index of this lane's voxel v
+    float vx[VPL], vy[VPL], vz[VPL];
     unsigned todo = 0u;        // bit v: this lane's voxel v exists, holds no point and is not known to be free
 #pragma unroll
-    for (int v = 0; v < kVPL; ++v) {
-      const int f = fbase + 32 * v + lane;
-      const bool active = f < V;
-      unsigned w = 0xffffffffu;
-      if (fbase + 32 * v < V) w = __ldg(bits + word0 + v) | *(volatile const uint32_t *)(free_bits + word0 + v);
-      todo |= ((active && !((w >> lane) & 1u)) ? 1u : 0u) << v;
+    for (int v = 0; v < VPL; ++v) {
+      bool active;
+      int f;
+      if (PHASE == 1) {
+        f = fbase + 32 * v + lane;
+        active = f < h.V;
+        unsigned w = 0xffffffffu;
+        const int64_t word = h.bits_off + (int64_t)chunk * VPL + v;
+        if (fbase + 32 * v < h.V) w = __ldg(bits + word) | *(volatile const uint32_t *)(free_bits + word);
+        active = active && !((w >> lane) & 1u);
+      } else {
+        const unsigned i = (unsigned)(fbase + 32 * v + lane);
+        active = i < __ldg(n_unk + t);
+        f = active ? __ldg(list + i) : 0;
+        if (active) {
+          const uint32_t w = *(volatile const uint32_t *)(free_bits + h.bits_off + (f >> 5));
+          active = !((w >> (f & 31)) & 1u);          // another slice may have freed it meanwhile
+        }
+      }
+      todo |= (active ? 1u : 0u) << v;
       const int fa = active ? f : 0;
+      vf[v] = fa;
       const int ix = fa / yz, rem = fa - ix * yz;
       const int iy = rem / dZ;
       vx[v] = (float)ix;
@@ -1168,34 +1312,25 @@ k_visibility_fast(int L, const int64_t *__restrict__ trk_frame_off,
       vz[v] = (float)(rem - iy * dZ);
     }
     unsigned steps = 0, found = 0u;
-    const int k0 = slice * kPairsPerItem, k1 = min(h.nact, k0 + kPairsPerItem);
-    const PairCoef *tp = pairs + h.pairs_base;
+    const int k0 = (PHASE == 1) ? 0 : kPhase1Pairs + slice * kPairsPerItem;
+    const int k1 = min(h.nact, k0 + (PHASE == 1 ? kPhase1Pairs : kPairsPerItem));
+    const PairHot *tp = pairs + h.pairs_base;
     for (int k = k0; k < k1; ++k) {
       if (!__any_sync(0xffffffffu, todo != 0u)) break;           // every voxel of the item is settled
-      const PairCoef pc = load64(tp + k);
-      if (k + 1 < k1) asm volatile("prefetch.global.L1 [%0];" ::"l"(tp + k + 1));
-      const SensCoef sc = load64(sens + pc.sens);
-      const float *ub = ub_pool + 2 * sc.tab_off + 1;
-      const uint16_t *lut = lut_pool + sc.tab_off * kLutPerRow;
-      const float *ri_img = ri_pool + sc.ri_off;
+      const PairHot pc = load128(tp + k);
+      if (k + 1 < k1) asm volatile("prefetch.global.L1 [%0];" ::"l"(tp + k + 1));   // one 128-byte line
+      const float *ub = ub_pool + 2 * pc.tab_off + 1;
+      const uint16_t *lut = lut_pool + pc.tab_off * kLutPerRow;
+      const float *ri_img = ri_pool + pc.ri_off;
       // materialise the three bases as 64-bit registers: per-test addresses are then ONE imad.wide each
       asm volatile("" : "+l"(ub), "+l"(lut), "+l"(ri_img));
-      PairConst kc;
-      kc.e15 = 1.5f * pc.eps;
-      kc.c1 = 2.01f * 1.7321f * pc.eps;
-      kc.c2 = 3.0003f * pc.eps * pc.eps;
-      kc.ecol = fmaf(kAtanErr + 3.0e-7f, sc.kcol, sc.c_col);
-      kc.e15k = kc.e15 * sc.kcol;
-      kc.nkcol = -sc.kcol;
-      kc.last = (unsigned)(sc.H - 1);
-      kc.ncm1 = (unsigned)(sc.ncell - 1);
-      // all kVPL tests are evaluated unconditionally (no divergence, their dependent chains interleave);
+      // all VPL tests are evaluated unconditionally (no divergence, their dependent chains interleave);
       // results of voxels this lane does not need are discarded
-      int res[kVPL];
+      int res[VPL];
 #pragma unroll
-      for (int v = 0; v < kVPL; ++v) res[v] = fast_test(pc, sc, kc, vx[v], vy[v], vz[v], ub, lut, ri_img);
+      for (int v = 0; v < VPL; ++v) res[v] = fast_test(pc, vx[v], vy[v], vz[v], ub, lut, ri_img);
 #pragma unroll
-      for (int v = 0; v < kVPL; ++v) {
+      for (int v = 0; v < VPL; ++v) {
         const bool need = (todo >> v) & 1u;
         res[v] = need ? ((pc.eps >= 0.f) ? res[v] : 1) : 0;
         steps += need ? 1u : 0u;
@@ -1209,12 +1344,11 @@ k_visibility_fast(int L, const int64_t *__restrict__ trk_frame_off,
           if (lane == 0) base = atomicAdd(counter + 1, (unsigned long long)__popc(umask));
           base = __shfl_sync(0xffffffffu, base, 0);
           if (res[v] == 1) {
-            const int f = fbase + 32 * v + lane;
             const unsigned long long slot = base + __popc(umask & ((1u << lane) - 1u));
             if (slot < (unsigned long long)queue_cap) {
-              queue[slot] = make_int4(t, f, pc.q, 0);
-            } else if (exact_from_ids(t, f, pc.q, L, vs, grids, trk_frame_off, poses, frame_sf, sensors, incl_pool,
-                                      ri_pool)) {                // queue full: decide right here
+              queue[slot] = make_int4(t, vf[v], pc.q, 0);
+            } else if (exact_from_ids(t, vf[v], pc.q, L, vs, grids, trk_frame_off, poses, frame_sf, sensors,
+                                      incl_pool, ri_pool)) {     // queue full: decide right here
               found |= 1u << v;
               todo &= ~(1u << v);
             }
@@ -1223,9 +1357,22 @@ k_visibility_fast(int L, const int64_t *__restrict__ trk_frame_off,
       }
     }
 #pragma unroll
-    for (int v = 0; v < kVPL; ++v) {
-      const unsigned fw = __ballot_sync(0xffffffffu, (found >> v) & 1u);
-      if (fw && lane == 0) atomicOr(free_bits + word0 + v, fw);
+    for (int v = 0; v < VPL; ++v) {
+      if (PHASE == 1) {
+        const unsigned fw = __ballot_sync(0xffffffffu, (found >> v) & 1u);
+        if (fw && lane == 0) atomicOr(free_bits + h.bits_off + (int64_t)chunk * VPL + v, fw);
+        if (h.nact > kPhase1Pairs) {                             // survivors go to the tracklet's phase-2 list
+          const unsigned left = __ballot_sync(0xffffffffu, (todo >> v) & 1u);
+          if (left) {
+            unsigned base = 0;
+            if (lane == 0) base = atomicAdd(n_unk + t, (unsigned)__popc(left));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if ((todo >> v) & 1u) list[base + __popc(left & ((1u << lane) - 1u))] = vf[v];
+          }
+        }
+      } else if ((found >> v) & 1u) {
+        atomicOr(free_bits + h.bits_off + (vf[v] >> 5), 1u << (vf[v] & 31));
+      }
     }
     for (int o = 16; o > 0; o >>= 1) steps += __shfl_xor_sync(0xffffffffu, steps, o);
     if (lane == 0 && n_steps && steps) atomicAdd((unsigned long long *)&n_steps[t], (unsigned long long)steps);
@@ -1335,7 +1482,7 @@ extern "C" int64_t occb200_annotate_items_cap(int32_t T, const int64_t *label_of
                                               int32_t L) {
   int64_t n = 0;
   for (int t = 0; t < T; ++t) {
-    const int64_t chunks = ceil_div(label_off[t + 1] - label_off[t], kFastChunk);
+    const int64_t chunks = ceil_div(label_off[t + 1] - label_off[t], 32 * (kVPL1 < kVPL ? kVPL1 : kVPL));
     const int64_t slices = ceil_div((trk_frame_off[t + 1] - trk_frame_off[t]) * L, kPairsPerItem);
     n += chunks * slices;
   }
@@ -1387,7 +1534,7 @@ extern "C" int occb200_annotate_batch(const occb200_annotate_args_t *a, int64_t 
     k_tracklet_presetup<<<(unsigned)ceil_div(a->T, 8), 256, 0, stream>>>(a->T, a->trk_frame_off, a->poses,
                                                                          a->frame_pt_off, a->label_off,
                                                                          vsf, chunk, w.grids, w.frame_trk, w.redo_count,
-                                                                         w.counter, a->n_unknown, a->n_steps);
+                                                                         w.counter, w.n_unk, a->n_unknown, a->n_steps);
     OCC_KERNEL_OK("k_tracklet_presetup");
   }
   if (a->F > 0) {
@@ -1445,7 +1592,7 @@ extern "C" int occb200_annotate_batch(const occb200_annotate_args_t *a, int64_t 
     // k_pair_compact reads the per-tracklet flags the redo pass may still be updating: join first
     if (a->F > 0) OCC_CUDA(cudaStreamWaitEvent(stream, side->join, 0));
     k_pair_compact<<<(unsigned)a->T, 256, 0, stream>>>(a->T, a->L, a->trk_frame_off, a->label_off, w.grids,
-                                                                    w.pairs, w.pairs_c, w.hot, w.item_map,
+                                                                    w.pairs, w.sens, w.pairs_c, w.hot, w.item_map,
                                                                     (long long)w.items_cap, w.counter, a->status);
     OCC_KERNEL_OK("k_pair_compact");
   }
@@ -1453,11 +1600,18 @@ extern "C" int occb200_annotate_batch(const occb200_annotate_args_t *a, int64_t 
     const int grid = (int)std::min<int64_t>(ceil_div(std::max<int64_t>(w.items_cap, 1), kFastWarps),
                                             (int64_t)kNumSMs * OCC_MINB);
     ProfScope ps(kProfVisibility, stream);
-    k_visibility_fast<<<grid, 32 * kFastWarps, 0, stream>>>(
+    k_visibility_fast<1, kVPL1><<<grid, 32 * kFastWarps, 0, stream>>>(
         a->L, a->trk_frame_off, a->poses, a->frame_sf, a->sensors, a->incl_pool, a->ri_pool, a->voxel_size, w.grids,
-        w.counter, (long long)w.items_cap, w.bits, w.free_bits, w.item_map, w.hot, w.pairs_c, w.sens, w.ub_pool,
-        w.lut_pool, w.queue, (long long)w.queue_cap, a->n_steps);
-    OCC_KERNEL_OK("k_visibility_fast");
+        w.counter, (long long)w.items_cap, w.bits, w.free_bits, w.item_map, w.hot, w.pairs_c, w.ub_pool,
+        w.lut_pool, w.queue, (long long)w.queue_cap, w.unk_list, w.n_unk, a->n_steps);
+    OCC_KERNEL_OK("k_visibility_fast<1>");
+    k_phase2_emit<<<(unsigned)a->T, 256, 0, stream>>>(w.hot, w.n_unk, w.item_map, (long long)w.items_cap, w.counter);
+    OCC_KERNEL_OK("k_phase2_emit");
+    k_visibility_fast<2, kVPL><<<grid, 32 * kFastWarps, 0, stream>>>(
+        a->L, a->trk_frame_off, a->poses, a->frame_sf, a->sensors, a->incl_pool, a->ri_pool, a->voxel_size, w.grids,
+        w.counter, (long long)w.items_cap, w.bits, w.free_bits, w.item_map, w.hot, w.pairs_c, w.ub_pool,
+        w.lut_pool, w.queue, (long long)w.queue_cap, w.unk_list, w.n_unk, a->n_steps);
+    OCC_KERNEL_OK("k_visibility_fast<2>");
   }
   {
     ProfScope ps(kProfRecheck, stream);

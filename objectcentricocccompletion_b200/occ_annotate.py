@@ -265,6 +265,27 @@ class DeviceTracklets:
             rc = _lib.lib().occb200_annotate_batch(C.byref(a), self.pk.total_slots, _lib.stream_ptr(self.device))
         _lib.check(rc, "occb200_annotate_batch")
 
+    def capture(self, flags: int = 0):
+        """Record the whole pipeline -- every kernel, the side-stream fork / join included -- into a CUDA graph;
+        ``replay(flags)`` then launches it with a single call (one graph launch instead of a dozen kernel launches
+        plus event traffic).  The graph is tied to this object's buffers; ``upload`` refreshes their contents."""
+        if not hasattr(self, "_graphs"):
+            self._graphs = {}
+        self.run(flags)                               # the library creates its side stream outside the capture
+        torch.cuda.synchronize(self.device)
+        n0 = _lib.launch_count()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.run(flags)
+        self._graphs[flags] = (g, _lib.launch_count() - n0)
+        return self._graphs[flags][1]
+
+    def replay(self, flags: int = 0) -> int:
+        """Launch the captured pipeline on the current stream; returns the number of kernels in the graph."""
+        g, n = self._graphs[flags]
+        g.replay()
+        return n
+
     def queue_stats(self, flags: int = 0):
         """(tests sent to the exact f64 recheck, queue capacity) of the last run (synchronises)."""
         a = self.args(flags)

@@ -187,3 +187,28 @@ def test_many_tracklets_two_pipes():
         assert e["status"] == want[i]["status"]
         if e["occ"] is not None:
             assert (e["occ"] == want[i]["occ"]).all()
+
+
+def test_graph_replay_matches_direct_launch():
+    """The captured CUDA graph (side-stream fork/join included) reproduces the direct launches, also after
+    the inputs are replaced by ``upload``."""
+    import torch
+
+    from objectcentricocccompletion_b200 import occ_annotate, synth
+
+    a = synth.make_batch(6, 14, 0.2, seed=1)
+    pk = occ_annotate.pack_tracklets(a)
+    d = occ_annotate.DeviceTracklets(pk)
+    host = occ_annotate.HostBuffers(pk)
+    d.upload(host)
+    d.run()
+    want = d.results()
+    n = d.capture()
+    assert n >= 8
+    d.labels.zero_()
+    d.upload(host)
+    assert d.replay() == n
+    torch.cuda.synchronize()
+    got = d.results()
+    for w, g in zip(want, got):
+        assert w["status"] == g["status"] and (w["occ"] == g["occ"]).all() and w["n_unknown"] == g["n_unknown"]
