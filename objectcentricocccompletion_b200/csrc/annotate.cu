@@ -157,6 +157,8 @@ struct Workspace {
   SensCoef *sens;        // [SF*L]
   float *ub_pool;        // [2*incl_len+2] u-space row boundaries, table at 2*incl_off+1 with a sentinel on each side
   uint16_t *lut_pool;    // [incl_len * kLutPerRow]
+  int32_t *tab_claim;    // [incl_len] 1 at a table's offset once a CTA has taken on building its lookup table
+  int64_t incl_len;
   PairCoef *pairs;       // [F*L]
   int4 *queue;           // recheck queue: (tracklet, voxel, pair index q = i*L + c, unused)
   int64_t queue_cap;
@@ -195,6 +197,7 @@ static int64_t ws_layout(int32_t T, int64_t F, int64_t total, int64_t SF, int32_
   int64_t o_tab = take(sizeof(SensCoef) * SF * L);
   int64_t o_ub = take(4 * (2 * incl_len + 2));
   int64_t o_lut = take(2 * incl_len * kLutPerRow);
+  int64_t o_claim = take(4 * std::max<int64_t>(incl_len, 1));
   int64_t o_pairs = take(sizeof(PairCoef) * F * L);
   // recheck queue: ~1% of the tests are expected; room for 1/16 of the nominal tests, bounded
   const double nominal = (double)total * (T > 0 ? (double)F / T : 0.0) * L;
@@ -230,6 +233,8 @@ static int64_t ws_layout(int32_t T, int64_t F, int64_t total, int64_t SF, int32_
     w->sens = (SensCoef *)(base + o_tab);
     w->ub_pool = (float *)(base + o_ub);
     w->lut_pool = (uint16_t *)(base + o_lut);
+    w->tab_claim = (int32_t *)(base + o_claim);
+    w->incl_len = incl_len;
     w->pairs = (PairCoef *)(base + o_pairs);
     w->queue = (int4 *)(base + o_q);
     w->queue_cap = qcap;
@@ -386,7 +391,10 @@ k_tracklet_presetup(int T, const int64_t *__restrict__ trk_frame_off, const occb
   if (n_steps) n_steps[t] = 0;
 }
 
-constexpr int kPtsPerThread = 4;                // independent point loads in flight per thread
+#ifndef OCC_PPT
+#define OCC_PPT 4
+#endif
+constexpr int kPtsPerThread = OCC_PPT;          // independent point loads in flight per thread
 __global__ void __launch_bounds__(kFrameThreads)
 k_frame_voxelize(const occb200_pose_t *__restrict__ poses, const float *__restrict__ points, int stride,
                  const int64_t *__restrict__ frame_pt_off, int32_t *__restrict__ frame_kept,
@@ -689,9 +697,11 @@ __device__ __forceinline__ double u_of_angle(double a) {
 
 __global__ void __launch_bounds__(256)
 k_table_setup(int64_t n_sensors, const occb200_sensor_t *__restrict__ sensors, const float *__restrict__ incl_pool,
-              SensCoef *__restrict__ sens, float *__restrict__ ub_pool, uint16_t *__restrict__ lut_pool) {
+              SensCoef *__restrict__ sens, float *__restrict__ ub_pool, uint16_t *__restrict__ lut_pool,
+              int32_t *__restrict__ tab_claim) {
   __shared__ float s_min[256];
   __shared__ SensCoef s_info;
+  __shared__ int s_builder;
   const int64_t e = blockIdx.x;
   if (e >= n_sensors) return;
   const occb200_sensor_t &sn = sensors[e];
@@ -754,10 +764,13 @@ k_table_setup(int64_t n_sensors, const occb200_sensor_t *__restrict__ sensors, c
     }
     s_info = sc;
     sens[e] = sc;
+    // the frames of a segment share one inclination table per LiDAR (same incl_off): every entry writes the same
+    // boundaries above, but only the first CTA to claim the table builds its lookup cells
+    s_builder = sc.ok ? (atomicCAS(tab_claim + off, 0, 1) == 0) : 0;
   }
   __syncthreads();
   const SensCoef sc = s_info;
-  if (!sc.ok) return;
+  if (!sc.ok || !s_builder) return;
   // lut[k] = number of boundaries above the (slightly raised) upper end of cell k, i.e. the row of a point at
   // the top of the cell.  It only has to be a good starting guess: the kernel accepts a row only after checking
   // the two boundaries around it.
@@ -824,26 +837,29 @@ k_pyr_build(const occb200_sensor_t *__restrict__ sensors, const float *__restric
   const float *img = ri_pool + sn.ri_off;
   float *out = pyr + pyr_off[e];
   constexpr int kU = 4;                            // tiles per warp in flight: 32 independent loads per lane
-  for (int tr = blockIdx.y; tr < ntr; tr += kPyrRowGroups) {
-    for (int tc0 = warp * kU; tc0 < ntc; tc0 += 8 * kU) {
-      float v[kU][kTileR];
+  // the image's tiles as one list, dealt to (row group, warp) in runs of kU: every warp is busy whatever the
+  // image shape (a 200 x 600 image has only 19 tiles per tile row)
+  const int ntile = ntr * ntc;
+  for (int i0 = (blockIdx.y * 8 + warp) * kU; i0 < ntile; i0 += kPyrRowGroups * 8 * kU) {
+    float v[kU][kTileR];
 #pragma unroll
-      for (int u = 0; u < kU; ++u) {
-        const int col = (tc0 + u) * kTileC + lane;
+    for (int u = 0; u < kU; ++u) {
+      const int tile = i0 + u;
+      const int tr = tile / ntc, tc = tile - tr * ntc;
+      const int col = tc * kTileC + lane;
 #pragma unroll
-        for (int r = 0; r < kTileR; ++r) {         // range images are >= 0 (0 = no return)
-          const int row = tr * kTileR + r;
-          v[u][r] = (tc0 + u < ntc && col < W && row < H) ? ld_stream(img + (int64_t)row * W + col) : 0.f;
-        }
+      for (int r = 0; r < kTileR; ++r) {           // range images are >= 0 (0 = no return)
+        const int row = tr * kTileR + r;
+        v[u][r] = (tile < ntile && col < W && row < H) ? ld_stream(img + (int64_t)row * W + col) : 0.f;
       }
+    }
 #pragma unroll
-      for (int u = 0; u < kU; ++u) {
-        float m = 0.f;
+    for (int u = 0; u < kU; ++u) {
+      float m = 0.f;
 #pragma unroll
-        for (int r = 0; r < kTileR; ++r) m = fmaxf(m, v[u][r]);
-        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-        if (lane == 0 && tc0 + u < ntc) out[tr * ntc + tc0 + u] = m;
-      }
+      for (int r = 0; r < kTileR; ++r) m = fmaxf(m, v[u][r]);
+      for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+      if (lane == 0 && i0 + u < ntile) out[i0 + u] = m;
     }
   }
 }
@@ -1515,8 +1531,9 @@ extern "C" int occb200_annotate_batch(const occb200_annotate_args_t *a, int64_t 
     OCC_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
     ProfScope ps(kProfPairSetup, side->stream);
     const int64_t n_sens = a->SF * a->L;
+    OCC_CUDA(cudaMemsetAsync(w.tab_claim, 0, 4 * (size_t)std::max<int64_t>(w.incl_len, 1), side->stream));
     k_table_setup<<<(unsigned)n_sens, 256, 0, side->stream>>>(n_sens, a->sensors, a->incl_pool, w.sens, w.ub_pool,
-                                                              w.lut_pool);
+                                                              w.lut_pool, w.tab_claim);
     OCC_KERNEL_OK("k_table_setup");
     k_pyr_scan<<<1, 1024, 0, side->stream>>>(n_sens, a->sensors, (a->flags & 2) ? (int64_t)-1 : w.pyr_tiles,
                                              w.pyr_off, w.pyr_flag);
