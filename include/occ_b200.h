@@ -255,6 +255,13 @@ int occb200_annotate_batch(const occb200_annotate_args_t *args, int64_t total_la
 int occb200_annotate_queue_stats(const occb200_annotate_args_t *args, int64_t total_label_slots,
                                  int64_t *out_host, void *stream);
 
+/* --save-mean-var support (tools/occ/occ_annotate.py:627-645).  Call after occb200_annotate_batch with the SAME
+ * args (it reads the final grids from the workspace and args->status).  For each of the N candidate points:
+ * loc_out f32 [N,3] = box-frame coordinates (occ_annotate.py:117-122), q_out int32 [N,4] = (tracklet, qx, qy, qz)
+ * raw quantised coordinates (:425) of a point the reference keeps (:430-431), (-1,0,0,0) otherwise. */
+int occb200_annotate_point_voxels(const occb200_annotate_args_t *args, int64_t total_label_slots, float *loc_out,
+                                  int32_t *q_out, void *stream);
+
 /* HOST helper: fills poses[i] from boxes7 f32 [n,7] and torch-evaluated trig f32 [n,4]
  * (cos(-yaw), sin(-yaw), cos(yaw), sin(yaw)); cos_pib/sin_pib come from the host libm. */
 void occb200_host_pose_pack(const float *boxes7, const float *trig4, int64_t n, occb200_pose_t *poses);

@@ -73,6 +73,7 @@ SIGNATURES = {
     "occb200_pyramid_tiles": (i64, [i32, i32]),
     "occb200_annotate_batch": (C.c_int, [C.POINTER(AnnotateArgs), i64, vp]),
     "occb200_annotate_queue_stats": (C.c_int, [C.POINTER(AnnotateArgs), i64, vp, vp]),
+    "occb200_annotate_point_voxels": (C.c_int, [C.POINTER(AnnotateArgs), i64, vp, vp, vp]),
     "occb200_host_pose_pack": (None, [vp, vp, i64, vp]),
     "occb200_point_cloud_to_range_image_idx": (C.c_int, [vp, C.c_int, i64, vp, vp, vp, C.c_int, C.c_int, vp, vp, vp]),
 }

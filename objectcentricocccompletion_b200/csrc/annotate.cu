@@ -480,6 +480,45 @@ k_frame_voxelize(const occb200_pose_t *__restrict__ poses, const float *__restri
   }
 }
 
+// --save-mean-var support (occ_annotate.py:627-645): for every candidate point, its box-frame coordinates and raw
+// quantised voxel coordinates with the tracklet's FINAL grid, exactly as k_frame_voxelize derives them.  Row
+// (t, qx, qy, qz) for a point the reference keeps (in the box, q < dims), (-1, 0, 0, 0) otherwise.  Negative
+// coordinates are NOT wrapped here: the reference groups by the raw values (sst_ops.py:150-181).
+__global__ void __launch_bounds__(256)
+k_frame_points(const occb200_pose_t *__restrict__ poses, const float *__restrict__ points, int stride,
+               const int64_t *__restrict__ frame_pt_off, const int32_t *__restrict__ frame_trk,
+               const TrkGrid *__restrict__ grids, const int32_t *__restrict__ status, float vsf,
+               float *__restrict__ loc_out, int32_t *__restrict__ q_out) {
+  const int64_t f = blockIdx.x;
+  const int t = frame_trk[f];
+  const TrkGrid g = grids[t];
+  const bool live = status[t] == OCCB200_OK;
+  const occb200_pose_t ps = poses[f];
+  const BoxTest bt = make_box_test(ps.box, ps.cos_pib, ps.sin_pib);
+  const float dX = (float)g.dims[0], dY = (float)g.dims[1], dZ = (float)g.dims[2];
+  for (int64_t j = frame_pt_off[f] + threadIdx.x; j < frame_pt_off[f + 1]; j += blockDim.x) {
+    const float *p = points + j * stride;
+    const float x = p[0], y = p[1], z = p[2];
+    float lx = 0.f, ly = 0.f, lz = 0.f;
+    int4 row = make_int4(-1, 0, 0, 0);
+    if (live && pt_in_box(bt, x, y, z)) {
+      const float c = ps.cos_m, s = ps.sin_m;
+      const float tx = __fadd_rn(x, -ps.box[0]), ty = __fadd_rn(y, -ps.box[1]), tz = __fadd_rn(z, -ps.box[2]);
+      lx = __fmaf_rn(ty, s, __fmul_rn(tx, c));
+      ly = __fmaf_rn(ty, c, __fmul_rn(tx, -s));
+      lz = tz;
+      const float qx = floorf(__fdiv_rn(__fsub_rn(lx, g.mb[0]), vsf));
+      const float qy = floorf(__fdiv_rn(__fsub_rn(ly, g.mb[1]), vsf));
+      const float qz = floorf(__fdiv_rn(__fsub_rn(lz, g.mb[2]), vsf));
+      if (qx < dX && qy < dY && qz < dZ) row = make_int4(t, (int)qx, (int)qy, (int)qz);
+    }
+    loc_out[3 * j + 0] = lx;
+    loc_out[3 * j + 1] = ly;
+    loc_out[3 * j + 2] = lz;
+    reinterpret_cast<int4 *>(q_out)[j] = row;
+  }
+}
+
 __global__ void __launch_bounds__(256)
 k_tracklet_setup(int T, const int64_t *__restrict__ trk_frame_off, const occb200_pose_t *__restrict__ poses,
                  const int64_t *__restrict__ frame_pt_off, const int32_t *__restrict__ frame_kept,
@@ -1035,8 +1074,10 @@ k_pair_compact(int T, int L, const int64_t *__restrict__ trk_frame_off, const in
   const int t = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const TrkGrid g = grids[t];
-  int status = g.status;                            // flags are final: both k_frame_voxelize passes have completed
-  if (status == OCCB200_OK) {
+  // the flags of a tracklet whose grid was right the first time are final; those of a corrected one are still
+  // being rewritten by the redo pass (side stream) -- it is treated as OK here and k_labels folds its flags in
+  int status = g.status;
+  if (status == OCCB200_OK && !g.redo) {
     if (g.flags & 2) status = OCCB200_INDEX_ERROR;
     else if (!(g.flags & 1)) status = OCCB200_EMPTY_AFTER_FILTER;
   }
@@ -1426,11 +1467,19 @@ k_visibility_recheck(int L, const int64_t *__restrict__ trk_frame_off, const occ
 
 // labels from the two bitsets: 1 occupied, 2 free, 0 unknown (occ_annotate.py:558-563); one CTA per tracklet
 __global__ void __launch_bounds__(256)
-k_labels(const TrkHot *__restrict__ hot, const uint32_t *__restrict__ bits, const uint32_t *__restrict__ free_bits,
-         int32_t *__restrict__ labels, int64_t *__restrict__ n_unknown) {
+k_labels(const TrkHot *__restrict__ hot, const TrkGrid *__restrict__ grids, const uint32_t *__restrict__ bits,
+         const uint32_t *__restrict__ free_bits, int32_t *__restrict__ labels, int64_t *__restrict__ n_unknown,
+         int32_t *__restrict__ status_out) {
   const int t = blockIdx.x;
   const TrkHot h = hot[t];
-  if (h.status != OCCB200_OK) return;
+  int status = h.status;
+  if (status == OCCB200_OK && grids[t].redo) {      // corrected tracklet: its flags are final only now
+    const int fl = grids[t].flags;
+    if (fl & 2) status = OCCB200_INDEX_ERROR;
+    else if (!(fl & 1)) status = OCCB200_EMPTY_AFTER_FILTER;
+    if (status != OCCB200_OK && threadIdx.x == 0 && blockIdx.y == 0) status_out[t] = status;
+  }
+  if (status != OCCB200_OK) return;
   int unk = 0;
   for (int f = blockIdx.y * blockDim.x + threadIdx.x; f < h.V; f += gridDim.y * blockDim.x) {
     const uint32_t o = bits[h.bits_off + (f >> 5)], fr = free_bits[h.bits_off + (f >> 5)];
@@ -1576,7 +1625,7 @@ extern "C" int occb200_annotate_batch(const occb200_annotate_args_t *a, int64_t 
         OCC_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
         rs = side->stream;
       }
-      k_frame_voxelize<<<(unsigned)std::min<int64_t>(a->F, kNumSMs * 7), kFrameThreads, 0, rs>>>(
+      k_frame_voxelize<<<(unsigned)std::min<int64_t>(a->F, kNumSMs * 2), kFrameThreads, 0, rs>>>(
           a->poses, a->points, a->point_stride, a->frame_pt_off, w.frame_kept, w.frame_trk, w.grids, w.bits, vsf,
           w.redo_list, w.redo_count);
       OCC_KERNEL_OK("k_frame_voxelize(redo)");
@@ -1606,13 +1655,12 @@ extern "C" int occb200_annotate_batch(const occb200_annotate_args_t *a, int64_t 
         n_pairs, a->L, a->poses, a->frame_sf, w.frame_trk, a->trk_frame_off, a->sensors, a->incl_pool, w.grids,
         w.sens, a->voxel_size, w.pyr_off, w.pyr, w.lut_pool, w.pyr_flag, w.pairs);
     OCC_KERNEL_OK("k_pair_setup");
-    // k_pair_compact reads the per-tracklet flags the redo pass may still be updating: join first
-    if (a->F > 0) OCC_CUDA(cudaStreamWaitEvent(stream, side->join, 0));
     k_pair_compact<<<(unsigned)a->T, 256, 0, stream>>>(a->T, a->L, a->trk_frame_off, a->label_off, w.grids,
                                                                     w.pairs, w.sens, w.pairs_c, w.hot, w.item_map,
                                                                     (long long)w.items_cap, w.counter, a->status);
     OCC_KERNEL_OK("k_pair_compact");
   }
+  if (fast && a->F > 0) OCC_CUDA(cudaStreamWaitEvent(stream, side->join, 0));   // redo pass done: bits and flags final
   {
     const int grid = (int)std::min<int64_t>(ceil_div(std::max<int64_t>(w.items_cap, 1), kFastWarps),
                                             (int64_t)kNumSMs * OCC_MINB);
@@ -1636,9 +1684,25 @@ extern "C" int occb200_annotate_batch(const occb200_annotate_args_t *a, int64_t 
                                                           a->incl_pool, a->ri_pool, a->voxel_size, w.grids, w.counter,
                                                           w.queue, (long long)w.queue_cap, w.free_bits, a->n_steps);
     OCC_KERNEL_OK("k_visibility_recheck");
-    k_labels<<<dim3((unsigned)a->T, 8), 256, 0, stream>>>(w.hot, w.bits, w.free_bits, a->labels, a->n_unknown);
+    k_labels<<<dim3((unsigned)a->T, 8), 256, 0, stream>>>(w.hot, w.grids, w.bits, w.free_bits, a->labels,
+                                                          a->n_unknown, a->status);
     OCC_KERNEL_OK("k_labels");
   }
+  return 0;
+}
+
+extern "C" int occb200_annotate_point_voxels(const occb200_annotate_args_t *a, int64_t total, float *loc_out,
+                                             int32_t *q_out, void *stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  OCC_REQUIRE(a != nullptr && loc_out != nullptr && q_out != nullptr, "NULL argument");
+  OCC_REQUIRE(((uintptr_t)q_out & 15) == 0, "q_out must be 16-byte aligned");
+  if (a->T == 0 || a->F == 0) return 0;
+  Workspace w;
+  ws_layout(a->T, a->F, total, a->SF, a->L, a->incl_len, a->pyr_tiles, a->items_cap, (char *)a->workspace, &w);
+  k_frame_points<<<(unsigned)a->F, 256, 0, stream>>>(a->poses, a->points, a->point_stride, a->frame_pt_off,
+                                                     w.frame_trk, w.grids, a->status, (float)a->voxel_size, loc_out,
+                                                     q_out);
+  OCC_KERNEL_OK("k_frame_points");
   return 0;
 }
 

@@ -296,6 +296,60 @@ class DeviceTracklets:
         _lib.check(rc, "occb200_annotate_queue_stats")
         return int(out[0]), int(out[1])
 
+    def point_voxels(self, flags: int = 0):
+        """After ``run``: (loc f32 [N,3], rows int32 [N,4]) for the N candidate points -- box-frame coordinates and
+        (tracklet, qx, qy, qz) with the final grids; rows of points the reference drops start with -1."""
+        n = max(int(self.pk.points.shape[0]), 1)
+        loc = torch.empty((n, 3), dtype=torch.float32, device=self.device)
+        rows = torch.empty((n, 4), dtype=torch.int32, device=self.device)
+        a = self.args(flags)
+        with torch.cuda.device(self.device):
+            rc = _lib.lib().occb200_annotate_point_voxels(C.byref(a), self.pk.total_slots, loc.data_ptr(),
+                                                          rows.data_ptr(), _lib.stream_ptr(self.device))
+        _lib.check(rc, "occb200_annotate_point_voxels")
+        n = int(self.pk.points.shape[0])
+        return loc[:n], rows[:n]
+
+    def mean_var(self, flags: int = 0) -> List[Optional[np.ndarray]]:
+        """``--save-mean-var`` (occ_annotate.py:627-645): per tracklet a dense f32 [X,Y,Z,6] grid with the mean of
+        the box-frame points of each voxel and the mean of their squared deviations, zeros elsewhere (None where
+        the reference writes no file).  ``scatter_v2`` does the reductions, exactly as in the reference; groups
+        are formed on the RAW quantised coordinates and a negative one lands on its wrapped cell (:641), the
+        last group in sorted order winning where two land on the same cell."""
+        from .sst_ops import scatter_v2
+
+        pk = self.pk
+        dims = self.dims.cpu().numpy()
+        status = self.status.cpu().numpy()
+        loc, rows = self.point_voxels(flags)
+        keep = rows[:, 0] >= 0
+        loc, rows = loc[keep].contiguous(), rows[keep].long().contiguous()
+        dense = torch.zeros((max(pk.total_slots, 1), 6), dtype=torch.float32, device=self.device)
+        if rows.shape[0]:
+            mean, new_coors, inv = scatter_v2(loc, rows, "mean", return_inv=True)
+            var = ((loc - mean[inv]) ** 2).contiguous()
+            var_m, _, _ = scatter_v2(var, rows, "mean", unq_inv=inv, new_coors=new_coors)
+            d = self.dims.long()[new_coors[:, 0]]                       # [M,3] dims of each group's tracklet
+            q = new_coors[:, 1:]
+            q = torch.where(q < 0, q + d, q)                            # PyTorch negative-index wrap (:641)
+            off = torch.from_numpy(pk.label_off[:-1]).to(self.device)[new_coors[:, 0]]
+            cell = off + (q[:, 0] * d[:, 1] + q[:, 1]) * d[:, 2] + q[:, 2]
+            # duplicates (a wrapped and an unwrapped group on one cell): the later row of the sorted list wins
+            last = torch.full((dense.shape[0],), -1, dtype=torch.long, device=self.device)
+            last.scatter_reduce_(0, cell, torch.arange(cell.shape[0], device=self.device), "amax")
+            sel = last[cell] == torch.arange(cell.shape[0], device=self.device)
+            dense[cell[sel]] = torch.cat([mean, var_m], 1)[sel]
+        dense = dense.cpu().numpy()
+        out = []
+        for t in range(pk.T):
+            if int(status[t]) != 0:
+                out.append(None)
+                continue
+            X, Y, Z = (int(v) for v in dims[t])
+            o = int(pk.label_off[t])
+            out.append(dense[o:o + X * Y * Z].reshape(X, Y, Z, 6).copy())
+        return out
+
     def results(self) -> List[dict]:
         """D2H of labels / dims / status and per-tracklet reshape (synchronises)."""
         pk = self.pk
@@ -319,7 +373,8 @@ class DeviceTracklets:
         return out
 
 
-def annotate_batch(batch, flags: int = 0, pack_override: Optional[dict] = None, device=None) -> List[dict]:
+def annotate_batch(batch, flags: int = 0, pack_override: Optional[dict] = None, device=None,
+                   save_mean_var: bool = False) -> List[dict]:
     """Annotate every tracklet of ``batch``: the batched equivalent of ``OccAnnotator.annotate_trk``.
 
     Returns one dict per tracklet: ``status`` (``ok`` or the reason the reference produces no file),
@@ -331,7 +386,11 @@ def annotate_batch(batch, flags: int = 0, pack_override: Optional[dict] = None, 
     dev = DeviceTracklets(pk, device)
     dev.upload(host)
     dev.run(flags)
-    return dev.results()
+    res = dev.results()
+    if save_mean_var:                                        # occ_annotate.py:627-645
+        for r, mv in zip(res, dev.mean_var(flags)):
+            r["mean_var"] = mv
+    return res
 
 
 def point_cloud_to_range_image_idx(points, extrinsics, inclinations, range_image_size):

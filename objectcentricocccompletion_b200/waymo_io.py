@@ -146,7 +146,10 @@ def annotate_from_disk(records: Sequence[TrackletRecord], data_root: str, out_di
                 continue
             path = out_name(out_dir, split, seg_name, records[i].id)
             os.makedirs(os.path.dirname(path), exist_ok=True)
-            np.savez(path, occ=res["occ"].astype(np.int32))                    # :647
+            if res.get("mean_var") is not None:                                # --save-mean-var, :643-645
+                np.savez(path, occ=res["occ"].astype(np.int32), mean_var=res["mean_var"])
+            else:
+                np.savez(path, occ=res["occ"].astype(np.int32))                # :647
             result[i] = path
     return result
 

@@ -132,5 +132,26 @@ def main():
     print("projection", f"{os.path.getsize(path) / 1024:.0f} KiB")
 
 
+def make_mean_var():
+    """--save-mean-var grids (occ_annotate.py:627-645) of the committed annotate fixtures, from the torch
+    reference glue, into tests/golden/mean_var.npz (keys <fixture>_<tracklet>)."""
+    assert torch_ref.available(), "needs /root/reference"
+    d = {}
+    for name in ("annotate_small", "annotate_edge"):
+        batch = arrays_to_batch(dict(np.load(os.path.join(OUT, name + ".npz"), allow_pickle=False)))
+        for t, r in enumerate(torch_ref.annotate_batch(batch)):
+            if r["occ"] is not None:
+                d[f"{name}_{t}"] = torch_ref.mean_var(r)
+    path = os.path.join(OUT, "mean_var.npz")
+    np.savez_compressed(path, **d)
+    print("mean_var", sorted(d), f"{os.path.getsize(path) / 1024:.0f} KiB")
+
+
 if __name__ == "__main__":
-    main()
+    import sys
+
+    if "--mean-var-only" in sys.argv:
+        make_mean_var()
+    else:
+        main()
+        make_mean_var()

@@ -389,3 +389,49 @@ def annotate_tracklet_debug(batch, t: int):
            C.c_long(cap), _p(nunk), _p(loc), _p(keep))
     return dict(status=STATUS.get(st, str(st)), dims=dims, size=size, labels=labels, n_unknown=int(nunk[0]),
                 loc=loc[:P], keep=keep[:P].astype(bool), packed=pk)
+
+
+def mean_var_grid(loc, q, dims):
+    """``--save-mean-var`` block of annotate_trk (tools/occ/occ_annotate.py:627-645) with scatter_v2
+    (mmdet3d/ops/sst/sst_ops.py:150-181) restated in numpy: rows of ``q`` (raw quantised coordinates, int64
+    [n,3], possibly negative) are grouped by ``np.unique(axis=0)`` (sorted, like torch.unique(dim=0)); mean =
+    f32 sum in point order / count (torch_scatter's CPU order); the second pass averages the squared deviations
+    from the gathered means; the dense f32 [X,Y,Z,6] grid is filled by index assignment, so a negative coordinate
+    wraps and the later group of the sorted list wins a shared cell (CPU index_put order)."""
+    X, Y, Z = (int(v) for v in dims)
+    out = np.zeros((X, Y, Z, 6), np.float32)
+    if len(q) == 0:
+        return out
+    loc = np.ascontiguousarray(loc, np.float32)
+    unq, inv = np.unique(np.asarray(q, np.int64), axis=0, return_inverse=True)
+    inv = inv.reshape(-1)
+    cnt = np.bincount(inv, minlength=len(unq)).astype(np.float32)[:, None]
+    s = np.zeros((len(unq), 3), np.float32)
+    np.add.at(s, inv, loc)                                   # sequential f32 accumulation in point order
+    mean = s / np.maximum(cnt, np.float32(1))
+    dev2 = (loc - mean[inv]) ** 2
+    v = np.zeros((len(unq), 3), np.float32)
+    np.add.at(v, inv, dev2)
+    var = v / np.maximum(cnt, np.float32(1))
+    both = np.concatenate([mean, var], 1)
+    for k in range(len(unq)):                                # sequential assignment: later rows overwrite
+        out[unq[k, 0], unq[k, 1], unq[k, 2]] = both[k]
+    return out
+
+
+def annotate_mean_var(batch):
+    """Per tracklet the [X,Y,Z,6] mean/variance grid of ``--save-mean-var`` (None where no file is written)."""
+    res = []
+    vsf = np.float32(batch.voxel_size)
+    for t in range(len(batch.tracklets)):
+        d = annotate_tracklet_debug(batch, t)
+        if d["status"] != "ok":
+            res.append(None)
+            continue
+        loc = d["loc"][d["keep"]]
+        size = d["size"].astype(np.float32)
+        min_bound = np.array([-size[0] * np.float32(0.5), -size[1] * np.float32(0.5), 0], np.float32)
+        q = np.floor((loc - min_bound) / vsf).astype(np.int64)            # occ_annotate.py:425
+        ok = (q < d["dims"][None].astype(np.int64)).all(1)                # :430-431
+        res.append(mean_var_grid(loc[ok], q[ok], d["dims"]))
+    return res

@@ -136,3 +136,24 @@ def annotate_tracklet(trk, segment, voxel_size):
 
 def annotate_batch(batch):
     return [annotate_tracklet(t, batch.segments[t.segment], batch.voxel_size) for t in batch.tracklets]
+
+
+def mean_var(res):
+    """The --save-mean-var block (occ_annotate.py:627-645) on the ``loc`` / ``q`` / ``dims`` of one
+    ``annotate_tracklet`` result, with scatter_v2's torch calls (sst_ops.py:150-181): torch.unique(dim=0) and a
+    scatter-mean written as index_add_ / count (torch_scatter itself is not installed; its CPU kernel
+    accumulates in index order, which index_add_ on CPU also does)."""
+    loc, q = torch.from_numpy(res["loc"]), torch.from_numpy(res["q"])
+    dims = [int(v) for v in res["dims"]]
+    new_coors, inv = torch.unique(q, return_inverse=True, dim=0)
+
+    def scatter_mean(feat):
+        out = torch.zeros((new_coors.shape[0], feat.shape[1]), dtype=feat.dtype).index_add_(0, inv, feat)
+        cnt = torch.zeros(new_coors.shape[0], dtype=feat.dtype).index_add_(0, inv, torch.ones(len(inv), dtype=feat.dtype))
+        return out / cnt.clamp(min=1)[:, None]
+
+    mean = scatter_mean(loc)
+    var = scatter_mean((loc - mean[inv]) ** 2)
+    dense = torch.zeros((dims[0], dims[1], dims[2], 6), dtype=loc.dtype)
+    dense[new_coors[:, 0], new_coors[:, 1], new_coors[:, 2], :] = torch.cat([mean, var], 1)
+    return dense.numpy()

@@ -212,3 +212,40 @@ def test_graph_replay_matches_direct_launch():
     got = d.results()
     for w, g in zip(want, got):
         assert w["status"] == g["status"] and (w["occ"] == g["occ"]).all() and w["n_unknown"] == g["n_unknown"]
+
+
+@pytest.mark.parametrize("name", ["annotate_small", "annotate_edge"])
+def test_mean_var_vs_reference_fixture(name):
+    """--save-mean-var grids: means within 1e-5 relative; mean squared deviations within 1e-5 relative plus
+    1e-7 m^2 (one ulp of a mean moves the deviation of a point that sits almost on it)."""
+    import os
+
+    from tests.util import GOLDEN, load_golden
+
+    gold = np.load(os.path.join(GOLDEN, "mean_var.npz"))
+    batch, override, status, _ = load_golden(name)
+    got = _cuda(batch, pack_override=override, save_mean_var=True)
+    for t, g in enumerate(got):
+        key = f"{name}_{t}"
+        assert (g["mean_var"] is None) == (key not in gold)
+        if g["mean_var"] is None:
+            continue
+        m, e = g["mean_var"], gold[key]
+        assert m.shape == e.shape and m.dtype == np.float32
+        assert ((m != 0).any(-1) == (e != 0).any(-1)).all()            # same cells filled
+        np.testing.assert_allclose(m[..., :3], e[..., :3], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(m[..., 3:], e[..., 3:], rtol=1e-5, atol=1e-7)
+
+
+def test_mean_var_vs_oracle_larger():
+    from objectcentricocccompletion_b200 import synth
+    from oracle import oracle
+
+    batch = synth.make_batch(6, 14, 0.2, seed=1)
+    exp = oracle.annotate_mean_var(batch)
+    got = _cuda(batch, save_mean_var=True)
+    for g, e in zip(got, exp):
+        assert (g["mean_var"] is None) == (e is None)
+        if e is not None:
+            np.testing.assert_allclose(g["mean_var"][..., :3], e[..., :3], rtol=1e-5, atol=1e-6)
+            np.testing.assert_allclose(g["mean_var"][..., 3:], e[..., 3:], rtol=1e-5, atol=1e-7)

@@ -166,3 +166,28 @@ def test_oracle_ignores_extra_point_columns():
     got = oracle.annotate_batch(b)
     for e, g in zip(exp, got):
         assert e["status"] == g["status"] and (e["occ"] == g["occ"]).all()
+
+
+def test_mean_var_oracle_matches_reference_fixture():
+    """--save-mean-var (occ_annotate.py:627-645): the numpy restatement reproduces the grids recorded from the
+    torch reference glue bit for bit (CPU accumulation order is the same)."""
+    import os
+
+    import numpy as np
+
+    from oracle import oracle
+    from tests.util import GOLDEN, load_golden
+
+    gold = np.load(os.path.join(GOLDEN, "mean_var.npz"))
+    seen = 0
+    for name in ("annotate_small", "annotate_edge"):
+        batch, _, status, _ = load_golden(name)
+        mv = oracle.annotate_mean_var(batch)
+        for t, m in enumerate(mv):
+            key = f"{name}_{t}"
+            assert (m is None) == (key not in gold)
+            if m is not None:
+                assert m.dtype == np.float32 and m.shape == gold[key].shape
+                assert (m.view(np.uint32) == gold[key].view(np.uint32)).all()
+                seen += 1
+    assert seen >= 5
