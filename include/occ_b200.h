@@ -262,6 +262,29 @@ int occb200_annotate_queue_stats(const occb200_annotate_args_t *args, int64_t to
 int occb200_annotate_point_voxels(const occb200_annotate_args_t *args, int64_t total_label_slots, float *loc_out,
                                   int32_t *q_out, void *stream);
 
+/*
+ * Range-image builder: waymo_open_dataset.utils.range_image_utils.build_range_image_from_point_cloud (v1.2.0) as
+ * the reference's converter calls it for *_RANGE_IMAGE_MERGE_VIRTUAL (tools/data_converter/waymo_converter.py:632-670).
+ * One descriptor per image; the caller concatenates the two returns' points (:641-652) on its side.
+ */
+typedef struct {
+  double v2l[12];     /* rows 0..2 of inv(extrinsic), evaluated in f64 on the host                          */
+  double azc;         /* atan2(E[1,0], E[0,0]) in f64                                                         */
+  int64_t incl_off;   /* offset of the image's inclination table in incl_pool, already reversed (:659)       */
+  int64_t ri_off;     /* offset of the image in ri_pool (float index)                                         */
+  int32_t H, W;
+  int32_t mono;       /* -1 table strictly descending, +1 strictly ascending, 0 unknown (linear argmin)       */
+  int32_t pad;
+} occb200_ri_desc_t;
+
+/* points f32 [*, point_stride] vehicle frame, image b owns rows [pt_off[b], pt_off[b+1]); max_points = the
+ * largest of those counts (sizes the grid).  ri_pool f32 [ri_len] receives, per image, min range per pixel and
+ * 0 where no point lands.  *n_bad (device) = points whose column fell outside [0, W) -- TF raises there; they
+ * are skipped.  Asynchronous on `stream`. */
+int occb200_build_range_images(const float *points, int point_stride, const int64_t *pt_off, int64_t max_points,
+                               const occb200_ri_desc_t *desc, int32_t n_images, const float *incl_pool,
+                               float *ri_pool, int64_t ri_len, unsigned long long *n_bad, void *stream);
+
 /* HOST helper: fills poses[i] from boxes7 f32 [n,7] and torch-evaluated trig f32 [n,4]
  * (cos(-yaw), sin(-yaw), cos(yaw), sin(yaw)); cos_pib/sin_pib come from the host libm. */
 void occb200_host_pose_pack(const float *boxes7, const float *trig4, int64_t n, occb200_pose_t *poses);

@@ -12,9 +12,10 @@ from .occ_annotate import (OccAnnotator, annotate_batch, pack_tracklets,  # noqa
                            point_cloud_to_range_image_idx)
 from .occ_ops import generate_dense_voxel_centers, quantize_points  # noqa: E402
 from .points_in_boxes import points_in_boxes_batch, points_in_boxes_gpu  # noqa: E402
+from .range_image import build_range_images  # noqa: E402
 from .sst_ops import scatter_v2  # noqa: E402
 from .voxel import DynamicScatter, Voxelization, dynamic_scatter, voxelization  # noqa: E402
 
 __all__ = ["Voxelization", "voxelization", "DynamicScatter", "dynamic_scatter", "points_in_boxes_gpu",
            "points_in_boxes_batch", "scatter_v2", "quantize_points", "generate_dense_voxel_centers",
-           "OccAnnotator", "annotate_batch", "pack_tracklets", "point_cloud_to_range_image_idx"]
+           "OccAnnotator", "annotate_batch", "pack_tracklets", "point_cloud_to_range_image_idx", "build_range_images"]

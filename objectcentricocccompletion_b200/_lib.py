@@ -45,6 +45,10 @@ SENSOR_DTYPE = np.dtype([("ri_off", "<i8"), ("incl_off", "<i8"), ("H", "<i4"), (
 assert POSE_DTYPE.itemsize == C.sizeof(Pose) == 64
 assert SENSOR_DTYPE.itemsize == C.sizeof(Sensor) == 80
 
+RI_DESC_DTYPE = np.dtype([("v2l", "<f8", (12,)), ("azc", "<f8"), ("incl_off", "<i8"), ("ri_off", "<i8"), ("H", "<i4"),
+                          ("W", "<i4"), ("mono", "<i4"), ("pad", "<i4")])
+assert RI_DESC_DTYPE.itemsize == 136
+
 # name -> (restype, argtypes); must list every symbol include/occ_b200.h declares
 SIGNATURES = {
     "occb200_abi_version": (C.c_int, []),
@@ -75,6 +79,7 @@ SIGNATURES = {
     "occb200_annotate_queue_stats": (C.c_int, [C.POINTER(AnnotateArgs), i64, vp, vp]),
     "occb200_annotate_point_voxels": (C.c_int, [C.POINTER(AnnotateArgs), i64, vp, vp, vp]),
     "occb200_host_pose_pack": (None, [vp, vp, i64, vp]),
+    "occb200_build_range_images": (C.c_int, [vp, C.c_int, vp, i64, vp, i32, vp, vp, i64, vp, vp]),
     "occb200_point_cloud_to_range_image_idx": (C.c_int, [vp, C.c_int, i64, vp, vp, vp, C.c_int, C.c_int, vp, vp, vp]),
 }
 

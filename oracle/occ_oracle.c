@@ -575,3 +575,48 @@ void orc_annotate_batch(int T, const orc_trk_t *trk, const float *boxes, const f
     free(sn);
   }
 }
+
+
+/* ---------------------------------------------------------------------------------------------
+ * Range-image builder: waymo_open_dataset.utils.range_image_utils.build_range_image_from_point_cloud
+ * (waymo-open-dataset-tf-2-1-0 == 1.2.0, requirements/optional.txt; NOT vendored under the reference: this
+ * restates its published algorithm, PARITY UNPINNED against the TF code itself), as called for one LiDAR of one
+ * frame at tools/data_converter/waymo_converter.py:653-668.  f64 throughout after the casts; the products
+ * accumulate as an FMA chain like the torch port of the same function (occ_annotate.py:161-164).
+ * v2l = rows 0..2 of inv(f64(extrinsic)) (host), azc = atan2(E[1,0], E[0,0]) in f64, incl = table reversed (:659).
+ * ri [H*W] = min range per pixel, 0 where no point lands; rows/cols/ranges per point (optional).
+ * Returns the number of points whose column is outside [0, W) (TF asserts; they are skipped). */
+long orc_build_range_image(const float *points, long n, int stride, const double *v2l, double azc,
+                           const float *incl, int H, int W, float *ri, int32_t *rows, int32_t *cols,
+                           float *ranges) {
+  const double two_pi = 6.28318530717958647692;
+  long bad = 0;
+  for (long k = 0; k < (long)H * W; k++) ri[k] = INFINITY;
+  for (long i = 0; i < n; i++) {
+    double x = points[i * stride], y = points[i * stride + 1], z = points[i * stride + 2], p[3];
+    for (int r = 0; r < 3; r++)
+      p[r] = fma(z, v2l[4 * r + 2], fma(y, v2l[4 * r + 1], x * v2l[4 * r])) + v2l[4 * r + 3];
+    double inc = atan2(p[2], sqrt(fma(p[1], p[1], p[0] * p[0])));
+    int row = 0;
+    double best = INFINITY;
+    for (int h = 0; h < H; h++) {
+      double d = fabs(inc - (double)incl[h]);
+      if (d < best) { best = d; row = h; }
+    }
+    double az = atan2(p[1], p[0]) + azc;
+    int gt = az > M_PI, lt = az < -M_PI;
+    if (gt) az -= two_pi;
+    if (lt) az += two_pi;
+    double colf = ((double)W - 1.0 + 0.5) - (az + M_PI) / two_pi * (double)W;
+    double cr = rint(colf);
+    float rng = (float)sqrt(fma(p[2], p[2], fma(p[1], p[1], p[0] * p[0])));
+    if (rows) rows[i] = row;
+    if (cols) cols[i] = (int32_t)cr;
+    if (ranges) ranges[i] = rng;
+    if (!(cr >= 0.0 && cr < (double)W)) { bad++; continue; }
+    float *px = ri + (long)row * W + (long)cr;
+    if (rng < *px) *px = rng;
+  }
+  for (long k = 0; k < (long)H * W; k++) if (isinf(ri[k])) ri[k] = 0.0f;
+  return bad;
+}

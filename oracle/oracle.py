@@ -435,3 +435,26 @@ def annotate_mean_var(batch):
         ok = (q < d["dims"][None].astype(np.int64)).all(1)                # :430-431
         res.append(mean_var_grid(loc[ok], q[ok], d["dims"]))
     return res
+
+
+def build_range_image(points, extrinsic, inclination, size):
+    """waymo_open_dataset ... build_range_image_from_point_cloud as called at
+    tools/data_converter/waymo_converter.py:653-668 for one LiDAR of one frame (C restatement:
+    ``orc_build_range_image``; the TF package is not vendored -> parity unpinned against TF itself).
+
+    points f32 [n,>=3] vehicle frame; extrinsic [4,4]; inclination f32 [H] as stored (reversed here, :659)
+    -> (ri f32 [H,W] min range per pixel / 0, rows int32 [n], cols int32 [n], ranges f32 [n], n_bad)."""
+    H, W = (int(v) for v in size)
+    E = np.asarray(extrinsic).astype(np.float64)
+    v2l = np.ascontiguousarray(np.linalg.inv(E)[:3, :].reshape(12))
+    incl = np.ascontiguousarray(np.asarray(inclination, np.float32)[::-1])
+    pts = np.ascontiguousarray(points, np.float32)
+    n = len(pts)
+    ri = np.zeros((H, W), np.float32)
+    rows, cols, rng = np.zeros(max(n, 1), np.int32), np.zeros(max(n, 1), np.int32), np.zeros(max(n, 1), np.float32)
+    f = lib().orc_build_range_image
+    f.restype = C.c_long
+    bad = f(_p(pts), C.c_long(n), C.c_int(pts.shape[1] if pts.ndim == 2 else 3), _p(v2l),
+            C.c_double(float(np.arctan2(E[1, 0], E[0, 0]))), _p(incl), C.c_int(H), C.c_int(W), _p(ri), _p(rows),
+            _p(cols), _p(rng))
+    return ri, rows[:n], cols[:n], rng[:n], int(bad)
