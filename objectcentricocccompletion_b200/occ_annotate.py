@@ -275,7 +275,8 @@ class DeviceTracklets:
         torch.cuda.synchronize(self.device)
         n0 = _lib.launch_count()
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
+        # thread_local: other threads of the process (e.g. NCCL's watchdog) may touch CUDA during the capture
+        with torch.cuda.graph(g, capture_error_mode="thread_local"):
             self.run(flags)
         self._graphs[flags] = (g, _lib.launch_count() - n0)
         return self._graphs[flags][1]
