@@ -230,6 +230,8 @@ typedef struct occb200_annotate_args {
   int32_t flags;                  /* bit 0: every visibility test in exact f64 (no f32 fast path);
                                      bit 1: no (frame, LiDAR) pair culling                          */
   int32_t pad1;
+  int64_t max_label_slots;        /* max_t (label_off[t+1] - label_off[t]), from the host copy of label_off; sizes the
+                                     shared-memory bitsets.  0 = unknown (the 32 KB maximum is requested)        */
 } occb200_annotate_args_t;
 
 int64_t occb200_annotate_workspace_bytes(int32_t T, int64_t F, int64_t total_label_slots, int64_t SF,

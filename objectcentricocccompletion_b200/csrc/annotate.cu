@@ -58,8 +58,15 @@ constexpr float kAtanErr = 2.0e-6f;     // bound on |atan2_fast - atan2| (deriva
 constexpr int kFrameStride = 8;          // pair order: frames 0,8,16,.. then 1,9,17,.. (spread viewpoints come first)
 constexpr int kLutPerRow = 64;      // lookup-table cells reserved per inclination-table entry
 constexpr int kTileR = 8, kTileC = 32;   // range-image max-pyramid tile (rows x columns)
-constexpr int kFrameThreads = 256;
-constexpr int kSmemBitWords = 8192; // 32 KB: grids up to 262 144 voxels keep their bitset in shared memory
+#ifndef OCC_FT
+#define OCC_FT 256
+#endif
+#ifndef OCC_FMINB
+#define OCC_FMINB 6
+#endif
+constexpr int kFrameThreads = OCC_FT;
+constexpr int kSmemBitWords = 8192; // 32 KB: grids up to 262 144 voxels keep their bitset in shared memory; the
+                                    // launch asks only for what the largest grid of the batch needs
 
 struct TrkGrid {
   int32_t dims[3];
@@ -395,13 +402,13 @@ k_tracklet_presetup(int T, const int64_t *__restrict__ trk_frame_off, const occb
 #define OCC_PPT 4
 #endif
 constexpr int kPtsPerThread = OCC_PPT;          // independent point loads in flight per thread
-__global__ void __launch_bounds__(kFrameThreads)
+__global__ void __launch_bounds__(kFrameThreads, OCC_FMINB)
 k_frame_voxelize(const occb200_pose_t *__restrict__ poses, const float *__restrict__ points, int stride,
                  const int64_t *__restrict__ frame_pt_off, int32_t *__restrict__ frame_kept,
                  const int32_t *__restrict__ frame_trk, TrkGrid *__restrict__ grids,
                  uint32_t *__restrict__ bits, float vsf, const int32_t *__restrict__ redo_list,
-                 const unsigned long long *__restrict__ redo_count) {
-  __shared__ uint32_t s_bits[kSmemBitWords];
+                 const unsigned long long *__restrict__ redo_count, int smem_words) {
+  extern __shared__ uint32_t s_bits[];            // smem_words words
   __shared__ int s_flags;
   // first pass: CTA b = tracklet-frame b.  second pass (redo_list != NULL): a small grid strides over the
   // frames of the tracklets whose optimistic grid was wrong -- usually none.
@@ -417,7 +424,7 @@ k_frame_voxelize(const occb200_pose_t *__restrict__ poses, const float *__restri
     continue;
   }
   const int words = (int)((g.V + 31) / 32);
-  const bool use_smem = words <= kSmemBitWords;
+  const bool use_smem = words <= smem_words;
   uint32_t *gbits = bits + g.bits_off;
   if (use_smem)
     for (int w = threadIdx.x; w < words; w += kFrameThreads) s_bits[w] = 0u;
@@ -1570,6 +1577,9 @@ extern "C" int occb200_annotate_batch(const occb200_annotate_args_t *a, int64_t 
   const int64_t need = ws_layout(a->T, a->F, total, a->SF, a->L, a->incl_len, a->pyr_tiles, a->items_cap, (char *)a->workspace, &w);
   OCC_REQUIRE(a->workspace != nullptr && a->workspace_bytes >= need, "workspace too small");
   const float vsf = (float)a->voxel_size;
+  // shared-memory bitset of k_frame_voxelize: as many words as the largest label slot needs (unknown: the maximum)
+  const int smem_words = (a->max_label_slots > 0)
+                             ? (int)std::min<int64_t>(a->max_label_slots / 32 + 2, kSmemBitWords) : kSmemBitWords;
   const bool f64_only = (a->flags & 1) != 0;
   const int chunk = f64_only ? kChunk : kFastChunk;
   SideStream *side = nullptr;
@@ -1605,9 +1615,9 @@ extern "C" int occb200_annotate_batch(const occb200_annotate_args_t *a, int64_t 
   }
   if (a->F > 0) {
     ProfScope ps(kProfVoxelize, stream);
-    k_frame_voxelize<<<(unsigned)a->F, kFrameThreads, 0, stream>>>(
+    k_frame_voxelize<<<(unsigned)a->F, kFrameThreads, 4 * smem_words, stream>>>(
         a->poses, a->points, a->point_stride, a->frame_pt_off, w.frame_kept, w.frame_trk, w.grids, w.bits, vsf, nullptr,
-        nullptr);
+        nullptr, smem_words);
     OCC_KERNEL_OK("k_frame_voxelize");
   }
   {
@@ -1625,9 +1635,9 @@ extern "C" int occb200_annotate_batch(const occb200_annotate_args_t *a, int64_t 
         OCC_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
         rs = side->stream;
       }
-      k_frame_voxelize<<<(unsigned)std::min<int64_t>(a->F, kNumSMs * 2), kFrameThreads, 0, rs>>>(
+      k_frame_voxelize<<<(unsigned)std::min<int64_t>(a->F, kNumSMs * 2), kFrameThreads, 4 * smem_words, rs>>>(
           a->poses, a->points, a->point_stride, a->frame_pt_off, w.frame_kept, w.frame_trk, w.grids, w.bits, vsf,
-          w.redo_list, w.redo_count);
+          w.redo_list, w.redo_count, smem_words);
       OCC_KERNEL_OK("k_frame_voxelize(redo)");
       if (fast) OCC_CUDA(cudaEventRecord(side->join, side->stream));
     }

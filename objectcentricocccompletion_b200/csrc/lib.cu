@@ -19,6 +19,6 @@ void set_error(const char *fmt, ...) {
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 }  // namespace occb200
 
-extern "C" int occb200_abi_version(void) { return 4; }
+extern "C" int occb200_abi_version(void) { return 5; }
 extern "C" const char *occb200_last_error(void) { return occb200::g_err; }
 extern "C" int64_t occb200_launch_count(void) { return occb200::g_launches.load(); }

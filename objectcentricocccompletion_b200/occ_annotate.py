@@ -256,6 +256,7 @@ class DeviceTracklets:
         a.workspace = self.workspace.data_ptr()
         a.workspace_bytes = self.workspace.numel()
         a.flags = flags
+        a.max_label_slots = int(np.diff(pk.label_off).max()) if pk.T else 0
         return a
 
     def run(self, flags: int = 0):
