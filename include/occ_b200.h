@@ -176,6 +176,13 @@ int occb200_dense_voxel_centers(const float *sizes, const int32_t *dims, const i
                                 int R, int64_t total, float voxel_size, const float *scale_wlh,
                                 const float *offset_wlh, float *centers, void *stream);
 
+/* MirrorOccLabel (mmdet3d/datasets/pipelines/occ_pinelines.py:82-126) on the label layout of
+ * occb200_annotate_batch: out[label_off[t] + f] = labels[...] with every unknown (0) voxel replaced by the label
+ * of its mirror image across the x mid-plane, read from the unmodified grid.  status may be NULL; tracklets with
+ * status != 0 are skipped.  max_voxels = the largest X*Y*Z (sizes the grid).  out must not alias labels. */
+int occb200_mirror_occ_label(const int32_t *labels, const int64_t *label_off, const int32_t *dims,
+                             const int32_t *status, int32_t T, int64_t max_voxels, int32_t *out, void *stream);
+
 /* ---- A2-A5: batched tracklet annotation (the "ray-cast") ------------------------------ */
 
 /* One box pose per tracklet-frame: box7 plus the yaw trigonometry the reference evaluates on

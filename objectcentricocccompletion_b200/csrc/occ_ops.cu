@@ -49,9 +49,45 @@ __global__ void k_dense_centers(const float *__restrict__ sizes, const int32_t *
   }
 }
 
+// MirrorOccLabel (mmdet3d/datasets/pipelines/occ_pinelines.py:82-126): every UNKNOWN voxel takes the label of its
+// mirror image across the grid's x mid-plane, read from the unmodified grid.  Mirror index as the reference
+// computes it: long((x + 0.5 - X//2) * -1.0 + X//2), truncation toward zero (so x = X-1 maps to 0 for odd X).
+__global__ void k_mirror_occ_label(const int32_t *__restrict__ labels, const int64_t *__restrict__ label_off,
+                                   const int32_t *__restrict__ dims, const int32_t *__restrict__ status, int T,
+                                   int32_t *__restrict__ out) {
+  const int t = blockIdx.y;
+  if (t >= T || (status && status[t] != 0)) return;
+  const int X = dims[3 * t], Y = dims[3 * t + 1], Z = dims[3 * t + 2];
+  const int64_t V = (int64_t)X * Y * Z, yz = (int64_t)Y * Z;
+  const int32_t *src = labels + label_off[t];
+  int32_t *dst = out + label_off[t];
+  const float mid = (float)(X / 2);
+  for (int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; f < V; f += (int64_t)gridDim.x * blockDim.x) {
+    int32_t v = src[f];
+    if (v == 0) {
+      const int64_t x = f / yz;
+      long long mx = (long long)__fadd_rn(__fmul_rn(__fsub_rn(__fadd_rn((float)x, 0.5f), mid), -1.0f), mid);
+      if (mx < 0) mx += X;                                      // PyTorch negative-index wrap (not reached)
+      v = src[mx * yz + (f - x * yz)];
+    }
+    dst[f] = v;
+  }
+}
+
 }  // namespace occb200
 
 using namespace occb200;
+
+extern "C" int occb200_mirror_occ_label(const int32_t *labels, const int64_t *label_off, const int32_t *dims,
+                                        const int32_t *status, int32_t T, int64_t max_voxels, int32_t *out,
+                                        void *stream) {
+  OCC_REQUIRE(T >= 0 && max_voxels >= 0, "bad sizes");
+  if (T == 0 || max_voxels == 0) return 0;
+  const dim3 grid((unsigned)std::min<int64_t>(ceil_div(max_voxels, 256), 4096), (unsigned)T);
+  k_mirror_occ_label<<<grid, 256, 0, (cudaStream_t)stream>>>(labels, label_off, dims, status, T, out);
+  OCC_KERNEL_OK("k_mirror_occ_label");
+  return 0;
+}
 
 extern "C" int occb200_quantize_points(const float *points, int64_t N, const float *rois, int roi_dim,
                                        const int64_t *roi_idx, float voxel_size, const float *scale_wlh,

@@ -70,3 +70,28 @@ def generate_dense_voxel_centers(bbox_sizes, voxel_size, scale_wlh=[1.0, 1.0, 1.
 def jitter_voxel_center(voxel_size, voxel_centers):
     """occ_ops.py:96-100 (plain torch RNG; not on the kernel path)."""
     return voxel_centers + (torch.rand_like(voxel_centers) * voxel_size - voxel_size / 2)
+
+
+def mirror_occ_label(occ_label_list):
+    """``MirrorOccLabel.__call__`` (mmdet3d/datasets/pipelines/occ_pinelines.py:88-126) for a list of CUDA label
+    grids int32 [X,Y,Z]: unknown voxels take the label of their mirror image across the x mid-plane; all grids of
+    the list in one launch.  Returns new tensors (the inputs are not modified)."""
+    if len(occ_label_list) == 0:
+        return []
+    _lib.require_cuda(*occ_label_list)
+    dev = occ_label_list[0].device
+    dims = np.array([list(g.shape) for g in occ_label_list], np.int32).reshape(-1, 3)
+    sizes = dims.astype(np.int64).prod(1)
+    off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    flat = torch.cat([g.to(torch.int32).reshape(-1) for g in occ_label_list]) if off[-1] else \
+        torch.zeros(1, dtype=torch.int32, device=dev)
+    out = torch.empty_like(flat)
+    off_d = torch.from_numpy(off).to(dev)
+    dims_d = torch.from_numpy(dims).to(dev)
+    with torch.cuda.device(dev):
+        rc = _lib.lib().occb200_mirror_occ_label(flat.data_ptr(), off_d.data_ptr(), dims_d.data_ptr(), None,
+                                                 len(occ_label_list), int(sizes.max()), out.data_ptr(),
+                                                 _lib.stream_ptr(dev))
+    _lib.check(rc, "occb200_mirror_occ_label")
+    return [out[int(off[i]): int(off[i + 1])].view(*[int(v) for v in dims[i]]).to(occ_label_list[i].dtype)
+            for i in range(len(occ_label_list))]

@@ -458,3 +458,18 @@ def build_range_image(points, extrinsic, inclination, size):
             C.c_double(float(np.arctan2(E[1, 0], E[0, 0]))), _p(incl), C.c_int(H), C.c_int(W), _p(ri), _p(rows),
             _p(cols), _p(rng))
     return ri, rows[:n], cols[:n], rng[:n], int(bad)
+
+
+def mirror_occ_label(occ):
+    """MirrorOccLabel (mmdet3d/datasets/pipelines/occ_pinelines.py:88-126) on one int grid [X,Y,Z], with the
+    reference's own float arithmetic for the mirror index (f32, truncation toward zero)."""
+    occ = np.asarray(occ)
+    X = occ.shape[0]
+    mid = X // 2
+    x = np.arange(X, dtype=np.int64)
+    mx = ((x.astype(np.float32) + np.float32(0.5) - np.float32(mid)) * np.float32(-1.0) + np.float32(mid)).astype(np.int64)
+    out = occ.copy()
+    mirrored = occ[mx]                      # [X,Y,Z]: row x holds the grid's mirror row (negative index would wrap)
+    unknown = occ == 0
+    out[unknown] = mirrored[unknown]
+    return out

@@ -276,3 +276,19 @@ def test_occ_ops_vs_oracle():
         assert len(e) == len(g)
         for a, b in zip(e, g):
             assert a.shape == tuple(b.shape) and (a == b.cpu().numpy()).all()
+
+
+def test_mirror_occ_label_gpu():
+    """occ_ops.mirror_occ_label vs the oracle on ragged grids (odd / even X, X = 1), one launch for the list."""
+    import numpy as np
+    import torch
+
+    import objectcentricocccompletion_b200.occ_ops as occ_ops
+    from oracle import oracle
+
+    rng = np.random.default_rng(3)
+    grids = [rng.integers(0, 3, s).astype(np.int32) for s in [(11, 24, 9), (12, 23, 10), (1, 3, 2), (29, 120, 35)]]
+    got = occ_ops.mirror_occ_label([torch.from_numpy(g).cuda() for g in grids])
+    for g, o in zip(grids, got):
+        assert o.shape == g.shape and (o.cpu().numpy() == oracle.mirror_occ_label(g)).all()
+    assert occ_ops.mirror_occ_label([]) == []

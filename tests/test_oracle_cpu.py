@@ -191,3 +191,25 @@ def test_mean_var_oracle_matches_reference_fixture():
                 assert (m.view(np.uint32) == gold[key].view(np.uint32)).all()
                 seen += 1
     assert seen >= 5
+
+
+def test_mirror_occ_label_oracle_matches_reference_ops():
+    """MirrorOccLabel (occ_pinelines.py:88-126): numpy restatement vs the reference's torch op sequence, copied
+    as a sequence of torch calls (the pipeline class itself needs mmdet's registry to import)."""
+    import numpy as np
+    import torch
+
+    from oracle import oracle
+
+    rng = np.random.default_rng(0)
+    for shape in [(11, 24, 9), (12, 23, 10), (1, 3, 2), (2, 2, 2)]:
+        g = torch.from_numpy(rng.integers(0, 3, shape).astype(np.int32))
+        XS, YS, ZS = g.shape
+        flat = g.clone().view(-1)
+        unknown = flat == 0
+        mid = XS // 2
+        vx, vy, vz = torch.meshgrid(torch.arange(XS), torch.arange(YS), torch.arange(ZS), indexing="ij")
+        mxx = ((vx + 0.5 - mid) * -1.0 + mid).long()
+        coors = torch.stack([mxx, vy, vz], -1).view(-1, 3)
+        flat[unknown] = g[coors[unknown][:, 0], coors[unknown][:, 1], coors[unknown][:, 2]]
+        assert (oracle.mirror_occ_label(g.numpy()) == flat.view(XS, YS, ZS).numpy()).all()
