@@ -21,3 +21,17 @@ occ.scatter_v2(p, c4.long(), 'max')
 occ.voxelization(p, [0.5]*3, [-210,-210,-5,210,210,9], 8, 3000)
 occ.points_in_boxes_gpu(p[None,:,:3].contiguous(), torch.tensor([[[0,0,0,4,4,4,0.3]]],device='cuda'))
 torch.cuda.synchronize(); print('sanitizer workload ok')
+# round-1 additions: save-mean-var, range-image builder, label mirror, tracklet point extraction, graph replay
+from objectcentricocccompletion_b200 import occ_annotate, range_image, track_input, occ_ops
+b = synth.make_batch(3, 12, 0.2, seed=1, small=True)
+r = occ.annotate_batch(b, save_mean_var=True)
+assert all(x["mean_var"] is not None for x in r if x["occ"] is not None)
+seg = b.segments[0]
+pts = [np.concatenate([t.points[0][:, :3] for t in b.tracklets], 0).astype(np.float32)] * 2
+range_image.build_range_images(pts, seg.extrinsics[0, :2], [seg.inclinations[0], seg.inclinations[1]],
+                               [seg.range_images[0][0].shape, seg.range_images[1][0].shape])
+occ_ops.mirror_occ_label([torch.from_numpy(x["occ"]).cuda() for x in r if x["occ"] is not None])
+track_input.crop_frame(pts[0], b.tracklets[0].boxes[:3], 0.5)
+pk = occ_annotate.pack_tracklets(b)
+d = occ_annotate.DeviceTracklets(pk); d.upload(occ_annotate.HostBuffers(pk)); d.capture(); d.replay()
+torch.cuda.synchronize(); print('sanitizer workload (round-1 additions) ok')
