@@ -118,6 +118,29 @@ def build_segment_batch(records: Sequence[TrackletRecord], ts2idx: Dict, data_ro
     return TrackletBatch(segments=[seg], tracklets=trks, voxel_size=float(voxel_size))
 
 
+def save_tracklet_records(path: str, records: Sequence[TrackletRecord]) -> None:
+    """Plain-numpy tracklet file (npz): the stand-in for the reference's ``<name>_tracklets.pkl`` cache
+    (occ_annotate.py:270-273), whose pickled ``LiDARTracklet`` objects need mmdet3d to load."""
+    np.savez(path, n=np.int64(len(records)),
+             **{f"seg{i}": np.array(r.segment_name) for i, r in enumerate(records)},
+             **{f"id{i}": np.array(r.id) for i, r in enumerate(records)},
+             **{f"type{i}": np.int64(r.type) for i, r in enumerate(records)},
+             **{f"boxes{i}": np.asarray(r.boxes, np.float32).reshape(-1, 7) for i, r in enumerate(records)},
+             **{f"ts{i}": np.asarray(r.ts_list, np.int64) for i, r in enumerate(records)})
+
+
+def load_tracklet_records(path: str) -> List[TrackletRecord]:
+    z = np.load(path, allow_pickle=False)
+    return [TrackletRecord(str(z[f"seg{i}"]), str(z[f"id{i}"]), int(z[f"type{i}"]), z[f"boxes{i}"],
+                           [int(t) for t in z[f"ts{i}"]]) for i in range(int(z["n"]))]
+
+
+def segments_of_rank(segment_names: Sequence[str], rank: int, world: int) -> List[str]:
+    """The reference deals sorted segments to its worker processes, worker ``wid`` on GPU ``wid % ngpus``
+    (occ_annotate.py:278, 320-322, 659-665); here one process per GPU takes every ``world``-th segment."""
+    return [s for i, s in enumerate(sorted(set(segment_names))) if i % world == rank]
+
+
 def annotate_from_disk(records: Sequence[TrackletRecord], data_root: str, out_dir: str, split: str = "training",
                        voxel_size: float = 0.2, overwrite: bool = False, annotate_fn=annotate_batch) -> List[Optional[str]]:
     """The job of ``OccAnnotator.annotate_segment`` (occ_annotate.py:649-671) on a converted Waymo directory:

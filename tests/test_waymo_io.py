@@ -68,3 +68,41 @@ def test_annotate_from_disk_gpu(tmp_path):
     for p, e in zip(paths[:2], exp):
         assert (np.load(p)["occ"] == e["occ"]).all()
     assert paths[2] is None
+
+
+def test_job_driver_cpu(tmp_path, monkeypatch):
+    """tools/occ_annotate_job.py: reference flags, type filter, segment dealing over two ranks, resume; the
+    annotate function is the oracle here (the CUDA one is the default)."""
+    import importlib.util
+
+    from objectcentricocccompletion_b200 import synth, waymo_io
+    from oracle import oracle
+
+    spec = importlib.util.spec_from_file_location("job", os.path.join(os.path.dirname(__file__), "..", "tools",
+                                                                      "occ_annotate_job.py"))
+    job = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(job)
+
+    root = str(tmp_path / "data")
+    batch = synth.make_batch(4, 10, 0.2, seed=40, tracklets_per_segment=2, small=True)      # two segments
+    recs = waymo_io.write_synthetic_dataset(batch, root)
+    recs[1].type = 2                                              # a pedestrian: filtered out by --object-type vehicle
+    trk_file = str(tmp_path / "tracklets.npz")
+    waymo_io.save_tracklet_records(trk_file, recs)
+    back = waymo_io.load_tracklet_records(trk_file)
+    assert [(r.segment_name, r.id, r.type, list(r.ts_list)) for r in back] == \
+        [(r.segment_name, r.id, r.type, list(r.ts_list)) for r in recs]
+    assert all((a.boxes == b.boxes).all() for a, b in zip(recs, back))
+    out = str(tmp_path / "out")
+    argv = ["--data-root", root, "--out-dir", out, "--tracklets", trk_file, "--voxel-size", "0.2"]
+    written = []
+    for rank in range(2):
+        monkeypatch.setenv("RANK", str(rank))
+        monkeypatch.setenv("WORLD_SIZE", "2")
+        written.append(job.main(argv, annotate_fn=oracle.annotate_batch))
+    assert len(written[0]) + len(written[1]) == 3                 # 4 tracklets, one filtered by type
+    files = [p for w in written for p in w if p]
+    assert len(files) == 3 and all(os.path.isfile(p) for p in files)
+    assert {os.path.basename(os.path.dirname(p)) for p in written[0] if p} == {"segment-0000"}
+    assert {os.path.basename(os.path.dirname(p)) for p in written[1] if p} == {"segment-0001"}
+
