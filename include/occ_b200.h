@@ -22,6 +22,9 @@ extern "C" {
 
 /* ABI version; bumped on any layout change of the structs below. */
 int occb200_abi_version(void);
+/* sizeof of occb200_pose_t, occb200_sensor_t, occb200_annotate_args_t, occb200_ri_desc_t as this library was
+ * compiled: a binding checks its own struct declarations against these before the first call. */
+void occb200_struct_sizes(int64_t *out4);
 /* Message of the last failing call on this host thread (never NULL). */
 const char *occb200_last_error(void);
 /* Number of kernels this library has launched in this process (bench.py's gpu_launches). */

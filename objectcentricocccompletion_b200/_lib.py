@@ -52,6 +52,7 @@ assert RI_DESC_DTYPE.itemsize == 136
 # name -> (restype, argtypes); must list every symbol include/occ_b200.h declares
 SIGNATURES = {
     "occb200_abi_version": (C.c_int, []),
+    "occb200_struct_sizes": (None, [vp]),
     "occb200_last_error": (C.c_char_p, []),
     "occb200_launch_count": (i64, []),
     "occb200_profile_enable": (None, [C.c_int]),
@@ -114,6 +115,11 @@ def lib() -> C.CDLL:
             fn.argtypes = args
         if L.occb200_abi_version() != ABI_VERSION:
             raise ImportError("libocc_b200.so ABI version mismatch; rebuild")
+        sizes = (i64 * 4)()
+        L.occb200_struct_sizes(C.addressof(sizes))
+        mine = (C.sizeof(Pose), C.sizeof(Sensor), C.sizeof(AnnotateArgs), RI_DESC_DTYPE.itemsize)
+        if tuple(sizes) != mine:
+            raise ImportError(f"struct layout mismatch between _lib.py {mine} and libocc_b200.so {tuple(sizes)}")
         _lib = L
     return _lib
 
