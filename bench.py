@@ -387,7 +387,7 @@ def main():
                      "kernel_share_of_step": vis_ms / step_ms_prof if step_ms_prof else None,
                      "kernels_ms": dict(zip(("k_tracklet_presetup", "k_tracklet_setup+redo", "k_scan_chunks", "k_frame_voxelize",
                                              "k_visibility", "side:k_table_setup+k_pyr_scan+k_pyr_build",
-                                             "k_visibility_recheck", "k_pair_setup+k_pair_compact"),
+                                             "k_visibility_recheck", "k_pair_build"),
                                             (kms / np.maximum(kn[4], 1)).round(5).tolist()))},
         "cpu_baseline": cpu, "clocks": clocks,
     }

@@ -34,7 +34,7 @@ int64_t occb200_launch_count(void);
  * events are recorded around each pipeline kernel on the caller's stream.  occb200_profile_read
  * synchronises those events and returns, per kernel kind (0 k_tracklet_presetup, 1 k_tracklet_setup + redo,
  * 2 k_scan_chunks, 3 k_frame_voxelize, 4 k_visibility_{fast,f64}, 5 side stream: k_table_setup + k_pyr_scan +
- * k_pyr_build, 6 k_visibility_recheck, 7 k_pair_setup + k_pair_compact), the summed milliseconds and
+ * k_pyr_build, 6 k_visibility_recheck, 7 k_pair_build), the summed milliseconds and
  * launch counts since the last read.
  * Both arrays have occb200_profile_kinds() entries (HOST). */
 void occb200_profile_enable(int on);

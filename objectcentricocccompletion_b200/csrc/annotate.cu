@@ -9,7 +9,7 @@
 //   k_tracklet_setup  one warp per tracklet: box size = max over KEPT frames; rare re-voxelisation (A2/A3)
 //   k_scan_chunks     one CTA: exclusive scan of per-tracklet work chunks -> work list
 //   k_table_setup     one CTA per (sensor frame, LiDAR): inclination row boundaries + lookup table
-//   k_pair_setup      one thread per (tracklet-frame, LiDAR): voxel-index -> sensor-frame affine map
+//   k_pair_build      one CTA per tracklet, one thread per (frame, LiDAR): voxel-index -> sensor-frame affine map,
 //   k_visibility_fast persistent CTAs over 32-voxel chunks: the range-image "ray-cast" in f32 with
 //                     rigorous error margins; tests whose outcome is not certain are queued    (A4/A5)
 //   k_visibility_recheck  the queued tests, re-evaluated with the reference's exact f64 arithmetic
@@ -110,13 +110,13 @@ struct __align__(16) PairCoef {
   float eps;        // bound on |f32 p - reference f64 p| per component (metres); < 0: no fast path
   int32_t sens;     // index into the SensCoef table
   int32_t q;        // pair index inside the tracklet: frame * L + LiDAR
-  int32_t cull;     // 1: no voxel of the tracklet can be free through this pair (see k_pair_setup)
+  int32_t cull;     // 1: no voxel of the tracklet can be free through this pair (see make_pair)
 };
 static_assert(sizeof(PairCoef) == 64, "PairCoef must be 64 bytes");
 
 // What one iteration of the fast visibility kernel needs of a surviving pair, in ONE 128-byte record (one L1 line,
 // 8 x LDG.128, prefetched one iteration ahead): the pair's affine map, the fields of its sensor entry and the
-// per-pair constants of the margins.  Built by k_pair_compact.
+// per-pair constants of the margins.  Built by k_pair_build.
 struct __align__(16) PairHot {
   float A[9];
   float b[3];
@@ -166,7 +166,6 @@ struct Workspace {
   uint16_t *lut_pool;    // [incl_len * kLutPerRow]
   int32_t *tab_claim;    // [incl_len] 1 at a table's offset once a CTA has taken on building its lookup table
   int64_t incl_len;
-  PairCoef *pairs;       // [F*L]
   int4 *queue;           // recheck queue: (tracklet, voxel, pair index q = i*L + c, unused)
   int64_t queue_cap;
   PairHot *pairs_c;      // [F*L] the non-culled pairs of each tracklet, compacted at trk_frame_off[t] * L
@@ -205,7 +204,6 @@ static int64_t ws_layout(int32_t T, int64_t F, int64_t total, int64_t SF, int32_
   int64_t o_ub = take(4 * (2 * incl_len + 2));
   int64_t o_lut = take(2 * incl_len * kLutPerRow);
   int64_t o_claim = take(4 * std::max<int64_t>(incl_len, 1));
-  int64_t o_pairs = take(sizeof(PairCoef) * F * L);
   // recheck queue: ~1% of the tests are expected; room for 1/16 of the nominal tests, bounded
   const double nominal = (double)total * (T > 0 ? (double)F / T : 0.0) * L;
   int64_t qcap = (int64_t)std::min(std::max(nominal / 16.0, 65536.0), 64.0 * 1024 * 1024);
@@ -242,7 +240,6 @@ static int64_t ws_layout(int32_t T, int64_t F, int64_t total, int64_t SF, int32_
     w->lut_pool = (uint16_t *)(base + o_lut);
     w->tab_claim = (int32_t *)(base + o_claim);
     w->incl_len = incl_len;
-    w->pairs = (PairCoef *)(base + o_pairs);
     w->queue = (int4 *)(base + o_q);
     w->queue_cap = qcap;
   }
@@ -251,7 +248,7 @@ static int64_t ws_layout(int32_t T, int64_t F, int64_t total, int64_t SF, int32_
 
 // ---------------------------------------------------------------------------------------------
 // The sensor-side setup (row tables, range-image pyramid) does not depend on the tracklets, so it runs on
-// a side stream concurrently with the crop/voxelise chain and joins before k_pair_setup (fork/join with
+// a side stream concurrently with the crop/voxelise chain and joins before k_pair_build (fork/join with
 // events; capturable in a CUDA graph).
 struct SideStream {
   cudaStream_t stream = nullptr;
@@ -927,20 +924,12 @@ k_pyr_build(const occb200_sensor_t *__restrict__ sensors, const float *__restric
 // If the largest return in that window (from the tile pyramid) is below d - R, `ri >= range` is
 // false for every voxel of the tracklet through this pair: the pair is dropped from the work list.
 // ---------------------------------------------------------------------------------------------
-__global__ void k_pair_setup(int64_t n_pairs, int L, const occb200_pose_t *__restrict__ poses,
-                             const int32_t *__restrict__ frame_sf, const int32_t *__restrict__ frame_trk,
-                             const int64_t *__restrict__ trk_frame_off,
-                             const occb200_sensor_t *__restrict__ sensors, const float *__restrict__ incl_pool,
-                             const TrkGrid *__restrict__ grids, const SensCoef *__restrict__ sens, double vs,
-                             const int64_t *__restrict__ pyr_off, const float *__restrict__ pyr,
-                             const uint16_t *__restrict__ lut_pool,
-                             const unsigned long long *__restrict__ counter, PairCoef *__restrict__ pairs) {
-  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= n_pairs) return;
-  const int64_t f = e / L;
-  const int c = (int)(e % L);
-  const int t = frame_trk[f];
-  const TrkGrid &g = grids[t];
+__device__ __forceinline__ PairCoef
+make_pair(int64_t f, int c, int q, int L, const TrkGrid &g, const occb200_pose_t *__restrict__ poses,
+          const int32_t *__restrict__ frame_sf, const occb200_sensor_t *__restrict__ sensors,
+          const SensCoef *__restrict__ sens, double vs, const int64_t *__restrict__ pyr_off,
+          const float *__restrict__ pyr, const uint16_t *__restrict__ lut_pool,
+          const unsigned long long *__restrict__ counter) {
   const occb200_pose_t &ps = poses[f];
   const int64_t se = (int64_t)frame_sf[f] * L + c;
   const occb200_sensor_t &sn = sensors[se];
@@ -980,7 +969,7 @@ __global__ void k_pair_setup(int64_t n_pairs, int L, const occb200_pose_t *__res
   const bool ok = sens[se].ok && isfinite(eps) && se < (1ll << 31);
   pc.eps = ok ? eps : -1.f;
   pc.sens = (int32_t)se;
-  pc.q = (int32_t)(e - trk_frame_off[t] * L);
+  pc.q = q;
   pc.cull = 0;
   // ---- cull test (conservative; any doubt keeps the pair)
   if (counter[0] != 0ull && g.status == OCCB200_OK && sn.incl_mono == -1 && sn.H >= 1 && sn.W >= 1) {
@@ -1052,7 +1041,7 @@ __global__ void k_pair_setup(int64_t n_pairs, int L, const occb200_pose_t *__res
       if (m < rmin) pc.cull = 1;
     }
   }
-  pairs[e] = pc;
+  return pc;
 }
 
 // j-th frame of a tracklet of B frames in the order 0, S, 2S, .., 1, S+1, .. (S = kFrameStride)
@@ -1066,16 +1055,20 @@ __device__ __forceinline__ int strided_frame(int j, int B) {
   return B - 1;                                   // not reached for j < B
 }
 
-// One CTA per tracklet: the surviving pairs are copied (merged with their sensor entry into 128-byte records) to
+// One CTA per tracklet, one thread per (frame, LiDAR) pair: the pair's affine map and cull decision (make_pair),
+// then the surviving pairs are written (merged with their sensor entry into 128-byte records) to
 // the front of the tracklet's slot -- frames in strided order, so that the first kPhase1Pairs pairs look at the
 // object from spread-out viewpoints; thread 0 fixes the final status and writes the tracklet's hot record; all
 // threads then emit the phase-1 work items (one per chunk of 32 * kVPL1 voxels).  Item ids come from an atomic counter, so their order across tracklets is arbitrary.
 __global__ void __launch_bounds__(256)
-k_pair_compact(int T, int L, const int64_t *__restrict__ trk_frame_off, const int64_t *__restrict__ label_off,
-               const TrkGrid *__restrict__ grids, const PairCoef *__restrict__ pairs,
-               const SensCoef *__restrict__ sens, PairHot *__restrict__ pairs_c,
-               TrkHot *__restrict__ hot, int2 *__restrict__ item_map, long long items_cap,
-               unsigned long long *__restrict__ counter, int32_t *__restrict__ status_out) {
+k_pair_build(int T, int L, const int64_t *__restrict__ trk_frame_off, const int64_t *__restrict__ label_off,
+             const TrkGrid *__restrict__ grids, const occb200_pose_t *__restrict__ poses,
+             const int32_t *__restrict__ frame_sf, const occb200_sensor_t *__restrict__ sensors,
+             const SensCoef *__restrict__ sens, double vs, const int64_t *__restrict__ pyr_off,
+             const float *__restrict__ pyr, const uint16_t *__restrict__ lut_pool,
+             const unsigned long long *__restrict__ pyr_flag, PairHot *__restrict__ pairs_c,
+             TrkHot *__restrict__ hot, int2 *__restrict__ item_map, long long items_cap,
+             unsigned long long *__restrict__ counter, int32_t *__restrict__ status_out) {
   __shared__ long long s_i0, s_nitems;
   __shared__ int s_cnt[8];
   const int t = blockIdx.x;
@@ -1102,7 +1095,9 @@ k_pair_compact(int T, int L, const int64_t *__restrict__ trk_frame_off, const in
     PairCoef pc;
     bool keep = false;
     if (j < n) {
-      pc = pairs[base + q];
+      const int i = q / L;
+      pc = make_pair(trk_frame_off[t] + i, q - i * L, q, L, g, poses, frame_sf, sensors, sens, vs, pyr_off, pyr,
+                     lut_pool, pyr_flag);
       keep = pc.cull == 0;
     }
     const unsigned mask = __ballot_sync(0xffffffffu, keep);
@@ -1627,7 +1622,7 @@ extern "C" int occb200_annotate_batch(const occb200_annotate_args_t *a, int64_t 
         w.redo_list, w.redo_count, a->dims, a->sizes, a->status);
     OCC_KERNEL_OK("k_tracklet_setup");
     if (a->F > 0) {   // frames of corrected tracklets only (device-side list, usually short); in the fast path
-                      // this runs on the side stream, next to k_pair_setup, and joins before the ray-cast
+                      // this runs on the side stream, next to k_pair_build, and joins before the ray-cast
       cudaStream_t rs = stream;
       if (fast) {
         OCC_CUDA(cudaStreamWaitEvent(stream, side->join, 0));      // the side stream is idle from here on
@@ -1660,15 +1655,11 @@ extern "C" int occb200_annotate_batch(const occb200_annotate_args_t *a, int64_t 
   }
   if (fast) {
     ProfScope ps(kProfPairCull, stream);
-    const int64_t n_pairs = a->F * a->L;
-    k_pair_setup<<<(unsigned)ceil_div(n_pairs, 64), 64, 0, stream>>>(
-        n_pairs, a->L, a->poses, a->frame_sf, w.frame_trk, a->trk_frame_off, a->sensors, a->incl_pool, w.grids,
-        w.sens, a->voxel_size, w.pyr_off, w.pyr, w.lut_pool, w.pyr_flag, w.pairs);
-    OCC_KERNEL_OK("k_pair_setup");
-    k_pair_compact<<<(unsigned)a->T, 256, 0, stream>>>(a->T, a->L, a->trk_frame_off, a->label_off, w.grids,
-                                                                    w.pairs, w.sens, w.pairs_c, w.hot, w.item_map,
-                                                                    (long long)w.items_cap, w.counter, a->status);
-    OCC_KERNEL_OK("k_pair_compact");
+    k_pair_build<<<(unsigned)a->T, 256, 0, stream>>>(a->T, a->L, a->trk_frame_off, a->label_off, w.grids, a->poses,
+                                                     a->frame_sf, a->sensors, w.sens, a->voxel_size, w.pyr_off, w.pyr,
+                                                     w.lut_pool, w.pyr_flag, w.pairs_c, w.hot, w.item_map,
+                                                     (long long)w.items_cap, w.counter, a->status);
+    OCC_KERNEL_OK("k_pair_build");
   }
   if (fast && a->F > 0) OCC_CUDA(cudaStreamWaitEvent(stream, side->join, 0));   // redo pass done: bits and flags final
   {
