@@ -176,7 +176,10 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "tracklets_per_s", "value": val, "unit": "tracklets/s", "n_gpus": args.gpus,
             "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOADS[args.workload], "tracklets_per_step": T},
+            # the same workload keys as the CUDA arm's config (one batch per step; the CPU arm runs it on rank 0 only)
+            "config": {"workload": WORKLOADS[args.workload], "tracklets_per_step_per_gpu": T, "frames": B, "lidars": L,
+                       "voxel_size": batch.voxel_size,
+                       "ok_tracklets": sum(r["occ"] is not None for r in res)},
             "voxel_steps_per_s": ws["steps"] / dt,
             "cpu_baseline": {"value": val, "unit": "tracklets/s", "cores": threads, "kind": "port",
                              "sample": f"full {args.workload} batch ({T} tracklets) per step, {steps} steps, OpenMP over tracklets"},
