@@ -238,7 +238,8 @@ typedef struct occb200_annotate_args {
   void *workspace;
   int64_t workspace_bytes;        /* >= occb200_annotate_workspace_bytes(T, F, label_off[T], SF, L, incl_len, pyr_tiles, items_cap) */
   int32_t flags;                  /* bit 0: every visibility test in exact f64 (no f32 fast path);
-                                     bit 1: no (frame, LiDAR) pair culling                          */
+                                     bit 1: no (frame, LiDAR) pair culling;
+                                     bit 3: (tests) 64-entry recheck queue: overflowing tests are decided in place */
   int32_t pad1;
   int64_t max_label_slots;        /* max_t (label_off[t+1] - label_off[t]), from the host copy of label_off; sizes the
                                      shared-memory bitsets.  0 = unknown (the 32 KB maximum is requested)        */

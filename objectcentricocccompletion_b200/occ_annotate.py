@@ -32,6 +32,7 @@ LiDAR_NAME_LIST = ["TOP", "FRONT", "SIDE_LEFT", "SIDE_RIGHT", "REAR"]     # occ_
 STATUS_NAMES = {0: "ok", 1: "skip_short", 2: "no_points", 3: "empty_after_filter", 4: "index_error", -1: "slot_too_small"}
 FLAG_FORCE_F64 = 1
 FLAG_NO_CULL = 2
+FLAG_TINY_QUEUE = 8        # tests: forces the recheck-queue overflow path
 
 
 # ------------------------------------------------------------------------------------------------

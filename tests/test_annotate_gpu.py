@@ -249,3 +249,17 @@ def test_mean_var_vs_oracle_larger():
         if e is not None:
             np.testing.assert_allclose(g["mean_var"][..., :3], e[..., :3], rtol=1e-5, atol=1e-6)
             np.testing.assert_allclose(g["mean_var"][..., 3:], e[..., 3:], rtol=1e-5, atol=1e-7)
+
+
+def test_recheck_queue_overflow_path():
+    """With a 64-entry recheck queue almost every undecided test is decided in place by the exact f64 routine:
+    labels must not change."""
+    from objectcentricocccompletion_b200 import occ_annotate, synth
+    from tests.util import assert_same_results
+
+    batch = synth.make_batch(6, 14, 0.2, seed=1)
+    want = _cuda(batch)
+    got = _cuda(batch, flags=occ_annotate.FLAG_TINY_QUEUE)
+    assert_same_results(got, want, "tiny queue")
+    got = _cuda(batch, flags=occ_annotate.FLAG_TINY_QUEUE | occ_annotate.FLAG_NO_CULL)
+    assert_same_results(got, want, "tiny queue, no culling")
