@@ -44,6 +44,11 @@ inline int64_t align_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }
   } while (0)
 
 // Streaming (read-once) global loads: keep them out of L1 so the small hot tables stay there.
+__device__ __forceinline__ float2 ld_stream2(const float2 *p) {   // 8-byte streaming load (read once)
+  float2 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+  return v;
+}
 __device__ __forceinline__ float ld_stream(const float *p) {
   float v;
   asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
