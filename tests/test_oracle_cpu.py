@@ -213,3 +213,30 @@ def test_mirror_occ_label_oracle_matches_reference_ops():
         coors = torch.stack([mxx, vy, vz], -1).view(-1, 3)
         flat[unknown] = g[coors[unknown][:, 0], coors[unknown][:, 1], coors[unknown][:, 2]]
         assert (oracle.mirror_occ_label(g.numpy()) == flat.view(XS, YS, ZS).numpy()).all()
+
+
+def test_brick_cull_rule_is_safe_and_useful():
+    """docs/ROUND2_BRICK_CULL.md section 2 (round-2 design, CPU restatement only): a (brick, frame, LiDAR) triple the
+    rule masks never contains a voxel centre whose reference visibility test succeeds, and the rule removes a
+    sizeable share of the tests of the voxels that stay unknown."""
+    import numpy as np
+
+    from objectcentricocccompletion_b200 import synth
+    from oracle import brick_cull, oracle
+
+    batch = synth.make_batch(2, 10, 0.2, seed=4, small=True)
+    res = oracle.annotate_batch(batch)
+    unknown_tests = culled_tests = 0
+    for t, r in enumerate(res):
+        assert r["status"] == "ok"
+        vox, rows, cols, rng, free = brick_cull.centre_tests(batch, t, r)
+        for tile in [(1, 1), (2, 8)]:
+            bricks, masked = brick_cull.brick_cull_masks(batch, t, r, brick=4, tile=tile)
+            nby, nbz = int(bricks[:, 1].max()) + 1, int(bricks[:, 2].max()) + 1
+            b_of_vox = ((vox[:, 0] // 4) * nby + vox[:, 1] // 4) * nbz + vox[:, 2] // 4
+            m = masked[b_of_vox].transpose(1, 2, 0)                      # [B, L, n] like `free`
+            assert not (m & free).any(), "a masked triple holds a centre the reference would free"
+        still_unknown = r["occ"][vox[:, 0], vox[:, 1], vox[:, 2]] == 0
+        unknown_tests += int(still_unknown.sum()) * m.shape[0] * m.shape[1]
+        culled_tests += int(m[:, :, still_unknown].sum())
+    assert culled_tests > 0.3 * unknown_tests, (culled_tests, unknown_tests)
