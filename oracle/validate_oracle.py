@@ -164,13 +164,55 @@ def check_scatter(quick):
     return ok
 
 
+def check_mean_var(quick):
+    """--save-mean-var grids (occ_annotate.py:627-645): numpy restatement vs the torch op sequence on the reference
+    glue's own kept points and quantised coordinates."""
+    from objectcentricocccompletion_b200 import synth
+    from .make_golden import edge_batch
+
+    ncell = bad = 0
+    batches = [synth.make_batch(3, 12, 0.2, seed=1, small=True), edge_batch()]
+    if not quick:
+        batches.append(synth.make_batch(2, 14, 0.2, seed=6))
+    for b in batches:
+        mine = oracle.annotate_mean_var(b)
+        for m, r in zip(mine, torch_ref.annotate_batch(b)):
+            if r["occ"] is None:
+                bad += m is not None
+                continue
+            e = torch_ref.mean_var(r)
+            ncell += int((e != 0).any(-1).sum())
+            bad += int((m.view(np.uint32) != e.view(np.uint32)).any(-1).sum())
+    print(f"[6] mean/var grids: {ncell} filled cells, {bad} cells with a bit mismatch")
+    return bad == 0
+
+
+def check_mirror(quick):
+    """MirrorOccLabel (occ_pinelines.py:88-126): numpy restatement vs the reference's torch op sequence."""
+    rng = np.random.default_rng(5)
+    ok = True
+    for shape in [(11, 24, 9), (12, 23, 10), (1, 3, 2), (29, 120, 35)]:
+        g = torch.from_numpy(rng.integers(0, 3, shape).astype(np.int32))
+        XS, YS, ZS = g.shape
+        flat = g.clone().view(-1)
+        unknown = flat == 0
+        mid = XS // 2
+        vx, vy, vz = torch.meshgrid(torch.arange(XS), torch.arange(YS), torch.arange(ZS), indexing="ij")
+        coors = torch.stack([((vx + 0.5 - mid) * -1.0 + mid).long(), vy, vz], -1).view(-1, 3)
+        flat[unknown] = g[coors[unknown][:, 0], coors[unknown][:, 1], coors[unknown][:, 2]]
+        ok &= bool((oracle.mirror_occ_label(g.numpy()) == flat.view(XS, YS, ZS).numpy()).all())
+    print(f"[7] MirrorOccLabel vs the reference's torch ops ok={ok}")
+    return ok
+
+
 def main():
     quick = "--quick" in sys.argv
     assert torch_ref.available(), "needs /root/reference"
     _build.build_oracle()
     _build.build_ref()
     t0 = time.time()
-    res = [check_annotate(quick), check_projection(quick), check_points_in_boxes(quick), check_voxelize(quick), check_scatter(quick)]
+    res = [check_annotate(quick), check_projection(quick), check_points_in_boxes(quick), check_voxelize(quick), check_scatter(quick),
+           check_mean_var(quick), check_mirror(quick)]
     print(f"oracle pinned: {all(res)}  ({time.time() - t0:.1f}s)")
     return 0 if all(res) else 1
 
