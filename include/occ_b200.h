@@ -54,7 +54,9 @@ enum {
   OCCB200_SKIP_SHORT = 1,         /* len(trk) < 10: returns silently     (tools/occ/occ_annotate.py:344)  */
   OCCB200_NO_POINTS = 2,          /* AssertionError "no points"          (occ_annotate.py:129, 356-359)   */
   OCCB200_EMPTY_AFTER_FILTER = 3, /* max() of an empty tensor raises     (occ_annotate.py:433-435)        */
-  OCCB200_INDEX_ERROR = 4         /* quantised coord < -dims: IndexError (occ_annotate.py:436)            */
+  OCCB200_INDEX_ERROR = 4,        /* quantised coord < -dims: IndexError (occ_annotate.py:436)            */
+  OCCB200_WORK_OVERFLOW = 5       /* internal: the ray-cast work list did not fit args.items_cap (a host bound
+                                     was violated); the tracklet's labels are NOT valid                    */
 };
 
 /* ---- A1: points in boxes -------------------------------------------------------------- */
@@ -239,10 +241,25 @@ typedef struct occb200_annotate_args {
   int64_t workspace_bytes;        /* >= occb200_annotate_workspace_bytes(T, F, label_off[T], SF, L, incl_len, pyr_tiles, items_cap) */
   int32_t flags;                  /* bit 0: every visibility test in exact f64 (no f32 fast path);
                                      bit 1: no (frame, LiDAR) pair culling;
-                                     bit 3: (tests) 64-entry recheck queue: overflowing tests are decided in place */
+                                     bit 3: (tests) 64-entry recheck queue: overflowing tests are decided in place;
+                                     bit 4: no brick-level culling (A/B measurement, parity);
+                                     bit 5: scalar divisions as torch-CUDA evaluates them (x * (1/vs), see
+                                            DESIGN.md section 4: "which arithmetic") instead of the CPU's x / vs */
   int32_t pad1;
   int64_t max_label_slots;        /* max_t (label_off[t+1] - label_off[t]), from the host copy of label_off; sizes the
                                      shared-memory bitsets.  0 = unknown (the 32 KB maximum is requested)        */
+  /* ---- ABI v6: what the host already knows is passed in instead of being re-derived by small kernels ---- */
+  uint8_t *labels_u8;             /* optional second label output, one byte per voxel, same layout as `labels`
+                                     (the int32 of occ_annotate.py:581 is only needed at the file boundary);
+                                     `labels` may be NULL when this is given                                */
+  const int32_t *frame_trk;       /* [F] tracklet of each tracklet-frame                                    */
+  const int64_t *pyr_off;         /* [SF*L + 1] prefix sum of occb200_pyramid_tiles(H, W) over the sensors
+                                     (pyr_off[SF*L] == pyr_tiles); required when pyr_tiles > 0              */
+  const int64_t *table_off;       /* [n_tables] incl_off of every DISTINCT inclination table (the frames of a
+                                     segment share one table per LiDAR: occ_annotate.py:526-528)            */
+  const int32_t *table_H;         /* [n_tables] its length                                                  */
+  int32_t n_tables;
+  int32_t max_pairs;              /* max_t (frames of t) * L: sizes the per-brick pair masks                 */
 } occb200_annotate_args_t;
 
 int64_t occb200_annotate_workspace_bytes(int32_t T, int64_t F, int64_t total_label_slots, int64_t SF,

@@ -24,6 +24,8 @@ Everything is NumPy on the host and depends only on the seed.
 """
 from __future__ import annotations
 
+import ctypes as C
+import os
 from dataclasses import dataclass, field
 from typing import List, Optional, Sequence
 
@@ -58,6 +60,7 @@ class Tracklet:
     segment: int                           # index into TrackletBatch.segments
     frame_ids: np.ndarray                  # i32 [B] frame index inside the segment
     kind: str = "vehicle"
+    flat: Optional[np.ndarray] = None      # f32 [sum n_i, 3]: `points` as one contiguous array (views into it)
 
     def __len__(self) -> int:
         return self.boxes.shape[0]
@@ -335,6 +338,152 @@ class _Renderer:
 
 
 # --------------------------------------------------------------------------
+# the same renderer with its per-pixel loops in C (csrc/synth_render.c, OpenMP): bit-identical output,
+# ~20x faster -- what makes the 10 000-tracklet job (BASELINE configs[4]) generable in seconds
+# --------------------------------------------------------------------------
+class _CLidar(C.Structure):
+    _fields_ = [("H", C.c_int32), ("W", C.c_int32), ("max_range", C.c_double), ("o", C.c_double * 3),
+                ("dirs", C.c_void_p), ("img", C.c_void_p), ("img32", C.c_void_p)]
+
+
+_WIN_DTYPE = np.dtype([("ok", "<i4"), ("r_lo", "<i4"), ("r_hi", "<i4"), ("ncols", "<i4")])
+_SYNTH_LIB = None
+
+
+def fast_lib():
+    """csrc/libocc_synth.so (built by `make` next to libocc_b200.so) or None."""
+    global _SYNTH_LIB
+    if _SYNTH_LIB is None:
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libocc_synth.so")
+        if not os.path.exists(path) or os.environ.get("OCCB200_SYNTH_NUMPY"):
+            _SYNTH_LIB = False
+        else:
+            L = C.CDLL(path)
+            vp = C.c_void_p
+            L.synth_render_objects.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp]
+            L.synth_render_objects.restype = None
+            L.synth_candidate_points.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp, C.c_double, vp, vp, vp, vp, vp]
+            L.synth_candidate_points.restype = None
+            L.synth_f64_to_f32.argtypes = [vp, vp, C.c_int64]
+            L.synth_f64_to_f32.restype = None
+            L.synth_repeat.argtypes = [vp, vp, C.c_int64, C.c_int]
+            L.synth_repeat.restype = None
+            _SYNTH_LIB = L
+    return _SYNTH_LIB or None
+
+
+class _FastRenderer:
+    """`_Renderer` with all objects of a segment handled per call: the windows of every object are derived
+    with the array expressions of `_Renderer._window` (vectorised over objects), the pixel loops run in C."""
+
+    def __init__(self, rig, num_frames):
+        self.lib = fast_lib()
+        self.rig = rig
+        self.B = num_frames
+        self.rays = [_pixel_rays(l) for l in rig]
+        self.dirs = [np.ascontiguousarray(d) for _, d, _ in self.rays]
+        self.images = []
+        for lidar, (o, d, fov) in zip(rig, self.rays):
+            base = np.ascontiguousarray(_base_image(o, d, fov, lidar["max_range"]))
+            img = np.empty((num_frames,) + base.shape, np.float64)
+            self.lib.synth_repeat(base.ctypes.data, img.ctypes.data, base.size, num_frames)
+            self.images.append(img)
+        self.images32 = None
+        self.incl_flip = [l["incl"].astype(np.float64)[::-1] for l in rig]
+
+    def _lidars(self):
+        arr = (_CLidar * len(self.rig))()
+        for li, lidar in enumerate(self.rig):
+            a = arr[li]
+            a.H, a.W, a.max_range = lidar["H"], lidar["W"], float(lidar["max_range"])
+            for k in range(3):
+                a.o[k] = float(self.rays[li][0][k])
+            a.dirs = self.dirs[li].ctypes.data
+            a.img = self.images[li].ctypes.data if self.images[li] is not None else None
+            a.img32 = self.images32[li].ctypes.data if self.images32 is not None else None
+        return arr
+
+    def _windows(self, boxes, pad):
+        """`_Renderer._window` for boxes [O,B,7] and every LiDAR: (win [O,L] records, col0 [O,L,B])."""
+        O, B = boxes.shape[:2]
+        L = len(self.rig)
+        win = np.zeros((O, L), _WIN_DTYPE)
+        col0 = np.zeros((O, L, B), np.int64)
+        if O == 0:
+            return win, col0
+        corners = _box_corners(boxes, pad_xy=pad, pad_z=pad)                  # O,B,8,3
+        ctr = boxes[..., :3].copy()
+        ctr[..., 2] += 0.5 * boxes[..., 5]
+        diag = 0.5 * np.linalg.norm(boxes[..., 3:6], axis=-1).max(-1)          # O
+        for li, lidar in enumerate(self.rig):
+            H, W = lidar["H"], lidar["W"]
+            inc, col, rng = _project_window(lidar, corners)                    # O,B,8
+            _, col_c, rng_c = _project_window(lidar, ctr)                      # O,B
+            ok = ~(rng.min((1, 2)) < 1.0)
+            ok &= ~(rng_c.min(1) - diag - pad > lidar["max_range"])
+            dcol = (col - col_c[..., None] + W / 2) % W - W / 2
+            half = np.ceil(np.abs(dcol).max((1, 2))).astype(np.int64) + 2      # O
+            full = 2 * half + 1 >= W
+            incf = self.incl_flip[li]
+            step = np.abs(np.diff(incf)).max()
+            lo, hi = inc.min((1, 2)) - step, inc.max((1, 2)) + step            # O
+            sel = (incf[None] >= lo[:, None]) & (incf[None] <= hi[:, None])    # O,H (incf is monotone: one run)
+            ok &= sel.any(1)
+            win["ok"][:, li] = ok
+            win["r_lo"][:, li] = sel.argmax(1)
+            win["r_hi"][:, li] = H - 1 - sel[:, ::-1].argmax(1)
+            win["ncols"][:, li] = np.where(full, W, 2 * half + 1)
+            col0[:, li] = np.where(full[:, None], 0, np.round(col_c).astype(np.int64) - half[:, None])
+        return win, col0
+
+    def add_objects(self, objs):
+        """objs: list of (boxes f64 [B,7], size_true [3], shape dict, frames bool [B] or None)."""
+        if not objs:
+            return
+        boxes = np.ascontiguousarray(np.stack([o[0] for o in objs]), np.float64)
+        rz = boxes[:, :, None, None, :][..., 6]
+        cs = np.ascontiguousarray(np.stack([np.cos(rz), np.sin(rz)], -1).reshape(len(objs), self.B, 2))
+        size = np.ascontiguousarray(np.stack([np.asarray(o[1], np.float64).reshape(3) for o in objs]))
+        keys = ("shrink", "body_h", "cab_w", "cab_back", "cab_front")
+        shape = np.ascontiguousarray([[float(o[2][k]) for k in keys] for o in objs], np.float64)
+        frames = np.ascontiguousarray(np.stack([np.ones(self.B, bool) if o[3] is None else o[3] for o in objs])
+                                      .astype(np.uint8))
+        win, col0 = self._windows(boxes, 0.0)
+        lid = self._lidars()
+        self.lib.synth_render_objects(C.addressof(lid), len(self.rig), self.B, len(objs),
+                                      boxes.ctypes.data, cs.ctypes.data, size.ctypes.data, shape.ctypes.data,
+                                      frames.ctypes.data, win.ctypes.data, col0.ctypes.data)
+
+    def finish(self):
+        """f64 working images -> the segment's f32 range images."""
+        self.images32 = []
+        for img in self.images:
+            out = np.empty(img.shape, np.float32)
+            self.lib.synth_f64_to_f32(img.ctypes.data, out.ctypes.data, img.size)
+            self.images32.append(out)
+        self.images = [None] * len(self.images32)      # the f64 copies are not needed any more
+        return self.images32
+
+    def candidate_points_all(self, boxes, pad=1.0):
+        """boxes f64 [O,B,7] -> (flat f32 [P,3], counts i64 [O,B]) in (object, frame, LiDAR, row, col) order."""
+        boxes = np.ascontiguousarray(boxes, np.float64)
+        O = boxes.shape[0]
+        rz = boxes[:, :, None, None, :][..., 6]
+        cs = np.ascontiguousarray(np.stack([np.cos(rz), np.sin(rz)], -1).reshape(O, self.B, 2))
+        win, col0 = self._windows(boxes, pad)
+        counts = np.zeros((O, self.B), np.int64)
+        lid = self._lidars()
+        args = (C.addressof(lid), len(self.rig), self.B, O, boxes.ctypes.data, cs.ctypes.data, float(pad),
+                win.ctypes.data, col0.ctypes.data)
+        self.lib.synth_candidate_points(*args, counts.ctypes.data, None, None)
+        off = np.zeros(O * self.B + 1, np.int64)
+        np.cumsum(counts.reshape(-1), out=off[1:])
+        flat = np.empty((int(off[-1]), 3), np.float32)
+        self.lib.synth_candidate_points(*args, None, off.ctypes.data, flat.ctypes.data)
+        return flat, counts
+
+
+# --------------------------------------------------------------------------
 # trajectories
 # --------------------------------------------------------------------------
 _KINDS = {
@@ -368,7 +517,7 @@ def _sample_track(rng, B, kind, extent, others, min_range=9.0, max_range=40.0):
         dist = np.linalg.norm(xy, axis=1)
         if dist.min() < min_range + 0.5 * size[1] or dist.max() > max_range:
             continue
-        if others and min(np.linalg.norm(xy - o[:, :2], axis=1).min() for o in others) < 0.5 * size[1] + 3.0:
+        if len(others) and np.linalg.norm(xy[None] - others[:, :, :2], axis=2).min() < 0.5 * size[1] + 3.0:
             continue
         boxes = np.zeros((B, 7))
         boxes[:, :2] = xy
@@ -383,22 +532,26 @@ def _sample_track(rng, B, kind, extent, others, min_range=9.0, max_range=40.0):
 # public builders
 # --------------------------------------------------------------------------
 def make_segment(rng, num_objects, num_frames, kind="vehicle", extent=40.0,
-                 small=False, occluder_prob=0.3):
-    """One segment with ``num_objects`` tracklets.  Returns (Segment, [boxes f32 [B,7]], [points])."""
+                 small=False, occluder_prob=0.3, fast=None):
+    """One segment with ``num_objects`` tracklets.  Returns (Segment, [boxes f32 [B,7]], [points], [flat]).
+
+    ``fast`` selects the C pixel loops (default: when csrc/libocc_synth.so is built); both paths consume the
+    random stream identically and produce the same bits."""
+    if fast is None:
+        fast = fast_lib() is not None
     rig = lidar_rig(rng, small=small)
-    ren = _Renderer(rig, num_frames)
     tracks, sizes, shapes = [], [], []
+    placed = np.zeros((0, num_frames, 7))
     for _ in range(num_objects):
-        boxes, size = _sample_track(rng, num_frames, kind, extent, tracks)
+        boxes, size = _sample_track(rng, num_frames, kind, extent, placed)
         tracks.append(boxes)
+        placed = np.concatenate([placed, boxes[None]], 0)
         sizes.append(size)
         shapes.append(dict(shrink=rng.uniform(0.88, 0.97), body_h=rng.uniform(0.45, 0.65),
                            cab_w=rng.uniform(0.75, 0.9), cab_back=rng.uniform(0.5, 0.9),
                            cab_front=rng.uniform(0.1, 0.5)))
     boxes32 = [b.astype(np.float32) for b in tracks]
-    for b32, size, shape in zip(boxes32, sizes, shapes):
-        b64 = b32.astype(np.float64)
-        ren.add_object(b64, np.broadcast_to(size, (num_frames, 3)), shape)
+    objs = [(b32.astype(np.float64), size, shape, None) for b32, size, shape in zip(boxes32, sizes, shapes)]
     # occluder slabs between the TOP LiDAR and a random object, in a subset of frames
     top_o = rig[0]["extrinsic"][:3, 3].astype(np.float64)
     for b32 in boxes32:
@@ -414,42 +567,75 @@ def make_segment(rng, num_objects, num_frames, kind="vehicle", extent=40.0,
         occ[:, 6] = rng.uniform(-np.pi, np.pi)
         if np.linalg.norm(occ[:, :2], axis=1).min() < 5.5:
             continue
-        ren.add_object(occ, occ[:, 3:6], dict(shrink=1.0, body_h=1.0, cab_w=0.0, cab_back=0.0, cab_front=0.0), frames)
-    points = [ren.candidate_points(b32.astype(np.float64)) for b32 in boxes32]
+        objs.append((occ, occ[0, 3:6].copy(), dict(shrink=1.0, body_h=1.0, cab_w=0.0, cab_back=0.0, cab_front=0.0),
+                     frames))
+    if fast:
+        ren = _FastRenderer(rig, num_frames)
+        ren.add_objects(objs)
+        images = ren.finish()
+        flat, counts = ren.candidate_points_all(np.stack([o[0] for o in objs[:num_objects]]) if num_objects
+                                                else np.zeros((0, num_frames, 7)))
+        bounds = np.concatenate([[0], np.cumsum(counts.reshape(-1))])
+        points, flats = [], []
+        for k in range(num_objects):
+            lo = k * num_frames
+            points.append([flat[bounds[lo + b]:bounds[lo + b + 1]] for b in range(num_frames)])
+            flats.append(flat[bounds[lo]:bounds[lo + num_frames]])
+    else:
+        ren = _Renderer(rig, num_frames)
+        for b64, size, shape, frames in objs:
+            ren.add_object(b64, np.broadcast_to(size, (num_frames, 3)), shape, frames)
+        points = [ren.candidate_points(b32.astype(np.float64)) for b32 in boxes32]
+        flats = [None] * num_objects
+        images = [img.astype(np.float32) for img in ren.images]
     E = np.stack([l["extrinsic"] for l in rig], 0)
     seg = Segment(
         extrinsics=np.ascontiguousarray(np.broadcast_to(E[None], (num_frames, NUM_LIDARS, 4, 4))).copy(),
         inclinations=[l["incl"].copy() for l in rig],
-        range_images=[img.astype(np.float32) for img in ren.images],
+        range_images=images,
     )
-    return seg, boxes32, points
+    return seg, boxes32, points, flats
+
+
+def segment_rng(seed, index):
+    """Random stream of segment ``index`` of a batch: segments are independent, so a rank can generate just its own."""
+    return np.random.default_rng(seed) if index == 0 else np.random.default_rng([int(seed), int(index)])
 
 
 def make_batch(num_tracklets, num_frames, voxel_size=0.2, kind="vehicle", seed=0,
-               tracklets_per_segment=None, small=False, extent=None, occluder_prob=0.3):
-    """``num_tracklets`` tracklets of ``num_frames`` frames spread over shared segments."""
-    rng = np.random.default_rng(seed)
+               tracklets_per_segment=None, small=False, extent=None, occluder_prob=0.3, fast=None,
+               only_segments=None):
+    """``num_tracklets`` tracklets of ``num_frames`` frames spread over shared segments.
+
+    ``only_segments``: iterable of segment indices to generate (the others are skipped entirely; the tracklets
+    returned are those of the generated segments, ``Tracklet.segment`` indexing the returned segment list, and
+    ``meta['global_tracklets']`` their indices in the full batch)."""
     tps = tracklets_per_segment or num_tracklets
     if extent is None:
         extent = 40.0
-    segments, tracklets = [], []
-    remaining = num_tracklets
-    while remaining > 0:
-        k = min(tps, remaining)
-        seg, boxes, points = make_segment(rng, k, num_frames, kind=kind, extent=extent,
-                                          small=small, occluder_prob=occluder_prob)
+    nseg = (num_tracklets + tps - 1) // tps if num_tracklets else 0
+    want = list(range(nseg)) if only_segments is None else sorted(int(i) for i in only_segments)
+    segments, tracklets, gidx = [], [], []
+    for i in want:
+        k = min(tps, num_tracklets - i * tps)
+        seg, boxes, points, flats = make_segment(segment_rng(seed, i), k, num_frames, kind=kind, extent=extent,
+                                                 small=small, occluder_prob=occluder_prob, fast=fast)
         si = len(segments)
         segments.append(seg)
-        for b, p in zip(boxes, points):
+        for j, (b, p, fl) in enumerate(zip(boxes, points, flats)):
             tracklets.append(Tracklet(boxes=b, points=p, segment=si,
-                                      frame_ids=np.arange(num_frames, dtype=np.int32), kind=kind))
-        remaining -= k
+                                      frame_ids=np.arange(num_frames, dtype=np.int32), kind=kind, flat=fl))
+            gidx.append(i * tps + j)
     return TrackletBatch(segments=segments, tracklets=tracklets, voxel_size=float(voxel_size),
-                         meta=dict(seed=seed, kind=kind, num_frames=num_frames))
+                         meta=dict(seed=seed, kind=kind, num_frames=num_frames, num_segments=nseg,
+                                   segment_ids=want, global_tracklets=gidx))
 
 
 # BASELINE.json configs (SURVEY.md section 8 sizes)
-def config_batch(name: str, seed: int = 0, small: bool = False) -> TrackletBatch:
+C5_TRACKLETS, C5_PER_SEGMENT = 10000, 64
+
+
+def config_batch(name: str, seed: int = 0, small: bool = False, only_segments=None) -> TrackletBatch:
     name = name.lower()
     if name == "c1":      # 1 vehicle tracklet, 20 frames, 0.2 m
         return make_batch(1, 20, 0.2, "vehicle", seed, small=small)
@@ -458,9 +644,11 @@ def config_batch(name: str, seed: int = 0, small: bool = False) -> TrackletBatch
     if name == "c3":      # truck / bus boxes at 0.1 m
         return make_batch(16, 40, 0.1, "large", seed, tracklets_per_segment=16, small=small)
     if name == "c5":      # 10k C2-shaped tracklets
-        return make_batch(10000, 40, 0.2, "vehicle", seed, tracklets_per_segment=64, small=small)
+        return make_batch(C5_TRACKLETS, 40, 0.2, "vehicle", seed, tracklets_per_segment=C5_PER_SEGMENT, small=small,
+                          only_segments=only_segments)
     if name == "c5s":     # 1/10 of C5 for quick scaling checks
-        return make_batch(1024, 40, 0.2, "vehicle", seed, tracklets_per_segment=64, small=small)
+        return make_batch(1024, 40, 0.2, "vehicle", seed, tracklets_per_segment=64, small=small,
+                          only_segments=only_segments)
     raise ValueError(f"unknown config {name}")
 
 
