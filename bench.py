@@ -356,7 +356,7 @@ def main():
     sec = ms / 1e3 / args.steps
     sec_e2e = ms_e2e / 1e3 / args.steps
     peak, peak_src = peaks()
-    vis_ms = kms[4] / max(kn[4], 1)
+    vis_ms = (kms[4] + kms[3]) / max(kn[4], 1)            # the ray-cast: k_brick_cull + k_visibility
     achieved = ws["vis_bytes"] / (vis_ms / 1e3) / 1e9 if vis_ms > 0 else 0.0
     step_ms_prof = kms.sum() / max(kn[4], 1)
 
@@ -388,9 +388,9 @@ def main():
                      "frac": achieved / peak, "traffic": ncu_traffic() if args.workload == "c2" else None, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": ws["vis_bytes"], "kernel_ms": vis_ms,
                      "kernel_share_of_step": vis_ms / step_ms_prof if step_ms_prof else None,
-                     "kernels_ms": dict(zip(("k_tracklet_presetup", "k_tracklet_setup+redo", "k_scan_chunks", "k_frame_voxelize",
-                                             "k_visibility", "side:k_table_setup+k_pyr_scan+k_pyr_build",
-                                             "k_visibility_recheck", "k_pair_build"),
+                     "kernels_ms": dict(zip(("k_crop_voxelize", "k_tracklet_setup+redo", "k_scan_chunks", "k_brick_cull",
+                                             "k_visibility", "side:k_pyr_build+k_table_setup",
+                                             "k_visibility_recheck", "k_pair_build", "k_labels"),
                                             (kms / np.maximum(kn[4], 1)).round(5).tolist()))},
         "cpu_baseline": cpu, "clocks": clocks,
     }

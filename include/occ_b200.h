@@ -40,8 +40,9 @@ int64_t occb200_launch_count(void);
 void occb200_profile_enable(int on);
 int occb200_profile_kinds(void);
 int occb200_profile_read(double *ms_per_kind, int64_t *launches_per_kind);
-/* Self-test: maximum |atan2_fast(y,x) - atan2(y,x)| (radians) of the f32 arctangent used by the fast
- * visibility kernel over n pseudo-random pairs; must stay below the 2e-6 the kernel's margins assume.
+/* Self-test of the f32 arctangents of the fast visibility kernel over n pseudo-random pairs (radians):
+ * max_err_host[0] = max |atan2_fast(y,x) - atan2(y,x)| (full quadrant; the margins assume 2e-6),
+ * max_err_host[1] = the same for the narrow path (x > 0, |y| <= x; the margins assume 1e-6).
  * Synchronises `stream`. */
 int occb200_selftest_atan2(int64_t n, uint64_t seed, double *max_err_host, void *stream);
 
@@ -227,7 +228,7 @@ typedef struct occb200_annotate_args {
   int64_t incl_len;               /* floats in incl_pool                                      */
   const float *ri_pool;
   int64_t pyr_tiles;              /* sum of occb200_pyramid_tiles(H, W) over the SF*L sensors; 0 = no pair culling */
-  int64_t items_cap;              /* occb200_annotate_items_cap(T, label_off, trk_frame_off, L) from the host copies */
+  int64_t items_cap;              /* reserved (ABI v5: bound of the work list; v6 sizes it from `bricks`)   */
   double voxel_size;              /* python float of --voxel-size (occ_annotate.py:215)       */
   const int64_t *label_off;       /* [T+1] slot of each tracklet in labels; slot size >= prod(ceil(max_frames(size)/vs)) */
   /* outputs */
@@ -238,7 +239,7 @@ typedef struct occb200_annotate_args {
   int64_t *n_unknown;             /* [T]    voxels tested for visibility (U)                  */
   int64_t *n_steps;               /* [T]    visibility tests actually evaluated (<= U*B*L; early exit) ; may be NULL */
   void *workspace;
-  int64_t workspace_bytes;        /* >= occb200_annotate_workspace_bytes(T, F, label_off[T], SF, L, incl_len, pyr_tiles, items_cap) */
+  int64_t workspace_bytes;        /* >= occb200_annotate_workspace_bytes(T, F, label_off[T], SF, L, incl_len, pyr_tiles, bricks, max_pairs) */
   int32_t flags;                  /* bit 0: every visibility test in exact f64 (no f32 fast path);
                                      bit 1: no (frame, LiDAR) pair culling;
                                      bit 3: (tests) 64-entry recheck queue: overflowing tests are decided in place;
@@ -259,13 +260,19 @@ typedef struct occb200_annotate_args {
                                      segment share one table per LiDAR: occ_annotate.py:526-528)            */
   const int32_t *table_H;         /* [n_tables] its length                                                  */
   int32_t n_tables;
-  int32_t max_pairs;              /* max_t (frames of t) * L: sizes the per-brick pair masks                 */
+  int32_t max_pairs;              /* max_t (frames of t) * L (<= 4096): sizes the per-brick pair masks and the
+                                     work lists                                                             */
+  const int64_t *brick_off;       /* [T+1] prefix sum of occb200_grid_bricks() over the tracklets' label slots
+                                     (the grid upper bound the slot was sized with): 4x4x4-voxel bricks are
+                                     the unit of work and of culling in the ray-cast                        */
+  int64_t bricks;                 /* brick_off[T], from the host copy                                        */
 } occb200_annotate_args_t;
 
 int64_t occb200_annotate_workspace_bytes(int32_t T, int64_t F, int64_t total_label_slots, int64_t SF,
-                                         int32_t L, int64_t incl_len, int64_t pyr_tiles, int64_t items_cap);
-/* HOST helper: upper bound of the ray-cast kernel's work items (for args.items_cap); HOST arrays. */
-int64_t occb200_annotate_items_cap(int32_t T, const int64_t *label_off, const int64_t *trk_frame_off, int32_t L);
+                                         int32_t L, int64_t incl_len, int64_t pyr_tiles, int64_t bricks,
+                                         int32_t max_pairs);
+/* HOST helper: 4x4x4-voxel bricks of a grid of X x Y x Z voxels (for args.brick_off). */
+int64_t occb200_grid_bricks(int32_t X, int32_t Y, int32_t Z);
 /* HOST helper: tiles the max-pyramid of one H x W range image needs (for args.pyr_tiles). */
 int64_t occb200_pyramid_tiles(int32_t H, int32_t W);
 

@@ -17,7 +17,7 @@ LIB_PATH = os.environ.get("OCCB200_LIB", os.path.join(CSRC, "libocc_b200.so"))
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "occ_b200.h")
 
 vp, i32, i64, f32, f64 = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_double
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 
 class Pose(C.Structure):
@@ -35,7 +35,9 @@ class AnnotateArgs(C.Structure):
                 ("points", vp), ("point_stride", i32), ("pad0", i32), ("frame_pt_off", vp), ("sensors", vp),
                 ("SF", i64), ("incl_pool", vp), ("incl_len", i64), ("ri_pool", vp), ("pyr_tiles", i64), ("items_cap", i64), ("voxel_size", f64), ("label_off", vp), ("labels", vp),
                 ("dims", vp), ("sizes", vp), ("status", vp), ("n_unknown", vp), ("n_steps", vp), ("workspace", vp),
-                ("workspace_bytes", i64), ("flags", i32), ("pad1", i32), ("max_label_slots", i64)]
+                ("workspace_bytes", i64), ("flags", i32), ("pad1", i32), ("max_label_slots", i64),
+                ("labels_u8", vp), ("frame_trk", vp), ("pyr_off", vp), ("table_off", vp), ("table_H", vp),
+                ("n_tables", i32), ("max_pairs", i32), ("brick_off", vp), ("bricks", i64)]
 
 
 POSE_DTYPE = np.dtype([("box", "<f4", (7,)), ("cos_pib", "<f4"), ("sin_pib", "<f4"), ("cos_m", "<f4"),
@@ -74,8 +76,8 @@ SIGNATURES = {
     "occb200_quantize_points": (C.c_int, [vp, i64, vp, C.c_int, vp, f32, vp, vp, C.c_int, vp, vp, vp]),
     "occb200_dense_voxel_centers": (C.c_int, [vp, vp, vp, C.c_int, i64, f32, vp, vp, vp, vp]),
     "occb200_mirror_occ_label": (C.c_int, [vp, vp, vp, vp, i32, i64, vp, vp]),
-    "occb200_annotate_workspace_bytes": (i64, [i32, i64, i64, i64, i32, i64, i64, i64]),
-    "occb200_annotate_items_cap": (i64, [i32, vp, vp, i32]),
+    "occb200_annotate_workspace_bytes": (i64, [i32, i64, i64, i64, i32, i64, i64, i64, i32]),
+    "occb200_grid_bricks": (i64, [i32, i32, i32]),
     "occb200_pyramid_tiles": (i64, [i32, i32]),
     "occb200_annotate_batch": (C.c_int, [C.POINTER(AnnotateArgs), i64, vp]),
     "occb200_annotate_queue_stats": (C.c_int, [C.POINTER(AnnotateArgs), i64, vp, vp]),

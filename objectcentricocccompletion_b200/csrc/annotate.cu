@@ -3,16 +3,25 @@
 // Reference path: tools/occ/occ_annotate.py get_local_point_list :91-138 and
 // OccAnnotator.annotate_trk :344-568 (normative step list: SURVEY.md Appendix A).
 //
-// Kernels (all on the caller's stream, no host synchronisation):
-//   k_tracklet_presetup  one warp per tracklet: optimistic grid (box size = max over all frames)
-//   k_frame_voxelize  one CTA per tracklet-frame: in-box -> box frame -> quantise -> bitset (A1/A2/A3)
+// Kernels (two streams with fork/join events, no host synchronisation; the whole call is capturable in a graph):
+//   main:  memset -> k_crop_voxelize -> k_tracklet_setup -> k_pair_build -> k_brick_cull -> k_visibility
+//          -> k_visibility_recheck -> k_labels
+//   side:  k_pyr_build (range-image max pyramid, two levels), k_table_setup (row lookup tables); later the
+//          re-voxelisation of the (rare) tracklets whose optimistic grid was wrong
+//
+//   k_crop_voxelize   one CTA per group of tracklet-frames: grid of the tracklet, in-box test, box frame,
+//                     quantise, bitset (A1/A2/A3)
 //   k_tracklet_setup  one warp per tracklet: box size = max over KEPT frames; rare re-voxelisation (A2/A3)
-//   k_scan_chunks     one CTA: exclusive scan of per-tracklet work chunks -> work list
-//   k_table_setup     one CTA per (sensor frame, LiDAR): inclination row boundaries + lookup table
-//   k_pair_build      one CTA per tracklet, one thread per (frame, LiDAR): voxel-index -> sensor-frame affine map,
-//   k_visibility_fast persistent CTAs over 32-voxel chunks: the range-image "ray-cast" in f32 with
-//                     rigorous error margins; tests whose outcome is not certain are queued    (A4/A5)
+//   k_table_setup     one CTA per DISTINCT inclination table: row boundaries + 8-byte lookup cells
+//   k_pyr_build       max of every 8x32 and 2x8 pixel tile of every range image
+//   k_pair_build      one CTA per tracklet, one thread per (frame, LiDAR): voxel-index -> sensor-frame affine map
+//                     (rotated so that the object sits on +x), pair-level cull, work items
+//   k_brick_cull      one thread per (4x4x4-voxel brick, surviving pair): proves "no voxel of the brick can be
+//                     free through this pair" from the fine pyramid level -> one mask bit
+//   k_visibility      persistent warps over (brick, 16-pair slice) items: the range-image "ray-cast" in f32 with
+//                     rigorous error margins; tests whose outcome is not certain are queued               (A4/A5)
 //   k_visibility_recheck  the queued tests, re-evaluated with the reference's exact f64 arithmetic
+//   k_labels          labels from the occupancy and free bitsets
 //   k_visibility_f64  (flags bit 0) every test in exact f64 -- the slow, margin-free formulation
 //
 // Why the fast kernel is still bit-exact.  Per test the reference takes three discrete decisions from
@@ -22,6 +31,8 @@
 // (derived at each use below).  A decision is accepted only if it stays the same anywhere inside that
 // bound; otherwise the test goes to a queue and k_visibility_recheck redoes it with project_exact().
 // Labels therefore never depend on f32 rounding; only the amount of rechecked work does.
+// tools/experiments/fast_test_v2_emulate.py is a numpy f32 port of make_pair / k_table_setup / fast_test
+// checked against the oracle's exact per-voxel decisions on the CPU.
 #include <math.h>
 
 #include <mutex>
@@ -33,31 +44,23 @@
 namespace occb200 {
 
 constexpr int kChunk = 256;         // f64 kernel: voxels per work item == threads per CTA
-#ifndef OCC_VPL
-#define OCC_VPL 2
-#endif
+constexpr int kFastWarps = 8;       // fast kernel: independent warps per CTA
 #ifndef OCC_MINB
 #define OCC_MINB 4
 #endif
-constexpr int kVPL = OCC_VPL;       // fast kernel, phase 2: voxels per lane
-#ifndef OCC_VPL1
-#define OCC_VPL1 2
-#endif
-constexpr int kVPL1 = OCC_VPL1;     // fast kernel, phase 1: voxels per lane
-constexpr int kFastChunk = 32 * kVPL;   // fast kernel: voxels per work item
-constexpr int kFastWarps = 8;       // fast kernel: independent warps per CTA
 #ifndef OCC_PPI
 #define OCC_PPI 16
 #endif
-constexpr int kPairsPerItem = OCC_PPI;   // fast kernel: (frame, LiDAR) pairs one work item covers for its 64 voxels
-#ifndef OCC_P1
-#define OCC_P1 8
-#endif
-constexpr int kPhase1Pairs = OCC_P1;     // pairs tested on EVERY non-occupied voxel before the survivors are compacted
-constexpr float kAtanErr = 2.0e-6f;     // bound on |atan2_fast - atan2| (derivation at atan2_fast)
+constexpr int kPairsPerItem = OCC_PPI;   // (frame, LiDAR) pairs one work item covers for its brick; divides 32
+static_assert(32 % OCC_PPI == 0, "a slice of pairs must sit inside one 32-bit mask word");
+constexpr int kMaxSlices = 256;          // => at most 4096 pairs (frames x LiDARs) per tracklet on the fast path
+constexpr float kAtanNarrow = 1.0e-6f;   // bound on |atan_poly(t) - atan(t)|, |t| <= 1 (derivation at atan_narrow)
+constexpr float kAtanWide = 2.0e-6f;     // bound on |atan2_fast - atan2| (derivation at atan2_fast)
 constexpr int kFrameStride = 8;          // pair order: frames 0,8,16,.. then 1,9,17,.. (spread viewpoints come first)
-constexpr int kLutPerRow = 64;      // lookup-table cells reserved per inclination-table entry
-constexpr int kTileR = 8, kTileC = 32;   // range-image max-pyramid tile (rows x columns)
+constexpr int kLutPerRow = 64;           // lookup-table cells reserved per inclination-table entry
+constexpr int kTileR = 8, kTileC = 32;   // range-image max-pyramid tile (rows x columns): pair-level cull
+constexpr int kFineR = 2, kFineC = 8;    // second pyramid level: brick-level cull; 16 fine tiles per coarse tile
+constexpr int kBrick = 4;                // brick edge in voxels: 64 voxels = 2 per lane of one warp
 #ifndef OCC_FT
 #define OCC_FT 256
 #endif
@@ -65,6 +68,7 @@ constexpr int kTileR = 8, kTileC = 32;   // range-image max-pyramid tile (rows x
 #define OCC_FMINB 6
 #endif
 constexpr int kFrameThreads = OCC_FT;
+constexpr int kMaxGroup = 8;             // tracklet-frames one crop CTA handles at most
 constexpr int kSmemBitWords = 8192; // 32 KB: grids up to 262 144 voxels keep their bitset in shared memory; the
                                     // launch asks only for what the largest grid of the batch needs
 
@@ -77,172 +81,171 @@ struct TrkGrid {
   int64_t bits_off; // word offset of the occupancy bitset
   int32_t nchunks;
   int32_t B;
-  int32_t redo;     // 1: the optimistic grid was wrong, k_frame_voxelize runs again for this tracklet
+  int32_t redo;     // 1: the optimistic grid was wrong, the crop kernel runs again for this tracklet
   int32_t pad;
 };
 
-// Per (sensor frame, LiDAR) constants of the fast path.  64 bytes, 4 x LDG.128.
-// Row lookup happens in "u space": u(inc) = sin/(|sin| + cos), monotone with slope in [1/2, 1] over
-// [-90, 90] degrees, so row boundaries never bunch up (unlike tan or sin).
-struct __align__(16) SensCoef {
-  float azc;
-  float kcol;       // W / (2 pi)
-  float Wf;
-  float c_col;      // evaluation error of the f32 column coordinate (pixels)
-  float u_lo, inv_w;   // lookup cell k covers [u_lo + k/inv_w, u_lo + (k+1)/inv_w); the cells span all of [-1, 1]
+// Per DISTINCT inclination table (stored at the table's offset in incl_pool).  Row lookup happens in "u space":
+// u(inc) = sin/(|sin| + cos), monotone with slope in [1/2, 1] over [-90, 90] degrees, so row boundaries never
+// bunch up (unlike tan or sin).  Cell k of the lookup table is centred on u_k = (k - cell0m) / inv_w.
+struct __align__(16) TabCoef {
+  float inv_w;      // 1 / cell width; the cell width is half the closest pair of boundaries
+  float cell0m;     // cell = rn(fma(u, inv_w, cell0m))
+  float w;          // cell width
   int32_t ncell;
   int32_t H;
-  int32_t W;
-  int32_t ok;       // 0: no fast path for this sensor (table not strictly descending, H < 2, ...)
-  int32_t tab_off;  // == incl_off: the table sits at 2*tab_off+1 in ub_pool (sentinels around it) and at
-                    // kLutPerRow*tab_off in lut_pool
-  float cell0;      // -u_lo * inv_w: cell = int(fma(u, inv_w, cell0))
-  int64_t ri_off;
-  float col0;       // W/2 - 0.5: colf = fma(az, -kcol, col0)
-  float pad1;
+  int32_t ok;       // 0: no fast path through this table (not strictly descending, H < 2, too many cells ...)
+  int32_t pad[2];
 };
-static_assert(sizeof(SensCoef) == 64, "SensCoef must be 64 bytes");
+static_assert(sizeof(TabCoef) == 32, "TabCoef must be 32 bytes");
 
-// One (tracklet-frame, LiDAR) pair: p_sensor = A * (x,y,z voxel index) + b.  64 bytes, 4 x LDG.128.
-struct __align__(16) PairCoef {
-  float A[9];
-  float b[3];
-  float eps;        // bound on |f32 p - reference f64 p| per component (metres); < 0: no fast path
-  int32_t sens;     // index into the SensCoef table
-  int32_t q;        // pair index inside the tracklet: frame * L + LiDAR
-  int32_t cull;     // 1: no voxel of the tracklet can be free through this pair (see make_pair)
+// One lookup cell: the row boundary inside the cell's extended interval [u_k - 0.75 w, u_k + 0.75 w] (at most
+// one, the cells being half as wide as the closest pair of boundaries) and its index; without one, b = -4 and
+// h = the number of boundaries above the cell.  row(u) = h + (b > u) for every u the cell can be selected for.
+struct __align__(8) LutCell {
+  float b;
+  int32_t h;
 };
-static_assert(sizeof(PairCoef) == 64, "PairCoef must be 64 bytes");
 
-// What one iteration of the fast visibility kernel needs of a surviving pair, in ONE 128-byte record (one L1 line,
-// 8 x LDG.128, prefetched one iteration ahead): the pair's affine map, the fields of its sensor entry and the
-// per-pair constants of the margins.  Built by k_pair_build.
+// One (tracklet-frame, LiDAR) pair, everything one iteration of the visibility kernel needs in ONE 128-byte record
+// (one L1 line, 8 x LDG.128 at a warp-uniform address).  Built by k_pair_build.
+//   p' = bc + A (idx - cen):  sensor-frame position of voxel centre `idx`, ROTATED about the sensor's z axis by
+//   -theta so that the centre of the tracklet's grid lies on the +x axis (y' ~ 0 there): azimuth = theta + atan(y'/x').
 struct __align__(16) PairHot {
   float A[9];
-  float b[3];
-  float eps;        // < 0: no fast path for this pair (every test goes to the exact recheck)
-  int32_t q;
-  float azc, inv_w, cell0m, col0;   // cell0m = cell0 - 0.5: the cell index is taken by round-to-nearest
-  int32_t W, tab_off;
-  int64_t ri_off;
-  float e15;        // 1.5 eps
-  float c1, c2;     // range margin: m = r * (r * 6e-7 + c1) + c2,  c1 = 2.01 sqrt(3) eps, c2 = 3 eps^2
-  float ecol;       // (kAtanErr + 3e-7) * kcol + c_col
-  float e15k;       // 1.5 eps * kcol
-  float nkcol;      // -kcol
-  uint32_t last;    // H - 1
+  float bc[3];
+  float eps;        // bound on the f32 position error (metres); < 0: no fast path for this pair (every test goes
+                    // to the exact recheck)
+  int32_t q;        // pair index inside the tracklet: frame * L + LiDAR
+  float inv_w, cell0m;
   uint32_t ncm1;    // ncell - 1
-  int32_t pad[2];
+  uint32_t last;    // H - 1
+  float e15z;       // row margin: m = e15z / r + 1.5e-6
+  float nkcol;      // -W / (2 pi)
+  float c0f;        // colf_rel = fma(phi, nkcol, c0f): column relative to cint
+  int32_t cint;
+  int32_t W;
+  float ecolk, ecol;   // column margin: ecolk / rho + ecol
+  float c1;         // range margin: m = r * 6.5e-7 + c1
+  int32_t lut_off;  // first LutCell of the pair's table in lut_pool
+  int32_t wide;     // 1: the object spans more than +-45 degrees of azimuth: full-quadrant arctangent
+  int64_t ri_off;
+  int32_t sens;     // sensor entry (pyramid offsets for the brick cull)
+  int32_t pad;
 };
 static_assert(sizeof(PairHot) == 128, "PairHot must be 128 bytes");
 
-// What the fast visibility kernel needs of a tracklet, in one 64-byte record (4 x LDG.128).
+// What the visibility kernels need of a tracklet, in one 64-byte record (4 x LDG.128).
 struct __align__(16) TrkHot {
-  int32_t V, dY, dZ;
-  int32_t status;       // final status (flags of k_frame_voxelize folded in)
+  int32_t V, dX, dY, dZ;
+  int32_t status;       // final status (flags of the crop kernel folded in)
   int32_t nact;         // pairs that survived culling
-  int32_t pad0;
   int64_t bits_off;
-  int64_t label_off;
-  int64_t pairs_base;   // first PairCoef of the tracklet in pairs_c
-  int64_t pad1[2];
+  int64_t pairs_base;   // first PairHot of the tracklet in pairs_c
+  int64_t brick_base;   // first brick of the tracklet (global brick index)
+  float cen[3];         // centre of the voxel-index lattice: (dims - 1) / 2
+  int32_t pad;
 };
 static_assert(sizeof(TrkHot) == 64, "TrkHot must be 64 bytes");
 
 struct Workspace {
   TrkGrid *grids;        // [T]
   int32_t *frame_kept;   // [F]
-  int32_t *frame_trk;    // [F]
   int32_t *redo_list;    // [F] frames of tracklets whose optimistic grid was wrong
-  unsigned long long *redo_count;
-  int64_t *chunk_off;    // [T+1]
-  unsigned long long *pyr_flag;  // [0] 1: pyramid built (fits), culling enabled -- written on the side stream
-  unsigned long long *counter;   // [0] phase-1 ticket, [1] recheck-queue length, [3] phase-1 items,
-                                 // [4] phase-2 ticket, [5] phase-2 items
-  uint32_t *bits;        // occupancy bitsets
+  int64_t *chunk_off;    // [T+1] (f64 path)
+  // ---- zeroed by ONE memset at the start of every call
+  char *zero_begin;
+  unsigned long long *counter;   // [0] f64-path ticket, [1] recheck-queue length, [2] redo frames,
+                                 // [8 + 2s] items of slice s, [9 + 2s] ticket of slice s
+  int32_t *trk_flags;    // [T] flags of the crop kernel (bit0 kept a point, bit1 index error)
+  uint32_t *bits;        // occupancy bitsets, linear voxel order, tracklet t at label_off[t]/32 + t
   int64_t bits_words;
-  SensCoef *sens;        // [SF*L]
-  float *ub_pool;        // [2*incl_len+2] u-space row boundaries, table at 2*incl_off+1 with a sentinel on each side
-  uint16_t *lut_pool;    // [incl_len * kLutPerRow]
-  int32_t *tab_claim;    // [incl_len] 1 at a table's offset once a CTA has taken on building its lookup table
+  uint32_t *free_brick;  // [2 * bricks] voxels proven free, BRICK order: bit j = lx*16 + ly*4 + lz of word pair 2*brick
+  uint32_t *pair_mask;   // [mask_words * bricks] bit k: pair k of the tracklet cannot free any voxel of the brick
+  TabCoef *tabcoef;      // [incl_len] (entries at table offsets only)
+  char *zero_end;
+  // ----
+  float *ub_pool;        // [incl_len] u-space row boundaries of each table (scratch of k_table_setup)
+  LutCell *lut_pool;     // [incl_len * kLutPerRow]
   int64_t incl_len;
-  int4 *queue;           // recheck queue: (tracklet, voxel, pair index q = i*L + c, unused)
+  int4 *queue;           // recheck queue: (tracklet, voxel, pair index q = i*L + c, local brick * 64 + j)
   int64_t queue_cap;
   PairHot *pairs_c;      // [F*L] the non-culled pairs of each tracklet, compacted at trk_frame_off[t] * L
   TrkHot *hot;           // [T]
-  uint32_t *free_bits;   // same layout as `bits`: voxels proven free
-  int2 *item_map;        // [items_cap] work items of the fast kernel: (tracklet, chunk | slice << 20)
-  int64_t items_cap;
-  int32_t *unk_list;     // [total] per tracklet (at label_off): voxels still undecided after phase 1, any order
-  uint32_t *n_unk;       // [T] length of each tracklet's list
-  int64_t *pyr_off;      // [SF*L + 1] first tile of each range image in pyr
+  int2 *item_map;        // [n_slices * bricks] work items of slice s at s * bricks: (tracklet, bx | by << 10 | bz << 20)
+  int64_t bricks;        // brick_off[T]
+  int32_t mask_words;    // ceil(max_pairs / 32)
+  int32_t n_slices;      // ceil(max_pairs / kPairsPerItem)
   float *pyr;            // [pyr_tiles] max of the range image over tiles of kTileR x kTileC pixels
+  float *pyr2;           // [16 * pyr_tiles] second level, kFineR x kFineC pixels; image e at 16 * pyr_off[e],
+                         // row length ceil(W / kFineC)
   int64_t pyr_tiles;
 };
 
 static int64_t ws_layout(int32_t T, int64_t F, int64_t total, int64_t SF, int32_t L, int64_t incl_len,
-                         int64_t pyr_tiles, int64_t items_cap, char *base, Workspace *w) {
+                         int64_t pyr_tiles, int64_t bricks, int32_t max_pairs, char *base, Workspace *w) {
   int64_t off = 0;
   auto take = [&](int64_t bytes) {
     int64_t o = off;
     off = align_up(off + bytes, 256);
     return o;
   };
+  const int32_t mask_words = (int32_t)std::max<int64_t>(ceil_div(std::max(max_pairs, 1), 32), 1);
+  const int32_t n_slices = (int32_t)std::max<int64_t>(ceil_div(std::max(max_pairs, 1), kPairsPerItem), 1);
   int64_t o_grid = take(sizeof(TrkGrid) * (int64_t)T);
   int64_t o_kept = take(4 * F);
-  int64_t o_ftrk = take(4 * F);
   int64_t o_redo = take(4 * F);
-  int64_t o_rc = take(8);
   int64_t o_choff = take(8 * ((int64_t)T + 1));
-  int64_t o_cnt = take(8 * 8);
-  int64_t o_pf = take(8);
+  // zeroed region
+  int64_t o_cnt = take(8 * (8 + 2 * kMaxSlices));
+  int64_t o_tf = take(4 * (int64_t)T);
   int64_t words = total / 32 + T + 1;
   int64_t o_bits = take(4 * words);
-  int64_t o_fbits = take(4 * words);
-  int64_t o_imap = take(8 * items_cap);
-  int64_t o_tab = take(sizeof(SensCoef) * SF * L);
-  int64_t o_ub = take(4 * (2 * incl_len + 2));
-  int64_t o_lut = take(2 * incl_len * kLutPerRow);
-  int64_t o_claim = take(4 * std::max<int64_t>(incl_len, 1));
-  // recheck queue: ~0.4 % of the EXECUTED tests (~0.1 % of the nominal ones) are undecided in f32; room for 1/64
-  // of the nominal tests, bounded.  Tests beyond the capacity are decided in place (exact_from_ids).
+  int64_t o_fb = take(8 * std::max<int64_t>(bricks, 1));
+  int64_t o_pm = take(4 * (int64_t)mask_words * std::max<int64_t>(bricks, 1));
+  int64_t o_tc = take(sizeof(TabCoef) * std::max<int64_t>(incl_len, 1));
+  int64_t o_zend = off;
+  int64_t o_ub = take(4 * std::max<int64_t>(incl_len, 1));
+  int64_t o_lut = take(sizeof(LutCell) * std::max<int64_t>(incl_len, 1) * kLutPerRow);
+  // recheck queue: ~0.1 % of the EXECUTED tests are undecided in f32; room for 1/64 of the nominal tests, bounded.
+  // Tests beyond the capacity are decided in place (exact_from_ids).
   const double nominal = (double)total * (T > 0 ? (double)F / T : 0.0) * L;
   int64_t qcap = (int64_t)std::min(std::max(nominal / 64.0, 65536.0), 16.0 * 1024 * 1024);
   int64_t o_q = take(16 * qcap);
   int64_t o_pc = take(sizeof(PairHot) * F * L);
   int64_t o_na = take(sizeof(TrkHot) * (int64_t)T);
-  int64_t o_po = take(8 * (SF * L + 1));
   int64_t o_py = take(4 * pyr_tiles);
-  int64_t o_ul = take(4 * total);
-  int64_t o_nu = take(4 * (int64_t)T);
+  int64_t o_py2 = take(4 * 16 * pyr_tiles);
+  int64_t o_im = take(8 * (int64_t)n_slices * std::max<int64_t>(bricks, 1));
+  (void)SF;
   if (w) {
-    w->unk_list = (int32_t *)(base + o_ul);
-    w->n_unk = (uint32_t *)(base + o_nu);
-    w->pairs_c = (PairHot *)(base + o_pc);
-    w->hot = (TrkHot *)(base + o_na);
-    w->pyr_off = (int64_t *)(base + o_po);
-    w->pyr = (float *)(base + o_py);
-    w->pyr_tiles = pyr_tiles;
     w->grids = (TrkGrid *)(base + o_grid);
     w->frame_kept = (int32_t *)(base + o_kept);
-    w->frame_trk = (int32_t *)(base + o_ftrk);
     w->redo_list = (int32_t *)(base + o_redo);
-    w->redo_count = (unsigned long long *)(base + o_rc);
     w->chunk_off = (int64_t *)(base + o_choff);
+    w->zero_begin = base + o_cnt;
     w->counter = (unsigned long long *)(base + o_cnt);
-    w->pyr_flag = (unsigned long long *)(base + o_pf);
+    w->trk_flags = (int32_t *)(base + o_tf);
     w->bits = (uint32_t *)(base + o_bits);
     w->bits_words = words;
-    w->free_bits = (uint32_t *)(base + o_fbits);
-    w->item_map = (int2 *)(base + o_imap);
-    w->items_cap = items_cap;
-    w->sens = (SensCoef *)(base + o_tab);
+    w->free_brick = (uint32_t *)(base + o_fb);
+    w->pair_mask = (uint32_t *)(base + o_pm);
+    w->tabcoef = (TabCoef *)(base + o_tc);
+    w->zero_end = base + o_zend;
     w->ub_pool = (float *)(base + o_ub);
-    w->lut_pool = (uint16_t *)(base + o_lut);
-    w->tab_claim = (int32_t *)(base + o_claim);
+    w->lut_pool = (LutCell *)(base + o_lut);
     w->incl_len = incl_len;
     w->queue = (int4 *)(base + o_q);
     w->queue_cap = qcap;
+    w->pairs_c = (PairHot *)(base + o_pc);
+    w->hot = (TrkHot *)(base + o_na);
+    w->item_map = (int2 *)(base + o_im);
+    w->bricks = bricks;
+    w->mask_words = mask_words;
+    w->n_slices = n_slices;
+    w->pyr = (float *)(base + o_py);
+    w->pyr2 = (float *)(base + o_py2);
+    w->pyr_tiles = pyr_tiles;
   }
   return off;
 }
@@ -275,8 +278,9 @@ static int side_stream(SideStream **out) {
 
 // ---------------------------------------------------------------------------------------------
 // Optional per-kernel timing (bench.py's roofline): CUDA events recorded around each kernel of the
-// pipeline on the caller's stream; durations are summed per kernel when the profile is read.
-enum { kProfInbox = 0, kProfSetup, kProfScan, kProfVoxelize, kProfVisibility, kProfPairSetup, kProfRecheck, kProfPairCull, kProfKinds };
+// pipeline on the launching stream; durations are summed per kernel when the profile is read.
+enum { kProfCrop = 0, kProfSetup, kProfScan, kProfBrickCull, kProfVisibility, kProfSide, kProfRecheck, kProfPairBuild,
+       kProfLabels, kProfKinds };
 struct ProfEntry { int kind; cudaEvent_t a, b; };
 static bool g_prof_on = false;
 static std::vector<ProfEntry> g_prof;
@@ -305,42 +309,76 @@ struct ProfScope {
 // Crop + voxelise.  The grid of a tracklet depends on its box size = max over the frames that have at
 // least one in-box point (occ_annotate.py:111-112, 132-133), which is only known after every frame has
 // been cropped.  Almost always every frame has such a point, so the pipeline is optimistic:
-//   k_tracklet_presetup  grid from the max over ALL frames
-//   k_frame_voxelize     ONE pass over the points: in-box test, box frame, quantise, set bits; records
-//                        which frames had in-box points
+//   k_crop_voxelize      every CTA derives the tracklet's grid from the max over ALL frames that have candidate
+//                        points, then ONE pass over the points of its frames: in-box test, box frame, quantise,
+//                        set bits; records which frames had in-box points
 //   k_tracklet_setup     recomputes the size from the kept frames; if it differs the tracklet's bits are
-//                        cleared and a second k_frame_voxelize pass redoes just that tracklet
+//                        cleared and a second k_crop_voxelize pass redoes just that tracklet
+// Scalar divisions: the reference divides tensors by the python float voxel_size (:414-416, :425).  torch-CPU
+// evaluates x / vs in IEEE f32; torch-CUDA evaluates x * (1 / vs) (its scalar-divisor fast path).  `inv_vs` == 0
+// selects the CPU arithmetic (what the oracle restates), otherwise the product with inv_vs = 1.0f / vs (flag bit 5).
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void grid_from_size(TrkGrid &g, const float sz[3], float vsf, int64_t cap, int chunk) {
+__device__ __forceinline__ float div_vs(float x, float vsf, float inv_vs) {
+  return inv_vs != 0.f ? __fmul_rn(x, inv_vs) : __fdiv_rn(x, vsf);
+}
+
+__device__ __forceinline__ void grid_from_size(TrkGrid &g, const float sz[3], float vsf, float inv_vs, int64_t cap,
+                                               int chunk) {
   g.status = OCCB200_OK;
-  for (int k = 0; k < 3; ++k) g.dims[k] = (int)ceilf(__fdiv_rn(sz[k], vsf));   // :414-416
+  for (int k = 0; k < 3; ++k) g.dims[k] = (int)ceilf(div_vs(sz[k], vsf, inv_vs));   // :414-416
   g.mb[0] = __fmul_rn(sz[0], -0.5f);           // min over corners of [0,0,0,w,l,h,0] (:422-423)
   g.mb[1] = __fmul_rn(sz[1], -0.5f);
   g.mb[2] = __fmul_rn(sz[2], 0.0f);
   g.V = (int64_t)g.dims[0] * g.dims[1] * g.dims[2];
-  if (g.V > cap || g.V <= 0 || g.V >= (1ll << 31)) {
+  if (g.V > cap || g.V <= 0 || g.V >= (1ll << 31) || g.dims[0] >= 4096 || g.dims[1] >= 4096 || g.dims[2] >= 4096) {
     g.status = -1;                             // caller's slot too small: reported, nothing written
     g.V = 0;
   }
   g.nchunks = (int)((g.V + chunk - 1) / chunk);
 }
 
-// One in-box point -> bit index in the tracklet's occupancy bitset, or -1; flags |= 1 kept, |= 2 index error.
-__device__ __forceinline__ int64_t voxel_of_point(const BoxTest &bt, const occb200_pose_t &ps, const TrkGrid &g,
-                                                  float vsf, float x, float y, float z, int &flags) {
-  if (!pt_in_box(bt, x, y, z)) return -1;
-  flags |= 4;                                   // the frame has an in-box point
+// The optimistic / true grid of tracklet t from a box size; everything but `flags` and `redo`.
+__device__ __forceinline__ TrkGrid make_grid(int t, int B, const float sz[3], float vsf, float inv_vs,
+                                             const int64_t *__restrict__ label_off, int chunk) {
+  TrkGrid g;
+  g.B = B;
+  g.flags = 0;
+  g.nchunks = 0;
+  g.V = 0;
+  g.redo = 0;
+  g.pad = 0;
+  g.bits_off = label_off[t] / 32 + t;
+  g.dims[0] = g.dims[1] = g.dims[2] = 0;
+  g.mb[0] = g.mb[1] = g.mb[2] = 0.f;
+  if (B < 10) g.status = OCCB200_SKIP_SHORT;                       // :344
+  else if (sz[0] == -INFINITY) g.status = OCCB200_NO_POINTS;      // no candidate point at all (:129)
+  else grid_from_size(g, sz, vsf, inv_vs, label_off[t + 1] - label_off[t], chunk);
+  return g;
+}
+
+struct FramePose {     // what the crop needs of one tracklet-frame, in shared memory
+  BoxTest bt;
+  float c, s;          // torch f32 cos/sin(-yaw)
+  float ox, oy, oz;
+};
+
+// One in-box point -> bit index in the tracklet's occupancy bitset, or -1; flags |= 1 kept, |= 2 index error,
+// |= 4 the frame has an in-box point.
+__device__ __forceinline__ int64_t voxel_of_point(const FramePose &fp, const TrkGrid &g, float vsf, float inv_vs,
+                                                  float x, float y, float z, int &flags) {
+  if (!pt_in_box(fp.bt, x, y, z)) return -1;
+  flags |= 4;
   // local = (p + (-origin)) @ [[c,-s,0],[s,c,0],[0,0,1]]  (:117-122, lidar_box3d.py:165-184):
   // sgemm accumulates k = 0,1,2 as an FMA chain; the k=2 terms are exact no-ops.
-  const float c = ps.cos_m, s = ps.sin_m;       // torch f32 cos/sin(-yaw)
-  const float tx = __fadd_rn(x, -ps.box[0]), ty = __fadd_rn(y, -ps.box[1]), tz = __fadd_rn(z, -ps.box[2]);
+  const float c = fp.c, s = fp.s;
+  const float tx = __fadd_rn(x, -fp.ox), ty = __fadd_rn(y, -fp.oy), tz = __fadd_rn(z, -fp.oz);
   const float lx = __fmaf_rn(ty, s, __fmul_rn(tx, c));
   const float ly = __fmaf_rn(ty, c, __fmul_rn(tx, -s));
   const float lz = tz;
   // q = floor((local - min_bound) / vs)  (:425)
-  float qx = floorf(__fdiv_rn(__fsub_rn(lx, g.mb[0]), vsf));
-  float qy = floorf(__fdiv_rn(__fsub_rn(ly, g.mb[1]), vsf));
-  float qz = floorf(__fdiv_rn(__fsub_rn(lz, g.mb[2]), vsf));
+  float qx = floorf(div_vs(__fsub_rn(lx, g.mb[0]), vsf, inv_vs));
+  float qy = floorf(div_vs(__fsub_rn(ly, g.mb[1]), vsf, inv_vs));
+  float qz = floorf(div_vs(__fsub_rn(lz, g.mb[2]), vsf, inv_vs));
   const float dX = (float)g.dims[0], dY = (float)g.dims[1], dZ = (float)g.dims[2];
   if (!(qx < dX && qy < dY && qz < dZ)) return -1;   // only the upper bound is filtered (:430-431)
   flags |= 1;
@@ -354,145 +392,166 @@ __device__ __forceinline__ int64_t voxel_of_point(const BoxTest &bt, const occb2
   return ((int64_t)qx * g.dims[1] + (int64_t)qy) * g.dims[2] + (int64_t)qz;
 }
 
-__global__ void __launch_bounds__(256)
-k_tracklet_presetup(int T, const int64_t *__restrict__ trk_frame_off, const occb200_pose_t *__restrict__ poses,
-                    const int64_t *__restrict__ frame_pt_off, const int64_t *__restrict__ label_off, float vsf, int chunk, TrkGrid *__restrict__ grids,
-                    int32_t *__restrict__ frame_trk, unsigned long long *__restrict__ redo_count,
-                    unsigned long long *__restrict__ counter, uint32_t *__restrict__ n_unk,
-                    int64_t *__restrict__ n_unknown, int64_t *__restrict__ n_steps) {
-  const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);   // one warp per tracklet
-  const int lane = threadIdx.x & 31;
-  if (blockIdx.x == 0 && threadIdx.x == 0) *redo_count = 0ull;
-  if (blockIdx.x == 0 && threadIdx.x < 8) counter[threadIdx.x] = 0ull;
-  if (t >= T) return;
-  const int64_t f0 = trk_frame_off[t], f1 = trk_frame_off[t + 1];
-  float sz[3] = {-INFINITY, -INFINITY, -INFINITY};
-  for (int64_t f = f0 + lane; f < f1; f += 32) {
-    frame_trk[f] = t;
-    if (frame_pt_off[f + 1] > frame_pt_off[f])     // a frame without candidates cannot be a kept frame
-#pragma unroll
-      for (int k = 0; k < 3; ++k) sz[k] = fmaxf(sz[k], poses[f].box[3 + k]);
-  }
-  for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-    for (int k = 0; k < 3; ++k) sz[k] = fmaxf(sz[k], __shfl_xor_sync(0xffffffffu, sz[k], o));
-  if (lane != 0) return;
-  TrkGrid g;
-  g.B = (int)(f1 - f0);
-  g.flags = 0;
-  g.nchunks = 0;
-  g.V = 0;
-  g.redo = 0;
-  g.pad = 0;
-  g.bits_off = label_off[t] / 32 + t;
-  g.dims[0] = g.dims[1] = g.dims[2] = 0;
-  g.mb[0] = g.mb[1] = g.mb[2] = 0.f;
-  if (g.B < 10) g.status = OCCB200_SKIP_SHORT;  // :344
-  else if (sz[0] == -INFINITY) g.status = OCCB200_NO_POINTS;   // no candidate point at all (:129)
-  else grid_from_size(g, sz, vsf, label_off[t + 1] - label_off[t], chunk);
-  grids[t] = g;
-  n_unknown[t] = 0;
-  n_unk[t] = 0u;
-  if (n_steps) n_steps[t] = 0;
+__device__ __forceinline__ FramePose load_frame_pose(const occb200_pose_t &ps) {
+  FramePose fp;
+  fp.bt = make_box_test(ps.box, ps.cos_pib, ps.sin_pib);
+  fp.c = ps.cos_m;
+  fp.s = ps.sin_m;
+  fp.ox = ps.box[0];
+  fp.oy = ps.box[1];
+  fp.oz = ps.box[2];
+  return fp;
 }
 
 #ifndef OCC_PPT
 #define OCC_PPT 4
 #endif
 constexpr int kPtsPerThread = OCC_PPT;          // independent point loads in flight per thread
+// First pass (redo_list == NULL): CTA b owns the tracklet-frames [b*G, (b+1)*G); they are processed in runs that
+// belong to one tracklet (a group may straddle a tracklet boundary).  For each run the CTA derives the tracklet's
+// optimistic grid itself (max box size over the tracklet's frames that have candidate points: 2 dependent loads +
+// one CTA reduction), zeroes a shared-memory bitset, streams the run's points as ONE flat range (the frames of a
+// tracklet are adjacent in `points`) with kPtsPerThread loads in flight per thread, and ORs the bitset into the
+// tracklet's global one.  Second pass (redo_list != NULL): a small grid strides over the frames of the tracklets
+// whose optimistic grid was wrong -- usually none -- with the true grid from grids[].
 __global__ void __launch_bounds__(kFrameThreads, OCC_FMINB)
-k_frame_voxelize(const occb200_pose_t *__restrict__ poses, const float *__restrict__ points, int stride,
-                 const int64_t *__restrict__ frame_pt_off, int32_t *__restrict__ frame_kept,
-                 const int32_t *__restrict__ frame_trk, TrkGrid *__restrict__ grids,
-                 uint32_t *__restrict__ bits, float vsf, const int32_t *__restrict__ redo_list,
-                 const unsigned long long *__restrict__ redo_count, int smem_words) {
+k_crop_voxelize(int64_t F, int G, const occb200_pose_t *__restrict__ poses, const float *__restrict__ points,
+                int stride, const int64_t *__restrict__ frame_pt_off, const int64_t *__restrict__ trk_frame_off,
+                const int64_t *__restrict__ label_off, const int32_t *__restrict__ frame_trk,
+                int32_t *__restrict__ frame_kept, int32_t *__restrict__ trk_flags, const TrkGrid *__restrict__ grids,
+                uint32_t *__restrict__ bits, float vsf, float inv_vs, const int32_t *__restrict__ redo_list,
+                const unsigned long long *__restrict__ redo_count, int smem_words) {
   extern __shared__ uint32_t s_bits[];            // smem_words words
+  __shared__ FramePose s_fp[kMaxGroup];
+  __shared__ int64_t s_off[kMaxGroup + 1];
+  __shared__ int s_kept[kMaxGroup];
+  __shared__ float s_red[kFrameThreads / 32][3];
+  __shared__ TrkGrid s_grid;
   __shared__ int s_flags;
-  // first pass: CTA b = tracklet-frame b.  second pass (redo_list != NULL): a small grid strides over the
-  // frames of the tracklets whose optimistic grid was wrong -- usually none.
   const bool redo_pass = redo_list != nullptr;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long n_work = redo_pass ? (long long)*redo_count : (long long)gridDim.x;
   for (long long wi = blockIdx.x; wi < n_work; wi += gridDim.x) {
-  __syncthreads();
-  const int64_t f = redo_pass ? (int64_t)redo_list[wi] : (int64_t)wi;
-  const int t = frame_trk[f];
-  const TrkGrid g = grids[t];
-  if (g.status != OCCB200_OK) {
-    if (threadIdx.x == 0 && !redo_pass) frame_kept[f] = 0;
-    continue;
-  }
-  const int words = (int)((g.V + 31) / 32);
-  const bool use_smem = words <= smem_words;
-  uint32_t *gbits = bits + g.bits_off;
-  if (use_smem)
-    for (int w = threadIdx.x; w < words; w += kFrameThreads) s_bits[w] = 0u;
-  if (threadIdx.x == 0) s_flags = 0;
-  __syncthreads();
-
-  const occb200_pose_t ps = poses[f];
-  const BoxTest bt = make_box_test(ps.box, ps.cos_pib, ps.sin_pib);
-  const int64_t n0 = frame_pt_off[f], n1 = frame_pt_off[f + 1];
-  const int lane = threadIdx.x & 31;
-  int flags = 0;
-  for (int64_t base = n0; base < n1; base += kFrameThreads * kPtsPerThread) {   // warp-uniform trip count
-    float px[kPtsPerThread], py[kPtsPerThread], pz[kPtsPerThread];
+    int64_t fa = redo_pass ? (int64_t)redo_list[wi] : (int64_t)wi * G;
+    const int64_t fend = redo_pass ? fa + 1 : min(fa + (int64_t)G, F);
+    while (fa < fend) {                             // one run = consecutive frames of ONE tracklet
+      __syncthreads();                              // the previous run's shared state is no longer read
+      const int t = frame_trk[fa];
+      const int64_t f0 = trk_frame_off[t], f1 = trk_frame_off[t + 1];
+      const int64_t fb = min(f1, fend);
+      const int nfr = (int)(fb - fa);
+      if (redo_pass) {
+        if (threadIdx.x == 0) s_grid = grids[t];
+      } else {
+        float sz[3] = {-INFINITY, -INFINITY, -INFINITY};
+        for (int64_t f = f0 + threadIdx.x; f < f1; f += kFrameThreads)
+          if (frame_pt_off[f + 1] > frame_pt_off[f])   // a frame without candidates cannot be a kept frame
 #pragma unroll
-    for (int u = 0; u < kPtsPerThread; ++u) {
-      const int64_t j = base + u * kFrameThreads + threadIdx.x;
-      const float *p = points + j * stride;
-      const bool ok = j < n1;
-      px[u] = ok ? ld_stream(p) : 0.f;
-      py[u] = ok ? ld_stream(p + 1) : 0.f;
-      pz[u] = ok ? ld_stream(p + 2) : 0.f;
-    }
+            for (int k = 0; k < 3; ++k) sz[k] = fmaxf(sz[k], poses[f].box[3 + k]);
+        for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
-    for (int u = 0; u < kPtsPerThread; ++u) {
-      const int64_t j = base + u * kFrameThreads + threadIdx.x;
-      int64_t idx = -1;
-      if (j < n1) idx = voxel_of_point(bt, ps, g, vsf, px[u], py[u], pz[u], flags);
-      int word = -1;
-      uint32_t bit = 0u;
-      if (idx >= 0) {
-        word = (int)(idx >> 5);
-        bit = 1u << (idx & 31);
-        // most points land in voxels that are already marked: look before touching an atomic
-        const uint32_t cur = use_smem ? s_bits[word] : __ldg(gbits + word);
-        if (cur & bit) word = -1;
-      }
-      // warp-level dedup of what is left: lanes on the same bitset word merge their bits, one atomic per word
-      if (__any_sync(0xffffffffu, word >= 0)) {
-        const unsigned peers = __match_any_sync(0xffffffffu, word);
-        const uint32_t merged = __reduce_or_sync(peers, word >= 0 ? bit : 0u);
-        if (word >= 0 && lane == __ffs(peers) - 1) {
-          if (use_smem) atomicOr(&s_bits[word], merged);
-          else atomicOr(&gbits[word], merged);
+          for (int k = 0; k < 3; ++k) sz[k] = fmaxf(sz[k], __shfl_xor_sync(0xffffffffu, sz[k], o));
+        if (lane == 0)
+#pragma unroll
+          for (int k = 0; k < 3; ++k) s_red[warp][k] = sz[k];
+        __syncthreads();
+        if (threadIdx.x == 0) {
+#pragma unroll
+          for (int k = 0; k < 3; ++k)
+            for (int w2 = 1; w2 < kFrameThreads / 32; ++w2) sz[k] = fmaxf(sz[k], s_red[w2][k]);
+          s_grid = make_grid(t, (int)(f1 - f0), sz, vsf, inv_vs, label_off, 32);
         }
       }
+      if (threadIdx.x < nfr) {
+        s_fp[threadIdx.x] = load_frame_pose(poses[fa + threadIdx.x]);
+        s_off[threadIdx.x] = frame_pt_off[fa + threadIdx.x];
+        s_kept[threadIdx.x] = 0;
+      }
+      if (threadIdx.x == 0) {
+        s_off[nfr] = frame_pt_off[fb];
+        s_flags = 0;
+      }
+      __syncthreads();
+      const TrkGrid g = s_grid;
+      if (g.status != OCCB200_OK) {
+        if (threadIdx.x < nfr && !redo_pass) frame_kept[fa + threadIdx.x] = 0;
+        fa = fb;
+        continue;
+      }
+      const int words = (int)((g.V + 31) / 32);
+      const bool use_smem = words <= smem_words;
+      uint32_t *gbits = bits + g.bits_off;
+      if (use_smem)
+        for (int w2 = threadIdx.x; w2 < words; w2 += kFrameThreads) s_bits[w2] = 0u;
+      __syncthreads();
+
+      const int64_t n0 = s_off[0], n1 = s_off[nfr];
+      int flags = 0;
+      for (int64_t base = n0; base < n1; base += kFrameThreads * kPtsPerThread) {   // warp-uniform trip count
+        float px[kPtsPerThread], py[kPtsPerThread], pz[kPtsPerThread];
+#pragma unroll
+        for (int u = 0; u < kPtsPerThread; ++u) {
+          const int64_t j = base + u * kFrameThreads + threadIdx.x;
+          const float *p = points + j * stride;
+          const bool ok = j < n1;
+          px[u] = ok ? ld_stream(p) : 0.f;
+          py[u] = ok ? ld_stream(p + 1) : 0.f;
+          pz[u] = ok ? ld_stream(p + 2) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < kPtsPerThread; ++u) {
+          const int64_t j = base + u * kFrameThreads + threadIdx.x;
+          int64_t idx = -1;
+          if (j < n1) {
+            int k = 0;                              // frame of point j inside the run
+            for (int i = 1; i < nfr; ++i) k += (j >= s_off[i]) ? 1 : 0;
+            int fl = 0;
+            idx = voxel_of_point(s_fp[k], g, vsf, inv_vs, px[u], py[u], pz[u], fl);
+            if ((fl & 4) && !s_kept[k]) s_kept[k] = 1;      // benign race: every writer stores 1
+            flags |= fl & 3;
+          }
+          int word = -1;
+          uint32_t bit = 0u;
+          if (idx >= 0) {
+            word = (int)(idx >> 5);
+            bit = 1u << (idx & 31);
+            // most points land in voxels that are already marked: look before touching an atomic
+            const uint32_t cur = use_smem ? s_bits[word] : __ldg(gbits + word);
+            if (cur & bit) word = -1;
+          }
+          // warp-level dedup of what is left: lanes on the same bitset word merge their bits, one atomic per word
+          if (__any_sync(0xffffffffu, word >= 0)) {
+            const unsigned peers = __match_any_sync(0xffffffffu, word);
+            const uint32_t merged = __reduce_or_sync(peers, word >= 0 ? bit : 0u);
+            if (word >= 0 && lane == __ffs(peers) - 1) {
+              if (use_smem) atomicOr(&s_bits[word], merged);
+              else atomicOr(&gbits[word], merged);
+            }
+          }
+        }
+      }
+      if (flags) atomicOr(&s_flags, flags);
+      __syncthreads();
+      if (use_smem)
+        for (int w2 = threadIdx.x; w2 < words; w2 += kFrameThreads) {
+          const uint32_t v = s_bits[w2];
+          if (v) atomicOr(&gbits[w2], v);
+        }
+      if (threadIdx.x < nfr && !redo_pass) frame_kept[fa + threadIdx.x] = s_kept[threadIdx.x];
+      if (threadIdx.x == 0 && s_flags) atomicOr(&trk_flags[t], s_flags);
+      fa = fb;
     }
-  }
-  if (flags) atomicOr(&s_flags, flags);
-  __syncthreads();
-  if (use_smem)
-    for (int w = threadIdx.x; w < words; w += kFrameThreads) {
-      const uint32_t v = s_bits[w];
-      if (v) atomicOr(&gbits[w], v);
-    }
-  if (threadIdx.x == 0) {
-    const int fl = s_flags;
-    if (!redo_pass) frame_kept[f] = (fl & 4) ? 1 : 0;
-    if (fl & 3) atomicOr(&grids[t].flags, fl & 3);
-  }
   }
 }
 
 // --save-mean-var support (occ_annotate.py:627-645): for every candidate point, its box-frame coordinates and raw
-// quantised voxel coordinates with the tracklet's FINAL grid, exactly as k_frame_voxelize derives them.  Row
+// quantised voxel coordinates with the tracklet's FINAL grid, exactly as k_crop_voxelize derives them.  Row
 // (t, qx, qy, qz) for a point the reference keeps (in the box, q < dims), (-1, 0, 0, 0) otherwise.  Negative
 // coordinates are NOT wrapped here: the reference groups by the raw values (sst_ops.py:150-181).
 __global__ void __launch_bounds__(256)
 k_frame_points(const occb200_pose_t *__restrict__ poses, const float *__restrict__ points, int stride,
                const int64_t *__restrict__ frame_pt_off, const int32_t *__restrict__ frame_trk,
-               const TrkGrid *__restrict__ grids, const int32_t *__restrict__ status, float vsf,
+               const TrkGrid *__restrict__ grids, const int32_t *__restrict__ status, float vsf, float inv_vs,
                float *__restrict__ loc_out, int32_t *__restrict__ q_out) {
   const int64_t f = blockIdx.x;
   const int t = frame_trk[f];
@@ -512,9 +571,9 @@ k_frame_points(const occb200_pose_t *__restrict__ poses, const float *__restrict
       lx = __fmaf_rn(ty, s, __fmul_rn(tx, c));
       ly = __fmaf_rn(ty, c, __fmul_rn(tx, -s));
       lz = tz;
-      const float qx = floorf(__fdiv_rn(__fsub_rn(lx, g.mb[0]), vsf));
-      const float qy = floorf(__fdiv_rn(__fsub_rn(ly, g.mb[1]), vsf));
-      const float qz = floorf(__fdiv_rn(__fsub_rn(lz, g.mb[2]), vsf));
+      const float qx = floorf(div_vs(__fsub_rn(lx, g.mb[0]), vsf, inv_vs));
+      const float qy = floorf(div_vs(__fsub_rn(ly, g.mb[1]), vsf, inv_vs));
+      const float qz = floorf(div_vs(__fsub_rn(lz, g.mb[2]), vsf, inv_vs));
       if (qx < dX && qy < dY && qz < dZ) row = make_int4(t, (int)qx, (int)qy, (int)qz);
     }
     loc_out[3 * j + 0] = lx;
@@ -524,27 +583,31 @@ k_frame_points(const occb200_pose_t *__restrict__ poses, const float *__restrict
   }
 }
 
+// One warp per tracklet: the grid the crop kernel assumed (size = max over the frames with candidate points) against
+// the true one (max over KEPT frames, occ_annotate.py:111-112, :132-133, box_mode="max"); writes grids[t], dims,
+// sizes, the first status, and zeroes the per-tracklet counters of the call.
 __global__ void __launch_bounds__(256)
 k_tracklet_setup(int T, const int64_t *__restrict__ trk_frame_off, const occb200_pose_t *__restrict__ poses,
                  const int64_t *__restrict__ frame_pt_off, const int32_t *__restrict__ frame_kept,
-                 const int64_t *__restrict__ label_off, float vsf, int chunk,
-                 TrkGrid *__restrict__ grids, uint32_t *__restrict__ bits, int32_t *__restrict__ redo_list,
-                 unsigned long long *__restrict__ redo_count, int32_t *__restrict__ dims_out,
-                 float *__restrict__ sizes_out, int32_t *__restrict__ status_out) {
+                 const int64_t *__restrict__ label_off, float vsf, float inv_vs, int chunk,
+                 TrkGrid *__restrict__ grids, uint32_t *__restrict__ bits, int32_t *__restrict__ trk_flags,
+                 int32_t *__restrict__ redo_list, unsigned long long *__restrict__ redo_count,
+                 int32_t *__restrict__ dims_out, float *__restrict__ sizes_out, int32_t *__restrict__ status_out,
+                 int64_t *__restrict__ n_unknown, int64_t *__restrict__ n_steps) {
   const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);   // one warp per tracklet
   const int lane = threadIdx.x & 31;
   if (t >= T) return;
   const int64_t f0 = trk_frame_off[t], f1 = trk_frame_off[t + 1];
-  TrkGrid g = grids[t];
   float sz[3] = {-INFINITY, -INFINITY, -INFINITY}, sz_all[3] = {-INFINITY, -INFINITY, -INFINITY};
   int kept = 0;
   for (int64_t f = f0 + lane; f < f1; f += 32) {
-    const bool k_ = frame_kept[f] != 0;           // occ_annotate.py:111-112, :132-133 (box_mode="max")
+    const bool has = frame_pt_off[f + 1] > frame_pt_off[f];
+    const bool k_ = has && frame_kept[f] != 0;
     kept += k_ ? 1 : 0;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
       const float b = poses[f].box[3 + k];
-      if (frame_pt_off[f + 1] > frame_pt_off[f]) sz_all[k] = fmaxf(sz_all[k], b);   // what presetup assumed
+      if (has) sz_all[k] = fmaxf(sz_all[k], b);         // what the crop kernel assumed
       if (k_) sz[k] = fmaxf(sz[k], b);
     }
   }
@@ -556,7 +619,9 @@ k_tracklet_setup(int T, const int64_t *__restrict__ trk_frame_off, const occb200
       sz_all[k] = fmaxf(sz_all[k], __shfl_xor_sync(0xffffffffu, sz_all[k], o));
     }
   }
-  if (g.status == OCCB200_OK || g.status == -1) {
+  TrkGrid g = make_grid(t, (int)(f1 - f0), sz_all, vsf, inv_vs, label_off, chunk);   // the optimistic grid
+  g.flags = trk_flags[t];
+  if (g.status == OCCB200_OK) {                   // (-1, slot too small for the optimistic grid, stays -1)
     if (kept == 0) {
       g.status = OCCB200_NO_POINTS;               // :129
       g.V = 0;
@@ -564,18 +629,19 @@ k_tracklet_setup(int T, const int64_t *__restrict__ trk_frame_off, const occb200
       g.dims[0] = g.dims[1] = g.dims[2] = 0;
     } else if (sz[0] != sz_all[0] || sz[1] != sz_all[1] || sz[2] != sz_all[2]) {
       // a frame without in-box points carried the largest box: clear the bits set with the optimistic grid
-      // and let the second k_frame_voxelize pass redo this tracklet with the true one.
+      // and let the second crop pass redo this tracklet with the true one.
       const int old_words = (int)((g.V + 31) / 32);
-      grid_from_size(g, sz, vsf, label_off[t + 1] - label_off[t], chunk);
+      grid_from_size(g, sz, vsf, inv_vs, label_off[t + 1] - label_off[t], chunk);
       g.flags = 0;
       g.redo = 1;
       uint32_t *gbits = bits + g.bits_off;
       for (int w = lane; w < old_words; w += 32) gbits[w] = 0u;
+      if (lane == 0) trk_flags[t] = 0;
       unsigned long long base = 0;
       if (lane == 0) base = atomicAdd(redo_count, (unsigned long long)kept);
       base = __shfl_sync(0xffffffffu, base, 0);
       for (int64_t f = f0 + lane; f - lane < f1; f += 32) {        // kept frames, warp-compacted
-        const bool k_ = f < f1 && frame_kept[f] != 0;
+        const bool k_ = f < f1 && frame_pt_off[f + 1] > frame_pt_off[f] && frame_kept[f] != 0;
         const unsigned m = __ballot_sync(0xffffffffu, k_);
         if (k_) redo_list[base + __popc(m & ((1u << lane) - 1u))] = (int32_t)f;
         base += __popc(m);
@@ -588,13 +654,14 @@ k_tracklet_setup(int T, const int64_t *__restrict__ trk_frame_off, const occb200
     dims_out[3 * t + k] = g.dims[k];
     sizes_out[3 * t + k] = (g.status == OCCB200_OK) ? sz[k] : 0.f;
   }
-  status_out[t] = g.status;                    // refined by the visibility kernel (flags)
+  status_out[t] = g.status;                    // refined by k_pair_build / k_labels (flags)
+  n_unknown[t] = 0;
+  if (n_steps) n_steps[t] = 0;
 }
 
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024)
-k_scan_chunks(int T, const TrkGrid *__restrict__ grids, int64_t *__restrict__ chunk_off,
-              unsigned long long *__restrict__ counter) {
+k_scan_chunks(int T, const TrkGrid *__restrict__ grids, int64_t *__restrict__ chunk_off) {
   __shared__ int64_t s_part[1024];
   const int tid = threadIdx.x;
   const int per = (T + 1023) / 1024;
@@ -615,7 +682,6 @@ k_scan_chunks(int T, const TrkGrid *__restrict__ grids, int64_t *__restrict__ ch
     run += (grids[t].status == OCCB200_OK) ? grids[t].nchunks : 0;
   }
   if (tid == 1023) chunk_off[T] = s_part[1023];
-  if (tid < 8) counter[tid] = 0ull;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -668,7 +734,8 @@ k_visibility_f64(int T, int L, const int64_t *__restrict__ trk_frame_off,
                  const float *__restrict__ ri_pool, double vs, const int64_t *__restrict__ label_off,
                  const TrkGrid *__restrict__ grids, const int64_t *__restrict__ chunk_off,
                  unsigned long long *__restrict__ counter, const uint32_t *__restrict__ bits,
-                 int32_t *__restrict__ labels, int32_t *__restrict__ status_out,
+                 const int32_t *__restrict__ trk_flags, int32_t *__restrict__ labels,
+                 uint8_t *__restrict__ labels_u8, int32_t *__restrict__ status_out,
                  int64_t *__restrict__ n_unknown, int64_t *__restrict__ n_steps) {
   __shared__ long long s_item;
   const int lane = threadIdx.x & 31;
@@ -687,11 +754,12 @@ k_visibility_f64(int T, int L, const int64_t *__restrict__ trk_frame_off,
     const int t = lo;
     const TrkGrid g = grids[t];
     const int chunk = (int)(item - chunk_off[t]);
-    // status refinement once per tracklet (flags are final: k_frame_voxelize has completed)
+    // status refinement once per tracklet (flags are final: both crop passes have completed)
     int status = g.status;
     if (status == OCCB200_OK) {
-      if (g.flags & 2) status = OCCB200_INDEX_ERROR;
-      else if (!(g.flags & 1)) status = OCCB200_EMPTY_AFTER_FILTER;
+      const int fl = trk_flags[t];
+      if (fl & 2) status = OCCB200_INDEX_ERROR;
+      else if (!(fl & 1)) status = OCCB200_EMPTY_AFTER_FILTER;
     }
     if (chunk == 0 && threadIdx.x == 0) status_out[t] = status;
     if (status != OCCB200_OK) continue;          // the reference produces no output here
@@ -719,7 +787,11 @@ k_visibility_f64(int T, int L, const int64_t *__restrict__ trk_frame_off,
         if (__all_sync(0xffffffffu, !need || is_free)) break;
       }
     }
-    if (active) labels[label_off[t] + f] = occupied ? 1 : (is_free ? 2 : 0);   // :558-563
+    if (active) {                                  // :558-563
+      const int lab = occupied ? 1 : (is_free ? 2 : 0);
+      if (labels) labels[label_off[t] + f] = lab;
+      if (labels_u8) labels_u8[label_off[t] + f] = (uint8_t)lab;
+    }
     const unsigned nmask = __ballot_sync(0xffffffffu, need);
     for (int o = 16; o > 0; o >>= 1) steps += __shfl_xor_sync(0xffffffffu, steps, o);
     if (lane == 0) {
@@ -729,49 +801,47 @@ k_visibility_f64(int T, int L, const int64_t *__restrict__ trk_frame_off,
   }
 }
 
+
 // ---------------------------------------------------------------------------------------------
 // Fast path, part 1: per-table row lookup.  Table t_0 > t_1 > ... (flipped inclinations,
 // occ_annotate.py:528).  argmin_h |inc - t_h| (first index on ties, :168-173) == number of
-// midpoints m_h = (t_h + t_{h+1})/2 that lie above inc.  Boundaries are stored as ub_h = u(m_h).
+// midpoints m_h = (t_h + t_{h+1})/2 that lie above inc.  Boundaries are kept as ub_h = u(m_h).
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ double u_of_angle(double a) {
   const double s = sin(a), c = cos(a);
   return s / (fabs(s) + c);
 }
 
+// One CTA per DISTINCT table (the frames of a segment share one table per LiDAR): boundaries, cell geometry,
+// lookup cells.
 __global__ void __launch_bounds__(256)
-k_table_setup(int64_t n_sensors, const occb200_sensor_t *__restrict__ sensors, const float *__restrict__ incl_pool,
-              SensCoef *__restrict__ sens, float *__restrict__ ub_pool, uint16_t *__restrict__ lut_pool,
-              int32_t *__restrict__ tab_claim) {
+k_table_setup(int n_tables, const int64_t *__restrict__ table_off, const int32_t *__restrict__ table_H,
+              const float *__restrict__ incl_pool, TabCoef *__restrict__ tabcoef, float *__restrict__ ub_pool,
+              LutCell *__restrict__ lut_pool) {
   __shared__ float s_min[256];
-  __shared__ SensCoef s_info;
-  __shared__ int s_builder;
-  const int64_t e = blockIdx.x;
-  if (e >= n_sensors) return;
-  const occb200_sensor_t &sn = sensors[e];
-  const int H = sn.H;
-  const int64_t off = sn.incl_off;
+  __shared__ TabCoef s_tc;
+  const int e = blockIdx.x;
+  if (e >= n_tables) return;
+  const int H = table_H[e];
+  const int64_t off = table_off[e];
   const float *tab = incl_pool + off;
-  float *ub = ub_pool + 2 * off + 1;              // ub[-1] = +2 and ub[H-1] = -2 are sentinels
-  uint16_t *lut = lut_pool + off * kLutPerRow;
-  const bool candidate = (sn.incl_mono == -1) && H >= 2 && H < 65535 && off < (1ll << 24);
+  float *ub = ub_pool + off;                      // H - 1 boundaries
+  LutCell *lut = lut_pool + off * kLutPerRow;
+  const bool candidate = H >= 2 && H < 65535 && off < (1ll << 24);
   float local_min = INFINITY;
-  if (candidate) {
+  if (candidate)
     for (int h = threadIdx.x; h < H - 1; h += blockDim.x) {
       const double m = 0.5 * ((double)tab[h] + (double)tab[h + 1]);
       ub[h] = (float)u_of_angle(m);
     }
-    if (threadIdx.x == 0) {
-      ub[-1] = 2.f;
-      ub[H - 1] = -2.f;
-    }
-  }
   __syncthreads();
   if (candidate) {
     for (int h = threadIdx.x; h < H - 2; h += blockDim.x) local_min = fminf(local_min, ub[h] - ub[h + 1]);
-    // the table must stay inside (-90, 90) degrees for u() to be monotone
+    // the table must stay inside (-90, 90) degrees for u() to be monotone, and descend (tab[h] > tab[h+1]: a
+    // non-positive spacing fails the test below; NaN entries fail this one)
     for (int h = threadIdx.x; h < H; h += blockDim.x)
       if (!(fabsf(tab[h]) < 1.5707f)) local_min = -1.f;
+    if (H == 2 && threadIdx.x == 0 && !(tab[0] > tab[1])) local_min = -1.f;
   }
   s_min[threadIdx.x] = local_min;
   __syncthreads();
@@ -780,99 +850,65 @@ k_table_setup(int64_t n_sensors, const occb200_sensor_t *__restrict__ sensors, c
     __syncthreads();
   }
   if (threadIdx.x == 0) {
-    SensCoef sc;
-    sc.azc = sn.azc;
-    sc.kcol = (float)((double)sn.W / 6.28318530717958647692);
-    sc.Wf = (float)sn.W;
-    sc.col0 = 0.5f * (float)sn.W - 0.5f;
-    // colf = fma(az, -kcol, W/2 - 0.5) with |az| <= 2 pi (no wrap: the column is taken modulo W afterwards): one
-    // rounding at magnitude <= 1.5 W, the rounding of kcol (<= 2^-24 * W) and of az's sum (in kAtanErr's slack);
-    // the reference wraps with float32(2 pi), which moves its colf by W * 2.8e-8 relative to an exact wrap
-    sc.c_col = 3.0f * (float)sn.W * 1.1920929e-07f + (float)sn.W * 4e-8f;
-    sc.u_lo = 0.f; sc.inv_w = 0.f; sc.ncell = 0; sc.cell0 = 0.f;
-    sc.H = H; sc.W = sn.W; sc.ok = 0;
-    sc.tab_off = (int32_t)off; sc.ri_off = sn.ri_off; sc.pad1 = 0.f;
+    TabCoef tc;
+    tc.inv_w = 0.f; tc.cell0m = 0.f; tc.w = 0.f; tc.ncell = 0; tc.H = H; tc.ok = 0; tc.pad[0] = tc.pad[1] = 0;
     float spacing = s_min[0];
-    if (candidate && H == 2) spacing = 0.25f;
-    if (candidate && spacing > 1e-6f && isfinite(spacing) && sn.W >= 2 && sn.W < (1 << 22)) {
-      // cells half as wide as the closest pair of boundaries (so a cell holds at most one), covering [-1, 1]
+    if (candidate && H == 2 && spacing > 0.f) spacing = 0.25f;
+    if (candidate && spacing > 1e-6f && isfinite(spacing)) {
+      // cells half as wide as the closest pair of boundaries, centred on u_k = (k - cell0m) / inv_w, covering
+      // [-1.02, 1.02]
       const float w = 0.5f * spacing;
-      const int ncell = (int)ceilf(2.04f / w) + 1;
+      const int ncell = (int)ceilf(2.04f / w) + 2;
       if (ncell <= H * kLutPerRow) {
-        sc.u_lo = -1.02f;
-        sc.inv_w = 1.0f / w;
-        sc.cell0 = 1.02f * sc.inv_w;
-        sc.ncell = ncell;
-        sc.ok = 1;
+        tc.w = w;
+        tc.inv_w = 1.0f / w;
+        tc.cell0m = 1.02f * tc.inv_w;
+        tc.ncell = ncell;
+        tc.ok = 1;
       }
     }
-    s_info = sc;
-    sens[e] = sc;
-    // the frames of a segment share one inclination table per LiDAR (same incl_off): every entry writes the same
-    // boundaries above, but only the first CTA to claim the table builds its lookup cells
-    s_builder = sc.ok ? (atomicCAS(tab_claim + off, 0, 1) == 0) : 0;
+    s_tc = tc;
+    tabcoef[off] = tc;
   }
   __syncthreads();
-  const SensCoef sc = s_info;
-  if (!sc.ok || !s_builder) return;
-  // lut[k] = number of boundaries above the (slightly raised) upper end of cell k, i.e. the row of a point at
-  // the top of the cell.  It only has to be a good starting guess: the kernel accepts a row only after checking
-  // the two boundaries around it.
-  const float w = 1.0f / sc.inv_w;
-  for (int k = threadIdx.x; k < sc.ncell; k += blockDim.x) {
-    const float ue = sc.u_lo + (float)(k + 1) * w + 0.02f * w;
-    int lo = 0, hi = H - 1;                       // count of ub_h > ue (ub descending)
+  const TabCoef tc = s_tc;
+  if (!tc.ok) return;
+  const double w = (double)tc.w, inv_w = (double)tc.inv_w, c0 = (double)tc.cell0m;
+  for (int k = threadIdx.x; k < tc.ncell; k += blockDim.x) {
+    const double uk = ((double)k - c0) / inv_w;
+    int lo = 0, hi = H - 1;                       // count of ub_h > uk (ub descending)
     while (lo < hi) {
       const int mid = (lo + hi) >> 1;
-      if (ub[mid] > ue) lo = mid + 1; else hi = mid;
+      if ((double)ub[mid] > uk) lo = mid + 1; else hi = mid;
     }
-    lut[k] = (uint16_t)lo;
+    // the boundary nearest to uk is ub[lo - 1] (just above) or ub[lo] (at or below); at most one of them can sit in
+    // the extended cell [uk - 0.75 w, uk + 0.75 w]: the boundaries are >= 2 w apart
+    LutCell c;
+    c.b = -4.f;
+    c.h = lo;
+    if (lo >= 1 && (double)ub[lo - 1] - uk <= 0.75 * w) { c.b = ub[lo - 1]; c.h = lo - 1; }
+    else if (lo < H - 1 && uk - (double)ub[lo] <= 0.75 * w) { c.b = ub[lo]; c.h = lo; }
+    lut[k] = c;
   }
 }
 
-// ---------------------------------------------------------------------------------------------
-// Range-image max pyramid: pyr[tile] = max of the image over kTileR x kTileC pixels.  Used only to
-// PROVE that a (frame, LiDAR) pair cannot free any voxel of a tracklet (all returns in the window
-// the tracklet projects to are nearer than its nearest voxel), so that pair is skipped entirely.
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024)
-k_pyr_scan(int64_t n, const occb200_sensor_t *__restrict__ sensors, int64_t cap, int64_t *__restrict__ pyr_off,
-           unsigned long long *__restrict__ counter) {
-  __shared__ int64_t s_part[1024];
-  const int tid = threadIdx.x;
-  const int64_t per = (n + 1023) / 1024;
-  const int64_t a = min((int64_t)tid * per, n), b = min(a + per, n);
-  auto tiles = [&](int64_t e) {
-    const int H = sensors[e].H, W = sensors[e].W;
-    return (int64_t)((H + kTileR - 1) / kTileR) * ((W + kTileC - 1) / kTileC);
-  };
-  int64_t sum = 0;
-  for (int64_t e = a; e < b; ++e) sum += tiles(e);
-  s_part[tid] = sum;
-  __syncthreads();
-  for (int d = 1; d < 1024; d <<= 1) {
-    int64_t v = (tid >= d) ? s_part[tid - d] : 0;
-    __syncthreads();
-    s_part[tid] += v;
-    __syncthreads();
-  }
-  int64_t run = s_part[tid] - sum;
-  for (int64_t e = a; e < b; ++e) {
-    pyr_off[e] = run;
-    run += tiles(e);
-  }
-  if (tid == 1023) {
-    pyr_off[n] = s_part[1023];
-    counter[0] = (s_part[1023] <= cap) ? 1ull : 0ull;      // 1: pyramid fits, culling enabled
-  }
+// row(u) = number of boundaries above u, for ANY u (the caller supplies the error padding): used by the culls.
+__device__ __forceinline__ int row_of_u(const LutCell *__restrict__ lut, float inv_w, float cell0m, int ncell,
+                                        float u) {
+  const int cell = max(0, min((int)rintf(fmaf(u, inv_w, cell0m)), ncell - 1));
+  const LutCell c = lut[cell];
+  return c.h + ((c.b > u) ? 1 : 0);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Range-image max pyramid: pyr[tile] = max of the image over kTileR x kTileC pixels, pyr2 over kFineR x kFineC.
+// Used only to PROVE that a (frame, LiDAR) pair cannot free any voxel of a tracklet / a brick (all returns in
+// the window it projects to are nearer than its nearest voxel), so that the pair is skipped.
+// ---------------------------------------------------------------------------------------------
 constexpr int kPyrRowGroups = 8;
 __global__ void __launch_bounds__(256)
 k_pyr_build(const occb200_sensor_t *__restrict__ sensors, const float *__restrict__ ri_pool,
-            const int64_t *__restrict__ pyr_off, const unsigned long long *__restrict__ counter,
-            float *__restrict__ pyr) {
-  if (counter[0] == 0ull) return;
+            const int64_t *__restrict__ pyr_off, float *__restrict__ pyr, float *__restrict__ pyr2) {
   const int e = blockIdx.x;                        // sensor entry; blockIdx.y = row group
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const occb200_sensor_t &sn = sensors[e];
@@ -880,6 +916,8 @@ k_pyr_build(const occb200_sensor_t *__restrict__ sensors, const float *__restric
   const int ntr = (H + kTileR - 1) / kTileR, ntc = (W + kTileC - 1) / kTileC;
   const float *img = ri_pool + sn.ri_off;
   float *out = pyr + pyr_off[e];
+  float *out2 = pyr2 + 16 * pyr_off[e];            // fine level: 16 slots per coarse tile always suffice
+  const int nr2 = (H + kFineR - 1) / kFineR, nc2 = (W + kFineC - 1) / kFineC;
   constexpr int kU = 4;                            // tiles per warp in flight: 32 independent loads per lane
   // the image's tiles as one list, dealt to (row group, warp) in runs of kU: every warp is busy whatever the
   // image shape (a 200 x 600 image has only 19 tiles per tile row)
@@ -912,6 +950,15 @@ k_pyr_build(const occb200_sensor_t *__restrict__ sensors, const float *__restric
         float m = 0.f;
 #pragma unroll
         for (int r = 0; r < kTileR; ++r) m = fmaxf(m, fmaxf(v[u][r].x, v[u][r].y));
+        // fine level: 2 rows x 8 columns = rows (2j, 2j+1) of the four lanes that share columns [8g, 8g+8)
+#pragma unroll
+        for (int j = 0; j < kTileR / kFineR; ++j) {
+          float m2 = fmaxf(fmaxf(v[u][2 * j].x, v[u][2 * j].y), fmaxf(v[u][2 * j + 1].x, v[u][2 * j + 1].y));
+          m2 = fmaxf(m2, __shfl_xor_sync(0xffffffffu, m2, 1));
+          m2 = fmaxf(m2, __shfl_xor_sync(0xffffffffu, m2, 2));
+          const int r2 = tr * (kTileR / kFineR) + j, c2 = tp * (2 * kTileC / kFineC) + (lane >> 2);
+          if ((lane & 3) == 0 && p < npair && r2 < nr2 && c2 < nc2) out2[r2 * nc2 + c2] = m2;
+        }
         for (int o = 8; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));   // within 16 lanes
         const int tc = 2 * tp + (lane >> 4);       // lanes 0-15: first tile of the pair, 16-31: second
         if ((lane & 15) == 0 && p < npair && tc < ntc) out[tr * ntc + tc] = m;
@@ -937,6 +984,19 @@ k_pyr_build(const occb200_sensor_t *__restrict__ sensors, const float *__restric
       float m = 0.f;
 #pragma unroll
       for (int r = 0; r < kTileR; ++r) m = fmaxf(m, v[u][r]);
+      {                                            // fine level: rows (2j, 2j+1) of the eight lanes of a column group
+        const int tile = i0 + u;
+        const int tr = tile / ntc, tc = tile - tr * ntc;
+#pragma unroll
+        for (int j = 0; j < kTileR / kFineR; ++j) {
+          float m2 = fmaxf(v[u][2 * j], v[u][2 * j + 1]);
+          m2 = fmaxf(m2, __shfl_xor_sync(0xffffffffu, m2, 1));
+          m2 = fmaxf(m2, __shfl_xor_sync(0xffffffffu, m2, 2));
+          m2 = fmaxf(m2, __shfl_xor_sync(0xffffffffu, m2, 4));
+          const int r2 = tr * (kTileR / kFineR) + j, c2 = tc * (kTileC / kFineC) + (lane >> 3);
+          if ((lane & 7) == 0 && tile < ntile && r2 < nr2 && c2 < nc2) out2[r2 * nc2 + c2] = m2;
+        }
+      }
       for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
       if (lane == 0 && i0 + u < ntile) out[i0 + u] = m;
     }
@@ -949,27 +1009,31 @@ k_pyr_build(const occb200_sensor_t *__restrict__ sensors, const float *__restric
 //   ego    = Rm centre + o, Rm = [[c, s, 0], [-s, c, 0], [0, 0, 1]] (:490-498)
 //   p      = V ego + tv                                              (:161-164)
 //   =>  p = A idx + b,  A = vs V Rm,  b = V Rm c0 + V o + tv
-// eps bounds |f32 chain - reference f64 chain| per component: the three FMAs round at most
-// 3 * 2^-24 * M, the f32 coefficients contribute at most 2^-24 * M, M = |b| + sum |A| * max idx; the
-// reference's own f64 roundings (~1e-14 m) vanish in the slack of the factor 6.
+// The record stores the map ROTATED about the sensor's z axis by -theta, theta = azimuth of the centre of the
+// index lattice, and relative to that centre:  p' = bc + A' (idx - cen),  bc = Rz(-theta) p(cen) = (rho_c, ~0, z_c).
+// Then azimuth(p) = theta + atan2(y', x') with |y'/x'| small, and the f32 rounding of y' happens at the magnitude
+// of the OBJECT (metres), not of its distance (tens of metres).
 //
-// Culling.  All voxel centres lie in the ball (centre pc = p(grid centre), radius R = half the grid
+// Error bounds (per component; 2^-24 = half an ulp; factor 6 = 3 FMA roundings + coefficient roundings + slack):
+//   eps_y  = 6 * 2^-24 * (|bc_y| + sum_k |A'_yk| span_k / 2)          -- bc_y ~ 0
+//   eps_xz = 6 * 2^-24 * max over x, z of (|bc_r| + sum_k |A'_rk| span_k / 2)
+// the reference's own f64 roundings (~1e-14 m) vanish in the slack.
+//
+// Pair-level culling.  All voxel centres lie in the ball (centre pc = p(cen), radius R = half the lattice
 // diagonal).  Seen from the sensor the ball spans inclinations inc_c +- asin(R/d) and azimuths
 // az_c +- asin(R/rho_c); the reference's row/column rules are monotone in those angles, so every
-// pixel any centre can map to lies in the row/column window of the interval ends (padded by one).
+// pixel any centre can map to lies in the row/column window of the interval ends (padded).
 // If the largest return in that window (from the tile pyramid) is below d - R, `ri >= range` is
 // false for every voxel of the tracklet through this pair: the pair is dropped from the work list.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ PairCoef
+__device__ __forceinline__ bool
 make_pair(int64_t f, int c, int q, int L, const TrkGrid &g, const occb200_pose_t *__restrict__ poses,
           const int32_t *__restrict__ frame_sf, const occb200_sensor_t *__restrict__ sensors,
-          const SensCoef *__restrict__ sens, double vs, const int64_t *__restrict__ pyr_off,
-          const float *__restrict__ pyr, const uint16_t *__restrict__ lut_pool,
-          const unsigned long long *__restrict__ counter) {
+          const TabCoef *__restrict__ tabcoef, const LutCell *__restrict__ lut_pool, double vs,
+          const int64_t *__restrict__ pyr_off, const float *__restrict__ pyr, int cull_on, PairHot &p) {
   const occb200_pose_t &ps = poses[f];
   const int64_t se = (int64_t)frame_sf[f] * L + c;
   const occb200_sensor_t &sn = sensors[se];
-  PairCoef pc;
   const double rc = (double)ps.cos_p, rs = (double)ps.sin_p;
   const double Rm[9] = {rc, rs, 0, -rs, rc, 0, 0, 0, 1};
   double V[12];
@@ -979,71 +1043,114 @@ make_pair(int64_t f, int c, int q, int L, const TrkGrid &g, const occb200_pose_t
     for (int k = 0; k < 3; ++k) VR[3 * r + k] = V[4 * r] * Rm[k] + V[4 * r + 1] * Rm[3 + k] + V[4 * r + 2] * Rm[6 + k];
   const double c0[3] = {(double)g.mb[0] + vs / 2, (double)g.mb[1] + vs / 2, (double)g.mb[2] + vs / 2};
   const double o[3] = {(double)ps.box[0], (double)ps.box[1], (double)ps.box[2]};
-  float eps = 0.f;
-  double pcen[3], R2 = 0.0;
+  double half[3], pcen[3], A64[9], R2 = 0.0;
+  for (int k = 0; k < 3; ++k) half[k] = 0.5 * (double)(g.dims[k] > 0 ? g.dims[k] - 1 : 0);
   for (int r = 0; r < 3; ++r) {
     const double b = VR[3 * r] * c0[0] + VR[3 * r + 1] * c0[1] + VR[3 * r + 2] * c0[2] + V[4 * r] * o[0] +
                      V[4 * r + 1] * o[1] + V[4 * r + 2] * o[2] + V[4 * r + 3];
-    double M = fabs(b);
     pcen[r] = b;
     for (int k = 0; k < 3; ++k) {
-      const double a = vs * VR[3 * r + k];
-      const double span = (double)(g.dims[k] > 0 ? g.dims[k] - 1 : 0);
-      pc.A[3 * r + k] = (float)a;
-      M += fabs(a) * span;
-      pcen[r] += 0.5 * span * a;
+      A64[3 * r + k] = vs * VR[3 * r + k];
+      pcen[r] += half[k] * A64[3 * r + k];
     }
-    pc.b[r] = (float)b;
-    eps = fmaxf(eps, (float)(6.0 * 5.9604644775390625e-08 * M));
   }
-  for (int k = 0; k < 3; ++k) {                    // half diagonal of the centre grid in the sensor frame
+  for (int k = 0; k < 3; ++k) {                    // half diagonal of the centre lattice in the sensor frame
     double col2 = 0.0;
-    for (int r = 0; r < 3; ++r) col2 += VR[3 * r + k] * VR[3 * r + k];
-    const double span = vs * (double)(g.dims[k] > 0 ? g.dims[k] - 1 : 0);
-    R2 += col2 * span * span;
+    for (int r = 0; r < 3; ++r) col2 += A64[3 * r + k] * A64[3 * r + k];
+    R2 += col2 * half[k] * half[k];
   }
-  const bool ok = sens[se].ok && isfinite(eps) && se < (1ll << 31);
-  pc.eps = ok ? eps : -1.f;
-  pc.sens = (int32_t)se;
-  pc.q = q;
-  pc.cull = 0;
+  // the columns of VR are orthogonal only up to the f32 inverse: 1.001 covers it, +1 mm absolute
+  const double R = sqrt(R2) * 1.001 + 1e-3;
+  const double rho_c = sqrt(pcen[0] * pcen[0] + pcen[1] * pcen[1]);
+  const double d_c = sqrt(rho_c * rho_c + pcen[2] * pcen[2]);
+  const bool has_dir = rho_c > 1e-9;
+  const double ct = has_dir ? pcen[0] / rho_c : 1.0, st = has_dir ? pcen[1] / rho_c : 0.0;
+  const double theta = has_dir ? atan2(pcen[1], pcen[0]) : 0.0;
+  double A2[9], bc[3], M[3];
+  for (int k = 0; k < 3; ++k) {
+    A2[k] = ct * A64[k] + st * A64[3 + k];
+    A2[3 + k] = -st * A64[k] + ct * A64[3 + k];
+    A2[6 + k] = A64[6 + k];
+  }
+  bc[0] = ct * pcen[0] + st * pcen[1];
+  bc[1] = -st * pcen[0] + ct * pcen[1];
+  bc[2] = pcen[2];
+  for (int r = 0; r < 3; ++r) {
+    M[r] = fabs(bc[r]);
+    for (int k = 0; k < 3; ++k) {
+      M[r] += fabs(A2[3 * r + k]) * half[k];
+      p.A[3 * r + k] = (float)A2[3 * r + k];
+    }
+    p.bc[r] = (float)bc[r];
+  }
+  const double k6 = 6.0 * 5.9604644775390625e-08;
+  const double eps_y = k6 * M[1], eps_xz = k6 * fmax(M[0], M[2]);
+  const bool narrow = rho_c > 2.1 * R;
+  const double tmax = narrow ? fmin(R / (rho_c - R), 1.0) : 1.0;
+  const int W = sn.W, H = sn.H;
+  const double kcol = (double)W / 6.28318530717958647692;
+  // colf = (W - 0.5) - (az + pi) / (2 pi) * W with az = theta + phi + azc  (:176-191); taken modulo W
+  const double C0 = ((double)W - 0.5) - (theta + (double)sn.azc + 3.14159265358979323846) / 6.28318530717958647692 * (double)W;
+  const double C0m = C0 - floor(C0 / (double)W) * (double)W;       // in [0, W)
+  int cint = (int)floor(C0m);
+  cint = max(0, min(cint, W - 1));
+  const double phimax = narrow ? atan(tmax) : 3.14159265358979323846;
+  // colf_rel = fma(phi, -kcol, c0f): one rounding at magnitude <= kcol * phimax + 1, the rounding of kcol and of
+  // c0f; the reference wraps with float32(2 pi), which moves its colf by W * 3e-8 relative to an exact wrap
+  const double c_col = 3.0 * 5.9604644775390625e-08 * (kcol * phimax + 2.0) + (double)W * 4e-8;
+  const double katan = narrow ? (double)kAtanNarrow : (double)kAtanWide;
+  const TabCoef tc = tabcoef[sn.incl_off];
+  const double e15z = 1.5 * fmax(eps_xz, eps_y);
+  const double d_min = d_c - R;
+  bool ok = tc.ok && tc.H == H && sn.incl_mono == -1 && isfinite(eps_xz) && isfinite(eps_y) && se < (1ll << 31) &&
+            W >= 2 && W < (1 << 22) && d_min > 0.05;
+  // the row test needs its margin below a fifth of a lookup cell (k_table_setup / fast_test)
+  if (ok && !(e15z / d_min + 1.5e-6 < 0.2 * (double)tc.w)) ok = false;
+  p.eps = ok ? (float)fmax(eps_xz, eps_y) : -1.f;
+  p.q = q;
+  p.inv_w = tc.inv_w;
+  p.cell0m = tc.cell0m;
+  p.ncm1 = (uint32_t)max(tc.ncell - 1, 0);
+  p.last = (uint32_t)max(H - 1, 0);
+  p.e15z = (float)e15z;
+  p.nkcol = (float)(-kcol);
+  p.c0f = (float)(C0m - (double)cint);
+  p.cint = cint;
+  p.W = W;
+  p.ecolk = (float)(1.5 * (eps_y + tmax * eps_xz) * kcol);
+  p.ecol = (float)((katan + 3.0e-7) * kcol + c_col);
+  p.c1 = (float)(1.6 * eps_xz + 1.1 * eps_y);
+  p.lut_off = (int32_t)(sn.incl_off * kLutPerRow);
+  p.wide = narrow ? 0 : 1;
+  p.ri_off = sn.ri_off;
+  p.sens = (int32_t)se;
+  p.pad = 0;
   // ---- cull test (conservative; any doubt keeps the pair)
-  if (counter[0] != 0ull && g.status == OCCB200_OK && sn.incl_mono == -1 && sn.H >= 1 && sn.W >= 1) {
-    // f32 geometry: the window is padded by 1e-4 rad (>> f32 error, << a pixel) and one extra row / column
-    // the columns of VR are orthogonal only up to the f32 inverse: 1.001 covers it, +1 mm absolute
-    const float R = 0.5f * sqrtf((float)R2) * 1.001f + 1e-3f;
-    const float cxs = (float)pcen[0], cys = (float)pcen[1], czs = (float)pcen[2];
-    const float rho = sqrtf(cxs * cxs + cys * cys);
-    const float d = sqrtf(rho * rho + czs * czs);
-    if (d > 1.25f * R) {
-      const float rmin = d - R - 1e-3f * (1.f + d * 1e-3f);
-      const float delta = asinf(R / d) + 1e-4f;
-      const float inc_c = atan2f(czs, rho);
-      // rows of the interval ends: the table lookup gives the row at the top of a cell (the true row is that
-      // or the next one), which is all a conservative window needs; sensors without a table use every row
-      int r0 = 0, r1 = sn.H - 1;
-      const SensCoef sc = sens[se];
-      if (sc.ok) {
-        const uint16_t *lut = lut_pool + (int64_t)sc.tab_off * kLutPerRow;
+  if (cull_on && g.status == OCCB200_OK && sn.incl_mono == -1 && H >= 1 && W >= 1) {
+    // f32 geometry: the window is padded by 1e-4 rad (>> f32 error, << a pixel) and extra rows / columns
+    const float Rf = (float)R;
+    const float rho = (float)rho_c, d = (float)d_c;
+    if (d > 1.25f * Rf) {
+      const float rmin = d - Rf - 1e-3f * (1.f + d * 1e-3f);
+      const float delta = asinf(Rf / d) + 1e-4f;
+      const float inc_c = atan2f((float)pcen[2], rho);
+      int r0 = 0, r1 = H - 1;
+      if (tc.ok && tc.H == H) {
+        const LutCell *lut = lut_pool + sn.incl_off * kLutPerRow;
         float sh, ch, sl, cl;
         sincosf(fminf(inc_c + delta, 1.5707f), &sh, &ch);
         sincosf(fmaxf(inc_c - delta, -1.5707f), &sl, &cl);
         const float u_hi = sh / (fabsf(sh) + ch) + 1e-5f;
         const float u_lo = sl / (fabsf(sl) + cl) - 1e-5f;
-        const int c_hi = max(0, min((int)floorf(fmaf(u_hi, sc.inv_w, sc.cell0)) + 2, sc.ncell - 1));
-        const int c_lo = max(0, min((int)floorf(fmaf(u_lo, sc.inv_w, sc.cell0)) - 2, sc.ncell - 1));
-        r0 = max((int)lut[c_hi] - 1, 0);
-        r1 = min((int)lut[c_lo] + 2, sn.H - 1);
+        r0 = max(row_of_u(lut, tc.inv_w, tc.cell0m, tc.ncell, u_hi) - 1, 0);
+        r1 = min(row_of_u(lut, tc.inv_w, tc.cell0m, tc.ncell, u_lo) + 1, H - 1);
       }
-      const int W = sn.W;
       const int ntc = (W + kTileC - 1) / kTileC;
       long long c_lo = 0, c_hi = W - 1;            // column window, possibly beyond [0, W): taken modulo W
-      if (rho > 1.05f * R) {
-        const float daz = asinf(R / rho) + 1e-4f;
-        const float az_c = atan2f(cys, cxs) + sn.azc;
-        const float kc = (float)W / 6.2831853f;
-        const float cf_lo = ((float)W - 0.5f) - (az_c + daz + 3.14159265f) * kc;
-        const float cf_hi = ((float)W - 0.5f) - (az_c - daz + 3.14159265f) * kc;
+      if (rho > 1.05f * Rf) {
+        const float daz = asinf(Rf / rho) + 1e-4f;
+        const float kc = (float)kcol, cc = (float)C0m;
+        const float cf_lo = cc - daz * kc, cf_hi = cc + daz * kc;
         if (cf_hi - cf_lo + 6.0f < (float)W) {
           c_lo = (long long)floorf(cf_lo) - 2;
           c_hi = (long long)ceilf(cf_hi) + 2;
@@ -1067,17 +1174,17 @@ make_pair(int64_t f, int c, int q, int L, const TrkGrid &g, const occb200_pose_t
         const float *prow = pimg + (int64_t)tr * ntc;
         for (int seg = 0; seg < 2; ++seg) {
           const int s0 = seg ? 0 : ta, s1 = seg ? tw : tb;
-          for (int tc = s0; tc <= s1 && m < rmin; tc += 4) {
-            const float v0 = prow[tc], v1 = prow[min(tc + 1, s1)], v2 = prow[min(tc + 2, s1)],
-                        v3 = prow[min(tc + 3, s1)];
+          for (int tcx = s0; tcx <= s1 && m < rmin; tcx += 4) {
+            const float v0 = prow[tcx], v1 = prow[min(tcx + 1, s1)], v2 = prow[min(tcx + 2, s1)],
+                        v3 = prow[min(tcx + 3, s1)];
             m = fmaxf(fmaxf(m, fmaxf(v0, v1)), fmaxf(v2, v3));
           }
         }
       }
-      if (m < rmin) pc.cull = 1;
+      if (m < rmin) return false;
     }
   }
-  return pc;
+  return true;
 }
 
 // j-th frame of a tracklet of B frames in the order 0, S, 2S, .., 1, S+1, .. (S = kFrameStride)
@@ -1091,22 +1198,26 @@ __device__ __forceinline__ int strided_frame(int j, int B) {
   return B - 1;                                   // not reached for j < B
 }
 
-// One CTA per tracklet, one thread per (frame, LiDAR) pair: the pair's affine map and cull decision (make_pair),
-// then the surviving pairs are written (merged with their sensor entry into 128-byte records) to
-// the front of the tracklet's slot -- frames in strided order, so that the first kPhase1Pairs pairs look at the
-// object from spread-out viewpoints; thread 0 fixes the final status and writes the tracklet's hot record; all
-// threads then emit the phase-1 work items (one per chunk of 32 * kVPL1 voxels).  Item ids come from an atomic counter, so their order across tracklets is arbitrary.
+__device__ __forceinline__ int bricks_of(int n) { return (n + kBrick - 1) / kBrick; }
+
+// One CTA per tracklet, one thread per (frame, LiDAR) pair: the pair's record and cull decision (make_pair); the
+// surviving pairs are written to the front of the tracklet's slot -- frames in strided order and, inside a frame,
+// LiDARs in reference order, so that the first slice of pairs looks at the object from spread-out viewpoints;
+// thread 0 fixes the final status and writes the tracklet's hot record; all threads then emit the work items:
+// one per (slice of kPairsPerItem pairs, brick), appended to the slice's own list (the kernels walk the lists
+// slice by slice, so the pairs that free most voxels are tested first, on every brick of the batch).
 __global__ void __launch_bounds__(256)
-k_pair_build(int T, int L, const int64_t *__restrict__ trk_frame_off, const int64_t *__restrict__ label_off,
-             const TrkGrid *__restrict__ grids, const occb200_pose_t *__restrict__ poses,
-             const int32_t *__restrict__ frame_sf, const occb200_sensor_t *__restrict__ sensors,
-             const SensCoef *__restrict__ sens, double vs, const int64_t *__restrict__ pyr_off,
-             const float *__restrict__ pyr, const uint16_t *__restrict__ lut_pool,
-             const unsigned long long *__restrict__ pyr_flag, PairHot *__restrict__ pairs_c,
-             TrkHot *__restrict__ hot, int2 *__restrict__ item_map, long long items_cap,
+k_pair_build(int T, int L, const int64_t *__restrict__ trk_frame_off, const int64_t *__restrict__ brick_off,
+             const TrkGrid *__restrict__ grids, const int32_t *__restrict__ trk_flags,
+             const occb200_pose_t *__restrict__ poses, const int32_t *__restrict__ frame_sf,
+             const occb200_sensor_t *__restrict__ sensors, const TabCoef *__restrict__ tabcoef,
+             const LutCell *__restrict__ lut_pool, double vs, const int64_t *__restrict__ pyr_off,
+             const float *__restrict__ pyr, int cull_on, PairHot *__restrict__ pairs_c, TrkHot *__restrict__ hot,
+             int2 *__restrict__ item_map, long long bricks_total, int n_slices,
              unsigned long long *__restrict__ counter, int32_t *__restrict__ status_out) {
-  __shared__ long long s_i0, s_nitems;
+  __shared__ long long s_i0[kMaxSlices];
   __shared__ int s_cnt[8];
+  __shared__ int s_status;
   const int t = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const TrkGrid g = grids[t];
@@ -1114,27 +1225,28 @@ k_pair_build(int T, int L, const int64_t *__restrict__ trk_frame_off, const int6
   // being rewritten by the redo pass (side stream) -- it is treated as OK here and k_labels folds its flags in
   int status = g.status;
   if (status == OCCB200_OK && !g.redo) {
-    if (g.flags & 2) status = OCCB200_INDEX_ERROR;
-    else if (!(g.flags & 1)) status = OCCB200_EMPTY_AFTER_FILTER;
+    const int fl = trk_flags[t];
+    if (fl & 2) status = OCCB200_INDEX_ERROR;
+    else if (!(fl & 1)) status = OCCB200_EMPTY_AFTER_FILTER;
   }
+  const int nbx = bricks_of(g.dims[0]), nby = bricks_of(g.dims[1]), nbz = bricks_of(g.dims[2]);
+  const long long nbricks = (long long)nbx * nby * nbz;
   const int64_t base = trk_frame_off[t] * L;
   const int B = (int)(trk_frame_off[t + 1] - trk_frame_off[t]);
+  if (status == OCCB200_OK && (nbricks > brick_off[t + 1] - brick_off[t] || (long long)B * L > (long long)n_slices * kPairsPerItem))
+    status = OCCB200_WORK_OVERFLOW;                 // a host bound (brick_off / max_pairs) is violated: never silently
   const int n = (status == OCCB200_OK) ? B * L : 0;
   int count = 0;                                    // surviving pairs so far (same value in every thread)
   for (int j0 = 0; j0 < n; j0 += 256) {             // 256 pairs per pass, one per thread
     const int j = j0 + threadIdx.x;
-    int q = 0;
-    if (j < n) {
-      const int pf = j / L;
-      q = strided_frame(pf, B) * L + (j - pf * L);
-    }
-    PairCoef pc;
+    PairHot p;
     bool keep = false;
     if (j < n) {
+      const int pf = j / L;
+      const int q = strided_frame(pf, B) * L + (j - pf * L);
       const int i = q / L;
-      pc = make_pair(trk_frame_off[t] + i, q - i * L, q, L, g, poses, frame_sf, sensors, sens, vs, pyr_off, pyr,
-                     lut_pool, pyr_flag);
-      keep = pc.cull == 0;
+      keep = make_pair(trk_frame_off[t] + i, q - i * L, q, L, g, poses, frame_sf, sensors, tabcoef, lut_pool, vs,
+                       pyr_off, pyr, cull_on, p);
     }
     const unsigned mask = __ballot_sync(0xffffffffu, keep);
     if (lane == 0) s_cnt[warp] = __popc(mask);
@@ -1147,24 +1259,6 @@ k_pair_build(int T, int L, const int64_t *__restrict__ trk_frame_off, const int6
     }
     if (keep) {
       const int dst = count + before + __popc(mask & ((1u << lane) - 1u));
-      const SensCoef sc = sens[pc.sens];
-      PairHot p;
-#pragma unroll
-      for (int k = 0; k < 9; ++k) p.A[k] = pc.A[k];
-#pragma unroll
-      for (int k = 0; k < 3; ++k) p.b[k] = pc.b[k];
-      p.eps = pc.eps; p.q = pc.q;
-      p.azc = sc.azc; p.inv_w = sc.inv_w; p.cell0m = sc.cell0 - 0.5f; p.col0 = sc.col0;
-      p.W = sc.W; p.tab_off = sc.tab_off; p.ri_off = sc.ri_off;
-      p.e15 = 1.5f * pc.eps;
-      p.c1 = 2.01f * 1.7321f * pc.eps;
-      p.c2 = 3.0003f * pc.eps * pc.eps;
-      p.ecol = fmaf(kAtanErr + 3.0e-7f, sc.kcol, sc.c_col);
-      p.e15k = p.e15 * sc.kcol;
-      p.nkcol = -sc.kcol;
-      p.last = (uint32_t)(sc.H - 1);
-      p.ncm1 = (uint32_t)(sc.ncell - 1);
-      p.pad[0] = p.pad[1] = 0;
       const float4 *src = reinterpret_cast<const float4 *>(&p);
       float4 *d4 = reinterpret_cast<float4 *>(pairs_c + base + dst);
 #pragma unroll
@@ -1173,47 +1267,143 @@ k_pair_build(int T, int L, const int64_t *__restrict__ trk_frame_off, const int6
     count += total;
     __syncthreads();                                // s_cnt is reused by the next pass
   }
+  const int nslice = (status == OCCB200_OK) ? (count + kPairsPerItem - 1) / kPairsPerItem : 0;
   if (threadIdx.x == 0) {
-    const long long nitems =
-        (status == OCCB200_OK && count > 0) ? (long long)((g.V + 32 * kVPL1 - 1) / (32 * kVPL1)) : 0;
-    s_nitems = nitems;
-    s_i0 = nitems ? (long long)atomicAdd(counter + 3, (unsigned long long)nitems) : 0;
     TrkHot h;
-    h.V = (int32_t)g.V; h.dY = g.dims[1]; h.dZ = g.dims[2];
-    h.status = status; h.nact = count; h.pad0 = 0;
-    h.bits_off = g.bits_off; h.label_off = label_off[t]; h.pairs_base = base;
-    h.pad1[0] = h.pad1[1] = 0;
+    h.V = (int32_t)g.V; h.dX = g.dims[0]; h.dY = g.dims[1]; h.dZ = g.dims[2];
+    h.status = status; h.nact = count;
+    h.bits_off = g.bits_off; h.pairs_base = base; h.brick_base = brick_off[t];
+    for (int k = 0; k < 3; ++k) h.cen[k] = 0.5f * (float)(g.dims[k] > 0 ? g.dims[k] - 1 : 0);
+    h.pad = 0;
     hot[t] = h;
     status_out[t] = status;
   }
+  for (int s = threadIdx.x; s < nslice; s += blockDim.x)
+    s_i0[s] = (long long)atomicAdd(counter + 8 + 2 * s, (unsigned long long)nbricks);
   __syncthreads();
-  const long long i0 = s_i0, nitems = s_nitems;
-  for (long long i = threadIdx.x; i < nitems; i += blockDim.x)
-    if (i0 + i < items_cap) item_map[i0 + i] = make_int2(t, (int)i);
+  const int nyz = nby * nbz;
+  for (long long i = threadIdx.x; i < nbricks * nslice; i += blockDim.x) {
+    const int s = (int)(i / nbricks);
+    const int b = (int)(i - (long long)s * nbricks);
+    const int bx = b / nyz, rem = b - bx * nyz;
+    const int by = rem / nbz, bz = rem - by * nbz;
+    item_map[(long long)s * bricks_total + s_i0[s] + b] = make_int2(t, bx | (by << 10) | (bz << 20));
+  }
 }
 
-// After phase 1: one CTA per tracklet emits the phase-2 work items -- (64 listed voxels) x (slice of kPairsPerItem
-// of the pairs phase 1 did not cover).  item_map is reused: phase 1 has finished with it.
+// ---------------------------------------------------------------------------------------------
+// Brick-level cull (docs/ROUND2_BRICK_CULL.md).  Brick = the voxel centres idx in [4bx, 4bx+3] x [4by, 4by+3] x
+// [4bz, 4bz+3].  Through a pair they map to a convex body with corners v_0..v_7 (corners of the FULL brick: a
+// superset of a clipped one).  With c the image of the brick centre and u = c/|c|:
+//   range    r_lo = min_i v_i.u  <=  |p|  <=  max_i |v_i| = r_hi   (a linear function attains its minimum, a convex
+//            one its maximum, over a convex body at a corner)
+//   columns  azimuth extremes of a convex body clear of the sensor's z axis are attained at corners
+//   rows     z is linear, and sin(inc) = z / |p| is bracketed with r_lo / r_hi by the sign of z
+// If the largest return over that pixel footprint (fine pyramid level, footprint snapped outwards to whole tiles) is
+// below r_lo, `ri >= range` is false for every centre of the brick through the pair: its mask bit is set and the
+// visibility kernel never evaluates the pair for the brick.  f32 geometry with generous padding (1e-4 rad, 1 mm +
+// the pair's error bound, extra rows / columns); any doubt keeps the pair.  The cull only removes tests that must
+// fail, so labels cannot change (flag bit 4 switches it off for the A/B parity tests).
+// One thread per (work item of slice s, pair of the slice): blockIdx.y = slice.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float u_of_sin(float s) {
+  return s / (fabsf(s) + sqrtf(fmaxf(1.f - s * s, 0.f)));
+}
+
 __global__ void __launch_bounds__(256)
-k_phase2_emit(const TrkHot *__restrict__ hot, const uint32_t *__restrict__ n_unk, int2 *__restrict__ item_map,
-              long long items_cap, unsigned long long *__restrict__ counter) {
-  __shared__ long long s_i0, s_nitems;
-  __shared__ int s_nslice;
-  const int t = blockIdx.x;
-  if (threadIdx.x == 0) {
-    const int nact = hot[t].nact;
-    const long long nchunk = (hot[t].status == OCCB200_OK) ? ((long long)n_unk[t] + kFastChunk - 1) / kFastChunk : 0;
-    const int nslice = nact > kPhase1Pairs ? (nact - kPhase1Pairs + kPairsPerItem - 1) / kPairsPerItem : 0;
-    const long long nitems = nchunk * nslice;
-    s_nslice = nslice;
-    s_nitems = nitems;
-    s_i0 = nitems ? (long long)atomicAdd(counter + 5, (unsigned long long)nitems) : 0;
+k_brick_cull(const int2 *__restrict__ item_map, long long bricks_total, const unsigned long long *__restrict__ counter,
+             const TrkHot *__restrict__ hot, const PairHot *__restrict__ pairs, const LutCell *__restrict__ lut_pool,
+             const int64_t *__restrict__ pyr_off, const float *__restrict__ pyr2, int mask_words,
+             uint32_t *__restrict__ pair_mask) {
+  const int s = blockIdx.y;
+  const long long n_items = (long long)counter[8 + 2 * s];
+  for (long long gidx = (long long)blockIdx.x * blockDim.x + threadIdx.x; gidx < n_items * kPairsPerItem;
+       gidx += (long long)gridDim.x * blockDim.x) {
+    const long long item = gidx / kPairsPerItem;
+    const int k = s * kPairsPerItem + (int)(gidx - item * kPairsPerItem);
+    const int2 m = __ldg(item_map + (long long)s * bricks_total + item);
+    const TrkHot &h = hot[m.x];
+    if (k >= h.nact) continue;
+    const PairHot &p = pairs[h.pairs_base + k];
+    if (!(p.eps >= 0.f)) continue;
+    const int bx = m.y & 1023, by = (m.y >> 10) & 1023, bz = (m.y >> 20) & 1023;
+    const int W = p.W, H = (int)p.last + 1;
+    const float hs = 0.5f * (kBrick - 1);
+    // image of the brick centre (rotated frame) and half diagonal of the brick's centre lattice
+    const float cx = (float)(kBrick * bx) + hs - h.cen[0], cy = (float)(kBrick * by) + hs - h.cen[1],
+                cz = (float)(kBrick * bz) + hs - h.cen[2];
+    const float pcx = fmaf(cz, p.A[2], fmaf(cy, p.A[1], fmaf(cx, p.A[0], p.bc[0])));
+    const float pcy = fmaf(cz, p.A[5], fmaf(cy, p.A[4], fmaf(cx, p.A[3], p.bc[1])));
+    const float pcz = fmaf(cz, p.A[8], fmaf(cy, p.A[7], fmaf(cx, p.A[6], p.bc[2])));
+    float R2 = 0.f;
+#pragma unroll
+    for (int c = 0; c < 9; ++c) R2 = fmaf(p.A[c], p.A[c], R2);
+    const float R = hs * sqrtf(R2) * 1.001f + 1e-3f;
+    const float rho2 = pcx * pcx + pcy * pcy;
+    const float rho_c = sqrtf(rho2), d = sqrtf(rho2 + pcz * pcz);
+    if (!(d > 1.25f * R && rho_c > 1.05f * R)) continue;
+    const float inv_d = 1.f / d;
+    const float ux = pcx * inv_d, uy = pcy * inv_d, uz = pcz * inv_d;
+    float r_lo = INFINITY, r_hi2 = 0.f, zmin = INFINITY, zmax = -INFINITY, tmin = INFINITY, tmax = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const float ox = (c & 1) ? hs : -hs, oy = (c & 2) ? hs : -hs, oz = (c & 4) ? hs : -hs;
+      const float vx = fmaf(oz, p.A[2], fmaf(oy, p.A[1], fmaf(ox, p.A[0], pcx)));
+      const float vy = fmaf(oz, p.A[5], fmaf(oy, p.A[4], fmaf(ox, p.A[3], pcy)));
+      const float vz = fmaf(oz, p.A[8], fmaf(oy, p.A[7], fmaf(ox, p.A[6], pcz)));
+      r_lo = fminf(r_lo, fmaf(vz, uz, fmaf(vy, uy, vx * ux)));
+      r_hi2 = fmaxf(r_hi2, fmaf(vz, vz, fmaf(vy, vy, vx * vx)));
+      zmin = fminf(zmin, vz);
+      zmax = fmaxf(zmax, vz);
+      // azimuth relative to the brick centre's: tan = cross / dot; dot > 0 for every corner because rho_c > 1.05 R
+      const float dot = fmaf(pcy, vy, pcx * vx), crs = fmaf(pcx, vy, -(pcy * vx));
+      const float tq = crs / dot;
+      tmin = fminf(tmin, tq);
+      tmax = fmaxf(tmax, tq);
+    }
+    const float slack = 1e-3f + 2.f * p.eps + 1e-5f * d;
+    r_lo -= slack;
+    const float r_hi = sqrtf(r_hi2) + slack;
+    zmin -= slack;
+    zmax += slack;
+    if (!(r_lo > 0.f) || !(tmin > -8.f) || !(tmax < 8.f)) continue;
+    // rows: sin(inc) = z / |p| bracketed by the corner extremes, through the u-space lookup like the pair cull
+    const float s_hi = fminf(fmaxf(zmax / (zmax > 0.f ? r_lo : r_hi), -1.f), 1.f);
+    const float s_lo = fminf(fmaxf(zmin / (zmin > 0.f ? r_hi : r_lo), -1.f), 1.f);
+    const float u_hi = u_of_sin(s_hi) + 2e-4f, u_lo = u_of_sin(s_lo) - 2e-4f;
+    const LutCell *lut = lut_pool + p.lut_off;
+    const int ncell = (int)p.ncm1 + 1;
+    const int r0 = max(row_of_u(lut, p.inv_w, p.cell0m, ncell, u_hi) - 1, 0);
+    const int r1 = min(row_of_u(lut, p.inv_w, p.cell0m, ncell, u_lo) + 1, H - 1);
+    // columns: colf_rel = c0f - kcol * phi with phi = atan2(pcy, pcx) + [atan(tmin), atan(tmax)] (padded)
+    const float kc = -p.nkcol;
+    const float phi_c = atan2f(pcy, pcx);
+    const float cf_lo = p.c0f - (phi_c + atanf(tmax) + 1e-4f) * kc;
+    const float cf_hi = p.c0f - (phi_c + atanf(tmin) - 1e-4f) * kc;
+    const long long q_lo = (long long)p.cint + (long long)floorf(cf_lo) - 2,
+                    q_hi = (long long)p.cint + (long long)ceilf(cf_hi) + 2;
+    const long long len = q_hi - q_lo + 1;
+    if (!(len > 0 && len < W / 2)) continue;
+    // fine tiles covering rows [r0, r1] and columns [q_lo, q_hi] modulo W
+    const int nc2 = (W + kFineC - 1) / kFineC;
+    const float *pimg = pyr2 + 16 * pyr_off[p.sens];
+    const long long a0 = ((q_lo % W) + W) % W;
+    const int ta = (int)(a0 / kFineC), tb = (int)((min(a0 + len, (long long)W) - 1) / kFineC);
+    const int tw = (a0 + len > W) ? (int)((a0 + len - W - 1) / kFineC) : -1;
+    float mx = 0.f;
+    for (int tr = r0 / kFineR; tr <= r1 / kFineR && mx < r_lo; ++tr) {
+      const float *prow = pimg + (int64_t)tr * nc2;
+      for (int seg = 0; seg < 2; ++seg) {
+        const int s0 = seg ? 0 : ta, s1 = seg ? tw : tb;
+        for (int tcx = s0; tcx <= s1 && mx < r_lo; tcx += 2)
+          mx = fmaxf(mx, fmaxf(prow[tcx], prow[min(tcx + 1, s1)]));
+      }
+    }
+    if (mx < r_lo) {
+      const int lb = (bx * bricks_of(h.dY) + by) * bricks_of(h.dZ) + bz;
+      atomicOr(pair_mask + (h.brick_base + lb) * mask_words + (k >> 5), 1u << (k & 31));
+    }
   }
-  __syncthreads();
-  const long long i0 = s_i0, nitems = s_nitems;
-  const int nslice = s_nslice;
-  for (long long i = threadIdx.x; i < nitems; i += blockDim.x)
-    if (i0 + i < items_cap) item_map[i0 + i] = make_int2(t, (int)(i / nslice) | ((int)(i % nslice) << 20));
 }
 
 // Approximate f32 primitives (flush-to-zero MUFU forms, <= 2 ulp): their error is part of every margin.
@@ -1228,15 +1418,9 @@ __device__ __forceinline__ float rcp_approx(float x) {
   return r;
 }
 
-// atan2 in f32: a * P(a^2), a = min/max in [0,1], P of degree 6 (|atan(a) - a P(a^2)| <= 2.5e-7 in exact
-// arithmetic, checked on 2e6 points), plus Horner rounding (<= 4e-7), the approximate division
-// (2 ulp of a: <= 2.4e-7) and the quadrant fix-ups (2 roundings at <= pi: 2.4e-7 each).
-// Total < 1.4e-6 rad; kAtanErr = 2e-6 is the bound used for every margin below (occb200_selftest_atan2
-// measures the actual maximum on the device).
-__device__ __forceinline__ float atan2_fast(float y, float x) {
-  const float ax = fabsf(x), ay = fabsf(y);
-  const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
-  const float a = mn * rcp_approx(mx);
+// atan(a) = a * P(a^2), P of degree 6: |atan(a) - a P(a^2)| <= 2.5e-7 for |a| <= 1 in exact arithmetic (checked on
+// 2e6 points); Horner rounding <= 4e-7; the caller's approximate division (2 ulp of a) <= 2.4e-7.
+__device__ __forceinline__ float atan_poly(float a) {
   const float s = a * a;
   float p = 0.006811790633946657f;
   p = fmaf(p, s, -0.0336042158305645f);
@@ -1245,7 +1429,19 @@ __device__ __forceinline__ float atan2_fast(float y, float x) {
   p = fmaf(p, s, 0.19807815551757812f);
   p = fmaf(p, s, -0.3331736922264099f);
   p = fmaf(p, s, 0.9999961256980896f);
-  float r = p * a;
+  return p * a;
+}
+
+// Narrow pairs: x > 0 and |y / x| <= 1 by construction (make_pair): atan2(y, x) = atan(y / x), no quadrant logic.
+// Total error < 9e-7 rad; kAtanNarrow = 1e-6 is the bound used by the margins.
+__device__ __forceinline__ float atan_narrow(float y, float x) { return atan_poly(y * rcp_approx(x)); }
+
+// Full-quadrant atan2 for the wide pairs: a = min/max in [0,1], plus the quadrant fix-ups (2 roundings at <= pi:
+// 2.4e-7 each).  Total < 1.4e-6 rad; kAtanWide = 2e-6 (occb200_selftest_atan2 measures both on the device).
+__device__ __forceinline__ float atan2_fast(float y, float x) {
+  const float ax = fabsf(x), ay = fabsf(y);
+  const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+  float r = atan_poly(mn * rcp_approx(mx));
   if (ay > ax) r = 1.57079632679489661923f - r;
   if (x < 0.f) r = 3.14159265358979323846f - r;
   return (y < 0.f) ? -r : r;
@@ -1256,51 +1452,54 @@ __device__ __forceinline__ float atan2_fast(float y, float x) {
 constexpr float kMagic = 12582912.f;              // 1.5 * 2^23
 __device__ __forceinline__ int magic_int(float biased) { return __float_as_int(biased) - 0x4B400000; }
 
-// One fast test.  Returns 2 = certainly free, 0 = certainly not free, 1 = undecided (recheck in f64).
-// `ub` points at the table's boundary 0 (sentinels at ub[-1] = +2 and ub[H-1] = -2).
-__device__ __forceinline__ int fast_test(const PairHot &p, float x, float y, float z, const float *__restrict__ ub,
-                                         const uint16_t *__restrict__ lut, const float *__restrict__ ri_img) {
-  const float px = fmaf(z, p.A[2], fmaf(y, p.A[1], fmaf(x, p.A[0], p.b[0])));
-  const float py = fmaf(z, p.A[5], fmaf(y, p.A[4], fmaf(x, p.A[3], p.b[1])));
-  const float pz = fmaf(z, p.A[8], fmaf(y, p.A[7], fmaf(x, p.A[6], p.b[2])));
+// One fast test of the voxel centre at lattice offset (dx, dy, dz) = idx - cen.
+// Returns 2 = certainly free, 0 = certainly not free, 1 = undecided (recheck in f64).
+//
+//   position  p' = bc + A d (3 FMAs per component): |p' - p_ref| <= eps_y in y', eps_xz in x' and z' (make_pair)
+//   row       u = z' / (|z'| + rho); |u - u_ref| <= 1.42 max(eps) / r + evaluation (~6 ulp of 1).  The lookup cell
+//             (nearest) holds the only boundary b within its extended interval and the row count h above it:
+//             row = h + (b > u), accepted iff |u - b| > margin.  Proof of exactness: u lies within 0.5005 cell widths
+//             of the cell centre, the reference's value within margin (< 0.2 widths, checked per pair) of u, so
+//             both sit inside the extended interval (+-0.75 widths), where b is the only boundary.
+//   column    phi = atan(y'/x') (narrow) or atan2 (wide); colf_rel = c0f - kcol phi; col = cint + rint(colf_rel)
+//             modulo W, accepted iff colf_rel is farther from a half-integer than ecolk / rho + ecol
+//   range     free iff ri >= |p_ref|;  | r - |p_ref| | <= 1.42 eps_xz + eps_y + 6.5e-7 r
+template <bool WIDE>
+__device__ __forceinline__ int fast_test(const PairHot &p, float dx, float dy, float dz,
+                                         const int2 *__restrict__ lut, const float *__restrict__ ri_img) {
+  const float px = fmaf(dz, p.A[2], fmaf(dy, p.A[1], fmaf(dx, p.A[0], p.bc[0])));
+  const float py = fmaf(dz, p.A[5], fmaf(dy, p.A[4], fmaf(dx, p.A[3], p.bc[1])));
+  const float pz = fmaf(dz, p.A[8], fmaf(dy, p.A[7], fmaf(dx, p.A[6], p.bc[2])));
   const float s2 = fmaf(py, py, px * px);
   const float r2 = fmaf(pz, pz, s2);
   const float inv_rho = rsqrt_approx(s2);
   const float inv_r = rsqrt_approx(r2);
 
-  // ---- row: u = pz / (|pz| + rho);  |u - u_ref| <= 1.42 eps / r  +  evaluation (~6 ulp of 1)
+  // ---- row
   const float u = pz * rcp_approx(fmaf(s2, inv_rho, fabsf(pz)));
-  // the lookup cell is only a starting guess (checked against the boundaries below): nearest instead of floor
   const unsigned cell = min((unsigned)magic_int(fmaf(u, p.inv_w, p.cell0m) + kMagic), p.ncm1);
-  const unsigned row0 = min((unsigned)__ldg(lut + cell), p.last);                  // row at the top of the cell
-  const float *ubr = ub + row0;
-  const float b_up = __ldg(ubr - 1), b_here = __ldg(ubr), b_dn = __ldg(ubr + 1);   // ub[H] is never selected
-  const bool step = b_here > u;                               // a cell holds at most one boundary
-  const unsigned row = row0 + (step ? 1u : 0u);
-  const float below = step ? b_dn : b_here;                   // boundary between row and row + 1
-  const float above = step ? b_here : b_up;                   // boundary between row - 1 and row
-  // accepted only if u lies strictly between the two boundaries of `row`, by more than its error
-  const bool ok_row = fminf(u - below, above - u) > fmaf(p.e15, inv_r, 1.5e-6f) && row <= p.last;
+  const int2 lc = __ldg(lut + cell);                          // (boundary, rows above it)
+  const float b = __int_as_float(lc.x);
+  const unsigned row = (unsigned)lc.y + ((b > u) ? 1u : 0u);
+  const bool ok_row = fabsf(u - b) > fmaf(p.e15z, inv_r, 1.5e-6f);
 
-  // ---- column: az = atan2(py, px) + azc (not wrapped: |az| <= 2 pi and the column is taken modulo W);
-  //      colf = (W - 0.5) - (az + pi) / (2 pi) * W  (:176-191);  |az - az_ref| <= kAtanErr + 1.42 eps / rho
-  const float az = atan2_fast(py, px) + p.azc;
-  const float colf = fmaf(az, p.nkcol, p.col0);
-  const float cb = colf + kMagic;                             // |colf| <= 1.5 W < 2^22
+  // ---- column
+  const float phi = WIDE ? atan2_fast(py, px) : atan_narrow(py, px);
+  const float colf = fmaf(phi, p.nkcol, p.c0f);
+  const float cb = colf + kMagic;                             // |colf| <= W / 2 + 1 < 2^22
   const float cr = cb - kMagic;                               // == rintf(colf)
-  const bool ok_col = fabsf(colf - cr) + fmaf(p.e15k, inv_rho, p.ecol) < 0.5f;
-  int col = magic_int(cb);
+  const bool ok_col = fabsf(colf - cr) + fmaf(p.ecolk, inv_rho, p.ecol) < 0.5f;
+  int col = magic_int(cb) + p.cint;
   col += (col < 0) ? p.W : 0;                                 // fmod(round(colf), W) (:191) and
   col -= (col >= p.W) ? p.W : 0;                              // negative index wrap (:543)
   col = min((unsigned)col, (unsigned)(p.W - 1));
 
-  // ---- range: free iff ri >= |p_ref|;  | |p| - |p_ref| | <= sqrt(3) eps
+  // ---- range
   const float ri = __ldg(ri_img + (min(row, p.last) * (unsigned)p.W + (unsigned)col));
   const float r = r2 * inv_r;
-  const float m = fmaf(r, fmaf(r, 6.0e-7f, p.c1), p.c2);      // margin on squared ranges
-  const float ri2 = ri * ri;
-  const bool yes = ri2 >= r2 + m, no = ri2 <= r2 - m;
-  return (ok_row && ok_col && (yes || no)) ? (yes ? 2 : 0) : 1;
+  const float dd = ri - r;
+  const bool ok_rng = fabsf(dd) > fmaf(r, 6.5e-7f, p.c1);     // ri == 0 (no return): dd = -r, certainly not free
+  return (ok_row && ok_col && ok_rng) ? ((dd > 0.f) ? 2 : 0) : 1;
 }
 
 template <typename T16>
@@ -1339,138 +1538,183 @@ __device__ __noinline__ bool exact_from_ids(int t, int f, int q, int L, double v
   return exact_test(cx, cy, cz, poses + f0 + i, sn, incl_pool, ri_pool);
 }
 
-// Every warp is on its own: it claims a work item from an atomic counter, tests, and ORs the voxels it proved
-// free into the global free bitset.  No shared memory, no barriers.  Two launches:
-//   PHASE 1  item = 64 consecutive voxels of a tracklet x its first kPhase1Pairs surviving pairs.  Most voxels that
-//            can be freed at all are freed here; what is left (non-occupied, not free) is appended to the
-//            tracklet's list (warp-aggregated atomics, arbitrary order).
-//   PHASE 2  item = 64 LISTED voxels x a slice of kPairsPerItem of the remaining pairs: every lane holds a voxel
-//            that really needs the tests (dense lanes), and voxels freed in phase 1 are never tested again.
-// Labels are written afterwards by k_labels from the occupancy and free bitsets.
-template <int PHASE, int VPL>
-__global__ void __launch_bounds__(32 * kFastWarps, OCC_MINB)
-k_visibility_fast(int L, const int64_t *__restrict__ trk_frame_off,
-                  const occb200_pose_t *__restrict__ poses, const int32_t *__restrict__ frame_sf,
-                  const occb200_sensor_t *__restrict__ sensors, const float *__restrict__ incl_pool,
-                  const float *__restrict__ ri_pool, double vs, const TrkGrid *__restrict__ grids,
-                  unsigned long long *__restrict__ counter, long long items_cap,
-                  const uint32_t *__restrict__ bits, uint32_t *__restrict__ free_bits,
-                  const int2 *__restrict__ item_map, const TrkHot *__restrict__ hot,
-                  const PairHot *__restrict__ pairs,
-                  const float *__restrict__ ub_pool, const uint16_t *__restrict__ lut_pool,
-                  int4 *__restrict__ queue, long long queue_cap, int32_t *__restrict__ unk_list,
-                  uint32_t *__restrict__ n_unk, int64_t *__restrict__ n_steps) {
+struct VisArgs {                 // what the visibility kernel needs (passed by value: one constant-bank block)
+  int L;
+  int mask_words;
+  int n_slices;
+  int pad;
+  long long bricks_total;
+  long long queue_cap;
+  double vs;
+  const int64_t *trk_frame_off;
+  const occb200_pose_t *poses;
+  const int32_t *frame_sf;
+  const occb200_sensor_t *sensors;
+  const float *incl_pool;
+  const float *ri_pool;
+  const TrkGrid *grids;
+  unsigned long long *counter;
+  const uint32_t *bits;
+  uint32_t *free_brick;
+  const uint32_t *pair_mask;
+  const int2 *item_map;
+  const TrkHot *hot;
+  const PairHot *pairs;
+  const LutCell *lut_pool;
+  int4 *queue;
+  int64_t *n_steps;
+};
+
+// The pair loop of one work item: VPL voxels per lane (lattice offsets d*, brick-local ids vj, -1 = none).
+// Returns the bits of the voxels proven free (bit v = this lane's voxel v).
+template <int VPL>
+__device__ __forceinline__ unsigned run_pairs(const VisArgs &a, int t, const TrkHot &h, int bx, int by, int bz, int lb,
+                                              unsigned live, int k0, unsigned todo, const float (&dx)[VPL],
+                                              const float (&dy)[VPL], const float (&dz)[VPL], const int (&vj)[VPL],
+                                              unsigned &steps) {
   const int lane = threadIdx.x & 31;
-  unsigned long long *ticket = counter + (PHASE == 1 ? 0 : 4);
-  const long long total = min((long long)counter[PHASE == 1 ? 3 : 5], items_cap);
-  for (;;) {
-    long long item = 0;
-    if (lane == 0) item = (long long)atomicAdd(ticket, 1ull);
-    item = __shfl_sync(0xffffffffu, item, 0);
-    if (item >= total) break;
-    const int2 m = __ldg(item_map + item);
-    const int t = m.x, chunk = m.y & 0xfffff, slice = m.y >> 20;
-    const TrkHot h = load64(hot + t);
-    const int dZ = h.dZ, yz = h.dY * dZ;
-    const int fbase = chunk * (32 * VPL);
-    int32_t *list = unk_list + h.label_off;
-    int vf[VPL];              // flat voxel index of this lane's voxel v
-    float vx[VPL], vy[VPL], vz[VPL];
-    unsigned todo = 0u;        // bit v: this lane's voxel v exists, holds no point and is not known to be free
+  const PairHot *tp = a.pairs + h.pairs_base + k0;
+  unsigned found = 0u;
+  while (live) {
+    if (!__any_sync(0xffffffffu, todo != 0u)) break;           // every voxel of the item is settled
+    const int kk = __ffs(live) - 1;
+    live &= live - 1u;
+    const PairHot pc = load128(tp + kk);
+    if (live) asm volatile("prefetch.global.L1 [%0];" ::"l"(tp + (__ffs(live) - 1)));   // next record: one 128-byte line
+    const int2 *lut = reinterpret_cast<const int2 *>(a.lut_pool) + pc.lut_off;
+    const float *ri_img = a.ri_pool + pc.ri_off;
+    // materialise the bases as 64-bit registers: per-test addresses are then ONE imad.wide each
+    asm volatile("" : "+l"(lut), "+l"(ri_img));
+    // all VPL tests are evaluated unconditionally (no divergence, their dependent chains interleave);
+    // results of voxels this lane does not need are discarded
+    int res[VPL];
+    if (pc.wide) {
+#pragma unroll
+      for (int v = 0; v < VPL; ++v) res[v] = fast_test<true>(pc, dx[v], dy[v], dz[v], lut, ri_img);
+    } else {
+#pragma unroll
+      for (int v = 0; v < VPL; ++v) res[v] = fast_test<false>(pc, dx[v], dy[v], dz[v], lut, ri_img);
+    }
 #pragma unroll
     for (int v = 0; v < VPL; ++v) {
-      bool active;
-      int f;
-      if (PHASE == 1) {
-        f = fbase + 32 * v + lane;
-        active = f < h.V;
-        unsigned w = 0xffffffffu;
-        const int64_t word = h.bits_off + (int64_t)chunk * VPL + v;
-        if (fbase + 32 * v < h.V) w = __ldg(bits + word) | *(volatile const uint32_t *)(free_bits + word);
-        active = active && !((w >> lane) & 1u);
-      } else {
-        const unsigned i = (unsigned)(fbase + 32 * v + lane);
-        active = i < __ldg(n_unk + t);
-        f = active ? __ldg(list + i) : 0;
-        if (active) {
-          const uint32_t w = *(volatile const uint32_t *)(free_bits + h.bits_off + (f >> 5));
-          active = !((w >> (f & 31)) & 1u);          // another slice may have freed it meanwhile
-        }
+      const bool need = (todo >> v) & 1u;
+      res[v] = need ? ((pc.eps >= 0.f) ? res[v] : 1) : 0;
+      steps += need ? 1u : 0u;
+      if (res[v] == 2) {
+        found |= 1u << v;
+        todo &= ~(1u << v);
       }
-      todo |= (active ? 1u : 0u) << v;
-      const int fa = active ? f : 0;
-      vf[v] = fa;
-      const int ix = fa / yz, rem = fa - ix * yz;
-      const int iy = rem / dZ;
-      vx[v] = (float)ix;
-      vy[v] = (float)iy;
-      vz[v] = (float)(rem - iy * dZ);
-    }
-    unsigned steps = 0, found = 0u;
-    const int k0 = (PHASE == 1) ? 0 : kPhase1Pairs + slice * kPairsPerItem;
-    const int k1 = min(h.nact, k0 + (PHASE == 1 ? kPhase1Pairs : kPairsPerItem));
-    const PairHot *tp = pairs + h.pairs_base;
-    for (int k = k0; k < k1; ++k) {
-      if (!__any_sync(0xffffffffu, todo != 0u)) break;           // every voxel of the item is settled
-      const PairHot pc = load128(tp + k);
-      if (k + 1 < k1) asm volatile("prefetch.global.L1 [%0];" ::"l"(tp + k + 1));   // one 128-byte line
-      const float *ub = ub_pool + 2 * pc.tab_off + 1;
-      const uint16_t *lut = lut_pool + pc.tab_off * kLutPerRow;
-      const float *ri_img = ri_pool + pc.ri_off;
-      // materialise the three bases as 64-bit registers: per-test addresses are then ONE imad.wide each
-      asm volatile("" : "+l"(ub), "+l"(lut), "+l"(ri_img));
-      // all VPL tests are evaluated unconditionally (no divergence, their dependent chains interleave);
-      // results of voxels this lane does not need are discarded
-      int res[VPL];
-#pragma unroll
-      for (int v = 0; v < VPL; ++v) res[v] = fast_test(pc, vx[v], vy[v], vz[v], ub, lut, ri_img);
-#pragma unroll
-      for (int v = 0; v < VPL; ++v) {
-        const bool need = (todo >> v) & 1u;
-        res[v] = need ? ((pc.eps >= 0.f) ? res[v] : 1) : 0;
-        steps += need ? 1u : 0u;
-        if (res[v] == 2) {
-          found |= 1u << v;
-          todo &= ~(1u << v);
-        }
-        const unsigned umask = __ballot_sync(0xffffffffu, res[v] == 1);
-        if (umask) {                                             // queue the undecided tests (warp-aggregated)
-          unsigned long long base = 0;
-          if (lane == 0) base = atomicAdd(counter + 1, (unsigned long long)__popc(umask));
-          base = __shfl_sync(0xffffffffu, base, 0);
-          if (res[v] == 1) {
-            const unsigned long long slot = base + __popc(umask & ((1u << lane) - 1u));
-            if (slot < (unsigned long long)queue_cap) {
-              queue[slot] = make_int4(t, vf[v], pc.q, 0);
-            } else if (exact_from_ids(t, vf[v], pc.q, L, vs, grids, trk_frame_off, poses, frame_sf, sensors,
-                                      incl_pool, ri_pool)) {     // queue full: decide right here
-              found |= 1u << v;
-              todo &= ~(1u << v);
-            }
+      const unsigned umask = __ballot_sync(0xffffffffu, res[v] == 1);
+      if (umask) {                                             // queue the undecided tests (warp-aggregated)
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(a.counter + 1, (unsigned long long)__popc(umask));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (res[v] == 1) {
+          const int j = vj[v];
+          const int f = ((kBrick * bx + (j >> 4)) * h.dY + kBrick * by + ((j >> 2) & 3)) * h.dZ + kBrick * bz + (j & 3);
+          const unsigned long long slot = base + __popc(umask & ((1u << lane) - 1u));
+          if (slot < (unsigned long long)a.queue_cap) {
+            a.queue[slot] = make_int4(t, f, pc.q, lb * 64 + j);
+          } else if (exact_from_ids(t, f, pc.q, a.L, a.vs, a.grids, a.trk_frame_off, a.poses, a.frame_sf, a.sensors,
+                                    a.incl_pool, a.ri_pool)) {     // queue full: decide right here
+            found |= 1u << v;
+            todo &= ~(1u << v);
           }
         }
       }
     }
+  }
+  return found;
+}
+
+// Every warp is on its own: it claims a work item from the atomic ticket of the current slice, tests, and ORs the
+// voxels it proved free into the global free bitset (brick order).  No shared memory, no barriers.
+//   item = one 4x4x4 brick of a tracklet x one slice of kPairsPerItem of its surviving pairs, minus the pairs
+//   k_brick_cull masked for the brick.  The lists are walked slice by slice: slice 0 (spread-out viewpoints)
+//   frees most of the voxels that can be freed at all; an item re-reads the free bits when it starts, so later
+//   slices never test a voxel an earlier one has freed.  A brick with more than 32 undecided voxels runs two per
+//   lane; otherwise the undecided voxels are dealt one per lane (dense lanes).
+// Labels are written afterwards by k_labels from the occupancy and free bitsets.
+__global__ void __launch_bounds__(32 * kFastWarps, OCC_MINB) k_visibility(const VisArgs a) {
+  const int lane = threadIdx.x & 31;
+  for (int s = 0; s < a.n_slices; ++s) {
+    const long long total = (long long)a.counter[8 + 2 * s];
+    if (total == 0) break;                                      // slices are filled front to back
+    unsigned long long *ticket = a.counter + 9 + 2 * s;
+    const int2 *items = a.item_map + (long long)s * a.bricks_total;
+    for (;;) {
+      long long item = 0;
+      if (lane == 0) item = (long long)atomicAdd(ticket, 1ull);
+      item = __shfl_sync(0xffffffffu, item, 0);
+      if (item >= total) break;
+      const int2 m = __ldg(items + item);
+      const int t = m.x;
+      const int bx = m.y & 1023, by = (m.y >> 10) & 1023, bz = (m.y >> 20) & 1023;
+      const TrkHot h = load64(a.hot + t);
+      const int k0 = s * kPairsPerItem;
+      const int npair = min(h.nact - k0, kPairsPerItem);         // >= 1 by construction of the lists
+      const int lb = (bx * ((h.dY + kBrick - 1) / kBrick) + by) * ((h.dZ + kBrick - 1) / kBrick) + bz;
+      const long long gb = h.brick_base + lb;
+      const unsigned mw = __ldg(a.pair_mask + gb * a.mask_words + (k0 >> 5));
+      const unsigned live = ~(mw >> (k0 & 31)) & (npair >= 32 ? 0xffffffffu : ((1u << npair) - 1u));
+      if (!live) continue;
+      // the brick's voxels: j = 32 v + lane -> (j >> 4, (j >> 2) & 3, j & 3); undecided = inside the grid, holds no
+      // point, not yet proven free
+      unsigned und[2];
 #pragma unroll
-    for (int v = 0; v < VPL; ++v) {
-      if (PHASE == 1) {
-        const unsigned fw = __ballot_sync(0xffffffffu, (found >> v) & 1u);
-        if (fw && lane == 0) atomicOr(free_bits + h.bits_off + (int64_t)chunk * VPL + v, fw);
-        if (h.nact > kPhase1Pairs) {                             // survivors go to the tracklet's phase-2 list
-          const unsigned left = __ballot_sync(0xffffffffu, (todo >> v) & 1u);
-          if (left) {
-            unsigned base = 0;
-            if (lane == 0) base = atomicAdd(n_unk + t, (unsigned)__popc(left));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if ((todo >> v) & 1u) list[base + __popc(left & ((1u << lane) - 1u))] = vf[v];
-          }
+      for (int v = 0; v < 2; ++v) {
+        const int j = 32 * v + lane;
+        const int x = kBrick * bx + (j >> 4), y = kBrick * by + ((j >> 2) & 3), z = kBrick * bz + (j & 3);
+        bool need = x < h.dX && y < h.dY && z < h.dZ;
+        if (need) {
+          const int f = (x * h.dY + y) * h.dZ + z;
+          need = !((__ldg(a.bits + h.bits_off + (f >> 5)) >> (f & 31)) & 1u);
         }
-      } else if ((found >> v) & 1u) {
-        atomicOr(free_bits + h.bits_off + (vf[v] >> 5), 1u << (vf[v] & 31));
+        const unsigned fw = *(volatile const uint32_t *)(a.free_brick + 2 * gb + v);
+        und[v] = __ballot_sync(0xffffffffu, need) & ~fw;
+      }
+      const int n0 = __popc(und[0]), n = n0 + __popc(und[1]);
+      if (n == 0) continue;
+      unsigned steps = 0;
+      if (n > 32) {                                              // two voxels per lane, natural mapping
+        float dx[2], dy[2], dz[2];
+        int vj[2];
+        unsigned todo = 0u;
+#pragma unroll
+        for (int v = 0; v < 2; ++v) {
+          const int j = 32 * v + lane;
+          vj[v] = j;
+          dx[v] = (float)(kBrick * bx + (j >> 4)) - h.cen[0];
+          dy[v] = (float)(kBrick * by + ((j >> 2) & 3)) - h.cen[1];
+          dz[v] = (float)(kBrick * bz + (j & 3)) - h.cen[2];
+          todo |= ((und[v] >> lane) & 1u) << v;
+        }
+        const unsigned found = run_pairs<2>(a, t, h, bx, by, bz, lb, live, k0, todo, dx, dy, dz, vj, steps);
+#pragma unroll
+        for (int v = 0; v < 2; ++v) {
+          const unsigned fw = __ballot_sync(0xffffffffu, (found >> v) & 1u);
+          if (fw && lane == 0) atomicOr(a.free_brick + 2 * gb + v, fw);
+        }
+      } else {                                                   // one voxel per lane: lane i takes the i-th undecided
+        const bool mine = lane < n;
+        const unsigned src = (lane < n0) ? und[0] : und[1];
+        const int rank = (lane < n0) ? lane : lane - n0;
+        const int pos = mine ? (int)__fns(src, 0, rank + 1) : 0;
+        float dx[1], dy[1], dz[1];
+        int vj[1];
+        const int j = (mine ? pos : 0) + ((lane < n0) ? 0 : 32);
+        vj[0] = j & 63;
+        dx[0] = (float)(kBrick * bx + (vj[0] >> 4)) - h.cen[0];
+        dy[0] = (float)(kBrick * by + ((vj[0] >> 2) & 3)) - h.cen[1];
+        dz[0] = (float)(kBrick * bz + (vj[0] & 3)) - h.cen[2];
+        const unsigned found = run_pairs<1>(a, t, h, bx, by, bz, lb, live, k0, mine ? 1u : 0u, dx, dy, dz, vj, steps);
+        if (found) atomicOr(a.free_brick + 2 * gb + (vj[0] >> 5), 1u << (vj[0] & 31));
+      }
+      if (a.n_steps) {
+        for (int o = 16; o > 0; o >>= 1) steps += __shfl_xor_sync(0xffffffffu, steps, o);
+        if (lane == 0 && steps) atomicAdd((unsigned long long *)&a.n_steps[t], (unsigned long long)steps);
       }
     }
-    for (int o = 16; o > 0; o >>= 1) steps += __shfl_xor_sync(0xffffffffu, steps, o);
-    if (lane == 0 && n_steps && steps) atomicAdd((unsigned long long *)&n_steps[t], (unsigned long long)steps);
   }
 }
 
@@ -1478,16 +1722,16 @@ __global__ void __launch_bounds__(256)
 k_visibility_recheck(int L, const int64_t *__restrict__ trk_frame_off, const occb200_pose_t *__restrict__ poses,
                      const int32_t *__restrict__ frame_sf, const occb200_sensor_t *__restrict__ sensors,
                      const float *__restrict__ incl_pool, const float *__restrict__ ri_pool, double vs,
-                     const TrkGrid *__restrict__ grids, const unsigned long long *__restrict__ counter,
-                     const int4 *__restrict__ queue, long long queue_cap, uint32_t *__restrict__ free_bits,
-                     int64_t *__restrict__ n_steps) {
+                     const TrkGrid *__restrict__ grids, const TrkHot *__restrict__ hot,
+                     const unsigned long long *__restrict__ counter, const int4 *__restrict__ queue,
+                     long long queue_cap, uint32_t *__restrict__ free_brick, int64_t *__restrict__ n_steps) {
   const long long n = min((long long)counter[1], queue_cap);
   for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) {
     const int4 it = queue[k];
     const int t = it.x, f = it.y, q = it.z;
     const TrkGrid &g = grids[t];
-    uint32_t *word = free_bits + g.bits_off + (f >> 5);
-    const uint32_t bit = 1u << (f & 31);
+    uint32_t *word = free_brick + 2 * (hot[t].brick_base + (it.w >> 6)) + ((it.w >> 5) & 1);
+    const uint32_t bit = 1u << (it.w & 31);
     if (*(volatile uint32_t *)word & bit) continue;            // already proven free by another test
     double cx, cy, cz;
     voxel_centre(g, f, vs, cx, cy, cz);
@@ -1503,26 +1747,35 @@ k_visibility_recheck(int L, const int64_t *__restrict__ trk_frame_off, const occ
   }
 }
 
-// labels from the two bitsets: 1 occupied, 2 free, 0 unknown (occ_annotate.py:558-563); one CTA per tracklet
+// labels from the two bitsets: 1 occupied, 2 free, 0 unknown (occ_annotate.py:558-563); grid (tracklet, 8)
 __global__ void __launch_bounds__(256)
-k_labels(const TrkHot *__restrict__ hot, const TrkGrid *__restrict__ grids, const uint32_t *__restrict__ bits,
-         const uint32_t *__restrict__ free_bits, int32_t *__restrict__ labels, int64_t *__restrict__ n_unknown,
-         int32_t *__restrict__ status_out) {
+k_labels(const TrkHot *__restrict__ hot, const TrkGrid *__restrict__ grids, const int32_t *__restrict__ trk_flags,
+         const int64_t *__restrict__ label_off, const uint32_t *__restrict__ bits,
+         const uint32_t *__restrict__ free_brick, int32_t *__restrict__ labels, uint8_t *__restrict__ labels_u8,
+         int64_t *__restrict__ n_unknown, int32_t *__restrict__ status_out) {
   const int t = blockIdx.x;
   const TrkHot h = hot[t];
   int status = h.status;
   if (status == OCCB200_OK && grids[t].redo) {      // corrected tracklet: its flags are final only now
-    const int fl = grids[t].flags;
+    const int fl = trk_flags[t];
     if (fl & 2) status = OCCB200_INDEX_ERROR;
     else if (!(fl & 1)) status = OCCB200_EMPTY_AFTER_FILTER;
     if (status != OCCB200_OK && threadIdx.x == 0 && blockIdx.y == 0) status_out[t] = status;
   }
   if (status != OCCB200_OK) return;
+  const int yz = h.dY * h.dZ, nby = (h.dY + kBrick - 1) / kBrick, nbz = (h.dZ + kBrick - 1) / kBrick;
+  const int64_t lo = label_off[t];
   int unk = 0;
   for (int f = blockIdx.y * blockDim.x + threadIdx.x; f < h.V; f += gridDim.y * blockDim.x) {
-    const uint32_t o = bits[h.bits_off + (f >> 5)], fr = free_bits[h.bits_off + (f >> 5)];
-    const bool occ = (o >> (f & 31)) & 1u;
-    labels[h.label_off + f] = occ ? 1 : (((fr >> (f & 31)) & 1u) ? 2 : 0);
+    const bool occ = (bits[h.bits_off + (f >> 5)] >> (f & 31)) & 1u;
+    const int x = f / yz, rem = f - x * yz;
+    const int y = rem / h.dZ, z = rem - y * h.dZ;
+    const int64_t gb = h.brick_base + ((x >> 2) * nby + (y >> 2)) * nbz + (z >> 2);
+    const int j = ((x & 3) << 4) | ((y & 3) << 2) | (z & 3);
+    const bool fr = (free_brick[2 * gb + (j >> 5)] >> (j & 31)) & 1u;
+    const int lab = occ ? 1 : (fr ? 2 : 0);
+    if (labels) labels[lo + f] = lab;
+    if (labels_u8) labels_u8[lo + f] = (uint8_t)lab;
     unk += occ ? 0 : 1;
   }
   for (int o = 16; o > 0; o >>= 1) unk += __shfl_xor_sync(0xffffffffu, unk, o);
@@ -1553,18 +1806,22 @@ __global__ void k_project_points(const double *__restrict__ points, int B, int64
   ri_range[(int64_t)b * N + i] = rng;
 }
 
-// self-test hook: max |atan2_fast - atan2| over n pseudo-random f32 pairs (device-side check of kAtanErr)
-__global__ void k_selftest_atan2(long long n, unsigned long long seed, unsigned long long *__restrict__ max_err) {
+// self-test hook: max |atan - atan2| over n pseudo-random f32 pairs (device-side check of kAtanWide / kAtanNarrow)
+__global__ void k_selftest_atan2(long long n, unsigned long long seed, int narrow, unsigned long long *__restrict__ max_err) {
   double worst = 0.0;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     unsigned long long h = (unsigned long long)i * 0x9E3779B97F4A7C15ull + seed;
     h ^= h >> 31; h *= 0xBF58476D1CE4E5B9ull; h ^= h >> 29;
     const float mag_x = exp2f((float)((h >> 8) & 31) - 20.f), mag_y = exp2f((float)((h >> 13) & 31) - 20.f);
-    const float x = ((float)((h >> 20) & 0xfffff) / 524288.f - 1.f) * mag_x;
-    const float y = ((float)((h >> 40) & 0xfffff) / 524288.f - 1.f) * mag_y;
+    float x = ((float)((h >> 20) & 0xfffff) / 524288.f - 1.f) * mag_x;
+    float y = ((float)((h >> 40) & 0xfffff) / 524288.f - 1.f) * mag_y;
+    if (narrow) {                                  // the narrow path's domain: x > 0, |y| <= x
+      x = fabsf(x);
+      if (fabsf(y) > x) { const float t = x; x = fabsf(y); y = (y < 0.f) ? -t : t; }
+    }
     if (x == 0.f && y == 0.f) continue;
-    const double err = fabs((double)atan2_fast(y, x) - atan2((double)y, (double)x));
-    worst = fmax(worst, err);
+    const double got = narrow ? (double)atan_narrow(y, x) : (double)atan2_fast(y, x);
+    worst = fmax(worst, fabs(got - atan2((double)y, (double)x)));
   }
   for (int o = 16; o > 0; o >>= 1) worst = fmax(worst, __shfl_xor_sync(0xffffffffu, worst, o));
   // non-negative doubles order like their bit patterns
@@ -1576,86 +1833,88 @@ __global__ void k_selftest_atan2(long long n, unsigned long long seed, unsigned 
 using namespace occb200;
 
 extern "C" int64_t occb200_annotate_workspace_bytes(int32_t T, int64_t F, int64_t total_label_slots, int64_t SF,
-                                                    int32_t L, int64_t incl_len, int64_t pyr_tiles, int64_t items_cap) {
-  return ws_layout(T, F, total_label_slots, SF, L, incl_len, pyr_tiles, items_cap, nullptr, nullptr);
-}
-
-// HOST helper: upper bound of the fast kernel's work items, from the host copies of label_off / trk_frame_off.
-extern "C" int64_t occb200_annotate_items_cap(int32_t T, const int64_t *label_off, const int64_t *trk_frame_off,
-                                              int32_t L) {
-  int64_t n = 0;
-  for (int t = 0; t < T; ++t) {
-    const int64_t chunks = ceil_div(label_off[t + 1] - label_off[t], 32 * (kVPL1 < kVPL ? kVPL1 : kVPL));
-    const int64_t slices = ceil_div((trk_frame_off[t + 1] - trk_frame_off[t]) * L, kPairsPerItem);
-    n += chunks * slices;
-  }
-  return n;
+                                                    int32_t L, int64_t incl_len, int64_t pyr_tiles, int64_t bricks,
+                                                    int32_t max_pairs) {
+  return ws_layout(T, F, total_label_slots, SF, L, incl_len, pyr_tiles, bricks, max_pairs, nullptr, nullptr);
 }
 
 extern "C" int64_t occb200_pyramid_tiles(int32_t H, int32_t W) {
   return (int64_t)((H + kTileR - 1) / kTileR) * ((W + kTileC - 1) / kTileC);
 }
 
+// HOST helper: bricks of a grid of (at most) X x Y x Z voxels.
+extern "C" int64_t occb200_grid_bricks(int32_t X, int32_t Y, int32_t Z) {
+  return (int64_t)((X + kBrick - 1) / kBrick) * ((Y + kBrick - 1) / kBrick) * ((Z + kBrick - 1) / kBrick);
+}
+
+static int crop_group(int64_t F) {                  // tracklet-frames per crop CTA: ~4 CTAs per SM on small batches
+  const int64_t g = F / ((int64_t)kNumSMs * 4);
+  return (int)std::max<int64_t>(1, std::min<int64_t>(g, kMaxGroup));
+}
+
 extern "C" int occb200_annotate_batch(const occb200_annotate_args_t *a, int64_t total, void *stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   OCC_REQUIRE(a != nullptr, "args is NULL");
   OCC_REQUIRE(a->T >= 0 && a->F >= 0 && a->L >= 1, "bad T/F/L");
-  OCC_REQUIRE(a->SF >= 0 && a->incl_len >= 0 && a->pyr_tiles >= 0 && a->items_cap >= 0, "bad SF / incl_len / pyr_tiles / items_cap");
+  OCC_REQUIRE(a->SF >= 0 && a->incl_len >= 0 && a->pyr_tiles >= 0, "bad SF / incl_len / pyr_tiles");
   OCC_REQUIRE(a->point_stride >= 3, "point_stride must be >= 3");
   OCC_REQUIRE(a->voxel_size > 0, "voxel_size must be positive");
+  OCC_REQUIRE(a->labels != nullptr || a->labels_u8 != nullptr, "labels and labels_u8 are both NULL");
   if (a->T == 0) return 0;
+  OCC_REQUIRE(a->F == 0 || a->frame_trk != nullptr, "frame_trk is NULL");
+  OCC_REQUIRE(a->F == 0 || a->SF > 0, "tracklet-frames without sensor frames");
+  OCC_REQUIRE(a->brick_off != nullptr && a->bricks >= 0, "brick_off is NULL");
+  OCC_REQUIRE(a->max_pairs >= 0 && a->max_pairs <= kMaxSlices * kPairsPerItem, "max_pairs out of range");
+  OCC_REQUIRE(a->n_tables >= 0 && (a->n_tables == 0 || (a->table_off && a->table_H)), "table list missing");
+  OCC_REQUIRE(a->pyr_tiles == 0 || a->pyr_off != nullptr, "pyr_off is NULL");
   Workspace w;
-  const int64_t need = ws_layout(a->T, a->F, total, a->SF, a->L, a->incl_len, a->pyr_tiles, a->items_cap, (char *)a->workspace, &w);
+  const int64_t need = ws_layout(a->T, a->F, total, a->SF, a->L, a->incl_len, a->pyr_tiles, a->bricks, a->max_pairs,
+                                 (char *)a->workspace, &w);
   OCC_REQUIRE(a->workspace != nullptr && a->workspace_bytes >= need, "workspace too small");
   const float vsf = (float)a->voxel_size;
-  // shared-memory bitset of k_frame_voxelize: as many words as the largest label slot needs (unknown: the maximum)
+  const float inv_vs = (a->flags & 32) ? 1.0f / vsf : 0.f;       // flag bit 5: torch-CUDA's x * (1 / vs)
+  // shared-memory bitset of the crop kernel: as many words as the largest label slot needs (unknown: the maximum)
   const int smem_words = (a->max_label_slots > 0)
                              ? (int)std::min<int64_t>(a->max_label_slots / 32 + 2, kSmemBitWords) : kSmemBitWords;
   const bool f64_only = (a->flags & 1) != 0;
-  const int chunk = f64_only ? kChunk : kFastChunk;
+  const int chunk = f64_only ? kChunk : 32;
+  const bool fast = !f64_only && a->F > 0;
+  const bool cull = fast && a->pyr_tiles > 0 && !(a->flags & 2);
+  const bool brick_cull = cull && !(a->flags & 16);
+  // one memset: counters, crop flags, both bitsets, pair masks, table records
+  OCC_CUDA(cudaMemsetAsync(w.zero_begin, 0, (size_t)(w.zero_end - w.zero_begin), stream));
   SideStream *side = nullptr;
-  const bool fast = !f64_only && a->F > 0 && a->SF > 0;
   if (fast) {                                       // fork: sensor-side setup on the side stream
     if (side_stream(&side)) return 1;
     OCC_CUDA(cudaEventRecord(side->fork, stream));
     OCC_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
-    ProfScope ps(kProfPairSetup, side->stream);
+    ProfScope ps(kProfSide, side->stream);
     const int64_t n_sens = a->SF * a->L;
-    OCC_CUDA(cudaMemsetAsync(w.tab_claim, 0, 4 * (size_t)std::max<int64_t>(w.incl_len, 1), side->stream));
-    k_table_setup<<<(unsigned)n_sens, 256, 0, side->stream>>>(n_sens, a->sensors, a->incl_pool, w.sens, w.ub_pool,
-                                                              w.lut_pool, w.tab_claim);
-    OCC_KERNEL_OK("k_table_setup");
-    k_pyr_scan<<<1, 1024, 0, side->stream>>>(n_sens, a->sensors, (a->flags & 2) ? (int64_t)-1 : w.pyr_tiles,
-                                             w.pyr_off, w.pyr_flag);
-    OCC_KERNEL_OK("k_pyr_scan");
-    if (w.pyr_tiles > 0 && !(a->flags & 2)) {
-      k_pyr_build<<<dim3((unsigned)n_sens, kPyrRowGroups), 256, 0, side->stream>>>(a->sensors, a->ri_pool, w.pyr_off,
-                                                                                   w.pyr_flag, w.pyr);
+    if (cull) {
+      k_pyr_build<<<dim3((unsigned)n_sens, kPyrRowGroups), 256, 0, side->stream>>>(a->sensors, a->ri_pool, a->pyr_off,
+                                                                                   w.pyr, w.pyr2);
       OCC_KERNEL_OK("k_pyr_build");
+    }
+    if (a->n_tables > 0) {
+      k_table_setup<<<(unsigned)a->n_tables, 256, 0, side->stream>>>(a->n_tables, a->table_off, a->table_H,
+                                                                     a->incl_pool, w.tabcoef, w.ub_pool, w.lut_pool);
+      OCC_KERNEL_OK("k_table_setup");
     }
     OCC_CUDA(cudaEventRecord(side->join, side->stream));
   }
-  OCC_CUDA(cudaMemsetAsync(w.bits, 0, (char *)(w.free_bits + w.bits_words) - (char *)w.bits, stream));   // both bitsets
-  {
-    ProfScope ps(kProfInbox, stream);
-    k_tracklet_presetup<<<(unsigned)ceil_div(a->T, 8), 256, 0, stream>>>(a->T, a->trk_frame_off, a->poses,
-                                                                         a->frame_pt_off, a->label_off,
-                                                                         vsf, chunk, w.grids, w.frame_trk, w.redo_count,
-                                                                         w.counter, w.n_unk, a->n_unknown, a->n_steps);
-    OCC_KERNEL_OK("k_tracklet_presetup");
-  }
   if (a->F > 0) {
-    ProfScope ps(kProfVoxelize, stream);
-    k_frame_voxelize<<<(unsigned)a->F, kFrameThreads, 4 * smem_words, stream>>>(
-        a->poses, a->points, a->point_stride, a->frame_pt_off, w.frame_kept, w.frame_trk, w.grids, w.bits, vsf, nullptr,
-        nullptr, smem_words);
-    OCC_KERNEL_OK("k_frame_voxelize");
+    ProfScope ps(kProfCrop, stream);
+    const int G = crop_group(a->F);
+    k_crop_voxelize<<<(unsigned)ceil_div(a->F, G), kFrameThreads, 4 * smem_words, stream>>>(
+        a->F, G, a->poses, a->points, a->point_stride, a->frame_pt_off, a->trk_frame_off, a->label_off, a->frame_trk,
+        w.frame_kept, w.trk_flags, w.grids, w.bits, vsf, inv_vs, nullptr, nullptr, smem_words);
+    OCC_KERNEL_OK("k_crop_voxelize");
   }
   {
     ProfScope ps(kProfSetup, stream);
     k_tracklet_setup<<<(unsigned)ceil_div(a->T, 8), 256, 0, stream>>>(
-        a->T, a->trk_frame_off, a->poses, a->frame_pt_off, w.frame_kept, a->label_off, vsf, chunk, w.grids, w.bits,
-        w.redo_list, w.redo_count, a->dims, a->sizes, a->status);
+        a->T, a->trk_frame_off, a->poses, a->frame_pt_off, w.frame_kept, a->label_off, vsf, inv_vs, chunk, w.grids,
+        w.bits, w.trk_flags, w.redo_list, w.counter + 2, a->dims, a->sizes, a->status, a->n_unknown, a->n_steps);
     OCC_KERNEL_OK("k_tracklet_setup");
     if (a->F > 0) {   // frames of corrected tracklets only (device-side list, usually short); in the fast path
                       // this runs on the side stream, next to k_pair_build, and joins before the ray-cast
@@ -1666,65 +1925,77 @@ extern "C" int occb200_annotate_batch(const occb200_annotate_args_t *a, int64_t 
         OCC_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
         rs = side->stream;
       }
-      k_frame_voxelize<<<(unsigned)std::min<int64_t>(a->F, kNumSMs * 2), kFrameThreads, 4 * smem_words, rs>>>(
-          a->poses, a->points, a->point_stride, a->frame_pt_off, w.frame_kept, w.frame_trk, w.grids, w.bits, vsf,
-          w.redo_list, w.redo_count, smem_words);
-      OCC_KERNEL_OK("k_frame_voxelize(redo)");
+      k_crop_voxelize<<<(unsigned)std::min<int64_t>(a->F, kNumSMs * 2), kFrameThreads, 4 * smem_words, rs>>>(
+          a->F, 1, a->poses, a->points, a->point_stride, a->frame_pt_off, a->trk_frame_off, a->label_off, a->frame_trk,
+          w.frame_kept, w.trk_flags, w.grids, w.bits, vsf, inv_vs, w.redo_list, w.counter + 2, smem_words);
+      OCC_KERNEL_OK("k_crop_voxelize(redo)");
       if (fast) OCC_CUDA(cudaEventRecord(side->join, side->stream));
     }
   }
   if (f64_only) {
-    ProfScope ps(kProfScan, stream);
-    k_scan_chunks<<<1, 1024, 0, stream>>>(a->T, w.grids, w.chunk_off, w.counter);
-    OCC_KERNEL_OK("k_scan_chunks");
-  }
-  const int64_t max_items = ceil_div(total, chunk) + a->T;
-  if (f64_only) {
+    {
+      ProfScope ps(kProfScan, stream);
+      k_scan_chunks<<<1, 1024, 0, stream>>>(a->T, w.grids, w.chunk_off);
+      OCC_KERNEL_OK("k_scan_chunks");
+    }
+    const int64_t max_items = ceil_div(total, chunk) + a->T;
     const int grid = (int)std::min<int64_t>(max_items, (int64_t)kNumSMs * 8);
     ProfScope ps(kProfVisibility, stream);
     k_visibility_f64<<<grid, kChunk, 0, stream>>>(a->T, a->L, a->trk_frame_off, a->poses, a->frame_sf, a->sensors,
                                                   a->incl_pool, a->ri_pool, a->voxel_size, a->label_off, w.grids,
-                                                  w.chunk_off, w.counter, w.bits, a->labels, a->status,
-                                                  a->n_unknown, a->n_steps);
+                                                  w.chunk_off, w.counter, w.bits, w.trk_flags, a->labels,
+                                                  a->labels_u8, a->status, a->n_unknown, a->n_steps);
     OCC_KERNEL_OK("k_visibility_f64");
     return 0;
   }
-  if (fast) {
-    ProfScope ps(kProfPairCull, stream);
-    k_pair_build<<<(unsigned)a->T, 256, 0, stream>>>(a->T, a->L, a->trk_frame_off, a->label_off, w.grids, a->poses,
-                                                     a->frame_sf, a->sensors, w.sens, a->voxel_size, w.pyr_off, w.pyr,
-                                                     w.lut_pool, w.pyr_flag, w.pairs_c, w.hot, w.item_map,
-                                                     (long long)w.items_cap, w.counter, a->status);
+  if (!fast) {                                      // no tracklet-frames at all: statuses are final, nothing to label
+    return 0;
+  }
+  {
+    ProfScope ps(kProfPairBuild, stream);
+    k_pair_build<<<(unsigned)a->T, 256, 0, stream>>>(a->T, a->L, a->trk_frame_off, a->brick_off, w.grids, w.trk_flags,
+                                                     a->poses, a->frame_sf, a->sensors, w.tabcoef, w.lut_pool,
+                                                     a->voxel_size, a->pyr_off, w.pyr, cull ? 1 : 0, w.pairs_c, w.hot,
+                                                     w.item_map, (long long)w.bricks, w.n_slices, w.counter, a->status);
     OCC_KERNEL_OK("k_pair_build");
   }
-  if (fast && a->F > 0) OCC_CUDA(cudaStreamWaitEvent(stream, side->join, 0));   // redo pass done: bits and flags final
+  if (brick_cull && w.bricks > 0) {
+    ProfScope ps(kProfBrickCull, stream);
+    const unsigned gx = (unsigned)std::min<int64_t>(ceil_div(w.bricks * kPairsPerItem, 256), (int64_t)kNumSMs * 16);
+    k_brick_cull<<<dim3(gx, (unsigned)w.n_slices), 256, 0, stream>>>(w.item_map, (long long)w.bricks, w.counter, w.hot,
+                                                                     w.pairs_c, w.lut_pool, a->pyr_off, w.pyr2,
+                                                                     w.mask_words, w.pair_mask);
+    OCC_KERNEL_OK("k_brick_cull");
+  }
+  OCC_CUDA(cudaStreamWaitEvent(stream, side->join, 0));   // redo pass done: bits and flags final
   // flag bit 3 (tests): the kernels see a 64-entry recheck queue, so the decide-in-place path runs
   const long long queue_cap_used = (a->flags & 8) ? std::min<long long>(64, (long long)w.queue_cap) : (long long)w.queue_cap;
   {
-    const int grid = (int)std::min<int64_t>(ceil_div(std::max<int64_t>(w.items_cap, 1), kFastWarps),
+    VisArgs va;
+    va.L = a->L; va.mask_words = w.mask_words; va.n_slices = w.n_slices; va.pad = 0;
+    va.bricks_total = (long long)w.bricks; va.queue_cap = queue_cap_used; va.vs = a->voxel_size;
+    va.trk_frame_off = a->trk_frame_off; va.poses = a->poses; va.frame_sf = a->frame_sf; va.sensors = a->sensors;
+    va.incl_pool = a->incl_pool; va.ri_pool = a->ri_pool; va.grids = w.grids; va.counter = w.counter;
+    va.bits = w.bits; va.free_brick = w.free_brick; va.pair_mask = w.pair_mask; va.item_map = w.item_map;
+    va.hot = w.hot; va.pairs = w.pairs_c; va.lut_pool = w.lut_pool; va.queue = w.queue; va.n_steps = a->n_steps;
+    const int grid = (int)std::min<int64_t>(ceil_div(std::max<int64_t>(w.bricks * w.n_slices, 1), kFastWarps),
                                             (int64_t)kNumSMs * OCC_MINB);
     ProfScope ps(kProfVisibility, stream);
-    k_visibility_fast<1, kVPL1><<<grid, 32 * kFastWarps, 0, stream>>>(
-        a->L, a->trk_frame_off, a->poses, a->frame_sf, a->sensors, a->incl_pool, a->ri_pool, a->voxel_size, w.grids,
-        w.counter, (long long)w.items_cap, w.bits, w.free_bits, w.item_map, w.hot, w.pairs_c, w.ub_pool,
-        w.lut_pool, w.queue, queue_cap_used, w.unk_list, w.n_unk, a->n_steps);
-    OCC_KERNEL_OK("k_visibility_fast<1>");
-    k_phase2_emit<<<(unsigned)a->T, 256, 0, stream>>>(w.hot, w.n_unk, w.item_map, (long long)w.items_cap, w.counter);
-    OCC_KERNEL_OK("k_phase2_emit");
-    k_visibility_fast<2, kVPL><<<grid, 32 * kFastWarps, 0, stream>>>(
-        a->L, a->trk_frame_off, a->poses, a->frame_sf, a->sensors, a->incl_pool, a->ri_pool, a->voxel_size, w.grids,
-        w.counter, (long long)w.items_cap, w.bits, w.free_bits, w.item_map, w.hot, w.pairs_c, w.ub_pool,
-        w.lut_pool, w.queue, queue_cap_used, w.unk_list, w.n_unk, a->n_steps);
-    OCC_KERNEL_OK("k_visibility_fast<2>");
+    k_visibility<<<grid, 32 * kFastWarps, 0, stream>>>(va);
+    OCC_KERNEL_OK("k_visibility");
   }
   {
     ProfScope ps(kProfRecheck, stream);
     k_visibility_recheck<<<kNumSMs * 4, 256, 0, stream>>>(a->L, a->trk_frame_off, a->poses, a->frame_sf, a->sensors,
-                                                          a->incl_pool, a->ri_pool, a->voxel_size, w.grids, w.counter,
-                                                          w.queue, queue_cap_used, w.free_bits, a->n_steps);
+                                                          a->incl_pool, a->ri_pool, a->voxel_size, w.grids, w.hot,
+                                                          w.counter, w.queue, queue_cap_used, w.free_brick, a->n_steps);
     OCC_KERNEL_OK("k_visibility_recheck");
-    k_labels<<<dim3((unsigned)a->T, 8), 256, 0, stream>>>(w.hot, w.grids, w.bits, w.free_bits, a->labels,
-                                                          a->n_unknown, a->status);
+  }
+  {
+    ProfScope ps(kProfLabels, stream);
+    k_labels<<<dim3((unsigned)a->T, 8), 256, 0, stream>>>(w.hot, w.grids, w.trk_flags, a->label_off, w.bits,
+                                                          w.free_brick, a->labels, a->labels_u8, a->n_unknown,
+                                                          a->status);
     OCC_KERNEL_OK("k_labels");
   }
   return 0;
@@ -1737,10 +2008,11 @@ extern "C" int occb200_annotate_point_voxels(const occb200_annotate_args_t *a, i
   OCC_REQUIRE(((uintptr_t)q_out & 15) == 0, "q_out must be 16-byte aligned");
   if (a->T == 0 || a->F == 0) return 0;
   Workspace w;
-  ws_layout(a->T, a->F, total, a->SF, a->L, a->incl_len, a->pyr_tiles, a->items_cap, (char *)a->workspace, &w);
+  ws_layout(a->T, a->F, total, a->SF, a->L, a->incl_len, a->pyr_tiles, a->bricks, a->max_pairs, (char *)a->workspace, &w);
+  const float vsf = (float)a->voxel_size;
   k_frame_points<<<(unsigned)a->F, 256, 0, stream>>>(a->poses, a->points, a->point_stride, a->frame_pt_off,
-                                                     w.frame_trk, w.grids, a->status, (float)a->voxel_size, loc_out,
-                                                     q_out);
+                                                     a->frame_trk, w.grids, a->status, vsf,
+                                                     (a->flags & 32) ? 1.0f / vsf : 0.f, loc_out, q_out);
   OCC_KERNEL_OK("k_frame_points");
   return 0;
 }
@@ -1749,7 +2021,7 @@ extern "C" int occb200_annotate_queue_stats(const occb200_annotate_args_t *a, in
                                             void *stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   Workspace w;
-  ws_layout(a->T, a->F, total, a->SF, a->L, a->incl_len, a->pyr_tiles, a->items_cap, (char *)a->workspace, &w);
+  ws_layout(a->T, a->F, total, a->SF, a->L, a->incl_len, a->pyr_tiles, a->bricks, a->max_pairs, (char *)a->workspace, &w);
   unsigned long long n = 0;
   OCC_CUDA(cudaMemcpyAsync(&n, w.counter + 1, 8, cudaMemcpyDeviceToHost, stream));
   OCC_CUDA(cudaStreamSynchronize(stream));
@@ -1782,13 +2054,16 @@ extern "C" int occb200_profile_read(double *ms_per_kind, int64_t *launches_per_k
 }
 
 extern "C" int occb200_selftest_atan2(int64_t n, uint64_t seed, double *max_err_host, void *stream_) {
+  // max_err_host[0]: full-quadrant path (bound kAtanWide), max_err_host[1]: narrow path (bound kAtanNarrow)
   cudaStream_t stream = (cudaStream_t)stream_;
   unsigned long long *d = nullptr;
-  OCC_CUDA(cudaMallocAsync((void **)&d, 8, stream));
-  OCC_CUDA(cudaMemsetAsync(d, 0, 8, stream));
-  k_selftest_atan2<<<kNumSMs * 4, 256, 0, stream>>>(n, seed, d);
+  OCC_CUDA(cudaMallocAsync((void **)&d, 16, stream));
+  OCC_CUDA(cudaMemsetAsync(d, 0, 16, stream));
+  k_selftest_atan2<<<kNumSMs * 4, 256, 0, stream>>>(n, seed, 0, d);
   OCC_KERNEL_OK("k_selftest_atan2");
-  OCC_CUDA(cudaMemcpyAsync(max_err_host, d, 8, cudaMemcpyDeviceToHost, stream));
+  k_selftest_atan2<<<kNumSMs * 4, 256, 0, stream>>>(n, seed, 1, d + 1);
+  OCC_KERNEL_OK("k_selftest_atan2");
+  OCC_CUDA(cudaMemcpyAsync(max_err_host, d, 16, cudaMemcpyDeviceToHost, stream));
   OCC_CUDA(cudaFreeAsync(d, stream));
   OCC_CUDA(cudaStreamSynchronize(stream));
   return 0;

@@ -29,10 +29,13 @@ import torch
 from . import _lib
 
 LiDAR_NAME_LIST = ["TOP", "FRONT", "SIDE_LEFT", "SIDE_RIGHT", "REAR"]     # occ_annotate.py:235
-STATUS_NAMES = {0: "ok", 1: "skip_short", 2: "no_points", 3: "empty_after_filter", 4: "index_error", -1: "slot_too_small"}
+STATUS_NAMES = {0: "ok", 1: "skip_short", 2: "no_points", 3: "empty_after_filter", 4: "index_error",
+                5: "work_overflow", -1: "slot_too_small"}
 FLAG_FORCE_F64 = 1
 FLAG_NO_CULL = 2
 FLAG_TINY_QUEUE = 8        # tests: forces the recheck-queue overflow path
+FLAG_NO_BRICK_CULL = 16    # A/B: pair-level culling only
+FLAG_CUDA_ARITH = 32       # scalar divisions as torch-CUDA evaluates them (x * (1/vs)); default: torch-CPU's x / vs
 
 
 # ------------------------------------------------------------------------------------------------
@@ -62,7 +65,12 @@ def _mono(table: np.ndarray) -> int:
 
 @dataclass
 class PackedTracklets:
-    """Flat host arrays in the layout of ``occb200_annotate_args_t`` (include/occ_b200.h)."""
+    """Host arrays in the layout of ``occb200_annotate_args_t`` (include/occ_b200.h).
+
+    The two large inputs are NOT concatenated on the host: ``ri_parts`` / ``pt_parts`` list the source arrays
+    (range images of one LiDAR of one segment; candidate points of one tracklet) with their offsets in the
+    device pools, and ``upload`` copies each straight into its slot.  ``ri_pool`` / ``points`` materialise
+    the concatenation on demand (tests, fixtures)."""
 
     T: int
     L: int
@@ -71,20 +79,60 @@ class PackedTracklets:
     trk_frame_off: np.ndarray      # i64 [T+1]
     poses: np.ndarray              # POSE_DTYPE [F]
     frame_sf: np.ndarray           # i32 [F]
-    points: np.ndarray             # f32 [P, stride]
+    frame_trk: np.ndarray          # i32 [F]
     frame_pt_off: np.ndarray       # i64 [F+1]
     sensors: np.ndarray            # SENSOR_DTYPE [SF, L]
     incl_pool: np.ndarray          # f32
-    ri_pool: np.ndarray            # f32
     label_off: np.ndarray          # i64 [T+1]
+    brick_off: np.ndarray          # i64 [T+1]
+    pyr_off: np.ndarray            # i64 [SF*L+1]
+    table_off: np.ndarray          # i64 [n_tables]
+    table_H: np.ndarray            # i32 [n_tables]
+    max_pairs: int
+    point_stride: int
+    n_points: int
+    ri_len: int
+    pt_parts: list                 # [(row offset, f32 [n, stride] array)]
+    ri_parts: list                 # [(float offset, f32 [nb, H, W] array)]
 
     @property
     def total_slots(self) -> int:
         return int(self.label_off[-1])
 
+    @property
+    def points(self) -> np.ndarray:
+        out = np.zeros((self.n_points, self.point_stride), np.float32)
+        for off, a in self.pt_parts:
+            out[off:off + len(a)] = a
+        return out
+
+    @property
+    def ri_pool(self) -> np.ndarray:
+        out = np.zeros(self.ri_len, np.float32)
+        for off, a in self.ri_parts:
+            out[off:off + a.size] = a.reshape(-1)
+        return out
+
     def input_bytes(self) -> int:
-        return sum(a.nbytes for a in (self.trk_frame_off, self.poses, self.frame_sf, self.points, self.frame_pt_off,
-                                      self.sensors, self.incl_pool, self.ri_pool, self.label_off))
+        return (sum(getattr(self, n).nbytes for n in _SMALL_FIELDS) + 4 * self.ri_len
+                + 4 * self.n_points * self.point_stride)
+
+
+_SMALL_FIELDS = ("trk_frame_off", "poses", "frame_sf", "frame_trk", "frame_pt_off", "sensors", "incl_pool",
+                 "label_off", "brick_off", "pyr_off", "table_off", "table_H")
+
+
+def _same_memory(flat, pieces) -> bool:
+    """``flat`` is exactly the concatenation of ``pieces`` (views into it, in order)."""
+    if flat is None or flat.ndim != 2 or not flat.flags.c_contiguous or flat.dtype != np.float32:
+        return False
+    addr = flat.__array_interface__["data"][0]
+    for p_ in pieces:
+        if p_.dtype != np.float32 or p_.ndim != 2 or p_.shape[1] != flat.shape[1] or (len(p_) and (
+                not p_.flags.c_contiguous or p_.__array_interface__["data"][0] != addr)):
+            return False
+        addr += p_.nbytes
+    return addr == flat.__array_interface__["data"][0] + flat.nbytes
 
 
 def pack_tracklets(batch, pack_override: Optional[dict] = None) -> PackedTracklets:
@@ -99,16 +147,20 @@ def pack_tracklets(batch, pack_override: Optional[dict] = None) -> PackedTrackle
     sf_base = np.cumsum([0] + [s.num_frames for s in segs]).astype(np.int64)
     SF = int(sf_base[-1])
     sensors = np.zeros((SF, L), _lib.SENSOR_DTYPE)
-    incl_parts, ri_parts = [], []
+    incl_parts, ri_parts, table_off, table_H = [], [], [], []
     incl_off = ri_off = 0
+    ext = np.concatenate([np.asarray(s.extrinsics, np.float32).reshape(s.num_frames, L, 4, 4) for s in segs], 0) \
+        if segs else np.zeros((0, L, 4, 4), np.float32)
+    v2l_all, azc_all = _host_calib(ext) if SF else (np.zeros((0, 12), np.float32), np.zeros(0, np.float32))
+    sensors["v2l"] = v2l_all.reshape(SF, L, 12)
+    sensors["azc"] = azc_all.reshape(SF, L)
     for si, s in enumerate(segs):
-        v2l, azc = _host_calib(s.extrinsics)
-        v2l = v2l.reshape(s.num_frames, L, 12)
-        azc = azc.reshape(s.num_frames, L)
         sl = slice(int(sf_base[si]), int(sf_base[si + 1]))
         for c in range(L):
             table = np.ascontiguousarray(s.inclinations[c][::-1], np.float32)      # flip (:528)
-            img = np.ascontiguousarray(s.range_images[c], np.float32)
+            img = s.range_images[c]
+            if img.dtype != np.float32 or not img.flags.c_contiguous:
+                img = np.ascontiguousarray(img, np.float32)
             nb, H, W = img.shape
             assert table.shape[0] == H and nb == s.num_frames
             sensors["incl_off"][sl, c] = incl_off
@@ -116,23 +168,44 @@ def pack_tracklets(batch, pack_override: Optional[dict] = None) -> PackedTrackle
             sensors["ri_off"][sl, c] = ri_off + np.arange(nb, dtype=np.int64) * H * W
             sensors["H"][sl, c] = H
             sensors["W"][sl, c] = W
-            sensors["v2l"][sl, c] = v2l[:, c]
-            sensors["azc"][sl, c] = azc[:, c]
             incl_parts.append(table)
-            ri_parts.append(img.reshape(-1))
+            table_off.append(incl_off)
+            table_H.append(H)
+            ri_parts.append((ri_off, img))
             incl_off += H
             ri_off += nb * H * W
-    nfr = [len(t) for t in trks]
-    trk_frame_off = np.cumsum([0] + nfr).astype(np.int64)
+    L_ = _lib.lib()
+    sn = sensors.reshape(-1)
+    tiles = np.zeros(sn.size + 1, np.int64)
+    if sn.size:
+        hw, inv = np.unique(np.stack([sn["H"], sn["W"]], 1), axis=0, return_inverse=True)
+        per = np.array([L_.occb200_pyramid_tiles(int(h), int(w_)) for h, w_ in hw], np.int64)
+        np.cumsum(per[inv.reshape(-1)], out=tiles[1:])
+    nfr = np.array([len(t) for t in trks], np.int64)
+    trk_frame_off = np.concatenate([[0], np.cumsum(nfr)]).astype(np.int64)
     F = int(trk_frame_off[-1])
     boxes = np.concatenate([t.boxes for t in trks], 0).astype(np.float32) if F else np.zeros((0, 7), np.float32)
     frame_sf = (np.concatenate([sf_base[t.segment] + np.asarray(t.frame_ids, np.int64) for t in trks]).astype(np.int32)
                 if F else np.zeros(0, np.int32))
-    per_frame = [p for t in trks for p in t.points]
-    frame_pt_off = np.cumsum([0] + [len(p) for p in per_frame]).astype(np.int64)
-    stride = per_frame[0].shape[1] if per_frame else 3
-    points = (np.concatenate(per_frame, 0).astype(np.float32) if frame_pt_off[-1] > 0
-              else np.zeros((0, stride), np.float32))
+    frame_trk = np.repeat(np.arange(T, dtype=np.int32), nfr)
+    # candidate points: one part per tracklet when its frames are views of one contiguous array, else per frame
+    pt_parts, lens, stride, row = [], [], None, 0
+    for t in trks:
+        n_t = [len(p_) for p_ in t.points]
+        lens.extend(n_t)
+        if len(t.points) and stride is None:
+            stride = int(t.points[0].shape[1])
+        if getattr(t, "flat", None) is not None and _same_memory(t.flat, t.points):
+            if len(t.flat):
+                pt_parts.append((row, t.flat))
+            row += len(t.flat)
+        else:
+            for p_ in t.points:
+                if len(p_):
+                    pt_parts.append((row, np.ascontiguousarray(p_, np.float32)))
+                row += len(p_)
+    stride = stride or 3
+    frame_pt_off = np.concatenate([[0], np.cumsum(np.asarray(lens, np.int64))]).astype(np.int64)
     trig = _host_trig(boxes[:, 6]) if F else np.zeros((0, 4), np.float32)
     if pack_override and "trig" in pack_override:
         trig = np.ascontiguousarray(pack_override["trig"], np.float32)
@@ -140,7 +213,7 @@ def pack_tracklets(batch, pack_override: Optional[dict] = None) -> PackedTrackle
     if F:
         boxes = np.ascontiguousarray(boxes)
         trig = np.ascontiguousarray(trig, np.float32)
-        _lib.lib().occb200_host_pose_pack(boxes.ctypes.data, trig.ctypes.data, F, poses.ctypes.data)
+        L_.occb200_host_pose_pack(boxes.ctypes.data, trig.ctypes.data, F, poses.ctypes.data)
     if pack_override:
         if "pib" in pack_override:
             poses["cos_pib"] = pack_override["pib"][:, 0]
@@ -149,83 +222,99 @@ def pack_tracklets(batch, pack_override: Optional[dict] = None) -> PackedTrackle
             sensors["v2l"] = np.asarray(pack_override["v2l"], np.float32).reshape(SF, L, 12)
         if "azc" in pack_override:
             sensors["azc"] = np.asarray(pack_override["azc"], np.float32).reshape(SF, L)
-    # label slots: upper bound of the grid = ceil(max over ALL frames of the box size / vs) in f32
+    # label slots: upper bound of the grid = ceil(max over ALL frames of the box size / vs) in f32; the reciprocal
+    # form (torch-CUDA arithmetic, flag bit 5) may round one voxel higher, so the slot takes the larger of the two
     vsf = np.float32(batch.voxel_size)
-    caps = []
-    for t in trks:
-        if len(t) == 0:
-            caps.append(0)
-            continue
-        d = np.ceil(t.boxes[:, 3:6].astype(np.float32).max(0) / vsf).astype(np.int64)
-        caps.append(int(max(d[0], 0) * max(d[1], 0) * max(d[2], 0)))
-    label_off = np.cumsum([0] + caps).astype(np.int64)
+    caps = np.zeros((T, 3), np.int64)
+    if F:
+        nz = nfr > 0
+        mx = np.maximum.reduceat(boxes[:, 3:6], trk_frame_off[:-1][nz], axis=0)
+        d = np.maximum(np.ceil(mx / vsf), np.ceil(mx * (np.float32(1.0) / vsf))).astype(np.int64)
+        caps[nz] = np.maximum(d, 0)
+    label_off = np.concatenate([[0], np.cumsum(caps.prod(1))]).astype(np.int64)
+    brick_off = np.concatenate([[0], np.cumsum(((caps + 3) // 4).prod(1))]).astype(np.int64)
     return PackedTracklets(
         T=T, L=L, F=F, voxel_size=float(batch.voxel_size), trk_frame_off=trk_frame_off, poses=poses,
-        frame_sf=frame_sf, points=points, frame_pt_off=frame_pt_off, sensors=sensors,
-        incl_pool=np.concatenate(incl_parts) if incl_parts else np.zeros(0, np.float32),
-        ri_pool=np.concatenate(ri_parts) if ri_parts else np.zeros(0, np.float32), label_off=label_off)
+        frame_sf=frame_sf, frame_trk=frame_trk, frame_pt_off=frame_pt_off, sensors=sensors,
+        incl_pool=np.concatenate(incl_parts) if incl_parts else np.zeros(0, np.float32), label_off=label_off,
+        brick_off=brick_off, pyr_off=tiles, table_off=np.asarray(table_off, np.int64),
+        table_H=np.asarray(table_H, np.int32), max_pairs=int(nfr.max()) * L if T else 0, point_stride=stride,
+        n_points=int(frame_pt_off[-1]), ri_len=int(ri_off), pt_parts=pt_parts, ri_parts=ri_parts)
 
 
 # ------------------------------------------------------------------------------------------------
 # device side
 # ------------------------------------------------------------------------------------------------
-_FIELDS = ("trk_frame_off", "poses", "frame_sf", "points", "frame_pt_off", "sensors", "incl_pool", "ri_pool",
-           "label_off")
-
-
 def _as_bytes(a: np.ndarray) -> torch.Tensor:
     a = np.ascontiguousarray(a)
     return torch.from_numpy(a.view(np.uint8).reshape(-1)) if a.size else torch.zeros(0, dtype=torch.uint8)
 
 
 class HostBuffers:
-    """Pinned host copies of a PackedTracklets, ready for asynchronous H2D."""
+    """Pinned host copies of a PackedTracklets' arrays, ready for asynchronous H2D: one buffer per small field and
+    one per part of the two pools (a loader that reads into pinned memory would hand these over directly)."""
 
     def __init__(self, pk: PackedTracklets, pin: bool = True):
         self.pk = pk
-        self.bufs = {}
-        for name in _FIELDS:
-            t = _as_bytes(getattr(pk, name))
-            self.bufs[name] = t.pin_memory() if (pin and t.numel()) else t
+
+        def host(a):
+            t = _as_bytes(a)
+            return t.pin_memory() if (pin and t.numel()) else t
+
+        self.bufs = {name: host(getattr(pk, name)) for name in _SMALL_FIELDS}
+        self.pt_parts = [(off * pk.point_stride * 4, host(a)) for off, a in pk.pt_parts]
+        self.ri_parts = [(off * 4, host(a)) for off, a in pk.ri_parts]
 
     def nbytes(self) -> int:
-        return sum(t.numel() for t in self.bufs.values())
+        return (sum(t.numel() for t in self.bufs.values()) + sum(t.numel() for _, t in self.pt_parts)
+                + sum(t.numel() for _, t in self.ri_parts))
 
 
 class DeviceTracklets:
-    """Device-resident inputs + outputs + workspace of one batch; reusable across calls."""
+    """Device-resident inputs + outputs + workspace of one batch; reusable across calls.
 
-    def __init__(self, pk: PackedTracklets, device=None):
+    ``labels="i32"`` (default) allocates the reference's int32 labels, ``"u8"`` one byte per voxel (what a job
+    keeps on the device and gathers; the int32 of occ_annotate.py:581 is produced at the file boundary),
+    ``"both"`` both.  ``labels_u8`` may be a caller-owned uint8 tensor slice (a rank's common label buffer)."""
+
+    def __init__(self, pk: PackedTracklets, device=None, labels: str = "i32", labels_u8: Optional[torch.Tensor] = None):
         _lib.require_cuda()
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.pk = pk
-        self.bufs = {name: torch.empty(max(getattr(pk, name).nbytes, 16), dtype=torch.uint8, device=self.device)
-                     for name in _FIELDS}
-        T, total = pk.T, pk.total_slots
         dev = self.device
-        self.labels = torch.zeros(max(total, 1), dtype=torch.int32, device=dev)
+        self.bufs = {name: torch.empty(max(getattr(pk, name).nbytes, 16), dtype=torch.uint8, device=dev)
+                     for name in _SMALL_FIELDS}
+        self.bufs["points"] = torch.empty(max(4 * pk.n_points * pk.point_stride, 16), dtype=torch.uint8, device=dev)
+        self.bufs["ri_pool"] = torch.empty(max(4 * pk.ri_len, 16), dtype=torch.uint8, device=dev)
+        T, total = pk.T, pk.total_slots
+        self.labels = torch.zeros(max(total, 1), dtype=torch.int32, device=dev) if labels in ("i32", "both") else None
+        if labels_u8 is not None:
+            assert labels_u8.dtype == torch.uint8 and labels_u8.numel() >= total and labels_u8.is_cuda
+            self.labels_u8 = labels_u8
+        else:
+            self.labels_u8 = (torch.zeros(max(total, 1), dtype=torch.uint8, device=dev)
+                              if labels in ("u8", "both") else None)
         self.dims = torch.zeros((max(T, 1), 3), dtype=torch.int32, device=dev)
         self.sizes = torch.zeros((max(T, 1), 3), dtype=torch.float32, device=dev)
         self.status = torch.zeros(max(T, 1), dtype=torch.int32, device=dev)
         self.n_unknown = torch.zeros(max(T, 1), dtype=torch.int64, device=dev)
         self.n_steps = torch.zeros(max(T, 1), dtype=torch.int64, device=dev)
-        L_ = _lib.lib()
-        sn = pk.sensors.reshape(-1)
-        self.pyr_tiles = int(sum(L_.occb200_pyramid_tiles(int(h), int(w_)) * int(n) for (h, w_), n in
-                                 zip(*np.unique(np.stack([sn["H"], sn["W"]], 1), axis=0, return_counts=True)))) if sn.size else 0
-        self.items_cap = int(L_.occb200_annotate_items_cap(T, pk.label_off.ctypes.data, pk.trk_frame_off.ctypes.data,
-                                                           pk.L)) if T else 0
-        ws = L_.occb200_annotate_workspace_bytes(T, pk.F, total, pk.sensors.shape[0], pk.L, pk.incl_pool.size,
-                                                 self.pyr_tiles, self.items_cap)
+        self.pyr_tiles = int(pk.pyr_off[-1])
+        ws = _lib.lib().occb200_annotate_workspace_bytes(T, pk.F, total, pk.sensors.shape[0], pk.L, pk.incl_pool.size,
+                                                         self.pyr_tiles, int(pk.brick_off[-1]), pk.max_pairs)
         self.workspace = torch.empty(max(ws, 16), dtype=torch.uint8, device=dev)
 
     def upload(self, host: HostBuffers):
         """Asynchronous H2D of every input on the current stream; returns the bytes copied."""
         n = 0
-        for name in _FIELDS:
+        for name in _SMALL_FIELDS:
             src = host.bufs[name]
             if src.numel():
                 self.bufs[name][: src.numel()].copy_(src, non_blocking=True)
+                n += src.numel()
+        for dst, parts in ((self.bufs["points"], host.pt_parts), (self.bufs["ri_pool"], host.ri_parts)):
+            for off, src in parts:
+                dst[off: off + src.numel()].copy_(src, non_blocking=True)
                 n += src.numel()
         return n
 
@@ -237,7 +326,7 @@ class DeviceTracklets:
         a.poses = b["poses"].data_ptr()
         a.frame_sf = b["frame_sf"].data_ptr()
         a.points = b["points"].data_ptr()
-        a.point_stride = pk.points.shape[1] if pk.points.ndim == 2 else 3
+        a.point_stride = pk.point_stride
         a.frame_pt_off = b["frame_pt_off"].data_ptr()
         a.sensors = b["sensors"].data_ptr()
         a.SF = pk.sensors.shape[0]
@@ -245,10 +334,19 @@ class DeviceTracklets:
         a.incl_len = pk.incl_pool.size
         a.ri_pool = b["ri_pool"].data_ptr()
         a.pyr_tiles = self.pyr_tiles
-        a.items_cap = self.items_cap
+        a.items_cap = 0
         a.voxel_size = pk.voxel_size
         a.label_off = b["label_off"].data_ptr()
-        a.labels = self.labels.data_ptr()
+        a.labels = self.labels.data_ptr() if self.labels is not None else None
+        a.labels_u8 = self.labels_u8.data_ptr() if self.labels_u8 is not None else None
+        a.frame_trk = b["frame_trk"].data_ptr()
+        a.pyr_off = b["pyr_off"].data_ptr()
+        a.table_off = b["table_off"].data_ptr()
+        a.table_H = b["table_H"].data_ptr()
+        a.n_tables = int(pk.table_off.size)
+        a.max_pairs = pk.max_pairs
+        a.brick_off = b["brick_off"].data_ptr()
+        a.bricks = int(pk.brick_off[-1])
         a.dims = self.dims.data_ptr()
         a.sizes = self.sizes.data_ptr()
         a.status = self.status.data_ptr()
@@ -302,7 +400,7 @@ class DeviceTracklets:
     def point_voxels(self, flags: int = 0):
         """After ``run``: (loc f32 [N,3], rows int32 [N,4]) for the N candidate points -- box-frame coordinates and
         (tracklet, qx, qy, qz) with the final grids; rows of points the reference drops start with -1."""
-        n = max(int(self.pk.points.shape[0]), 1)
+        n = max(int(self.pk.n_points), 1)
         loc = torch.empty((n, 3), dtype=torch.float32, device=self.device)
         rows = torch.empty((n, 4), dtype=torch.int32, device=self.device)
         a = self.args(flags)
@@ -310,7 +408,7 @@ class DeviceTracklets:
             rc = _lib.lib().occb200_annotate_point_voxels(C.byref(a), self.pk.total_slots, loc.data_ptr(),
                                                           rows.data_ptr(), _lib.stream_ptr(self.device))
         _lib.check(rc, "occb200_annotate_point_voxels")
-        n = int(self.pk.points.shape[0])
+        n = int(self.pk.n_points)
         return loc[:n], rows[:n]
 
     def mean_var(self, flags: int = 0) -> List[Optional[np.ndarray]]:
@@ -356,7 +454,7 @@ class DeviceTracklets:
     def results(self) -> List[dict]:
         """D2H of labels / dims / status and per-tracklet reshape (synchronises)."""
         pk = self.pk
-        labels = self.labels.cpu().numpy()
+        labels = (self.labels if self.labels is not None else self.labels_u8).cpu().numpy()
         dims = self.dims.cpu().numpy()
         sizes = self.sizes.cpu().numpy()
         status = self.status.cpu().numpy()
@@ -371,7 +469,7 @@ class DeviceTracklets:
                 continue
             X, Y, Z = (int(v) for v in dims[t])
             o = int(pk.label_off[t])
-            out.append(dict(status="ok", occ=labels[o:o + X * Y * Z].reshape(X, Y, Z).copy(), dims=dims[t].copy(),
+            out.append(dict(status="ok", occ=labels[o:o + X * Y * Z].reshape(X, Y, Z).astype(np.int32), dims=dims[t].copy(),
                             size=sizes[t].copy(), n_unknown=int(nunk[t]), n_steps=int(nsteps[t])))
         return out
 
@@ -385,7 +483,7 @@ def annotate_batch(batch, flags: int = 0, pack_override: Optional[dict] = None, 
     ``size``, ``n_unknown`` (U) and ``n_steps`` (visibility tests evaluated).
     """
     pk = pack_tracklets(batch, pack_override)
-    host = HostBuffers(pk)
+    host = HostBuffers(pk, pin=False)       # one-shot call: the arrays are uploaded from where they lie
     dev = DeviceTracklets(pk, device)
     dev.upload(host)
     dev.run(flags)
