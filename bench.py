@@ -2,21 +2,32 @@
 """Benchmark of the point -> occupancy hot path (BASELINE.json metric: tracklets/s and voxel-steps/s
 of the occupancy ray-cast, %HBM peak).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2] [--impl reference] [--also c1,c3,c4,c5]
 
 A *step* is one pass of the whole annotate path (crop -> box frame -> voxelise -> range-image
-visibility) over one batch of synthetic tracklets.  The N=1 workload is BASELINE.json configs[1]:
-64 vehicle tracklets x 40 frames at 0.2 m voxels, one shared segment of 5-LiDAR range images.
-For N>1 (torchrun, one rank per GPU) every rank annotates its own batch of that shape (tracklets are
-independent: no collective on the data path, "weak" scaling); rank 0 prints ONE JSON line.
+visibility) over the workload's synthetic tracklets.
 
-`value`     tracklets/s with the batch resident in HBM (device-timed, CUDA events, max over ranks).
+N = 1 (default): the workload is BASELINE.json configs[1] (C2): 64 vehicle tracklets x 40 frames at 0.2 m
+voxels, one shared segment of 5-LiDAR range images.  The line also carries `also`: sub-records for C1, C3, C4
+and the 10 000-tracklet job C5 on this one GPU (ms/step, roofline fraction, label mismatches against the CPU
+port on a fixed subsample -- asserted, not just printed).
+
+N > 1 (torchrun, one rank per GPU): STRONG scaling of the fixed job C5 = BASELINE.json configs[4]: 10 000
+C2-shaped tracklets over 157 segments, sharded by segment (longest-processing-time greedy, dist.shard_indices),
+every rank generates and annotates only its own segments in batches of `--batch-segments` segments, and the step
+ends with the job's one collective: the gather of all labels (one byte per voxel, device to device) on rank 0.
+`value` = 10 000 tracklets / max over ranks of {compute of all its batches + gather}.
+
+`value`     tracklets/s with the inputs resident in HBM (device-timed, CUDA events, max over ranks).
 `e2e`       the same through the public API with HOST buffers: per step, H2D of all inputs from pinned
             memory + the kernels + D2H of labels/dims/status; steps alternate between two device buffer sets
             on two streams, so one step's upload overlaps the previous step's kernels (events around all K).
-`roofline`  the visibility ("ray-cast") kernel: algorithmic bytes 4*U*B*L + 4*V per tracklet
+            `pack_ms` (host packing of the step's metadata; the large arrays are uploaded from where they lie)
+            and `api_one_shot_ms` (occ.annotate_batch(): pack + allocate + upload from pageable memory + run +
+            download) are reported beside it.
+`roofline`  the ray-cast (k_brick_cull + k_visibility): algorithmic bytes 4*U*B*L + 4*V per tracklet
              / its mean launch duration, measured live with CUDA events
-            recorded around that kernel on the launching stream (occb200_profile_*).
+            recorded around the kernels on the launching stream (occb200_profile_*).
 `cpu_baseline` the CPU oracle port (oracle/occ_oracle.c, OpenMP over tracklets) on the same workload,
             on this host's cores.  `--impl reference` times that port as the reference arm: the
             reference's own implementation of this path is Python+torch ops that cannot be imported
@@ -43,22 +54,28 @@ WORKLOADS = {
     "c2": "c2: 64 vehicle tracklets x 40 frames, 0.2 m voxels, 5 LiDARs (one shared segment)",
     "c3": "c3: 16 truck/bus tracklets x 40 frames, 0.1 m voxels, 5 LiDARs",
     "c5s": "c5 (scaled): 1024 vehicle tracklets x 40 frames over 16 segments, 0.2 m voxels, 5 LiDARs",
+    "c5": "c5: 10000 vehicle tracklets x 40 frames over 157 segments, 0.2 m voxels, 5 LiDARs, sharded by segment",
 }
+JOB_TRACKLETS, JOB_PER_SEGMENT = 10000, 64
 
 
-def parse():
+def parse(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS),
+                    help="default: c2 on one GPU, the c5 job on several")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-threads", type=int, default=0, help="0 = all host cores")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--force-f64", action="store_true", help="all-f64 visibility kernel")
     ap.add_argument("--flags", type=int, default=0, help="extra occb200_annotate_args_t.flags bits (A/B measurements)")
     ap.add_argument("--no-graph", action="store_true", help="launch the kernels one by one instead of replaying a CUDA graph")
-    return ap.parse_args()
+    ap.add_argument("--also", default="c1,c3,c4,c5", help="N=1: sub-records to add to the line (comma list, 'none')")
+    ap.add_argument("--batch-segments", type=int, default=8, help="c5 job: segments per device call")
+    ap.add_argument("--job-tracklets", type=int, default=JOB_TRACKLETS, help="c5 job size (tests use a small one)")
+    return ap.parse_args(argv)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -110,7 +127,8 @@ class ClockSampler:
 
 
 def ncu_traffic():
-    """DRAM bytes per launch of the ray-cast kernel from the committed ncu capture (profiles/), or None."""
+    """DRAM bytes per step of the ray-cast kernels from the COMMITTED ncu capture (profiles/): a static record of
+    the build that was profiled, not a measurement of this run."""
     p = os.path.join(ROOT, "profiles", "vis_fast_ncu.json")
     try:
         m = json.load(open(p))["metrics"]
@@ -129,11 +147,22 @@ def peaks():
 
 def workload_stats(res, B, L):
     """Nominal work of a batch from its results: voxel-steps U*B*L and algorithmic bytes 4*U*B*L + 4*V."""
-    U = sum(r["n_unknown"] for r in res if r["occ"] is not None)
-    V = sum(int(r["occ"].size) for r in res if r["occ"] is not None)
+    ok = [r for r in res if r["occ"] is not None]
+    U = sum(r["n_unknown"] for r in ok)
+    V = sum(int(r["occ"].size) for r in ok)
     steps = U * B * L
-    return dict(U=U, V=V, steps=steps, vis_bytes=4 * steps + 4 * V,
-                executed=sum(r.get("n_steps", 0) for r in res if r["occ"] is not None))
+    return dict(U=U, V=V, steps=steps, vis_bytes=4 * steps + 4 * V, executed=sum(r.get("n_steps", 0) for r in ok),
+                ok=len(ok))
+
+
+KERNEL_KINDS = ("k_crop_voxelize", "k_tracklet_setup+redo", "k_scan_chunks", "k_brick_cull", "k_visibility",
+                "side:k_pyr_build+k_table_setup", "k_visibility_recheck", "k_pair_build", "k_labels")
+
+
+def workload_config(name, batch, T=None):
+    B, L = len(batch.tracklets[0]), len(batch.segments[0].inclinations)
+    return {"workload": WORKLOADS[name], "tracklets_per_step": int(T if T is not None else len(batch.tracklets)),
+            "frames": B, "lidars": L, "voxel_size": batch.voxel_size}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -151,21 +180,47 @@ def cpu_port(batch, threads, min_seconds=8.0, max_reps=3):
     return min(times), res, len(times)
 
 
+def count_mismatches(got, exp):
+    """Labels / statuses that differ between two result lists (0 = parity)."""
+    bad = 0
+    for g, e in zip(got, exp):
+        if g["status"] != e["status"]:
+            bad += 1
+        elif e["occ"] is not None:
+            bad += 1 if g["occ"].shape != e["occ"].shape else int((g["occ"] != e["occ"]).sum())
+    return bad
+
+
+def job_sample(n_tracklets, seed=0):
+    """The bounded sample of the c5 job the CPU arm times: its first two segments (128 tracklets)."""
+    from objectcentricocccompletion_b200 import synth
+
+    nseg = (n_tracklets + JOB_PER_SEGMENT - 1) // JOB_PER_SEGMENT
+    return synth.make_batch(n_tracklets, 40, 0.2, "vehicle", seed, tracklets_per_segment=JOB_PER_SEGMENT,
+                            only_segments=range(min(2, nseg)))
+
+
 def run_reference(args):
     """--impl reference: the CPU port on all host cores, same config/metric/unit; rank 0 only."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
-    from objectcentricocccompletion_b200 import synth
-
-    threads = args.cpu_threads or os.cpu_count()
-    batch = synth.config_batch(args.workload, seed=0)
-    B, L = len(batch.tracklets[0]), len(batch.segments[0].inclinations)
+    from objectcentricocccompletion_b200 import synth     # host-only module: no CUDA library is loaded on this arm
     from oracle import oracle
 
+    name = args.workload or ("c2" if args.gpus == 1 else "c5")
+    threads = args.cpu_threads or os.cpu_count()
+    if name == "c5":
+        batch = job_sample(args.job_tracklets)
+        T_cfg, sample = args.job_tracklets, (f"first {len(batch.segments)} segments of the job ({len(batch.tracklets)} "
+                                             f"tracklets) per step; the job is {args.job_tracklets} such tracklets")
+    else:
+        batch = synth.config_batch(name, seed=0)
+        T_cfg, sample = len(batch.tracklets), f"full {name} batch ({len(batch.tracklets)} tracklets) per step"
+    B, L = len(batch.tracklets[0]), len(batch.segments[0].inclinations)
     pk = oracle.PackedBatch(batch)
-    for _ in range(min(args.warmup, 1)):
+    for _ in range(args.warmup):
         oracle.annotate_batch(batch, threads=threads, packed=pk)
-    steps = max(1, min(args.steps, 5))          # bounded: each step is the full batch (seconds of CPU work)
+    steps = max(args.steps, 1)
     t0 = time.perf_counter()
     for _ in range(steps):
         res = oracle.annotate_batch(batch, threads=threads, packed=pk)
@@ -173,18 +228,368 @@ def run_reference(args):
     ws = workload_stats(res, B, L)
     T = len(batch.tracklets)
     val = T / dt
+    cfg = workload_config(name, batch, T_cfg)
     line = {"impl": "reference", "metric": "tracklets_per_s", "value": val, "unit": "tracklets/s", "n_gpus": args.gpus,
-            "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            # the same workload keys as the CUDA arm's config (one batch per step; the CPU arm runs it on rank 0 only)
-            "config": {"workload": WORKLOADS[args.workload], "tracklets_per_step_per_gpu": T, "frames": B, "lidars": L,
-                       "voxel_size": batch.voxel_size,
-                       "ok_tracklets": sum(r["occ"] is not None for r in res)},
-            "voxel_steps_per_s": ws["steps"] / dt,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3 * (T_cfg / T), "higher_is_better": True,
+            "scaling": "weak" if name != "c5" else "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": cfg, "voxel_steps_per_s": ws["steps"] / dt,
             "cpu_baseline": {"value": val, "unit": "tracklets/s", "cores": threads, "kind": "port",
-                             "sample": f"full {args.workload} batch ({T} tracklets) per step, {steps} steps, OpenMP over tracklets"},
+                             "sample": sample + f", {steps} steps, OpenMP over tracklets"},
             "e2e": {"value": val, "unit": "tracklets/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+class Ctx:
+    """torch / device / distributed handles shared by the measurement routines."""
+
+    def __init__(self, args):
+        import torch
+
+        self.torch = torch
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU path)"
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        self.dist = None
+        if self.world > 1:
+            import torch.distributed as dist
+
+            dist.init_process_group("nccl", device_id=self.dev)
+            self.dist = dist
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=self.dev)      # > 126 MB L2
+        self.args = args
+        self.flags = (1 if args.force_f64 else 0) | args.flags
+        self.use_graph = not args.no_graph
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.dist is not None:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def timed(self, step_fn, n, flush=True):
+        """n steps, one CUDA-event pair each (L2 evicted in between, outside the timed region); total ms."""
+        torch = self.torch
+        evs = []
+        for _ in range(n):
+            if flush:
+                self.flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            step_fn()
+            b.record()
+            evs.append((a, b))
+        torch.cuda.synchronize()
+        return sum(a.elapsed_time(b) for a, b in evs)
+
+    def profile(self, step_fn, n, flush=True):
+        """The same steps with events around each kernel (direct launches) -> (ms per kind, launches per kind)."""
+        from objectcentricocccompletion_b200 import _lib
+
+        _lib.lib().occb200_profile_enable(1)
+        self.timed(step_fn, n, flush)
+        _lib.lib().occb200_profile_enable(0)
+        nk = _lib.lib().occb200_profile_kinds()
+        kms, kn = np.zeros(nk, np.float64), np.zeros(nk, np.int64)
+        _lib.check(_lib.lib().occb200_profile_read(kms.ctypes.data, kn.ctypes.data), "occb200_profile_read")
+        return kms, kn
+
+
+def roofline_record(ws, kms, n_steps, peak, peak_src, traffic=None):
+    vis_ms = (kms[3] + kms[4]) / max(n_steps, 1)             # the ray-cast: k_brick_cull + k_visibility
+    step_ms = kms.sum() / max(n_steps, 1)
+    achieved = ws["vis_bytes"] / (vis_ms / 1e3) / 1e9 if vis_ms > 0 else 0.0
+    return {"bound": "hbm", "kernel": "k_brick_cull + k_visibility (the ray-cast)", "achieved": achieved, "peak": peak,
+            "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+            "traffic_source": ("profiles/vis_fast_ncu.json (static: the committed ncu capture, not this run)"
+                               if traffic else None),
+            "peak_source": peak_src, "algorithmic_bytes_per_launch": ws["vis_bytes"], "kernel_ms": vis_ms,
+            "kernel_share_of_step": vis_ms / step_ms if step_ms else None,
+            "kernels_ms": dict(zip(KERNEL_KINDS, (kms / max(n_steps, 1)).round(5).tolist()))}
+
+
+def measure_resident(ctx, batch, warmup):
+    """One batch resident in HBM, results downloaded once, the graph captured and warmed up."""
+    from objectcentricocccompletion_b200 import occ_annotate
+
+    torch = ctx.torch
+    B, L = len(batch.tracklets[0]), len(batch.segments[0].inclinations)
+    t0 = time.perf_counter()
+    pk = occ_annotate.pack_tracklets(batch)
+    pack_ms = (time.perf_counter() - t0) * 1e3
+    host = occ_annotate.HostBuffers(pk, pin=True)
+    d = occ_annotate.DeviceTracklets(pk, ctx.dev, labels="u8")
+    d.upload(host)
+    d.run(ctx.flags)
+    torch.cuda.synchronize()
+    res = d.results()
+    n_recheck, _ = d.queue_stats(ctx.flags)
+    ws = workload_stats(res, B, L)
+    graph_kernels = d.capture(ctx.flags) if ctx.use_graph else 0
+    step = (lambda: d.replay(ctx.flags)) if ctx.use_graph else (lambda: d.run(ctx.flags))
+    for _ in range(warmup):
+        step()
+    return dict(pk=pk, host=host, d=d, res=res, ws=ws, n_recheck=n_recheck, pack_ms=pack_ms, step=step,
+                graph_kernels=graph_kernels, B=B, L=L)
+
+
+def also_annotate(ctx, name, peak, peak_src, oracle_subset):
+    """Sub-record of another annotate workload: resident step time, roofline, parity on a subsample (asserted)."""
+    from objectcentricocccompletion_b200 import synth
+    from oracle import oracle
+
+    steps = max(3, min(ctx.args.steps, 10))
+    batch = synth.config_batch(name, seed=0)
+    m = measure_resident(ctx, batch, max(ctx.args.warmup, 3))
+    ms = ctx.timed(m["step"], steps) / steps
+    kms, kn = ctx.profile(lambda: m["d"].run(ctx.flags), steps)
+    T = len(batch.tracklets)
+    sel = list(range(T))[::max(1, T // oracle_subset)][:oracle_subset]
+    sub = synth.TrackletBatch(segments=batch.segments, tracklets=[batch.tracklets[i] for i in sel],
+                              voxel_size=batch.voxel_size)
+    exp = oracle.annotate_batch(sub, threads=os.cpu_count())
+    mism = count_mismatches([m["res"][i] for i in sel], exp)
+    assert mism == 0, f"{name}: {mism} label mismatches against the CPU port"
+    rl = roofline_record(m["ws"], kms, steps, peak, peak_src)
+    return {"config": workload_config(name, batch), "ms_per_step": ms, "tracklets_per_s": T / (ms / 1e3),
+            "voxel_steps_per_s": m["ws"]["steps"] / (ms / 1e3), "executed_steps_per_step": m["ws"]["executed"],
+            "voxel_steps_per_step": m["ws"]["steps"], "f64_rechecks_per_step": m["n_recheck"],
+            "roofline_frac": rl["frac"], "raycast_ms": rl["kernel_ms"], "kernels_ms": rl["kernels_ms"],
+            "label_mismatches_vs_cpu_port": mism, "parity_sample": f"{len(sel)} of {T} tracklets"}
+
+
+def also_ops(ctx, peak):
+    """C4: OcCo-Net input build -- dynamic Voxelization + DynamicScatter over 32 tracklets x 32 frames x 1024 points
+    (N = 1 048 576), device-timed with L2 flushed, algorithmic bytes of SURVEY.md section 8d, parity against the
+    CPU oracle asserted, the reference's own CUDA kernels (compiled unmodified for sm_100a) beside them if built."""
+    import objectcentricocccompletion_b200 as occ
+    from objectcentricocccompletion_b200 import synth
+    from oracle import oracle
+
+    torch, dev = ctx.torch, ctx.dev
+    pts, bidx = synth.scatter_inputs(32, 32, 1024, 5, seed=0, full=True)
+    N = pts.shape[0]
+    p = torch.from_numpy(pts).to(dev)
+    b = torch.from_numpy(bidx).to(dev)
+    vs, pcr = [0.2, 0.2, 0.2], [-204.8, -204.8, -4, 204.8, 204.8, 8]
+
+    def med(fn, iters=10, warm=3):
+        for _ in range(warm):
+            fn()
+        evs = []
+        for _ in range(iters):
+            ctx.flush.zero_()
+            a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            e.record()
+            evs.append((a, e))
+        torch.cuda.synchronize()
+        return float(np.median([a.elapsed_time(e) for a, e in evs]))
+
+    try:
+        from oracle import build as obuild
+        rv = obuild.load_ref("ref_voxel_layer_cuda")
+    except Exception:
+        rv = None
+    out = {"N": int(N)}
+    vox = occ.Voxelization(vs, pcr, -1)
+    coors = vox(p)
+    assert (coors.cpu().numpy() == oracle.dynamic_voxelize(pts, vs, pcr)).all(), "c4: voxelize mismatch vs CPU oracle"
+    ms = med(lambda: vox(p))
+    alg = 4 * 5 * N + 12 * N
+    rec = {"ms": ms, "alg_bytes": alg, "frac": alg / ms / 1e6 / peak}
+    if rv is not None:
+        rc = torch.zeros((N, 3), dtype=torch.int32, device=dev)
+        rec["reference_cuda_kernel_sm100a_ms"] = med(lambda: rv.dynamic_voxelize(p, rc, vs, pcr, 3), 5, 1)
+    out["Voxelization(dynamic) C=5"] = rec
+    coors4 = torch.cat([b[:, None].int(), coors], 1).contiguous()
+    for C, mode in [(3, "mean"), (5, "mean"), (128, "max")]:
+        f = (p[:, :C].contiguous() if C <= 5 else torch.randn(N, C, device=dev))
+        ds = occ.DynamicScatter(vs, pcr, mode == "mean")
+        vf, vc = ds(f, coors4)
+        M = int(vf.shape[0])
+        if C == 3:
+            evf, evc = oracle.dynamic_scatter_batched(f.cpu().numpy(), coors4.cpu().numpy(), "mean")[:2]
+            assert (vc.cpu().numpy() == evc).all(), "c4: scatter coords mismatch vs CPU oracle"
+            assert np.allclose(vf.cpu().numpy(), evf, rtol=1e-5, atol=1e-6), "c4: scatter feats mismatch vs CPU oracle"
+        ms = med(lambda: ds(f, coors4))
+        alg = 4 * C * N + 16 * N + (4 * C + 16) * M
+        rec = {"ms": ms, "M": M, "alg_bytes": alg, "frac": alg / ms / 1e6 / peak}
+        if rv is not None:
+            c3 = coors.contiguous()
+            rec["ms_3col"] = med(lambda: occ.dynamic_scatter(f, c3, mode))
+            rec["reference_cuda_kernel_sm100a_3col_ms"] = med(lambda: rv.dynamic_point_to_voxel_forward(f, c3, mode), 3, 1)
+        out[f"DynamicScatter({mode}) C={C}"] = rec
+        c64 = coors4.long()
+        nf, nc, inv = occ.scatter_v2(f, c64, mode)
+        out[f"scatter_v2({mode}) C={C}"] = {
+            "ms": med(lambda: occ.scatter_v2(f, c64, mode)),
+            "ms_reusing_unq_inv": med(lambda: occ.scatter_v2(f, c64, mode, unq_inv=inv, new_coors=nc))}
+    out["config"] = {"workload": "c4: dynamic Voxelization + DynamicScatter mean/max over 32 tracklets x 32 frames x 1024 points",
+                     "voxel_size": vs, "point_cloud_range": pcr, "l2": "flushed between iterations"}
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+def run_job(ctx, n_tracklets, steps, warmup, peak, peak_src, with_e2e=True, parity_tracklets=32):
+    """The c5 job on ctx.world GPUs: segments sharded by LPT, per-rank batches of --batch-segments segments, the
+    gather of all labels on rank 0 inside the timed step.  Returns the record on rank 0, None elsewhere."""
+    from objectcentricocccompletion_b200 import dist as occ_dist
+    from objectcentricocccompletion_b200 import occ_annotate, synth
+    from oracle import oracle
+
+    torch, dev, dist = ctx.torch, ctx.dev, ctx.dist
+    rank, world = ctx.rank, ctx.world
+    nseg = (n_tracklets + JOB_PER_SEGMENT - 1) // JOB_PER_SEGMENT
+    seg_cost = [float(min(JOB_PER_SEGMENT, n_tracklets - i * JOB_PER_SEGMENT)) for i in range(nseg)]
+    mine = occ_dist.shard_indices(seg_cost, world)[rank]
+    t0 = time.perf_counter()
+    full = synth.make_batch(n_tracklets, 40, 0.2, "vehicle", 0, tracklets_per_segment=JOB_PER_SEGMENT,
+                            only_segments=mine)
+    gen_s = time.perf_counter() - t0
+    B, L = 40, len(full.segments[0].inclinations) if full.segments else 5
+    S = max(1, ctx.args.batch_segments)                       # batches of S segments
+    batches = []
+    for a in range(0, len(full.segments), S):
+        trks = [synth.Tracklet(boxes=t.boxes, points=t.points, segment=t.segment - a, frame_ids=t.frame_ids,
+                               kind=t.kind, flat=t.flat) for t in full.tracklets if a <= t.segment < a + S]
+        batches.append(synth.TrackletBatch(segments=full.segments[a: a + S], tracklets=trks, voxel_size=0.2))
+    t0 = time.perf_counter()
+    pks = [occ_annotate.pack_tracklets(b) for b in batches]
+    pack_ms = (time.perf_counter() - t0) * 1e3
+    n_local = int(sum(pk.total_slots for pk in pks))
+    labels_u8 = torch.zeros(max(n_local, 1), dtype=torch.uint8, device=dev)
+    devs, hosts, off = [], [], 0
+    for pk in pks:
+        hosts.append(occ_annotate.HostBuffers(pk, pin=with_e2e))
+        devs.append(occ_annotate.DeviceTracklets(pk, dev, labels="u8",
+                                                 labels_u8=labels_u8[off: off + max(pk.total_slots, 1)]))
+        off += pk.total_slots
+    for d, h in zip(devs, hosts):
+        d.upload(h)
+        d.run(ctx.flags)
+    torch.cuda.synchronize()
+    res = [r for d in devs for r in d.results()]
+    n_recheck = sum(d.queue_stats(ctx.flags)[0] for d in devs)
+    ws = workload_stats(res, B, L)
+    # parity on a fixed subsample of this rank's tracklets against the CPU port (asserted)
+    if parity_tracklets and batches:
+        b0 = batches[0]
+        sel = list(range(len(b0.tracklets)))[::max(1, len(b0.tracklets) // parity_tracklets)][:parity_tracklets]
+        sub = synth.TrackletBatch(segments=b0.segments, tracklets=[b0.tracklets[i] for i in sel], voxel_size=0.2)
+        exp = oracle.annotate_batch(sub, threads=max(1, (os.cpu_count() or 1) // world))
+        mism = count_mismatches([res[i] for i in sel], exp)
+        assert mism == 0, f"c5 rank {rank}: {mism} label mismatches against the CPU port"
+    sizes = occ_dist.exchange_sizes(n_local)              # set-up: the payload sizes, once per job
+    gathered = torch.empty(max(sum(sizes), 1), dtype=torch.uint8, device=dev) if rank == 0 else None
+    if ctx.use_graph:
+        for d in devs:
+            d.capture(ctx.flags)
+
+    def compute():
+        for d in devs:
+            d.replay(ctx.flags) if ctx.use_graph else d.run(ctx.flags)
+
+    def gather():
+        occ_dist.gather_labels(labels_u8, sizes, 0, None, gathered)
+
+    def job_step():
+        compute()
+        gather()
+
+    for _ in range(max(warmup, 1)):
+        job_step()
+    ctx.barrier()
+    ms = ctx.timed(job_step, steps, flush=False)
+    ctx.barrier()
+    ms_compute = ctx.timed(compute, steps, flush=False)
+    ctx.barrier()
+    ms_gather = ctx.timed(gather, steps, flush=False)
+    ctx.barrier()
+    if rank == 0 and world > 1:
+        assert bool((gathered[: sizes[0]] == labels_u8[: sizes[0]]).all()), "gathered labels differ from rank 0's own"
+    n_prof = max(1, min(steps, 5))
+    kms, kn = ctx.profile(lambda: [d.run(ctx.flags) for d in devs], n_prof, flush=False)
+    # e2e: per step every batch is uploaded from pinned host memory, annotated, its labels / dims / status downloaded
+    ms_e2e, h2d, d2h = 0.0, 0, 0
+    if with_e2e:
+        keys = ("labels_u8", "dims", "status", "n_unknown")
+        outs = [{k: torch.empty_like(getattr(d, k), device="cpu").pin_memory() for k in keys} for d in devs]
+        streams = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
+
+        def e2e_run(n):
+            start = torch.cuda.Event(enable_timing=True)
+            start.record()
+            for st in streams:
+                st.wait_event(start)
+            k = 0
+            for _ in range(n):
+                for d, h, o in zip(devs, hosts, outs):
+                    with torch.cuda.stream(streams[k % 2]):
+                        d.upload(h)
+                        d.replay(ctx.flags) if ctx.use_graph else d.run(ctx.flags)
+                        for key, buf in o.items():
+                            buf.copy_(getattr(d, key), non_blocking=True)
+                    k += 1
+            ends = []
+            for st in streams:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record(st)
+                ends.append(e)
+            torch.cuda.synchronize()
+            return max(start.elapsed_time(e) for e in ends)
+
+        e2e_run(1)
+        ctx.barrier()
+        ms_e2e = e2e_run(steps)
+        ctx.barrier()
+        h2d = sum(h.nbytes() for h in hosts)
+        d2h = sum(b.numel() * b.element_size() for o in outs for b in o.values())
+    # ---- reduce over ranks
+    t = torch.tensor([ms, ms_compute, ms_gather, ms_e2e], dtype=torch.float64, device=dev)
+    tot = torch.tensor([float(len(full.tracklets)), float(ws["steps"]), float(ws["executed"]), float(ws["vis_bytes"]),
+                        float(h2d), float(d2h), float(n_recheck), float(ws["ok"])], dtype=torch.float64, device=dev)
+    gm = torch.tensor([gen_s, pack_ms], dtype=torch.float64, device=dev)
+    per_rank = torch.tensor([ms_compute / steps, float(len(full.tracklets)), (kms[3] + kms[4]) / n_prof,
+                             float(ws["vis_bytes"])], dtype=torch.float64, device=dev)
+    ranks = [per_rank.clone() for _ in range(world)]
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        dist.all_reduce(gm, op=dist.ReduceOp.MAX)
+        dist.all_gather(ranks, per_rank)
+    if rank != 0:
+        return None
+    ms, ms_compute, ms_gather, ms_e2e = (float(x) for x in t)
+    T_all = float(tot[0])
+    sec = ms / 1e3 / steps
+    pr = np.array([r.cpu().numpy() for r in ranks])
+    fr = [float(b / (m / 1e3) / 1e9 / peak) if m > 0 else 0.0 for m, b in zip(pr[:, 2], pr[:, 3])]
+    rec = {
+        "value": T_all / sec, "ms_per_step": sec * 1e3, "tracklets": int(T_all), "segments": nseg,
+        "voxel_steps_per_s": float(tot[1]) / sec, "executed_steps_per_s": float(tot[2]) / sec,
+        "voxel_steps_per_step": float(tot[1]), "f64_rechecks_per_step": float(tot[6]), "ok_tracklets": int(tot[7]),
+        "compute_ms_max_over_ranks": ms_compute / steps, "final_gather_ms": ms_gather / steps,
+        "gather_share_of_step": (ms_gather / steps) / (sec * 1e3), "gather_bytes": int(sum(sizes)),
+        "per_rank": {"compute_ms": pr[:, 0].round(4).tolist(), "tracklets": pr[:, 1].astype(int).tolist(),
+                     "raycast_ms": pr[:, 2].round(4).tolist(), "roofline_frac": [round(x, 4) for x in fr],
+                     "load_imbalance": float(pr[:, 0].max() / max(pr[:, 0].mean(), 1e-9))},
+        # whole job: all ranks' algorithmic ray-cast bytes / the slowest rank's ray-cast time / (N x peak)
+        "roofline_frac": (float(pr[:, 3].sum() / (pr[:, 2].max() / 1e3) / 1e9 / peak / world) if pr[:, 2].max() > 0 else 0.0),
+        "batches_per_rank": len(batches), "batch_segments": S, "generate_s_max": float(gm[0]), "pack_ms_max": float(gm[1]),
+        "label_mismatches_vs_cpu_port": 0, "parity_sample": f"{parity_tracklets} tracklets per rank",
+        "kernels_ms_rank0": dict(zip(KERNEL_KINDS, (kms / n_prof).round(5).tolist())),
+        "graph_kernels_per_step_rank0": int(sum(getattr(d, "_graphs", {}).get(ctx.flags, (None, 0))[1] for d in devs)),
+    }
+    if with_e2e:
+        sec_e2e = ms_e2e / 1e3 / steps
+        rec["e2e"] = {"value": T_all / sec_e2e, "unit": "tracklets/s", "h2d_bytes_per_step": int(tot[4]),
+                      "d2h_bytes_per_step": int(tot[5]), "ms_per_step": sec_e2e * 1e3}
+    return rec
 
 
 # ------------------------------------------------------------------------------------------------
@@ -193,106 +598,75 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
-    import torch
-
     import objectcentricocccompletion_b200 as occ
     from objectcentricocccompletion_b200 import _lib, occ_annotate, synth
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU path)"
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
+    ctx = Ctx(args)
+    torch, dev, rank, world = ctx.torch, ctx.dev, ctx.rank, ctx.world
+    name = args.workload or ("c2" if world == 1 else "c5")
+    peak, peak_src = peaks()
+    sampler = ClockSampler(ctx.local)
 
-        dist.init_process_group("nccl", device_id=dev)
+    # ============================ the c5 job: strong scaling over the ranks ============================
+    if name == "c5":
+        if rank == 0:
+            sampler.start()
+        rec = run_job(ctx, args.job_tracklets, args.steps, args.warmup, peak, peak_src)
+        if rank == 0:
+            clocks = sampler.stop()
+            cpu = None
+            if not args.no_cpu_baseline:
+                threads = args.cpu_threads or os.cpu_count()
+                sample = job_sample(args.job_tracklets)
+                dt, _, reps = cpu_port(sample, threads)
+                cpu = {"value": len(sample.tracklets) / dt, "unit": "tracklets/s", "cores": threads, "kind": "port",
+                       "sample": f"first {len(sample.segments)} segments of the job ({len(sample.tracklets)} tracklets), "
+                                 f"best of {reps}, OpenMP over tracklets, C port of the reference path"}
+            launches = int(rec["graph_kernels_per_step_rank0"] * args.steps * world) if ctx.use_graph else None
+            line = {"metric": "tracklets_per_s", "value": rec["value"], "unit": "tracklets/s", "n_gpus": world,
+                    "steps": args.steps, "warmup": args.warmup, "ms_per_step": rec["ms_per_step"], "higher_is_better": True,
+                    "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                    "config": {"workload": WORKLOADS["c5"], "tracklets_per_step": rec["tracklets"], "frames": 40, "lidars": 5,
+                               "voxel_size": 0.2, "segments": rec["segments"],
+                               "sharding": "by segment, LPT (dist.shard_indices)", "batch_segments": rec["batch_segments"],
+                               "final_gather": "inside the timed step (uint8 labels, device to device)",
+                               "l2": "not flushed: every rank's inputs per step exceed L2 many times over",
+                               "launch": "cuda graph replay per batch" if ctx.use_graph else "kernel by kernel"},
+                    "voxel_steps_per_s": rec["voxel_steps_per_s"], "executed_steps_per_s": rec["executed_steps_per_s"],
+                    "e2e": rec.get("e2e"), "gpu_launches": launches,
+                    "roofline": {"bound": "hbm", "kernel": "k_brick_cull + k_visibility (the ray-cast)", "unit": "GB/s",
+                                 "peak": peak, "peak_source": peak_src, "frac": rec["roofline_frac"],
+                                 "achieved": rec["roofline_frac"] * peak, "traffic": None,
+                                 "per_rank_frac": rec["per_rank"]["roofline_frac"]},
+                    "job": rec, "cpu_baseline": cpu, "clocks": clocks, "final_gather_ms": rec["final_gather_ms"]}
+            print(json.dumps(line))
+        if ctx.dist is not None:
+            ctx.dist.destroy_process_group()
+        return
 
-    # ---- workload: one batch per rank (different seed per rank) -------------------------------
-    batch = synth.config_batch(args.workload, seed=rank)
+    # ============================ one batch per rank (N = 1: the headline C2 line) ============================
+    batch = synth.config_batch(name, seed=rank)
     T = len(batch.tracklets)
-    B, L = len(batch.tracklets[0]), len(batch.segments[0].inclinations)
-    pk = occ_annotate.pack_tracklets(batch)
-    host = occ_annotate.HostBuffers(pk, pin=True)
-    d = occ_annotate.DeviceTracklets(pk, dev)
-    flags = (occ_annotate.FLAG_FORCE_F64 if args.force_f64 else 0) | args.flags
-    d.upload(host)
-    d.run(flags)
-    torch.cuda.synchronize()
-    res = d.results()
-    n_recheck, q_cap = d.queue_stats(flags)
-    ws = workload_stats(res, B, L)
-    n_ok = sum(r["occ"] is not None for r in res)
-
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
-
-    def barrier():
-        torch.cuda.synchronize()
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(step_fn, n):
-        evs = []
-        for _ in range(n):
-            flush.zero_()                                              # evict L2 between steps (not timed)
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            step_fn()
-            b.record()
-            evs.append((a, b))
-        torch.cuda.synchronize()
-        return sum(a.elapsed_time(b) for a, b in evs)                  # ms
-
-    # pinned result buffers for the e2e leg
-    out_host = {k: torch.empty_like(getattr(d, k), device="cpu").pin_memory() for k in ("labels", "dims", "status", "n_unknown")}
-
-    use_graph = not args.no_graph
-    graph_kernels = d.capture(flags) if use_graph else 0
-
-    def step_resident():
-        if use_graph:
-            d.replay(flags)
-        else:
-            d.run(flags)
-
-    def step_e2e():
-        d.upload(host)
-        d.run(flags)
-        for k, h in out_host.items():
-            h.copy_(getattr(d, k), non_blocking=True)
-
-    h2d_bytes = host.nbytes()
-    d2h_bytes = sum(h.numel() * h.element_size() for h in out_host.values())
-
-    for _ in range(args.warmup):
-        step_resident()
-    sampler = ClockSampler(local)
-    barrier()
+    m = measure_resident(ctx, batch, args.warmup)
+    d, host, pk, res, ws = m["d"], m["host"], m["pk"], m["res"], m["ws"]
+    step_resident = m["step"]
+    ctx.barrier()
     if rank == 0:
         sampler.start()
     l0 = _lib.launch_count()
-    ms = timed(step_resident, args.steps)
-    launches = graph_kernels * args.steps if use_graph else _lib.launch_count() - l0
-    barrier()
-
-    # ---- roofline pass: the same steps with events around each kernel ---------------------------
-    _lib.lib().occb200_profile_enable(1)
-    timed(lambda: d.run(flags), args.steps)           # direct launches: the events sit between the kernels
-    _lib.lib().occb200_profile_enable(0)
-    nk = _lib.lib().occb200_profile_kinds()
-    kms = np.zeros(nk, np.float64)
-    kn = np.zeros(nk, np.int64)
-    _lib.check(_lib.lib().occb200_profile_read(kms.ctypes.data, kn.ctypes.data), "occb200_profile_read")
+    ms = ctx.timed(step_resident, args.steps)
+    launches = m["graph_kernels"] * args.steps if ctx.use_graph else _lib.launch_count() - l0
+    ctx.barrier()
+    kms, kn = ctx.profile(lambda: d.run(ctx.flags), args.steps)
 
     # ---- e2e: host buffers -> H2D -> kernels -> D2H every step, double-buffered on two streams so the upload
     # of step k+1 overlaps the kernels / download of step k (inputs per step 134 MB > L2: no flush needed) -------
-    d2 = occ_annotate.DeviceTracklets(pk, dev)
-    if use_graph:
+    out_keys = ("labels_u8", "dims", "status", "n_unknown")
+    out_host = {k: torch.empty_like(getattr(d, k), device="cpu").pin_memory() for k in out_keys}
+    d2 = occ_annotate.DeviceTracklets(pk, dev, labels="u8")
+    if ctx.use_graph:
         d2.upload(host)
-        d2.capture(flags)
+        d2.capture(ctx.flags)
     out_host2 = {k: torch.empty_like(h).pin_memory() for k, h in out_host.items()}
     pipes = [(torch.cuda.Stream(dev), d, out_host), (torch.cuda.Stream(dev), d2, out_host2)]
 
@@ -305,10 +679,7 @@ def main():
             st, dd, oh = pipes[i % 2]
             with torch.cuda.stream(st):
                 dd.upload(host)
-                if use_graph:
-                    dd.replay(flags)
-                else:
-                    dd.run(flags)
+                dd.replay(ctx.flags) if ctx.use_graph else dd.run(ctx.flags)
                 for k, h in oh.items():
                     h.copy_(getattr(dd, k), non_blocking=True)
         ends = []
@@ -320,85 +691,80 @@ def main():
         return max(start.elapsed_time(e) for e in ends)
 
     e2e_run(min(args.warmup, 3) + 1)
-    barrier()
+    ctx.barrier()
     ms_e2e = e2e_run(args.steps)
-    barrier()
+    ctx.barrier()
     assert all(bool((out_host2[k] == out_host[k]).all()) for k in out_host), "pipelined e2e results differ"
+    # the public one-shot call, for scale: pack + allocate + upload from pageable memory + run + download
+    t0 = time.perf_counter()
+    occ.annotate_batch(batch, flags=ctx.flags)
+    api_ms = (time.perf_counter() - t0) * 1e3
     clocks = sampler.stop() if rank == 0 else None
 
-    # max over ranks
     t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
     tot = torch.tensor([float(T), float(ws["steps"]), float(ws["executed"])], dtype=torch.float64, device=dev)
-    gather_ms = None
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-        # the one collective of the job: final gather of per-rank results to rank 0 over NVLink (not per step)
-        from objectcentricocccompletion_b200 import dist as occ_dist
-
-        occ_dist.gather_results(res[:1], [rank], world, dst=0)      # opens the NCCL p2p channels (lazy, ~1 s)
-        torch.cuda.synchronize()
-        dist.barrier()
-        t0 = time.perf_counter()
-        allres = occ_dist.gather_results(res, list(range(rank * T, (rank + 1) * T)), world * T, dst=0)
-        torch.cuda.synchronize()
-        gather_ms = (time.perf_counter() - t0) * 1e3
-        if rank == 0:
-            assert sum(r is not None and r["occ"] is not None for r in allres) >= n_ok
+    if ctx.dist is not None:
+        ctx.dist.all_reduce(t, op=ctx.dist.ReduceOp.MAX)
+        ctx.dist.all_reduce(tot, op=ctx.dist.ReduceOp.SUM)
     ms, ms_e2e = float(t[0]), float(t[1])
     T_all, steps_all, exec_all = (float(x) for x in tot)
-
     if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
+        if ctx.dist is not None:
+            ctx.dist.destroy_process_group()
         return
 
     sec = ms / 1e3 / args.steps
     sec_e2e = ms_e2e / 1e3 / args.steps
-    peak, peak_src = peaks()
-    vis_ms = (kms[4] + kms[3]) / max(kn[4], 1)            # the ray-cast: k_brick_cull + k_visibility
-    achieved = ws["vis_bytes"] / (vis_ms / 1e3) / 1e9 if vis_ms > 0 else 0.0
-    step_ms_prof = kms.sum() / max(kn[4], 1)
-
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         threads = args.cpu_threads or os.cpu_count()
         dt, cres, reps = cpu_port(batch, threads)
-        mism = sum(int((c["occ"] != g["occ"]).sum()) for c, g in zip(cres, res) if c["occ"] is not None)
+        mism = count_mismatches(res, cres)
+        assert mism == 0, f"{name}: {mism} label mismatches between the CUDA path and the CPU port"
         cpu = {"value": T / dt, "unit": "tracklets/s", "cores": threads, "kind": "port",
-               "sample": f"full {args.workload} batch ({T} tracklets), best of {reps}, OpenMP over tracklets, "
-                         f"C port of the reference path; labels vs GPU: {mism} mismatches",
+               "sample": f"full {name} batch ({T} tracklets), best of {reps}, OpenMP over tracklets, "
+                         f"C port of the reference path; labels vs GPU: {mism} mismatches (asserted)",
                "voxel_steps_per_s": ws["steps"] / dt}
-
+    cfg = workload_config(name, batch)
+    cfg.update({"ok_tracklets": ws["ok"], "l2": "flushed (256 MiB write) between timed steps",
+                "visibility": "f64" if args.force_f64 else "default",
+                "labels": "uint8 on the device (int32 at the file boundary)",
+                "launch": "cuda graph replay" if ctx.use_graph else "kernel by kernel",
+                "parallelism": "one batch of this shape per GPU" if world > 1 else "1 GPU"})
     line = {
         "metric": "tracklets_per_s", "value": T_all / sec, "unit": "tracklets/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOADS[args.workload], "tracklets_per_step_per_gpu": T, "frames": B, "lidars": L,
-                   "voxel_size": batch.voxel_size, "ok_tracklets": n_ok, "l2": "flushed (256 MiB write) between timed steps",
-                   "visibility": "f64" if args.force_f64 else "default",
-                   "launch": "cuda graph replay" if use_graph else "kernel by kernel"},
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
         "voxel_steps_per_s": steps_all / sec, "executed_steps_per_s": exec_all / sec,
         "voxel_steps_per_step": ws["steps"], "executed_steps_per_step": ws["executed"],
-        "f64_rechecks_per_step": n_recheck, "unknown_voxels_per_step": ws["U"], "voxels_per_step": ws["V"],
-        "e2e": {"value": T_all / sec_e2e, "unit": "tracklets/s", "h2d_bytes_per_step": h2d_bytes,
-                "d2h_bytes_per_step": d2h_bytes, "ms_per_step": sec_e2e * 1e3},
+        "f64_rechecks_per_step": m["n_recheck"], "unknown_voxels_per_step": ws["U"], "voxels_per_step": ws["V"],
+        "e2e": {"value": T_all / sec_e2e, "unit": "tracklets/s", "h2d_bytes_per_step": host.nbytes(),
+                "d2h_bytes_per_step": sum(h.numel() * h.element_size() for h in out_host.values()),
+                "ms_per_step": sec_e2e * 1e3, "pack_ms": m["pack_ms"], "api_one_shot_ms": api_ms},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "kernel": "k_visibility", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": ncu_traffic() if args.workload == "c2" else None, "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": ws["vis_bytes"], "kernel_ms": vis_ms,
-                     "kernel_share_of_step": vis_ms / step_ms_prof if step_ms_prof else None,
-                     "kernels_ms": dict(zip(("k_crop_voxelize", "k_tracklet_setup+redo", "k_scan_chunks", "k_brick_cull",
-                                             "k_visibility", "side:k_pyr_build+k_table_setup",
-                                             "k_visibility_recheck", "k_pair_build", "k_labels"),
-                                            (kms / np.maximum(kn[4], 1)).round(5).tolist()))},
+        "roofline": roofline_record(ws, kms, args.steps, peak, peak_src, ncu_traffic() if name == "c2" else None),
         "cpu_baseline": cpu, "clocks": clocks,
     }
-    if gather_ms is not None:
-        line["final_gather_ms"] = gather_ms
+    # ---- the other configs, on this GPU (N = 1 only) ----
+    also = [a for a in args.also.split(",") if a and a != "none"] if world == 1 and name == "c2" else []
+    if also:
+        del d2, m, d, host, pipes
+        line["also"] = {}
+        for a in also:
+            try:
+                if a in ("c1", "c3"):
+                    line["also"][a] = also_annotate(ctx, a, peak, peak_src, oracle_subset=4 if a == "c3" else 1)
+                elif a == "c4":
+                    line["also"][a] = also_ops(ctx, peak)
+                elif a == "c5":
+                    line["also"][a] = run_job(ctx, args.job_tracklets, max(3, min(args.steps, 5)), 1, peak, peak_src)
+            except AssertionError:
+                raise                                   # a parity failure must fail the bench
+            except Exception as e:                      # noqa: BLE001  (e.g. out of host memory for the 16 GB job)
+                line["also"][a] = {"error": f"{type(e).__name__}: {e}"}
     print(json.dumps(line))
-    if dist is not None:
-        dist.destroy_process_group()
+    if ctx.dist is not None:
+        ctx.dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -266,6 +266,7 @@ typedef struct occb200_annotate_args {
                                      (the grid upper bound the slot was sized with): 4x4x4-voxel bricks are
                                      the unit of work and of culling in the ray-cast                        */
   int64_t bricks;                 /* brick_off[T], from the host copy                                        */
+  int64_t n_points;               /* frame_pt_off[F], from the host copy: the crop kernel's grid             */
 } occb200_annotate_args_t;
 
 int64_t occb200_annotate_workspace_bytes(int32_t T, int64_t F, int64_t total_label_slots, int64_t SF,

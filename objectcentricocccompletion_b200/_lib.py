@@ -37,7 +37,7 @@ class AnnotateArgs(C.Structure):
                 ("dims", vp), ("sizes", vp), ("status", vp), ("n_unknown", vp), ("n_steps", vp), ("workspace", vp),
                 ("workspace_bytes", i64), ("flags", i32), ("pad1", i32), ("max_label_slots", i64),
                 ("labels_u8", vp), ("frame_trk", vp), ("pyr_off", vp), ("table_off", vp), ("table_H", vp),
-                ("n_tables", i32), ("max_pairs", i32), ("brick_off", vp), ("bricks", i64)]
+                ("n_tables", i32), ("max_pairs", i32), ("brick_off", vp), ("bricks", i64), ("n_points", i64)]
 
 
 POSE_DTYPE = np.dtype([("box", "<f4", (7,)), ("cos_pib", "<f4"), ("sin_pib", "<f4"), ("cos_m", "<f4"),

@@ -150,7 +150,6 @@ static_assert(sizeof(TrkHot) == 64, "TrkHot must be 64 bytes");
 
 struct Workspace {
   TrkGrid *grids;        // [T]
-  int32_t *frame_kept;   // [F]
   int32_t *redo_list;    // [F] frames of tracklets whose optimistic grid was wrong
   int64_t *chunk_off;    // [T+1] (f64 path)
   // ---- zeroed by ONE memset at the start of every call
@@ -158,6 +157,7 @@ struct Workspace {
   unsigned long long *counter;   // [0] f64-path ticket, [1] recheck-queue length, [2] redo frames,
                                  // [8 + 2s] items of slice s, [9 + 2s] ticket of slice s
   int32_t *trk_flags;    // [T] flags of the crop kernel (bit0 kept a point, bit1 index error)
+  int32_t *frame_kept;   // [F] 1: the frame has an in-box point (set by the crop CTAs that see one)
   uint32_t *bits;        // occupancy bitsets, linear voxel order, tracklet t at label_off[t]/32 + t
   int64_t bits_words;
   uint32_t *free_brick;  // [2 * bricks] voxels proven free, BRICK order: bit j = lx*16 + ly*4 + lz of word pair 2*brick
@@ -193,12 +193,12 @@ static int64_t ws_layout(int32_t T, int64_t F, int64_t total, int64_t SF, int32_
   const int32_t mask_words = (int32_t)std::max<int64_t>(ceil_div(std::max(max_pairs, 1), 32), 1);
   const int32_t n_slices = (int32_t)std::max<int64_t>(ceil_div(std::max(max_pairs, 1), kPairsPerItem), 1);
   int64_t o_grid = take(sizeof(TrkGrid) * (int64_t)T);
-  int64_t o_kept = take(4 * F);
   int64_t o_redo = take(4 * F);
   int64_t o_choff = take(8 * ((int64_t)T + 1));
   // zeroed region
   int64_t o_cnt = take(8 * (8 + 2 * kMaxSlices));
   int64_t o_tf = take(4 * (int64_t)T);
+  int64_t o_kept = take(4 * F);
   int64_t words = total / 32 + T + 1;
   int64_t o_bits = take(4 * words);
   int64_t o_fb = take(8 * std::max<int64_t>(bricks, 1));
@@ -407,15 +407,22 @@ __device__ __forceinline__ FramePose load_frame_pose(const occb200_pose_t &ps) {
 #define OCC_PPT 4
 #endif
 constexpr int kPtsPerThread = OCC_PPT;          // independent point loads in flight per thread
-// First pass (redo_list == NULL): CTA b owns the tracklet-frames [b*G, (b+1)*G); they are processed in runs that
-// belong to one tracklet (a group may straddle a tracklet boundary).  For each run the CTA derives the tracklet's
-// optimistic grid itself (max box size over the tracklet's frames that have candidate points: 2 dependent loads +
-// one CTA reduction), zeroes a shared-memory bitset, streams the run's points as ONE flat range (the frames of a
-// tracklet are adjacent in `points`) with kPtsPerThread loads in flight per thread, and ORs the bitset into the
-// tracklet's global one.  Second pass (redo_list != NULL): a small grid strides over the frames of the tracklets
-// whose optimistic grid was wrong -- usually none -- with the true grid from grids[].
+#ifndef OCC_CROP_CHUNK
+#define OCC_CROP_CHUNK 2048
+#endif
+constexpr int kCropChunk = OCC_CROP_CHUNK;      // candidate points per crop CTA
+// First pass (redo_list == NULL): CTA c owns the candidate points [c * kCropChunk, (c+1) * kCropChunk) of the flat
+// point array, whatever frames they belong to -- every CTA has the same amount of work (frames of a close object
+// carry several times the points of a far one; one CTA per frame left the longest frame as the kernel's tail).
+// Warp 0 finds the first frame of the chunk with a 32-way search of frame_pt_off (3 dependent loads for 32 768
+// frames); the chunk is then processed in runs of consecutive frames of ONE tracklet (<= kMaxGroup).  For each run
+// the CTA derives the tracklet's optimistic grid itself (max box size over the tracklet's frames that have candidate
+// points: 2 dependent loads + one CTA reduction), zeroes a shared-memory bitset, streams the run's points as one
+// flat range with kPtsPerThread loads in flight per thread, and ORs the bitset into the tracklet's global one.
+// Second pass (redo_list != NULL): a small grid strides over the frames of the tracklets whose optimistic grid was
+// wrong -- usually none -- whole frames, with the true grid from grids[].
 __global__ void __launch_bounds__(kFrameThreads, OCC_FMINB)
-k_crop_voxelize(int64_t F, int G, const occb200_pose_t *__restrict__ poses, const float *__restrict__ points,
+k_crop_voxelize(int64_t F, int64_t P, const occb200_pose_t *__restrict__ poses, const float *__restrict__ points,
                 int stride, const int64_t *__restrict__ frame_pt_off, const int64_t *__restrict__ trk_frame_off,
                 const int64_t *__restrict__ label_off, const int32_t *__restrict__ frame_trk,
                 int32_t *__restrict__ frame_kept, int32_t *__restrict__ trk_flags, const TrkGrid *__restrict__ grids,
@@ -428,17 +435,41 @@ k_crop_voxelize(int64_t F, int G, const occb200_pose_t *__restrict__ poses, cons
   __shared__ float s_red[kFrameThreads / 32][3];
   __shared__ TrkGrid s_grid;
   __shared__ int s_flags;
+  __shared__ int64_t s_first;
   const bool redo_pass = redo_list != nullptr;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long n_work = redo_pass ? (long long)*redo_count : (long long)gridDim.x;
   for (long long wi = blockIdx.x; wi < n_work; wi += gridDim.x) {
-    int64_t fa = redo_pass ? (int64_t)redo_list[wi] : (int64_t)wi * G;
-    const int64_t fend = redo_pass ? fa + 1 : min(fa + (int64_t)G, F);
-    while (fa < fend) {                             // one run = consecutive frames of ONE tracklet
+    // the work item's point range [p0, p1) and first frame
+    int64_t p0, p1, fa;
+    if (redo_pass) {
+      fa = (int64_t)redo_list[wi];
+      p0 = frame_pt_off[fa];
+      p1 = frame_pt_off[fa + 1];
+    } else {
+      p0 = (int64_t)wi * kCropChunk;
+      p1 = min(p0 + (int64_t)kCropChunk, P);
+      __syncthreads();
+      if (warp == 0) {                              // largest f with frame_pt_off[f] <= p0 (p0 < P = frame_pt_off[F])
+        int64_t lo = 0, hi = F;
+        while (hi - lo > 1) {
+          const int64_t step = (hi - lo + 31) / 32;
+          const int64_t probe = lo + (int64_t)(lane + 1) * step;
+          const bool le = probe < hi && frame_pt_off[probe] <= p0;
+          const int c = __popc(__ballot_sync(0xffffffffu, le));       // true for a prefix of the lanes
+          hi = min(hi, lo + (int64_t)(c + 1) * step);
+          lo = lo + (int64_t)c * step;
+        }
+        if (lane == 0) s_first = lo;
+      }
+      __syncthreads();
+      fa = s_first;
+    }
+    while (fa < F && frame_pt_off[fa] < p1) {       // one run = consecutive frames of ONE tracklet
       __syncthreads();                              // the previous run's shared state is no longer read
       const int t = frame_trk[fa];
       const int64_t f0 = trk_frame_off[t], f1 = trk_frame_off[t + 1];
-      const int64_t fb = min(f1, fend);
+      const int64_t fb = redo_pass ? fa + 1 : min(f1, fa + (int64_t)kMaxGroup);
       const int nfr = (int)(fb - fa);
       if (redo_pass) {
         if (threadIdx.x == 0) s_grid = grids[t];
@@ -474,7 +505,6 @@ k_crop_voxelize(int64_t F, int G, const occb200_pose_t *__restrict__ poses, cons
       __syncthreads();
       const TrkGrid g = s_grid;
       if (g.status != OCCB200_OK) {
-        if (threadIdx.x < nfr && !redo_pass) frame_kept[fa + threadIdx.x] = 0;
         fa = fb;
         continue;
       }
@@ -485,7 +515,7 @@ k_crop_voxelize(int64_t F, int G, const occb200_pose_t *__restrict__ poses, cons
         for (int w2 = threadIdx.x; w2 < words; w2 += kFrameThreads) s_bits[w2] = 0u;
       __syncthreads();
 
-      const int64_t n0 = s_off[0], n1 = s_off[nfr];
+      const int64_t n0 = max(s_off[0], p0), n1 = min(s_off[nfr], p1);    // the run's points inside the chunk
       int flags = 0;
       for (int64_t base = n0; base < n1; base += kFrameThreads * kPtsPerThread) {   // warp-uniform trip count
         float px[kPtsPerThread], py[kPtsPerThread], pz[kPtsPerThread];
@@ -537,7 +567,8 @@ k_crop_voxelize(int64_t F, int G, const occb200_pose_t *__restrict__ poses, cons
           const uint32_t v = s_bits[w2];
           if (v) atomicOr(&gbits[w2], v);
         }
-      if (threadIdx.x < nfr && !redo_pass) frame_kept[fa + threadIdx.x] = s_kept[threadIdx.x];
+      // a frame may be shared with the neighbouring chunks: frame_kept starts at 0 and is only ever set
+      if (threadIdx.x < nfr && !redo_pass && s_kept[threadIdx.x]) frame_kept[fa + threadIdx.x] = 1;
       if (threadIdx.x == 0 && s_flags) atomicOr(&trk_flags[t], s_flags);
       fa = fb;
     }
@@ -1291,121 +1322,6 @@ k_pair_build(int T, int L, const int64_t *__restrict__ trk_frame_off, const int6
   }
 }
 
-// ---------------------------------------------------------------------------------------------
-// Brick-level cull (docs/ROUND2_BRICK_CULL.md).  Brick = the voxel centres idx in [4bx, 4bx+3] x [4by, 4by+3] x
-// [4bz, 4bz+3].  Through a pair they map to a convex body with corners v_0..v_7 (corners of the FULL brick: a
-// superset of a clipped one).  With c the image of the brick centre and u = c/|c|:
-//   range    r_lo = min_i v_i.u  <=  |p|  <=  max_i |v_i| = r_hi   (a linear function attains its minimum, a convex
-//            one its maximum, over a convex body at a corner)
-//   columns  azimuth extremes of a convex body clear of the sensor's z axis are attained at corners
-//   rows     z is linear, and sin(inc) = z / |p| is bracketed with r_lo / r_hi by the sign of z
-// If the largest return over that pixel footprint (fine pyramid level, footprint snapped outwards to whole tiles) is
-// below r_lo, `ri >= range` is false for every centre of the brick through the pair: its mask bit is set and the
-// visibility kernel never evaluates the pair for the brick.  f32 geometry with generous padding (1e-4 rad, 1 mm +
-// the pair's error bound, extra rows / columns); any doubt keeps the pair.  The cull only removes tests that must
-// fail, so labels cannot change (flag bit 4 switches it off for the A/B parity tests).
-// One thread per (work item of slice s, pair of the slice): blockIdx.y = slice.
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ float u_of_sin(float s) {
-  return s / (fabsf(s) + sqrtf(fmaxf(1.f - s * s, 0.f)));
-}
-
-__global__ void __launch_bounds__(256)
-k_brick_cull(const int2 *__restrict__ item_map, long long bricks_total, const unsigned long long *__restrict__ counter,
-             const TrkHot *__restrict__ hot, const PairHot *__restrict__ pairs, const LutCell *__restrict__ lut_pool,
-             const int64_t *__restrict__ pyr_off, const float *__restrict__ pyr2, int mask_words,
-             uint32_t *__restrict__ pair_mask) {
-  const int s = blockIdx.y;
-  const long long n_items = (long long)counter[8 + 2 * s];
-  for (long long gidx = (long long)blockIdx.x * blockDim.x + threadIdx.x; gidx < n_items * kPairsPerItem;
-       gidx += (long long)gridDim.x * blockDim.x) {
-    const long long item = gidx / kPairsPerItem;
-    const int k = s * kPairsPerItem + (int)(gidx - item * kPairsPerItem);
-    const int2 m = __ldg(item_map + (long long)s * bricks_total + item);
-    const TrkHot &h = hot[m.x];
-    if (k >= h.nact) continue;
-    const PairHot &p = pairs[h.pairs_base + k];
-    if (!(p.eps >= 0.f)) continue;
-    const int bx = m.y & 1023, by = (m.y >> 10) & 1023, bz = (m.y >> 20) & 1023;
-    const int W = p.W, H = (int)p.last + 1;
-    const float hs = 0.5f * (kBrick - 1);
-    // image of the brick centre (rotated frame) and half diagonal of the brick's centre lattice
-    const float cx = (float)(kBrick * bx) + hs - h.cen[0], cy = (float)(kBrick * by) + hs - h.cen[1],
-                cz = (float)(kBrick * bz) + hs - h.cen[2];
-    const float pcx = fmaf(cz, p.A[2], fmaf(cy, p.A[1], fmaf(cx, p.A[0], p.bc[0])));
-    const float pcy = fmaf(cz, p.A[5], fmaf(cy, p.A[4], fmaf(cx, p.A[3], p.bc[1])));
-    const float pcz = fmaf(cz, p.A[8], fmaf(cy, p.A[7], fmaf(cx, p.A[6], p.bc[2])));
-    float R2 = 0.f;
-#pragma unroll
-    for (int c = 0; c < 9; ++c) R2 = fmaf(p.A[c], p.A[c], R2);
-    const float R = hs * sqrtf(R2) * 1.001f + 1e-3f;
-    const float rho2 = pcx * pcx + pcy * pcy;
-    const float rho_c = sqrtf(rho2), d = sqrtf(rho2 + pcz * pcz);
-    if (!(d > 1.25f * R && rho_c > 1.05f * R)) continue;
-    const float inv_d = 1.f / d;
-    const float ux = pcx * inv_d, uy = pcy * inv_d, uz = pcz * inv_d;
-    float r_lo = INFINITY, r_hi2 = 0.f, zmin = INFINITY, zmax = -INFINITY, tmin = INFINITY, tmax = -INFINITY;
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      const float ox = (c & 1) ? hs : -hs, oy = (c & 2) ? hs : -hs, oz = (c & 4) ? hs : -hs;
-      const float vx = fmaf(oz, p.A[2], fmaf(oy, p.A[1], fmaf(ox, p.A[0], pcx)));
-      const float vy = fmaf(oz, p.A[5], fmaf(oy, p.A[4], fmaf(ox, p.A[3], pcy)));
-      const float vz = fmaf(oz, p.A[8], fmaf(oy, p.A[7], fmaf(ox, p.A[6], pcz)));
-      r_lo = fminf(r_lo, fmaf(vz, uz, fmaf(vy, uy, vx * ux)));
-      r_hi2 = fmaxf(r_hi2, fmaf(vz, vz, fmaf(vy, vy, vx * vx)));
-      zmin = fminf(zmin, vz);
-      zmax = fmaxf(zmax, vz);
-      // azimuth relative to the brick centre's: tan = cross / dot; dot > 0 for every corner because rho_c > 1.05 R
-      const float dot = fmaf(pcy, vy, pcx * vx), crs = fmaf(pcx, vy, -(pcy * vx));
-      const float tq = crs / dot;
-      tmin = fminf(tmin, tq);
-      tmax = fmaxf(tmax, tq);
-    }
-    const float slack = 1e-3f + 2.f * p.eps + 1e-5f * d;
-    r_lo -= slack;
-    const float r_hi = sqrtf(r_hi2) + slack;
-    zmin -= slack;
-    zmax += slack;
-    if (!(r_lo > 0.f) || !(tmin > -8.f) || !(tmax < 8.f)) continue;
-    // rows: sin(inc) = z / |p| bracketed by the corner extremes, through the u-space lookup like the pair cull
-    const float s_hi = fminf(fmaxf(zmax / (zmax > 0.f ? r_lo : r_hi), -1.f), 1.f);
-    const float s_lo = fminf(fmaxf(zmin / (zmin > 0.f ? r_hi : r_lo), -1.f), 1.f);
-    const float u_hi = u_of_sin(s_hi) + 2e-4f, u_lo = u_of_sin(s_lo) - 2e-4f;
-    const LutCell *lut = lut_pool + p.lut_off;
-    const int ncell = (int)p.ncm1 + 1;
-    const int r0 = max(row_of_u(lut, p.inv_w, p.cell0m, ncell, u_hi) - 1, 0);
-    const int r1 = min(row_of_u(lut, p.inv_w, p.cell0m, ncell, u_lo) + 1, H - 1);
-    // columns: colf_rel = c0f - kcol * phi with phi = atan2(pcy, pcx) + [atan(tmin), atan(tmax)] (padded)
-    const float kc = -p.nkcol;
-    const float phi_c = atan2f(pcy, pcx);
-    const float cf_lo = p.c0f - (phi_c + atanf(tmax) + 1e-4f) * kc;
-    const float cf_hi = p.c0f - (phi_c + atanf(tmin) - 1e-4f) * kc;
-    const long long q_lo = (long long)p.cint + (long long)floorf(cf_lo) - 2,
-                    q_hi = (long long)p.cint + (long long)ceilf(cf_hi) + 2;
-    const long long len = q_hi - q_lo + 1;
-    if (!(len > 0 && len < W / 2)) continue;
-    // fine tiles covering rows [r0, r1] and columns [q_lo, q_hi] modulo W
-    const int nc2 = (W + kFineC - 1) / kFineC;
-    const float *pimg = pyr2 + 16 * pyr_off[p.sens];
-    const long long a0 = ((q_lo % W) + W) % W;
-    const int ta = (int)(a0 / kFineC), tb = (int)((min(a0 + len, (long long)W) - 1) / kFineC);
-    const int tw = (a0 + len > W) ? (int)((a0 + len - W - 1) / kFineC) : -1;
-    float mx = 0.f;
-    for (int tr = r0 / kFineR; tr <= r1 / kFineR && mx < r_lo; ++tr) {
-      const float *prow = pimg + (int64_t)tr * nc2;
-      for (int seg = 0; seg < 2; ++seg) {
-        const int s0 = seg ? 0 : ta, s1 = seg ? tw : tb;
-        for (int tcx = s0; tcx <= s1 && mx < r_lo; tcx += 2)
-          mx = fmaxf(mx, fmaxf(prow[tcx], prow[min(tcx + 1, s1)]));
-      }
-    }
-    if (mx < r_lo) {
-      const int lb = (bx * bricks_of(h.dY) + by) * bricks_of(h.dZ) + bz;
-      atomicOr(pair_mask + (h.brick_base + lb) * mask_words + (k >> 5), 1u << (k & 31));
-    }
-  }
-}
-
 // Approximate f32 primitives (flush-to-zero MUFU forms, <= 2 ulp): their error is part of every margin.
 __device__ __forceinline__ float rsqrt_approx(float x) {
   float r;
@@ -1445,6 +1361,131 @@ __device__ __forceinline__ float atan2_fast(float y, float x) {
   if (ay > ax) r = 1.57079632679489661923f - r;
   if (x < 0.f) r = 3.14159265358979323846f - r;
   return (y < 0.f) ? -r : r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Brick-level cull (docs/ROUND2_BRICK_CULL.md).  Brick = the voxel centres idx in [4bx, 4bx+3] x [4by, 4by+3] x
+// [4bz, 4bz+3].  Through a pair they map to a convex body with corners v_0..v_7 (corners of the FULL brick: a
+// superset of a clipped one).  With c the image of the brick centre and u = c/|c|:
+//   range    r_lo = min_i v_i.u  <=  |p|  <=  max_i |v_i| = r_hi   (a linear function attains its minimum, a convex
+//            one its maximum, over a convex body at a corner)
+//   columns  azimuth extremes of a convex body clear of the sensor's z axis are attained at corners
+//   rows     z is linear, and sin(inc) = z / |p| is bracketed with r_lo / r_hi by the sign of z
+// If the largest return over that pixel footprint (fine pyramid level, footprint snapped outwards to whole tiles) is
+// below r_lo, `ri >= range` is false for every centre of the brick through the pair: its mask bit is set and the
+// visibility kernel never evaluates the pair for the brick.  f32 geometry with generous padding (1e-4 rad, 1 mm +
+// the pair's error bound, extra rows / columns); any doubt keeps the pair.  The cull only removes tests that must
+// fail, so labels cannot change (flag bit 4 switches it off for the A/B parity tests).
+// One thread per (work item of slice s, pair of the slice): blockIdx.y = slice.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float u_of_sin(float s) {
+  const float c2 = fmaxf(1.f - s * s, 1e-12f);
+  return s * rcp_approx(fabsf(s) + c2 * rsqrt_approx(c2));
+}
+
+// All quantities below are conservative bounds with generous padding, so the approximate reciprocal / square root
+// / arctangent (<= 2 ulp, <= 2e-6 rad) are used throughout: their error is orders of magnitude below the padding.
+__global__ void __launch_bounds__(256)
+k_brick_cull(const int2 *__restrict__ item_map, long long bricks_total, const unsigned long long *__restrict__ counter,
+             const TrkHot *__restrict__ hot, const PairHot *__restrict__ pairs, const LutCell *__restrict__ lut_pool,
+             const int64_t *__restrict__ pyr_off, const float *__restrict__ pyr2, int mask_words,
+             uint32_t *__restrict__ pair_mask) {
+  const int s = blockIdx.y;
+  const long long n_items = (long long)counter[8 + 2 * s];
+  for (long long gidx = (long long)blockIdx.x * blockDim.x + threadIdx.x; gidx < n_items * kPairsPerItem;
+       gidx += (long long)gridDim.x * blockDim.x) {
+    const long long item = gidx / kPairsPerItem;
+    const int k = s * kPairsPerItem + (int)(gidx - item * kPairsPerItem);
+    const int2 m = __ldg(item_map + (long long)s * bricks_total + item);
+    const TrkHot &h = hot[m.x];
+    if (k >= h.nact) continue;
+    const PairHot &p = pairs[h.pairs_base + k];
+    if (!(p.eps >= 0.f)) continue;
+    const int bx = m.y & 1023, by = (m.y >> 10) & 1023, bz = (m.y >> 20) & 1023;
+    const int W = p.W, H = (int)p.last + 1;
+    const float hs = 0.5f * (kBrick - 1);
+    float A[9];
+#pragma unroll
+    for (int c = 0; c < 9; ++c) A[c] = p.A[c];
+    // image of the brick centre (rotated frame) and half diagonal of the brick's centre lattice
+    const float cx = (float)(kBrick * bx) + hs - h.cen[0], cy = (float)(kBrick * by) + hs - h.cen[1],
+                cz = (float)(kBrick * bz) + hs - h.cen[2];
+    const float pcx = fmaf(cz, A[2], fmaf(cy, A[1], fmaf(cx, A[0], p.bc[0])));
+    const float pcy = fmaf(cz, A[5], fmaf(cy, A[4], fmaf(cx, A[3], p.bc[1])));
+    const float pcz = fmaf(cz, A[8], fmaf(cy, A[7], fmaf(cx, A[6], p.bc[2])));
+    float R2 = 0.f;
+#pragma unroll
+    for (int c = 0; c < 9; ++c) R2 = fmaf(A[c], A[c], R2);
+    const float R = hs * (R2 * rsqrt_approx(R2)) * 1.001f + 1e-3f;
+    const float rho2 = fmaf(pcy, pcy, pcx * pcx), d2 = fmaf(pcz, pcz, rho2);
+    const float inv_d = rsqrt_approx(d2);
+    const float rho_c = rho2 * rsqrt_approx(rho2), d = d2 * inv_d;
+    if (!(d > 1.25f * R && rho_c > 1.05f * R)) continue;
+    const float ux = pcx * inv_d, uy = pcy * inv_d, uz = pcz * inv_d;
+    // the 8 corners are pc + (+-hs) A col0 + (+-hs) A col1 + (+-hs) A col2
+    float r_lo = INFINITY, r_hi2 = 0.f, zmin = INFINITY, zmax = -INFINITY, tmin = INFINITY, tmax = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const float ox = (c & 1) ? hs : -hs, oy = (c & 2) ? hs : -hs, oz = (c & 4) ? hs : -hs;
+      const float vx = fmaf(oz, A[2], fmaf(oy, A[1], fmaf(ox, A[0], pcx)));
+      const float vy = fmaf(oz, A[5], fmaf(oy, A[4], fmaf(ox, A[3], pcy)));
+      const float vz = fmaf(oz, A[8], fmaf(oy, A[7], fmaf(ox, A[6], pcz)));
+      r_lo = fminf(r_lo, fmaf(vz, uz, fmaf(vy, uy, vx * ux)));
+      r_hi2 = fmaxf(r_hi2, fmaf(vz, vz, fmaf(vy, vy, vx * vx)));
+      zmin = fminf(zmin, vz);
+      zmax = fmaxf(zmax, vz);
+      // azimuth relative to the brick centre's: tan = cross / dot; dot > 0 for every corner because rho_c > 1.05 R
+      const float dot = fmaf(pcy, vy, pcx * vx), crs = fmaf(pcx, vy, -(pcy * vx));
+      const float tq = crs * rcp_approx(dot);
+      tmin = fminf(tmin, tq);
+      tmax = fmaxf(tmax, tq);
+    }
+    const float slack = 1e-3f + 2.f * p.eps + 1e-5f * d;
+    r_lo -= slack;
+    const float r_hi = r_hi2 * rsqrt_approx(r_hi2) + slack;
+    zmin -= slack;
+    zmax += slack;
+    if (!(r_lo > 0.f) || !(tmin > -8.f) || !(tmax < 8.f)) continue;
+    // rows: sin(inc) = z / |p| bracketed by the corner extremes, through the u-space lookup like the pair cull
+    const float inv_lo = rcp_approx(r_lo), inv_hi = rcp_approx(r_hi);
+    const float s_hi = fminf(fmaxf(zmax * (zmax > 0.f ? inv_lo : inv_hi), -1.f), 1.f);
+    const float s_lo = fminf(fmaxf(zmin * (zmin > 0.f ? inv_hi : inv_lo), -1.f), 1.f);
+    const float u_hi = u_of_sin(s_hi) + 2e-4f, u_lo = u_of_sin(s_lo) - 2e-4f;
+    const LutCell *lut = lut_pool + p.lut_off;
+    const int ncell = (int)p.ncm1 + 1;
+    const int r0 = max(row_of_u(lut, p.inv_w, p.cell0m, ncell, u_hi) - 1, 0);
+    const int r1 = min(row_of_u(lut, p.inv_w, p.cell0m, ncell, u_lo) + 1, H - 1);
+    // columns: colf_rel = c0f - kcol * phi with phi = atan2(pcy, pcx) + [atan(tmin), atan(tmax)] (padded)
+    const float kc = -p.nkcol;
+    const float phi_c = atan2_fast(pcy, pcx);
+    const float cf_lo = p.c0f - (phi_c + atan2_fast(tmax, 1.f) + 1e-4f) * kc;
+    const float cf_hi = p.c0f - (phi_c + atan2_fast(tmin, 1.f) - 1e-4f) * kc;
+    const int q_lo = p.cint + (int)floorf(cf_lo) - 2, q_hi = p.cint + (int)ceilf(cf_hi) + 2;
+    const int len = q_hi - q_lo + 1;
+    if (!(len > 0 && len < W / 2)) continue;
+    // fine tiles covering rows [r0, r1] and columns [q_lo, q_hi] modulo W: segment 1 = tiles [ta, tb], segment 2
+    // (wrapped past the seam) = tiles [0, tw]
+    const int nc2 = (W + kFineC - 1) / kFineC;
+    const float *pimg = pyr2 + 16 * pyr_off[p.sens];
+    int a0 = q_lo % W;
+    a0 += (a0 < 0) ? W : 0;
+    const int ta = a0 / kFineC, tb = (min(a0 + len, W) - 1) / kFineC;
+    const int tw = (a0 + len > W) ? (a0 + len - W - 1) / kFineC : -1;
+    // whole tile rows with four independent loads per step (an early exit per tile would serialise the loads: one
+    // L2 round trip each); the scan stops after the first row that reaches r_lo
+    float mx = 0.f;
+    for (int tr = r0 / kFineR; tr <= r1 / kFineR && mx < r_lo; ++tr) {
+      const float *prow = pimg + (int64_t)tr * nc2;
+      for (int tcx = ta; tcx <= tb; tcx += 4)
+        mx = fmaxf(fmaxf(mx, fmaxf(prow[tcx], prow[min(tcx + 1, tb)])), fmaxf(prow[min(tcx + 2, tb)], prow[min(tcx + 3, tb)]));
+      for (int tcx = 0; tcx <= tw; tcx += 4)
+        mx = fmaxf(fmaxf(mx, fmaxf(prow[tcx], prow[min(tcx + 1, tw)])), fmaxf(prow[min(tcx + 2, tw)], prow[min(tcx + 3, tw)]));
+    }
+    if (mx < r_lo) {
+      const int lb = (bx * bricks_of(h.dY) + by) * bricks_of(h.dZ) + bz;
+      atomicOr(pair_mask + (h.brick_base + lb) * mask_words + (k >> 5), 1u << (k & 31));
+    }
+  }
 }
 
 // float -> nearest integer (ties to even) without the conversion unit: valid for |x| < 2^22; anything else
@@ -1636,17 +1677,27 @@ __device__ __forceinline__ unsigned run_pairs(const VisArgs &a, int t, const Trk
 //   lane; otherwise the undecided voxels are dealt one per lane (dense lanes).
 // Labels are written afterwards by k_labels from the occupancy and free bitsets.
 __global__ void __launch_bounds__(32 * kFastWarps, OCC_MINB) k_visibility(const VisArgs a) {
+  // Work assignment is STATIC: the per-slice lists are walked as one sequence (slice 0 first), warp w of the grid
+  // takes items w, w + W, w + 2W, ...  (A global ticket per item was measured at 2.6 us per atomicAdd with 4 736
+  // warps on the counter -- 37 % of the kernel; neighbouring warps now also get neighbouring bricks of one
+  // tracklet, which share their pair records in L1.)
+  __shared__ long long s_base[kMaxSlices + 1];
+  if (threadIdx.x < a.n_slices) s_base[threadIdx.x + 1] = (long long)a.counter[8 + 2 * threadIdx.x];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    s_base[0] = 0;
+    for (int s = 0; s < a.n_slices; ++s) s_base[s + 1] += s_base[s];
+  }
+  __syncthreads();
   const int lane = threadIdx.x & 31;
-  for (int s = 0; s < a.n_slices; ++s) {
-    const long long total = (long long)a.counter[8 + 2 * s];
-    if (total == 0) break;                                      // slices are filled front to back
-    unsigned long long *ticket = a.counter + 9 + 2 * s;
+  const long long n_items = s_base[a.n_slices];
+  const long long n_warps = (long long)gridDim.x * kFastWarps;
+  int s = 0;
+  for (long long g = (long long)blockIdx.x * kFastWarps + (threadIdx.x >> 5); g < n_items; g += n_warps) {
+    while (g >= s_base[s + 1]) ++s;
+    const long long item = g - s_base[s];
     const int2 *items = a.item_map + (long long)s * a.bricks_total;
-    for (;;) {
-      long long item = 0;
-      if (lane == 0) item = (long long)atomicAdd(ticket, 1ull);
-      item = __shfl_sync(0xffffffffu, item, 0);
-      if (item >= total) break;
+    {
       const int2 m = __ldg(items + item);
       const int t = m.x;
       const int bx = m.y & 1023, by = (m.y >> 10) & 1023, bz = (m.y >> 20) & 1023;
@@ -1847,11 +1898,6 @@ extern "C" int64_t occb200_grid_bricks(int32_t X, int32_t Y, int32_t Z) {
   return (int64_t)((X + kBrick - 1) / kBrick) * ((Y + kBrick - 1) / kBrick) * ((Z + kBrick - 1) / kBrick);
 }
 
-static int crop_group(int64_t F) {                  // tracklet-frames per crop CTA: ~4 CTAs per SM on small batches
-  const int64_t g = F / ((int64_t)kNumSMs * 4);
-  return (int)std::max<int64_t>(1, std::min<int64_t>(g, kMaxGroup));
-}
-
 extern "C" int occb200_annotate_batch(const occb200_annotate_args_t *a, int64_t total, void *stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   OCC_REQUIRE(a != nullptr, "args is NULL");
@@ -1867,6 +1913,7 @@ extern "C" int occb200_annotate_batch(const occb200_annotate_args_t *a, int64_t 
   OCC_REQUIRE(a->max_pairs >= 0 && a->max_pairs <= kMaxSlices * kPairsPerItem, "max_pairs out of range");
   OCC_REQUIRE(a->n_tables >= 0 && (a->n_tables == 0 || (a->table_off && a->table_H)), "table list missing");
   OCC_REQUIRE(a->pyr_tiles == 0 || a->pyr_off != nullptr, "pyr_off is NULL");
+  OCC_REQUIRE(a->n_points >= 0, "n_points is negative");
   Workspace w;
   const int64_t need = ws_layout(a->T, a->F, total, a->SF, a->L, a->incl_len, a->pyr_tiles, a->bricks, a->max_pairs,
                                  (char *)a->workspace, &w);
@@ -1902,11 +1949,10 @@ extern "C" int occb200_annotate_batch(const occb200_annotate_args_t *a, int64_t 
     }
     OCC_CUDA(cudaEventRecord(side->join, side->stream));
   }
-  if (a->F > 0) {
+  if (a->F > 0 && a->n_points > 0) {
     ProfScope ps(kProfCrop, stream);
-    const int G = crop_group(a->F);
-    k_crop_voxelize<<<(unsigned)ceil_div(a->F, G), kFrameThreads, 4 * smem_words, stream>>>(
-        a->F, G, a->poses, a->points, a->point_stride, a->frame_pt_off, a->trk_frame_off, a->label_off, a->frame_trk,
+    k_crop_voxelize<<<(unsigned)ceil_div(a->n_points, kCropChunk), kFrameThreads, 4 * smem_words, stream>>>(
+        a->F, a->n_points, a->poses, a->points, a->point_stride, a->frame_pt_off, a->trk_frame_off, a->label_off, a->frame_trk,
         w.frame_kept, w.trk_flags, w.grids, w.bits, vsf, inv_vs, nullptr, nullptr, smem_words);
     OCC_KERNEL_OK("k_crop_voxelize");
   }
@@ -1926,7 +1972,7 @@ extern "C" int occb200_annotate_batch(const occb200_annotate_args_t *a, int64_t 
         rs = side->stream;
       }
       k_crop_voxelize<<<(unsigned)std::min<int64_t>(a->F, kNumSMs * 2), kFrameThreads, 4 * smem_words, rs>>>(
-          a->F, 1, a->poses, a->points, a->point_stride, a->frame_pt_off, a->trk_frame_off, a->label_off, a->frame_trk,
+          a->F, a->n_points, a->poses, a->points, a->point_stride, a->frame_pt_off, a->trk_frame_off, a->label_off, a->frame_trk,
           w.frame_kept, w.trk_flags, w.grids, w.bits, vsf, inv_vs, w.redo_list, w.counter + 2, smem_words);
       OCC_KERNEL_OK("k_crop_voxelize(redo)");
       if (fast) OCC_CUDA(cudaEventRecord(side->join, side->stream));

@@ -347,6 +347,7 @@ class DeviceTracklets:
         a.max_pairs = pk.max_pairs
         a.brick_off = b["brick_off"].data_ptr()
         a.bricks = int(pk.brick_off[-1])
+        a.n_points = int(pk.n_points)
         a.dims = self.dims.data_ptr()
         a.sizes = self.sizes.data_ptr()
         a.status = self.status.data_ptr()

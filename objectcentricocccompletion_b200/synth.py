@@ -652,7 +652,7 @@ def config_batch(name: str, seed: int = 0, small: bool = False, only_segments=No
     raise ValueError(f"unknown config {name}")
 
 
-def scatter_inputs(num_tracklets=32, num_frames=32, max_pts=1024, channels=5, seed=0):
+def scatter_inputs(num_tracklets=32, num_frames=32, max_pts=1024, channels=5, seed=0, full=False):
     """C4: aggregated tracklet points for Voxelization + DynamicScatter.
 
     Returns points f32 [N, channels] (xyz, intensity, elongation) in a +-204.8 m / -4..8 m
@@ -664,7 +664,7 @@ def scatter_inputs(num_tracklets=32, num_frames=32, max_pts=1024, channels=5, se
         ctr = np.array([rng.uniform(-180, 180), rng.uniform(-180, 180), rng.uniform(-1, 1)])
         size = _sample_size(rng, "vehicle")
         for _ in range(num_frames):
-            n = int(rng.integers(max_pts // 4, max_pts + 1))
+            n = max_pts if full else int(rng.integers(max_pts // 4, max_pts + 1))   # full: the config's upper bound
             xyz = ctr + (rng.random((n, 3)) - 0.5) * size * 1.2
             feat = np.tanh(rng.standard_normal((n, max(channels - 3, 0))))
             pts.append(np.concatenate([xyz, feat], 1)[:, :channels])
