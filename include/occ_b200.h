@@ -169,11 +169,14 @@ int occb200_segment_reduce_backward(float *grad_feats, const float *grad_reduced
 /* ---- A10: occ_ops --------------------------------------------------------------------- */
 
 /* mmdet3d/ops/occ/occ_ops.py:53-93 quantize_points: rois f32 [R,roi_dim] (sizes in columns 4..6),
- * roi_idx int64 [N]; writes out_coor int64 [N,3] (to_center == 0) or out_center f32 [N,3]. */
-int occb200_quantize_points(const float *points, int64_t N, const float *rois, int roi_dim,
+ * roi_idx int64 [N] with PyTorch index semantics (a negative index counts from the end); writes out_coor
+ * int64 [N,3] (to_center == 0) or out_center f32 [N,3].  An index outside [-R, R) -- an IndexError in the
+ * reference -- is never dereferenced: the row gets INT64_MIN / NaN and is counted in *n_bad (device, may be
+ * NULL; the caller zeroes it). */
+int occb200_quantize_points(const float *points, int64_t N, const float *rois, int64_t R, int roi_dim,
                             const int64_t *roi_idx, float voxel_size, const float *scale_wlh,
                             const float *offset_wlh, int to_center, int64_t *out_coor,
-                            float *out_center, void *stream);
+                            float *out_center, unsigned long long *n_bad, void *stream);
 
 /* occ_ops.py:5-50 generate_dense_voxel_centers for R boxes: sizes f32 [R,3] (DEVICE),
  * dims int32 [R,3] and center_off int64 [R+1] (DEVICE, computed by the caller with

@@ -61,6 +61,8 @@ constexpr int kLutPerRow = 64;           // lookup-table cells reserved per incl
 constexpr int kTileR = 8, kTileC = 32;   // range-image max-pyramid tile (rows x columns): pair-level cull
 constexpr int kFineR = 2, kFineC = 8;    // second pyramid level: brick-level cull; 16 fine tiles per coarse tile
 constexpr int kBrick = 4;                // brick edge in voxels: 64 voxels = 2 per lane of one warp
+constexpr int kMinChunk = 8, kMaxChunk = 32;   // bricks per work item of k_visibility (one CTA: the 8 warps share the
+                                               // slice's pair records in shared memory)
 #ifndef OCC_FT
 #define OCC_FT 256
 #endif
@@ -155,7 +157,7 @@ struct Workspace {
   // ---- zeroed by ONE memset at the start of every call
   char *zero_begin;
   unsigned long long *counter;   // [0] f64-path ticket, [1] recheck-queue length, [2] redo frames,
-                                 // [8 + 2s] items of slice s, [9 + 2s] ticket of slice s
+                                 // [8 + 2s] brick items of slice s, [9 + 2s] work items (brick chunks) of slice s
   int32_t *trk_flags;    // [T] flags of the crop kernel (bit0 kept a point, bit1 index error)
   int32_t *frame_kept;   // [F] 1: the frame has an in-box point (set by the crop CTAs that see one)
   uint32_t *bits;        // occupancy bitsets, linear voxel order, tracklet t at label_off[t]/32 + t
@@ -172,7 +174,10 @@ struct Workspace {
   int64_t queue_cap;
   PairHot *pairs_c;      // [F*L] the non-culled pairs of each tracklet, compacted at trk_frame_off[t] * L
   TrkHot *hot;           // [T]
-  int2 *item_map;        // [n_slices * bricks] work items of slice s at s * bricks: (tracklet, bx | by << 10 | bz << 20)
+  int2 *item_map;        // [n_slices * bricks] brick items of slice s at s * bricks: (tracklet, bx | by << 10 | bz << 20)
+  int4 *sitems;          // [n_slices * sitem_cap] work items of k_visibility, slice s at s * sitem_cap:
+                         // (tracklet, slice, first brick, bricks) -- up to kMaxChunk consecutive bricks of one tracklet
+  int64_t sitem_cap;
   int64_t bricks;        // brick_off[T]
   int32_t mask_words;    // ceil(max_pairs / 32)
   int32_t n_slices;      // ceil(max_pairs / kPairsPerItem)
@@ -217,6 +222,8 @@ static int64_t ws_layout(int32_t T, int64_t F, int64_t total, int64_t SF, int32_
   int64_t o_py = take(4 * pyr_tiles);
   int64_t o_py2 = take(4 * 16 * pyr_tiles);
   int64_t o_im = take(8 * (int64_t)n_slices * std::max<int64_t>(bricks, 1));
+  const int64_t sitem_cap = bricks / kMinChunk + T + 1;
+  int64_t o_si = take(16 * (int64_t)n_slices * sitem_cap);
   (void)SF;
   if (w) {
     w->grids = (TrkGrid *)(base + o_grid);
@@ -240,6 +247,8 @@ static int64_t ws_layout(int32_t T, int64_t F, int64_t total, int64_t SF, int32_
     w->pairs_c = (PairHot *)(base + o_pc);
     w->hot = (TrkHot *)(base + o_na);
     w->item_map = (int2 *)(base + o_im);
+    w->sitems = (int4 *)(base + o_si);
+    w->sitem_cap = sitem_cap;
     w->bricks = bricks;
     w->mask_words = mask_words;
     w->n_slices = n_slices;
@@ -1244,9 +1253,10 @@ k_pair_build(int T, int L, const int64_t *__restrict__ trk_frame_off, const int6
              const occb200_sensor_t *__restrict__ sensors, const TabCoef *__restrict__ tabcoef,
              const LutCell *__restrict__ lut_pool, double vs, const int64_t *__restrict__ pyr_off,
              const float *__restrict__ pyr, int cull_on, PairHot *__restrict__ pairs_c, TrkHot *__restrict__ hot,
-             int2 *__restrict__ item_map, long long bricks_total, int n_slices,
-             unsigned long long *__restrict__ counter, int32_t *__restrict__ status_out) {
-  __shared__ long long s_i0[kMaxSlices];
+             int2 *__restrict__ item_map, long long bricks_total, int n_slices, int4 *__restrict__ sitems,
+             long long sitem_cap, int chunk, unsigned long long *__restrict__ counter,
+             int32_t *__restrict__ status_out) {
+  __shared__ long long s_i0[kMaxSlices], s_j0[kMaxSlices];
   __shared__ int s_cnt[8];
   __shared__ int s_status;
   const int t = blockIdx.x;
@@ -1309,9 +1319,18 @@ k_pair_build(int T, int L, const int64_t *__restrict__ trk_frame_off, const int6
     hot[t] = h;
     status_out[t] = status;
   }
-  for (int s = threadIdx.x; s < nslice; s += blockDim.x)
+  const int nchunk = (int)((nbricks + chunk - 1) / chunk);
+  for (int s = threadIdx.x; s < nslice; s += blockDim.x) {
     s_i0[s] = (long long)atomicAdd(counter + 8 + 2 * s, (unsigned long long)nbricks);
+    s_j0[s] = (long long)atomicAdd(counter + 9 + 2 * s, (unsigned long long)nchunk);
+  }
   __syncthreads();
+  for (int i = threadIdx.x; i < nchunk * nslice; i += blockDim.x) {
+    const int s = i / nchunk, c = i - s * nchunk;
+    const long long slot = s_j0[s] + c;
+    if (slot < sitem_cap)                            // always true: sitem_cap >= bricks / kMinChunk + T
+      sitems[(long long)s * sitem_cap + slot] = make_int4(t, s, c * chunk, (int)min((long long)chunk, nbricks - (long long)c * chunk));
+  }
   const int nyz = nby * nbz;
   for (long long i = threadIdx.x; i < nbricks * nslice; i += blockDim.x) {
     const int s = (int)(i / nbricks);
@@ -1471,15 +1490,13 @@ k_brick_cull(const int2 *__restrict__ item_map, long long bricks_total, const un
     a0 += (a0 < 0) ? W : 0;
     const int ta = a0 / kFineC, tb = (min(a0 + len, W) - 1) / kFineC;
     const int tw = (a0 + len > W) ? (a0 + len - W - 1) / kFineC : -1;
-    // whole tile rows with four independent loads per step (an early exit per tile would serialise the loads: one
-    // L2 round trip each); the scan stops after the first row that reaches r_lo
+    // every tile of the footprint, no early exit: the loads are independent of the running maximum, so they all
+    // go out back to back (a loop that stops at the first large tile pays one L2 round trip per iteration)
     float mx = 0.f;
-    for (int tr = r0 / kFineR; tr <= r1 / kFineR && mx < r_lo; ++tr) {
+    for (int tr = r0 / kFineR; tr <= r1 / kFineR; ++tr) {
       const float *prow = pimg + (int64_t)tr * nc2;
-      for (int tcx = ta; tcx <= tb; tcx += 4)
-        mx = fmaxf(fmaxf(mx, fmaxf(prow[tcx], prow[min(tcx + 1, tb)])), fmaxf(prow[min(tcx + 2, tb)], prow[min(tcx + 3, tb)]));
-      for (int tcx = 0; tcx <= tw; tcx += 4)
-        mx = fmaxf(fmaxf(mx, fmaxf(prow[tcx], prow[min(tcx + 1, tw)])), fmaxf(prow[min(tcx + 2, tw)], prow[min(tcx + 3, tw)]));
+      for (int tcx = ta; tcx <= tb; ++tcx) mx = fmaxf(mx, __ldg(prow + tcx));
+      for (int tcx = 0; tcx <= tw; ++tcx) mx = fmaxf(mx, __ldg(prow + tcx));
     }
     if (mx < r_lo) {
       const int lb = (bx * bricks_of(h.dY) + by) * bricks_of(h.dZ) + bz;
@@ -1598,7 +1615,8 @@ struct VisArgs {                 // what the visibility kernel needs (passed by 
   const uint32_t *bits;
   uint32_t *free_brick;
   const uint32_t *pair_mask;
-  const int2 *item_map;
+  const int4 *sitems;
+  long long sitem_cap;
   const TrkHot *hot;
   const PairHot *pairs;
   const LutCell *lut_pool;
@@ -1610,18 +1628,16 @@ struct VisArgs {                 // what the visibility kernel needs (passed by 
 // Returns the bits of the voxels proven free (bit v = this lane's voxel v).
 template <int VPL>
 __device__ __forceinline__ unsigned run_pairs(const VisArgs &a, int t, const TrkHot &h, int bx, int by, int bz, int lb,
-                                              unsigned live, int k0, unsigned todo, const float (&dx)[VPL],
-                                              const float (&dy)[VPL], const float (&dz)[VPL], const int (&vj)[VPL],
-                                              unsigned &steps) {
+                                              unsigned live, const PairHot *__restrict__ s_pairs, unsigned todo,
+                                              const float (&dx)[VPL], const float (&dy)[VPL], const float (&dz)[VPL],
+                                              const int (&vj)[VPL], unsigned &steps) {
   const int lane = threadIdx.x & 31;
-  const PairHot *tp = a.pairs + h.pairs_base + k0;
   unsigned found = 0u;
   while (live) {
     if (!__any_sync(0xffffffffu, todo != 0u)) break;           // every voxel of the item is settled
     const int kk = __ffs(live) - 1;
     live &= live - 1u;
-    const PairHot pc = load128(tp + kk);
-    if (live) asm volatile("prefetch.global.L1 [%0];" ::"l"(tp + (__ffs(live) - 1)));   // next record: one 128-byte line
+    const PairHot pc = s_pairs[kk];                             // shared memory, warp-uniform address: 8 x LDS.128
     const int2 *lut = reinterpret_cast<const int2 *>(a.lut_pool) + pc.lut_off;
     const float *ri_img = a.ri_pool + pc.ri_off;
     // materialise the bases as 64-bit registers: per-test addresses are then ONE imad.wide each
@@ -1668,43 +1684,55 @@ __device__ __forceinline__ unsigned run_pairs(const VisArgs &a, int t, const Trk
   return found;
 }
 
-// Every warp is on its own: it claims a work item from the atomic ticket of the current slice, tests, and ORs the
-// voxels it proved free into the global free bitset (brick order).  No shared memory, no barriers.
-//   item = one 4x4x4 brick of a tracklet x one slice of kPairsPerItem of its surviving pairs, minus the pairs
-//   k_brick_cull masked for the brick.  The lists are walked slice by slice: slice 0 (spread-out viewpoints)
-//   frees most of the voxels that can be freed at all; an item re-reads the free bits when it starts, so later
-//   slices never test a voxel an earlier one has freed.  A brick with more than 32 undecided voxels runs two per
-//   lane; otherwise the undecided voxels are dealt one per lane (dense lanes).
+// Work item = up to kMaxChunk consecutive 4x4x4 bricks of ONE tracklet x ONE slice of kPairsPerItem of its surviving
+// pairs; one CTA per item at a time.  The CTA stages the slice's pair records (<= 2 KB) and the tracklet record in
+// shared memory once -- every test of the item reads them from there instead of paying an L2 round trip per pair
+// -- and its 8 warps then take the bricks of the chunk round-robin, each on its own (no further barriers): a
+// warp tests its brick's undecided voxels against the slice's pairs, minus the pairs k_brick_cull masked for the
+// brick, and ORs the voxels it proved free into the global free bitset (brick order).
+//   * Work assignment is STATIC: the per-slice lists are walked as one sequence (slice 0 first), CTA c takes items
+//     c, c + gridDim, ...  (a global ticket per item was measured at 2.6 us per atomicAdd with 4 736 warps on
+//     one counter).  Slice 0 (spread-out viewpoints) frees most of the voxels that can be freed at all; an item
+//     re-reads the free bits when it starts, so later slices never test a voxel an earlier one has freed.
+//   * A brick with more than 32 undecided voxels runs two per lane; otherwise the undecided voxels are dealt one per
+//     lane (dense lanes).
 // Labels are written afterwards by k_labels from the occupancy and free bitsets.
 __global__ void __launch_bounds__(32 * kFastWarps, OCC_MINB) k_visibility(const VisArgs a) {
-  // Work assignment is STATIC: the per-slice lists are walked as one sequence (slice 0 first), warp w of the grid
-  // takes items w, w + W, w + 2W, ...  (A global ticket per item was measured at 2.6 us per atomicAdd with 4 736
-  // warps on the counter -- 37 % of the kernel; neighbouring warps now also get neighbouring bricks of one
-  // tracklet, which share their pair records in L1.)
   __shared__ long long s_base[kMaxSlices + 1];
-  if (threadIdx.x < a.n_slices) s_base[threadIdx.x + 1] = (long long)a.counter[8 + 2 * threadIdx.x];
+  __shared__ __align__(16) PairHot s_pairs[kPairsPerItem];
+  __shared__ __align__(16) TrkHot s_hot;
+  if (threadIdx.x < a.n_slices) s_base[threadIdx.x + 1] = (long long)a.counter[9 + 2 * threadIdx.x];
   __syncthreads();
   if (threadIdx.x == 0) {
     s_base[0] = 0;
     for (int s = 0; s < a.n_slices; ++s) s_base[s + 1] += s_base[s];
   }
   __syncthreads();
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long n_items = s_base[a.n_slices];
-  const long long n_warps = (long long)gridDim.x * kFastWarps;
   int s = 0;
-  for (long long g = (long long)blockIdx.x * kFastWarps + (threadIdx.x >> 5); g < n_items; g += n_warps) {
+  for (long long g = blockIdx.x; g < n_items; g += gridDim.x) {
     while (g >= s_base[s + 1]) ++s;
-    const long long item = g - s_base[s];
-    const int2 *items = a.item_map + (long long)s * a.bricks_total;
-    {
-      const int2 m = __ldg(items + item);
-      const int t = m.x;
-      const int bx = m.y & 1023, by = (m.y >> 10) & 1023, bz = (m.y >> 20) & 1023;
-      const TrkHot h = load64(a.hot + t);
-      const int k0 = s * kPairsPerItem;
-      const int npair = min(h.nact - k0, kPairsPerItem);         // >= 1 by construction of the lists
-      const int lb = (bx * ((h.dY + kBrick - 1) / kBrick) + by) * ((h.dZ + kBrick - 1) / kBrick) + bz;
+    const int4 it = __ldg(a.sitems + (long long)s * a.sitem_cap + (g - s_base[s]));
+    const int t = it.x, k0 = it.y * kPairsPerItem, b0 = it.z, nb = it.w;
+    __syncthreads();                                             // the previous item's records are no longer read
+    {                                                            // stage the tracklet record and the slice's pair records
+      const float4 *hsrc = reinterpret_cast<const float4 *>(a.hot + t);
+      if (threadIdx.x < 4) reinterpret_cast<float4 *>(&s_hot)[threadIdx.x] = __ldg(hsrc + threadIdx.x);
+      const int nact = __ldg(&a.hot[t].nact);
+      const long long pbase = __ldg(&a.hot[t].pairs_base);
+      const int npair = min(nact - k0, kPairsPerItem);
+      const float4 *psrc = reinterpret_cast<const float4 *>(a.pairs + pbase + k0);
+      if (threadIdx.x < npair * 8) reinterpret_cast<float4 *>(s_pairs)[threadIdx.x] = __ldg(psrc + threadIdx.x);
+    }
+    __syncthreads();
+    const TrkHot h = s_hot;
+    const int npair = min(h.nact - k0, kPairsPerItem);           // >= 1 by construction of the lists
+    const int nby = (h.dY + kBrick - 1) / kBrick, nbz = (h.dZ + kBrick - 1) / kBrick;
+    const int nyz = nby * nbz;
+    for (int lb = b0 + warp; lb < b0 + nb; lb += kFastWarps) {
+      const int bx = lb / nyz, brem = lb - bx * nyz;
+      const int by = brem / nbz, bz = brem - by * nbz;
       const long long gb = h.brick_base + lb;
       const unsigned mw = __ldg(a.pair_mask + gb * a.mask_words + (k0 >> 5));
       const unsigned live = ~(mw >> (k0 & 31)) & (npair >= 32 ? 0xffffffffu : ((1u << npair) - 1u));
@@ -1740,7 +1768,7 @@ __global__ void __launch_bounds__(32 * kFastWarps, OCC_MINB) k_visibility(const 
           dz[v] = (float)(kBrick * bz + (j & 3)) - h.cen[2];
           todo |= ((und[v] >> lane) & 1u) << v;
         }
-        const unsigned found = run_pairs<2>(a, t, h, bx, by, bz, lb, live, k0, todo, dx, dy, dz, vj, steps);
+        const unsigned found = run_pairs<2>(a, t, h, bx, by, bz, lb, live, s_pairs, todo, dx, dy, dz, vj, steps);
 #pragma unroll
         for (int v = 0; v < 2; ++v) {
           const unsigned fw = __ballot_sync(0xffffffffu, (found >> v) & 1u);
@@ -1758,7 +1786,7 @@ __global__ void __launch_bounds__(32 * kFastWarps, OCC_MINB) k_visibility(const 
         dx[0] = (float)(kBrick * bx + (vj[0] >> 4)) - h.cen[0];
         dy[0] = (float)(kBrick * by + ((vj[0] >> 2) & 3)) - h.cen[1];
         dz[0] = (float)(kBrick * bz + (vj[0] & 3)) - h.cen[2];
-        const unsigned found = run_pairs<1>(a, t, h, bx, by, bz, lb, live, k0, mine ? 1u : 0u, dx, dy, dz, vj, steps);
+        const unsigned found = run_pairs<1>(a, t, h, bx, by, bz, lb, live, s_pairs, mine ? 1u : 0u, dx, dy, dz, vj, steps);
         if (found) atomicOr(a.free_brick + 2 * gb + (vj[0] >> 5), 1u << (vj[0] & 31));
       }
       if (a.n_steps) {
@@ -1997,12 +2025,18 @@ extern "C" int occb200_annotate_batch(const occb200_annotate_args_t *a, int64_t 
   if (!fast) {                                      // no tracklet-frames at all: statuses are final, nothing to label
     return 0;
   }
+  // bricks per work item of k_visibility: large chunks amortise the staging of the pair records, small ones keep
+  // every SM busy on a small batch (about half of the nominal pairs survive the pair cull)
+  const int64_t est_items = w.bricks * std::max<int64_t>(1, std::min<int64_t>(w.n_slices, (a->max_pairs / 2 + kPairsPerItem - 1) / kPairsPerItem));
+  const int vis_chunk = est_items / 32 >= (int64_t)kNumSMs * OCC_MINB * 4 ? 32
+                        : est_items / 16 >= (int64_t)kNumSMs * OCC_MINB * 2 ? 16 : kMinChunk;
   {
     ProfScope ps(kProfPairBuild, stream);
     k_pair_build<<<(unsigned)a->T, 256, 0, stream>>>(a->T, a->L, a->trk_frame_off, a->brick_off, w.grids, w.trk_flags,
                                                      a->poses, a->frame_sf, a->sensors, w.tabcoef, w.lut_pool,
                                                      a->voxel_size, a->pyr_off, w.pyr, cull ? 1 : 0, w.pairs_c, w.hot,
-                                                     w.item_map, (long long)w.bricks, w.n_slices, w.counter, a->status);
+                                                     w.item_map, (long long)w.bricks, w.n_slices, w.sitems,
+                                                     (long long)w.sitem_cap, vis_chunk, w.counter, a->status);
     OCC_KERNEL_OK("k_pair_build");
   }
   if (brick_cull && w.bricks > 0) {
@@ -2022,10 +2056,10 @@ extern "C" int occb200_annotate_batch(const occb200_annotate_args_t *a, int64_t 
     va.bricks_total = (long long)w.bricks; va.queue_cap = queue_cap_used; va.vs = a->voxel_size;
     va.trk_frame_off = a->trk_frame_off; va.poses = a->poses; va.frame_sf = a->frame_sf; va.sensors = a->sensors;
     va.incl_pool = a->incl_pool; va.ri_pool = a->ri_pool; va.grids = w.grids; va.counter = w.counter;
-    va.bits = w.bits; va.free_brick = w.free_brick; va.pair_mask = w.pair_mask; va.item_map = w.item_map;
+    va.bits = w.bits; va.free_brick = w.free_brick; va.pair_mask = w.pair_mask; va.sitems = w.sitems;
+    va.sitem_cap = (long long)w.sitem_cap;
     va.hot = w.hot; va.pairs = w.pairs_c; va.lut_pool = w.lut_pool; va.queue = w.queue; va.n_steps = a->n_steps;
-    const int grid = (int)std::min<int64_t>(ceil_div(std::max<int64_t>(w.bricks * w.n_slices, 1), kFastWarps),
-                                            (int64_t)kNumSMs * OCC_MINB);
+    const int grid = (int)std::min<int64_t>(std::max<int64_t>(w.sitem_cap * w.n_slices, 1), (int64_t)kNumSMs * OCC_MINB);
     ProfScope ps(kProfVisibility, stream);
     k_visibility<<<grid, 32 * kFastWarps, 0, stream>>>(va);
     OCC_KERNEL_OK("k_visibility");

@@ -11,13 +11,25 @@ struct Wlh {
 };
 
 __global__ void k_quantize_points(const float *__restrict__ points, int64_t N, const float *__restrict__ rois,
-                                  int roi_dim, const int64_t *__restrict__ roi_idx, float vs, Wlh w, int to_center,
-                                  int64_t *__restrict__ out_coor, float *__restrict__ out_center) {
+                                  int64_t R, int roi_dim, const int64_t *__restrict__ roi_idx, float vs, Wlh w,
+                                  int to_center, int64_t *__restrict__ out_coor, float *__restrict__ out_center,
+                                  unsigned long long *__restrict__ n_bad) {
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= N * 3) return;
   const int64_t i = e / 3;
   const int j = (int)(e % 3);
-  const float *roi = rois + roi_idx[i] * roi_dim;
+  // roi_min_bound[rois_points_idx] (occ_ops.py:81) is PyTorch indexing: a negative index counts from the end,
+  // anything outside [-R, R) raises.  Such a row is counted in *n_bad and gets a sentinel (never an
+  // out-of-bounds read).
+  int64_t ri = roi_idx[i];
+  if (ri < 0) ri += R;
+  if (ri < 0 || ri >= R) {
+    if (j == 0 && n_bad) atomicAdd(n_bad, 1ull);
+    if (to_center) out_center[e] = __int_as_float(0x7fc00000);
+    else out_coor[e] = INT64_MIN;
+    return;
+  }
+  const float *roi = rois + ri * roi_dim;
   const float size = __fadd_rn(__fmul_rn(roi[4 + j], w.scale[j]), w.offset[j]);   // occ_ops.py:76-78
   const float mn = __fdiv_rn(-size, 2.0f);                                          // :80
   const float q = floorf(__fdiv_rn(__fsub_rn(points[e], mn), vs));                  // :82
@@ -89,17 +101,17 @@ extern "C" int occb200_mirror_occ_label(const int32_t *labels, const int64_t *la
   return 0;
 }
 
-extern "C" int occb200_quantize_points(const float *points, int64_t N, const float *rois, int roi_dim,
+extern "C" int occb200_quantize_points(const float *points, int64_t N, const float *rois, int64_t R, int roi_dim,
                                        const int64_t *roi_idx, float voxel_size, const float *scale_wlh,
                                        const float *offset_wlh, int to_center, int64_t *out_coor, float *out_center,
-                                       void *stream) {
-  OCC_REQUIRE(N >= 0 && roi_dim >= 7, "bad sizes");
+                                       unsigned long long *n_bad, void *stream) {
+  OCC_REQUIRE(N >= 0 && R >= 0 && roi_dim >= 7, "bad sizes");
   OCC_REQUIRE(to_center ? out_center != nullptr : out_coor != nullptr, "output pointer is NULL");
   if (N == 0) return 0;
   Wlh w;
   for (int j = 0; j < 3; ++j) { w.scale[j] = scale_wlh[j]; w.offset[j] = offset_wlh[j]; }
   k_quantize_points<<<(unsigned)ceil_div(N * 3, 256), 256, 0, (cudaStream_t)stream>>>(
-      points, N, rois, roi_dim, roi_idx, voxel_size, w, to_center, out_coor, out_center);
+      points, N, rois, R, roi_dim, roi_idx, voxel_size, w, to_center, out_coor, out_center, n_bad);
   OCC_KERNEL_OK("k_quantize_points");
   return 0;
 }

@@ -14,9 +14,11 @@ def _f3(v):
 
 
 def quantize_points(points, rois, rois_points_idx, voxel_size, scale_wlh=[1.0, 1.0, 1.0],
-                    offset_wlh=[0.0, 0.0, 0.0], to_center=False):
+                    offset_wlh=[0.0, 0.0, 0.0], to_center=False, check_index=True):
     """points [N,3] (ROI-local), rois [R,8|10], rois_points_idx [N] -> int64 [N,3] voxel coords, or the f32
-    voxel centres when ``to_center`` (occ_ops.py:53-93)."""
+    voxel centres when ``to_center`` (occ_ops.py:53-93).  ``rois_points_idx`` follows PyTorch indexing (negative
+    indices count from the end); an index outside [-R, R) raises IndexError as in the reference
+    (``check_index=False`` skips the device->host read of the error counter; bad rows then hold INT64_MIN / NaN)."""
     _lib.require_cuda(points, rois, rois_points_idx)
     pts = points.float().contiguous()
     r = rois.float().contiguous()
@@ -25,11 +27,15 @@ def quantize_points(points, rois, rois_points_idx, voxel_size, scale_wlh=[1.0, 1
     coor = None if to_center else torch.empty((N, 3), dtype=torch.long, device=pts.device)
     cen = torch.empty((N, 3), dtype=torch.float32, device=pts.device) if to_center else None
     sc, of = _f3(scale_wlh), _f3(offset_wlh)
+    n_bad = torch.zeros(1, dtype=torch.int64, device=pts.device) if check_index else None
     with torch.cuda.device(pts.device):
-        rc = _lib.lib().occb200_quantize_points(pts.data_ptr(), N, r.data_ptr(), r.size(1), idx.data_ptr(),
+        rc = _lib.lib().occb200_quantize_points(pts.data_ptr(), N, r.data_ptr(), r.size(0), r.size(1), idx.data_ptr(),
                                                 float(voxel_size), sc.ctypes.data, of.ctypes.data, int(to_center),
-                                                _lib.ptr(coor), _lib.ptr(cen), _lib.stream_ptr(pts.device))
+                                                _lib.ptr(coor), _lib.ptr(cen), _lib.ptr(n_bad),
+                                                _lib.stream_ptr(pts.device))
     _lib.check(rc, "occb200_quantize_points")
+    if check_index and int(n_bad) != 0:
+        raise IndexError(f"rois_points_idx: {int(n_bad)} indices out of range for {r.size(0)} rois")
     return cen if to_center else coor
 
 

@@ -13,6 +13,9 @@ Checks, all bit-exact unless noted:
      tests/test_models/test_voxel_encoder/test_voxel_generator.py:6-22.
   5. scatter: C oracle vs torch.unique + index_add_/index_reduce_ (the reference has no CPU
      kernel, voxelization.h:106; tolerance 1e-5 rel on features, exact on coords/maps).
+  6. --save-mean-var grids, 7. MirrorOccLabel: vs the reference's torch op sequences.
+  8. occ_ops: oracle quantize_points / generate_dense_voxel_centers vs the reference's own
+     mmdet3d/ops/occ/occ_ops.py loaded by file path (it needs nothing but torch).
 """
 from __future__ import annotations
 
@@ -205,6 +208,43 @@ def check_mirror(quick):
     return ok
 
 
+def check_occ_ops(quick):
+    """A10 against the reference module itself (mmdet3d/ops/occ/occ_ops.py:5-93, imports only torch)."""
+    import importlib.util
+    import os
+
+    path = os.path.join(_build.REFERENCE, "mmdet3d", "ops", "occ", "occ_ops.py")
+    spec = importlib.util.spec_from_file_location("ref_occ_ops", path)
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    rng = np.random.default_rng(3)
+    n_el = bad = 0
+    for rep in range(3 if quick else 12):
+        R, N = 40, 200_000 if quick else 1_000_000
+        rois = np.concatenate([rng.integers(0, 4, (R, 1)), rng.uniform(-40, 40, (R, 3)), rng.uniform(1.0, 12.0, (R, 3)),
+                               rng.uniform(-3, 3, (R, 1 + 2 * (rep % 2)))], 1).astype(np.float32)
+        idx = rng.integers(0, R, N)
+        pts = ((rng.random((N, 3)) - 0.5) * rois[idx, 4:7] * 1.3).astype(np.float32)
+        vs = [0.2, 0.1, 0.25, 0.3][rep % 4]
+        scale, offset = ([1.0, 1.0, 1.0], [0.0, 0.0, 0.0]) if rep % 3 == 0 else ([1.1, 1.05, 1.2], [0.4, 0.2, 0.1])
+        for to_center in (False, True):
+            want = ref.quantize_points(torch.from_numpy(pts), torch.from_numpy(rois), torch.from_numpy(idx), vs, scale,
+                                       offset, to_center).numpy()
+            got = oracle.quantize_points(pts, rois, idx, vs, scale, offset, to_center)
+            n_el += want.size
+            bad += int((np.ascontiguousarray(got).view(np.uint8) != np.ascontiguousarray(want).view(np.uint8)).any(-1).sum()) \
+                if got.shape == want.shape and got.dtype == want.dtype else want.size
+        sizes = rois[:8, 4:7]
+        want_c = ref.generate_dense_voxel_centers(torch.from_numpy(sizes), vs, scale, offset)
+        got_c = oracle.generate_dense_voxel_centers(sizes, vs, scale, offset)
+        for w_, g_ in zip(want_c, got_c):
+            w_ = w_.numpy()
+            n_el += w_.size
+            bad += int((g_.view(np.uint32) != w_.view(np.uint32)).sum()) if g_.shape == w_.shape else w_.size
+    print(f"[8] occ_ops vs the reference's own occ_ops.py: {n_el} elements, {bad} bit mismatches")
+    return bad == 0
+
+
 def main():
     quick = "--quick" in sys.argv
     assert torch_ref.available(), "needs /root/reference"
@@ -212,7 +252,7 @@ def main():
     _build.build_ref()
     t0 = time.time()
     res = [check_annotate(quick), check_projection(quick), check_points_in_boxes(quick), check_voxelize(quick), check_scatter(quick),
-           check_mean_var(quick), check_mirror(quick)]
+           check_mean_var(quick), check_mirror(quick), check_occ_ops(quick)]
     print(f"oracle pinned: {all(res)}  ({time.time() - t0:.1f}s)")
     return 0 if all(res) else 1
 

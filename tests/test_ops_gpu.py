@@ -270,6 +270,19 @@ def test_occ_ops_vs_oracle():
         e = oracle.quantize_points(pts, rois, idx, 0.2, sc, of, to_center)
         g = occ.quantize_points(_t(pts), _t(rois), _t(idx), 0.2, sc, of, to_center).cpu().numpy()
         assert g.dtype == e.dtype and (g == e).all()
+        if not to_center:
+            e_coor = e
+    # PyTorch index semantics of rois_points_idx (occ_ops.py:81): negative counts from the end, out of range raises
+    neg = idx.copy()
+    neg[::3] -= R
+    g = occ.quantize_points(_t(pts), _t(rois), _t(neg), 0.2, sc, of).cpu().numpy()
+    assert (g == oracle.quantize_points(pts, rois, idx, 0.2, sc, of)).all()
+    bad = idx.copy()
+    bad[5] = R
+    with pytest.raises(IndexError):
+        occ.quantize_points(_t(pts), _t(rois), _t(bad), 0.2, sc, of)
+    g = occ.quantize_points(_t(pts), _t(rois), _t(bad), 0.2, sc, of, check_index=False).cpu().numpy()
+    assert (g[5] == np.iinfo(np.int64).min).all() and (np.delete(g, 5, 0) == np.delete(e_coor, 5, 0)).all()
     for as_volume in (False, True):
         e = oracle.generate_dense_voxel_centers(rois[:, 4:7], 0.2, sc, of, as_volume)
         g = occ.generate_dense_voxel_centers(_t(rois[:, 4:7]), 0.2, sc, of, as_volume)
