@@ -69,16 +69,18 @@ enum {
  * boxes f32 [B,T,7] (x,y,z_bottom,w,l,h,rz), pts f32 [B,M,3] -> out int32 [B,M]:
  * index of the first box containing the point, else -1 (the kernel writes every element;
  * the reference wrapper's -1 pre-fill is not needed).
- * trig: optional f32 [B,T,2] = cosf/sinf(float(rz + pi/2)) computed by the caller (host libm
- * values make the result bit-identical to points_in_boxes_cpu); NULL = computed on device.
+ * trig: optional f32 [B,T,2] = cosf/sinf(float(rz + pi/2)) computed by the caller; NULL = computed on device.
+ * contract: 0 = the unfused products of points_in_boxes_cpu.cpp:27-28 (with host libm trig: bit-identical to
+ * points_in_boxes_cpu); 1 = the FMA contraction nvcc applies to points_in_boxes_cuda.cu:31-32 (with device
+ * trig: bit-identical to the reference's CUDA kernel).
  */
 int occb200_points_in_boxes_gpu(const float *boxes, const float *pts, const float *trig, int32_t *out,
-                                int B, int T, int M, void *stream);
+                                int B, int T, int M, int contract, void *stream);
 
 /* Replaces roiaware_pool3d_ext.points_in_boxes_batch (roiaware_pool3d.cpp:125-135,
  * points_in_boxes_cuda.cu:79-105): out int32 [B,M,T] multi-hot, every element written. */
 int occb200_points_in_boxes_batch(const float *boxes, const float *pts, const float *trig, int32_t *out,
-                                  int B, int T, int M, void *stream);
+                                  int B, int T, int M, int contract, void *stream);
 
 /* HOST helper: trig[i] = {cosf(a), sinf(a)}, a = float(double(rz_i) + M_PI/2), with the host libm,
  * exactly as points_in_boxes_cpu.cpp:16-23 evaluates it.  boxes7 / trig are HOST pointers. */

@@ -61,8 +61,8 @@ SIGNATURES = {
     "occb200_profile_kinds": (C.c_int, []),
     "occb200_profile_read": (C.c_int, [vp, vp]),
     "occb200_selftest_atan2": (C.c_int, [i64, C.c_uint64, vp, vp]),
-    "occb200_points_in_boxes_gpu": (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]),
-    "occb200_points_in_boxes_batch": (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]),
+    "occb200_points_in_boxes_gpu": (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
+    "occb200_points_in_boxes_batch": (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
     "occb200_host_box_trig": (None, [vp, i64, vp]),
     "occb200_dynamic_voxelize": (C.c_int, [vp, C.c_int, i64, C.c_int, vp, vp, vp, vp]),
     "occb200_hard_voxelize_workspace_bytes": (i64, [i64]),

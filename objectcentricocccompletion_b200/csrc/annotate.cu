@@ -401,9 +401,17 @@ __device__ __forceinline__ int64_t voxel_of_point(const FramePose &fp, const Trk
   return ((int64_t)qx * g.dims[1] + (int64_t)qy) * g.dims[2] + (int64_t)qz;
 }
 
-__device__ __forceinline__ FramePose load_frame_pose(const occb200_pose_t &ps) {
+// cuda_arith (flag bit 5): the in-box test as the reference's CUDA kernel evaluates it (device cosf / sinf, nvcc's
+// FMA contraction) instead of the CPU kernel's arithmetic with host libm trig.
+__device__ __forceinline__ BoxTest frame_box_test(const occb200_pose_t &ps, bool cuda_arith) {
+  if (!cuda_arith) return make_box_test(ps.box, ps.cos_pib, ps.sin_pib, 0);
+  const float a = box_rot_angle(ps.box[6]);
+  return make_box_test(ps.box, cosf(a), sinf(a), 1);
+}
+
+__device__ __forceinline__ FramePose load_frame_pose(const occb200_pose_t &ps, bool cuda_arith) {
   FramePose fp;
-  fp.bt = make_box_test(ps.box, ps.cos_pib, ps.sin_pib);
+  fp.bt = frame_box_test(ps, cuda_arith);
   fp.c = ps.cos_m;
   fp.s = ps.sin_m;
   fp.ox = ps.box[0];
@@ -478,7 +486,12 @@ k_crop_voxelize(int64_t F, int64_t P, const occb200_pose_t *__restrict__ poses, 
       __syncthreads();                              // the previous run's shared state is no longer read
       const int t = frame_trk[fa];
       const int64_t f0 = trk_frame_off[t], f1 = trk_frame_off[t + 1];
-      const int64_t fb = redo_pass ? fa + 1 : min(f1, fa + (int64_t)kMaxGroup);
+      int64_t fb = redo_pass ? fa + 1 : min(f1, fa + (int64_t)kMaxGroup);
+      if (!redo_pass) {                             // frames that start at or after the chunk's end belong to the next CTA
+        int c = 0;
+        for (int i = 1; i < (int)(fb - fa); ++i) c += (frame_pt_off[fa + i] < p1) ? 1 : 0;   // offsets are non-decreasing
+        fb = fa + 1 + c;
+      }
       const int nfr = (int)(fb - fa);
       if (redo_pass) {
         if (threadIdx.x == 0) s_grid = grids[t];
@@ -503,7 +516,7 @@ k_crop_voxelize(int64_t F, int64_t P, const occb200_pose_t *__restrict__ poses, 
         }
       }
       if (threadIdx.x < nfr) {
-        s_fp[threadIdx.x] = load_frame_pose(poses[fa + threadIdx.x]);
+        s_fp[threadIdx.x] = load_frame_pose(poses[fa + threadIdx.x], inv_vs != 0.f);
         s_off[threadIdx.x] = frame_pt_off[fa + threadIdx.x];
         s_kept[threadIdx.x] = 0;
       }
@@ -598,7 +611,7 @@ k_frame_points(const occb200_pose_t *__restrict__ poses, const float *__restrict
   const TrkGrid g = grids[t];
   const bool live = status[t] == OCCB200_OK;
   const occb200_pose_t ps = poses[f];
-  const BoxTest bt = make_box_test(ps.box, ps.cos_pib, ps.sin_pib);
+  const BoxTest bt = frame_box_test(ps, inv_vs != 0.f);
   const float dX = (float)g.dims[0], dY = (float)g.dims[1], dZ = (float)g.dims[2];
   for (int64_t j = frame_pt_off[f] + threadIdx.x; j < frame_pt_off[f + 1]; j += blockDim.x) {
     const float *p = points + j * stride;
@@ -1423,63 +1436,54 @@ k_brick_cull(const int2 *__restrict__ item_map, long long bricks_total, const un
     const int bx = m.y & 1023, by = (m.y >> 10) & 1023, bz = (m.y >> 20) & 1023;
     const int W = p.W, H = (int)p.last + 1;
     const float hs = 0.5f * (kBrick - 1);
-    float A[9];
-#pragma unroll
-    for (int c = 0; c < 9; ++c) A[c] = p.A[c];
-    // image of the brick centre (rotated frame) and half diagonal of the brick's centre lattice
+    // image of the brick centre (rotated frame) and the three half-edge vectors a, b, c of the brick's centre
+    // lattice: the 8 corners are pc +- a +- b +- c, so every corner extreme below is a sum of absolute values
     const float cx = (float)(kBrick * bx) + hs - h.cen[0], cy = (float)(kBrick * by) + hs - h.cen[1],
                 cz = (float)(kBrick * bz) + hs - h.cen[2];
-    const float pcx = fmaf(cz, A[2], fmaf(cy, A[1], fmaf(cx, A[0], p.bc[0])));
-    const float pcy = fmaf(cz, A[5], fmaf(cy, A[4], fmaf(cx, A[3], p.bc[1])));
-    const float pcz = fmaf(cz, A[8], fmaf(cy, A[7], fmaf(cx, A[6], p.bc[2])));
-    float R2 = 0.f;
-#pragma unroll
-    for (int c = 0; c < 9; ++c) R2 = fmaf(A[c], A[c], R2);
-    const float R = hs * (R2 * rsqrt_approx(R2)) * 1.001f + 1e-3f;
+    const float pcx = fmaf(cz, p.A[2], fmaf(cy, p.A[1], fmaf(cx, p.A[0], p.bc[0])));
+    const float pcy = fmaf(cz, p.A[5], fmaf(cy, p.A[4], fmaf(cx, p.A[3], p.bc[1])));
+    const float pcz = fmaf(cz, p.A[8], fmaf(cy, p.A[7], fmaf(cx, p.A[6], p.bc[2])));
+    const float ax = hs * p.A[0], ay = hs * p.A[3], az = hs * p.A[6];
+    const float bx_ = hs * p.A[1], by_ = hs * p.A[4], bz_ = hs * p.A[7];
+    const float cx_ = hs * p.A[2], cy_ = hs * p.A[5], cz_ = hs * p.A[8];
+    const float R2 = fmaf(cz_, cz_, fmaf(cy_, cy_, fmaf(cx_, cx_, fmaf(bz_, bz_, fmaf(by_, by_, fmaf(bx_, bx_,
+                     fmaf(az, az, fmaf(ay, ay, ax * ax))))))));
+    const float R = R2 * rsqrt_approx(R2) * 1.001f + 1e-3f;       // half diagonal (the edge vectors are orthogonal)
     const float rho2 = fmaf(pcy, pcy, pcx * pcx), d2 = fmaf(pcz, pcz, rho2);
     const float inv_d = rsqrt_approx(d2);
     const float rho_c = rho2 * rsqrt_approx(rho2), d = d2 * inv_d;
     if (!(d > 1.25f * R && rho_c > 1.05f * R)) continue;
     const float ux = pcx * inv_d, uy = pcy * inv_d, uz = pcz * inv_d;
-    // the 8 corners are pc + (+-hs) A col0 + (+-hs) A col1 + (+-hs) A col2
-    float r_lo = INFINITY, r_hi2 = 0.f, zmin = INFINITY, zmax = -INFINITY, tmin = INFINITY, tmax = -INFINITY;
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      const float ox = (c & 1) ? hs : -hs, oy = (c & 2) ? hs : -hs, oz = (c & 4) ? hs : -hs;
-      const float vx = fmaf(oz, A[2], fmaf(oy, A[1], fmaf(ox, A[0], pcx)));
-      const float vy = fmaf(oz, A[5], fmaf(oy, A[4], fmaf(ox, A[3], pcy)));
-      const float vz = fmaf(oz, A[8], fmaf(oy, A[7], fmaf(ox, A[6], pcz)));
-      r_lo = fminf(r_lo, fmaf(vz, uz, fmaf(vy, uy, vx * ux)));
-      r_hi2 = fmaxf(r_hi2, fmaf(vz, vz, fmaf(vy, vy, vx * vx)));
-      zmin = fminf(zmin, vz);
-      zmax = fmaxf(zmax, vz);
-      // azimuth relative to the brick centre's: tan = cross / dot; dot > 0 for every corner because rho_c > 1.05 R
-      const float dot = fmaf(pcy, vy, pcx * vx), crs = fmaf(pcx, vy, -(pcy * vx));
-      const float tq = crs * rcp_approx(dot);
-      tmin = fminf(tmin, tq);
-      tmax = fmaxf(tmax, tq);
-    }
     const float slack = 1e-3f + 2.f * p.eps + 1e-5f * d;
-    r_lo -= slack;
-    const float r_hi = r_hi2 * rsqrt_approx(r_hi2) + slack;
-    zmin -= slack;
-    zmax += slack;
-    if (!(r_lo > 0.f) || !(tmin > -8.f) || !(tmax < 8.f)) continue;
-    // rows: sin(inc) = z / |p| bracketed by the corner extremes, through the u-space lookup like the pair cull
+    // range: min over corners of v.u = pc.u - sum |e.u|;  max over corners of |v| <= |pc| + half diagonal
+    const float r_lo = d - (fabsf(fmaf(az, uz, fmaf(ay, uy, ax * ux))) + fabsf(fmaf(bz_, uz, fmaf(by_, uy, bx_ * ux))) +
+                            fabsf(fmaf(cz_, uz, fmaf(cy_, uy, cx_ * ux)))) - slack;
+    const float r_hi = d + R + slack;
+    const float zext = fabsf(az) + fabsf(bz_) + fabsf(cz_) + slack;
+    const float zmin = pcz - zext, zmax = pcz + zext;
+    // azimuth relative to the brick centre's: tan = cross(pc, v) / dot(pc, v) in the xy plane; over the corners
+    // |cross| <= sum |cross(pc, e)| and dot >= rho^2 - sum |dot(pc, e)| (> 0 because rho_c > 1.05 R)
+    const float crs = fabsf(fmaf(pcx, ay, -(pcy * ax))) + fabsf(fmaf(pcx, by_, -(pcy * bx_))) + fabsf(fmaf(pcx, cy_, -(pcy * cx_)));
+    const float dmin = rho2 - (fabsf(fmaf(pcy, ay, pcx * ax)) + fabsf(fmaf(pcy, by_, pcx * bx_)) + fabsf(fmaf(pcy, cy_, pcx * cx_)));
+    if (!(r_lo > 0.f) || !(dmin > 0.125f * rho2)) continue;
+    const float tq = crs * rcp_approx(dmin);                      // <= 8 R / rho: finite
+    // rows: sin(inc) = z / |p| bracketed by the corner extremes, through the u-space lookup like the pair cull;
+    // row_of_u counts the boundaries above u exactly, and u is padded by 2e-4 (>> the f32 evaluation error)
     const float inv_lo = rcp_approx(r_lo), inv_hi = rcp_approx(r_hi);
     const float s_hi = fminf(fmaxf(zmax * (zmax > 0.f ? inv_lo : inv_hi), -1.f), 1.f);
     const float s_lo = fminf(fmaxf(zmin * (zmin > 0.f ? inv_hi : inv_lo), -1.f), 1.f);
     const float u_hi = u_of_sin(s_hi) + 2e-4f, u_lo = u_of_sin(s_lo) - 2e-4f;
     const LutCell *lut = lut_pool + p.lut_off;
     const int ncell = (int)p.ncm1 + 1;
-    const int r0 = max(row_of_u(lut, p.inv_w, p.cell0m, ncell, u_hi) - 1, 0);
-    const int r1 = min(row_of_u(lut, p.inv_w, p.cell0m, ncell, u_lo) + 1, H - 1);
-    // columns: colf_rel = c0f - kcol * phi with phi = atan2(pcy, pcx) + [atan(tmin), atan(tmax)] (padded)
+    const int r0 = max(min(row_of_u(lut, p.inv_w, p.cell0m, ncell, u_hi), H - 1), 0);
+    const int r1 = max(min(row_of_u(lut, p.inv_w, p.cell0m, ncell, u_lo), H - 1), 0);
+    // columns: colf_rel = c0f - kcol * phi with phi = atan2(pcy, pcx) +- (atan(tq) + 1e-4)
     const float kc = -p.nkcol;
-    const float phi_c = atan2_fast(pcy, pcx);
-    const float cf_lo = p.c0f - (phi_c + atan2_fast(tmax, 1.f) + 1e-4f) * kc;
-    const float cf_hi = p.c0f - (phi_c + atan2_fast(tmin, 1.f) - 1e-4f) * kc;
-    const int q_lo = p.cint + (int)floorf(cf_lo) - 2, q_hi = p.cint + (int)ceilf(cf_hi) + 2;
+    const float phi_c = p.wide ? atan2_fast(pcy, pcx) : atan_narrow(pcy, pcx);
+    const float dphi = atan_poly(fminf(tq, 1.f)) + (tq > 1.f ? 1.f : 0.f) + 1e-4f;   // tq > 1: any bound >= atan(tq) keeps it safe
+    const float cf_lo = p.c0f - (phi_c + dphi) * kc;
+    const float cf_hi = p.c0f - (phi_c - dphi) * kc;
+    const int q_lo = p.cint + (int)floorf(cf_lo) - 1, q_hi = p.cint + (int)ceilf(cf_hi) + 1;
     const int len = q_hi - q_lo + 1;
     if (!(len > 0 && len < W / 2)) continue;
     // fine tiles covering rows [r0, r1] and columns [q_lo, q_hi] modulo W: segment 1 = tiles [ta, tb], segment 2
@@ -1615,8 +1619,7 @@ struct VisArgs {                 // what the visibility kernel needs (passed by 
   const uint32_t *bits;
   uint32_t *free_brick;
   const uint32_t *pair_mask;
-  const int4 *sitems;
-  long long sitem_cap;
+  const int2 *item_map;
   const TrkHot *hot;
   const PairHot *pairs;
   const LutCell *lut_pool;
@@ -1628,16 +1631,18 @@ struct VisArgs {                 // what the visibility kernel needs (passed by 
 // Returns the bits of the voxels proven free (bit v = this lane's voxel v).
 template <int VPL>
 __device__ __forceinline__ unsigned run_pairs(const VisArgs &a, int t, const TrkHot &h, int bx, int by, int bz, int lb,
-                                              unsigned live, const PairHot *__restrict__ s_pairs, unsigned todo,
-                                              const float (&dx)[VPL], const float (&dy)[VPL], const float (&dz)[VPL],
-                                              const int (&vj)[VPL], unsigned &steps) {
+                                              unsigned live, int k0, unsigned todo, const float (&dx)[VPL],
+                                              const float (&dy)[VPL], const float (&dz)[VPL], const int (&vj)[VPL],
+                                              unsigned &steps) {
   const int lane = threadIdx.x & 31;
+  const PairHot *tp = a.pairs + h.pairs_base + k0;
   unsigned found = 0u;
   while (live) {
     if (!__any_sync(0xffffffffu, todo != 0u)) break;           // every voxel of the item is settled
     const int kk = __ffs(live) - 1;
     live &= live - 1u;
-    const PairHot pc = s_pairs[kk];                             // shared memory, warp-uniform address: 8 x LDS.128
+    const PairHot pc = load128(tp + kk);
+    if (live) asm volatile("prefetch.global.L1 [%0];" ::"l"(tp + (__ffs(live) - 1)));   // next record: one 128-byte line
     const int2 *lut = reinterpret_cast<const int2 *>(a.lut_pool) + pc.lut_off;
     const float *ri_img = a.ri_pool + pc.ri_off;
     // materialise the bases as 64-bit registers: per-test addresses are then ONE imad.wide each
@@ -1684,55 +1689,43 @@ __device__ __forceinline__ unsigned run_pairs(const VisArgs &a, int t, const Trk
   return found;
 }
 
-// Work item = up to kMaxChunk consecutive 4x4x4 bricks of ONE tracklet x ONE slice of kPairsPerItem of its surviving
-// pairs; one CTA per item at a time.  The CTA stages the slice's pair records (<= 2 KB) and the tracklet record in
-// shared memory once -- every test of the item reads them from there instead of paying an L2 round trip per pair
-// -- and its 8 warps then take the bricks of the chunk round-robin, each on its own (no further barriers): a
-// warp tests its brick's undecided voxels against the slice's pairs, minus the pairs k_brick_cull masked for the
-// brick, and ORs the voxels it proved free into the global free bitset (brick order).
-//   * Work assignment is STATIC: the per-slice lists are walked as one sequence (slice 0 first), CTA c takes items
-//     c, c + gridDim, ...  (a global ticket per item was measured at 2.6 us per atomicAdd with 4 736 warps on
-//     one counter).  Slice 0 (spread-out viewpoints) frees most of the voxels that can be freed at all; an item
-//     re-reads the free bits when it starts, so later slices never test a voxel an earlier one has freed.
-//   * A brick with more than 32 undecided voxels runs two per lane; otherwise the undecided voxels are dealt one per
-//     lane (dense lanes).
+// Every warp is on its own: it claims a work item from the atomic ticket of the current slice, tests, and ORs the
+// voxels it proved free into the global free bitset (brick order).  No shared memory, no barriers.
+//   item = one 4x4x4 brick of a tracklet x one slice of kPairsPerItem of its surviving pairs, minus the pairs
+//   k_brick_cull masked for the brick.  The lists are walked slice by slice: slice 0 (spread-out viewpoints)
+//   frees most of the voxels that can be freed at all; an item re-reads the free bits when it starts, so later
+//   slices never test a voxel an earlier one has freed.  A brick with more than 32 undecided voxels runs two per
+//   lane; otherwise the undecided voxels are dealt one per lane (dense lanes).
 // Labels are written afterwards by k_labels from the occupancy and free bitsets.
 __global__ void __launch_bounds__(32 * kFastWarps, OCC_MINB) k_visibility(const VisArgs a) {
+  // Work assignment is STATIC: the per-slice lists are walked as one sequence (slice 0 first), warp w of the grid
+  // takes items w, w + W, w + 2W, ...  (A global ticket per item was measured at 2.6 us per atomicAdd with 4 736
+  // warps on the counter -- 37 % of the kernel; neighbouring warps now also get neighbouring bricks of one
+  // tracklet, which share their pair records in L1.)
   __shared__ long long s_base[kMaxSlices + 1];
-  __shared__ __align__(16) PairHot s_pairs[kPairsPerItem];
-  __shared__ __align__(16) TrkHot s_hot;
-  if (threadIdx.x < a.n_slices) s_base[threadIdx.x + 1] = (long long)a.counter[9 + 2 * threadIdx.x];
+  if (threadIdx.x < a.n_slices) s_base[threadIdx.x + 1] = (long long)a.counter[8 + 2 * threadIdx.x];
   __syncthreads();
   if (threadIdx.x == 0) {
     s_base[0] = 0;
     for (int s = 0; s < a.n_slices; ++s) s_base[s + 1] += s_base[s];
   }
   __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
   const long long n_items = s_base[a.n_slices];
+  const long long n_warps = (long long)gridDim.x * kFastWarps;
   int s = 0;
-  for (long long g = blockIdx.x; g < n_items; g += gridDim.x) {
+  for (long long g = (long long)blockIdx.x * kFastWarps + (threadIdx.x >> 5); g < n_items; g += n_warps) {
     while (g >= s_base[s + 1]) ++s;
-    const int4 it = __ldg(a.sitems + (long long)s * a.sitem_cap + (g - s_base[s]));
-    const int t = it.x, k0 = it.y * kPairsPerItem, b0 = it.z, nb = it.w;
-    __syncthreads();                                             // the previous item's records are no longer read
-    {                                                            // stage the tracklet record and the slice's pair records
-      const float4 *hsrc = reinterpret_cast<const float4 *>(a.hot + t);
-      if (threadIdx.x < 4) reinterpret_cast<float4 *>(&s_hot)[threadIdx.x] = __ldg(hsrc + threadIdx.x);
-      const int nact = __ldg(&a.hot[t].nact);
-      const long long pbase = __ldg(&a.hot[t].pairs_base);
-      const int npair = min(nact - k0, kPairsPerItem);
-      const float4 *psrc = reinterpret_cast<const float4 *>(a.pairs + pbase + k0);
-      if (threadIdx.x < npair * 8) reinterpret_cast<float4 *>(s_pairs)[threadIdx.x] = __ldg(psrc + threadIdx.x);
-    }
-    __syncthreads();
-    const TrkHot h = s_hot;
-    const int npair = min(h.nact - k0, kPairsPerItem);           // >= 1 by construction of the lists
-    const int nby = (h.dY + kBrick - 1) / kBrick, nbz = (h.dZ + kBrick - 1) / kBrick;
-    const int nyz = nby * nbz;
-    for (int lb = b0 + warp; lb < b0 + nb; lb += kFastWarps) {
-      const int bx = lb / nyz, brem = lb - bx * nyz;
-      const int by = brem / nbz, bz = brem - by * nbz;
+    const long long item = g - s_base[s];
+    const int2 *items = a.item_map + (long long)s * a.bricks_total;
+    {
+      const int2 m = __ldg(items + item);
+      const int t = m.x;
+      const int bx = m.y & 1023, by = (m.y >> 10) & 1023, bz = (m.y >> 20) & 1023;
+      const TrkHot h = load64(a.hot + t);
+      const int k0 = s * kPairsPerItem;
+      const int npair = min(h.nact - k0, kPairsPerItem);         // >= 1 by construction of the lists
+      const int lb = (bx * ((h.dY + kBrick - 1) / kBrick) + by) * ((h.dZ + kBrick - 1) / kBrick) + bz;
       const long long gb = h.brick_base + lb;
       const unsigned mw = __ldg(a.pair_mask + gb * a.mask_words + (k0 >> 5));
       const unsigned live = ~(mw >> (k0 & 31)) & (npair >= 32 ? 0xffffffffu : ((1u << npair) - 1u));
@@ -1768,7 +1761,7 @@ __global__ void __launch_bounds__(32 * kFastWarps, OCC_MINB) k_visibility(const 
           dz[v] = (float)(kBrick * bz + (j & 3)) - h.cen[2];
           todo |= ((und[v] >> lane) & 1u) << v;
         }
-        const unsigned found = run_pairs<2>(a, t, h, bx, by, bz, lb, live, s_pairs, todo, dx, dy, dz, vj, steps);
+        const unsigned found = run_pairs<2>(a, t, h, bx, by, bz, lb, live, k0, todo, dx, dy, dz, vj, steps);
 #pragma unroll
         for (int v = 0; v < 2; ++v) {
           const unsigned fw = __ballot_sync(0xffffffffu, (found >> v) & 1u);
@@ -1786,7 +1779,7 @@ __global__ void __launch_bounds__(32 * kFastWarps, OCC_MINB) k_visibility(const 
         dx[0] = (float)(kBrick * bx + (vj[0] >> 4)) - h.cen[0];
         dy[0] = (float)(kBrick * by + ((vj[0] >> 2) & 3)) - h.cen[1];
         dz[0] = (float)(kBrick * bz + (vj[0] & 3)) - h.cen[2];
-        const unsigned found = run_pairs<1>(a, t, h, bx, by, bz, lb, live, s_pairs, mine ? 1u : 0u, dx, dy, dz, vj, steps);
+        const unsigned found = run_pairs<1>(a, t, h, bx, by, bz, lb, live, k0, mine ? 1u : 0u, dx, dy, dz, vj, steps);
         if (found) atomicOr(a.free_brick + 2 * gb + (vj[0] >> 5), 1u << (vj[0] & 31));
       }
       if (a.n_steps) {
@@ -2056,10 +2049,10 @@ extern "C" int occb200_annotate_batch(const occb200_annotate_args_t *a, int64_t 
     va.bricks_total = (long long)w.bricks; va.queue_cap = queue_cap_used; va.vs = a->voxel_size;
     va.trk_frame_off = a->trk_frame_off; va.poses = a->poses; va.frame_sf = a->frame_sf; va.sensors = a->sensors;
     va.incl_pool = a->incl_pool; va.ri_pool = a->ri_pool; va.grids = w.grids; va.counter = w.counter;
-    va.bits = w.bits; va.free_brick = w.free_brick; va.pair_mask = w.pair_mask; va.sitems = w.sitems;
-    va.sitem_cap = (long long)w.sitem_cap;
+    va.bits = w.bits; va.free_brick = w.free_brick; va.pair_mask = w.pair_mask; va.item_map = w.item_map;
     va.hot = w.hot; va.pairs = w.pairs_c; va.lut_pool = w.lut_pool; va.queue = w.queue; va.n_steps = a->n_steps;
-    const int grid = (int)std::min<int64_t>(std::max<int64_t>(w.sitem_cap * w.n_slices, 1), (int64_t)kNumSMs * OCC_MINB);
+    const int grid = (int)std::min<int64_t>(ceil_div(std::max<int64_t>(w.bricks * w.n_slices, 1), kFastWarps),
+                                            (int64_t)kNumSMs * OCC_MINB);
     ProfScope ps(kProfVisibility, stream);
     k_visibility<<<grid, 32 * kFastWarps, 0, stream>>>(va);
     OCC_KERNEL_OK("k_visibility");

@@ -17,10 +17,15 @@ struct BoxTest {
   float cx, cy, czc;   // czc = float(double(z_bottom) + double(h)/2.0)
   float hx, hy, hz;    // half sizes: hx = l/2 bounds local_x, hy = w/2 bounds local_y, hz = h/2
   float cosa, sina;    // cos/sin(float(double(rz) + pi/2))
+  int contract;        // 0: the CPU kernel's unfused products (points_in_boxes_cpu.cpp:27-28); 1: the FMA contraction
+                       // nvcc applies to the reference's CUDA kernel (points_in_boxes_cuda.cu:31-32, SASS of the
+                       // unmodified source built for sm_100a: local_x = fma(sx, cosa, -(sy * sina)),
+                       // local_y = fma(sy, cosa, sx * sina))
 };
 
-__device__ __forceinline__ BoxTest make_box_test(const float *box7, float cosa, float sina) {
+__device__ __forceinline__ BoxTest make_box_test(const float *box7, float cosa, float sina, int contract = 0) {
   BoxTest b;
+  b.contract = contract;
   b.cx = box7[0];
   b.cy = box7[1];
   // `cz += h / 2.0` : double add, rounded back to float (points_in_boxes_cuda.cu:41)
@@ -42,8 +47,14 @@ __device__ __forceinline__ float box_rot_angle(float rz) {
 __device__ __forceinline__ bool pt_in_box(const BoxTest &b, float x, float y, float z) {
   if (fabsf(__fsub_rn(z, b.czc)) > b.hz) return false;
   float sx = __fsub_rn(x, b.cx), sy = __fsub_rn(y, b.cy);
-  float lx = __fadd_rn(__fmul_rn(sx, b.cosa), __fmul_rn(sy, -b.sina));
-  float ly = __fadd_rn(__fmul_rn(sx, b.sina), __fmul_rn(sy, b.cosa));
+  float lx, ly;
+  if (b.contract) {
+    lx = __fmaf_rn(sx, b.cosa, -__fmul_rn(sy, b.sina));
+    ly = __fmaf_rn(sy, b.cosa, __fmul_rn(sx, b.sina));
+  } else {
+    lx = __fadd_rn(__fmul_rn(sx, b.cosa), __fmul_rn(sy, -b.sina));
+    ly = __fadd_rn(__fmul_rn(sx, b.sina), __fmul_rn(sy, b.cosa));
+  }
   return (lx > -b.hx) & (lx < b.hx) & (ly > -b.hy) & (ly < b.hy);
 }
 

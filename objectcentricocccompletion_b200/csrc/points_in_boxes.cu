@@ -17,7 +17,7 @@ constexpr int kPibBoxTile = 256;   // boxes staged per pass
 template <bool kBatch>
 __global__ void __launch_bounds__(kPibThreads)
 k_points_in_boxes(const float *__restrict__ boxes, const float *__restrict__ pts, const float *__restrict__ trig,
-                  int32_t *__restrict__ out, int T, int M) {
+                  int32_t *__restrict__ out, int T, int M, int contract) {
   __shared__ BoxTest s_box[kPibBoxTile];
   const int b = blockIdx.y;
   const float *bx = boxes + (int64_t)b * T * 7;
@@ -59,7 +59,7 @@ k_points_in_boxes(const float *__restrict__ boxes, const float *__restrict__ pts
         ca = cosf(a);
         sa = sinf(a);
       }
-      s_box[k] = make_box_test(bk, ca, sa);
+      s_box[k] = make_box_test(bk, ca, sa, contract);
     }
     __syncthreads();
     if (kBatch) {
@@ -92,11 +92,11 @@ k_points_in_boxes(const float *__restrict__ boxes, const float *__restrict__ pts
 
 template <bool kBatch>
 static int launch_pib(const float *boxes, const float *pts, const float *trig, int32_t *out, int B, int T, int M,
-                      cudaStream_t stream) {
+                      int contract, cudaStream_t stream) {
   OCC_REQUIRE(B >= 0 && T >= 0 && M >= 0, "negative size");
   if (B == 0 || M == 0) return 0;
   dim3 grid((unsigned)ceil_div(M, kPibThreads * kPibPerThread), (unsigned)B);
-  k_points_in_boxes<kBatch><<<grid, kPibThreads, 0, stream>>>(boxes, pts, trig, out, T, M);
+  k_points_in_boxes<kBatch><<<grid, kPibThreads, 0, stream>>>(boxes, pts, trig, out, T, M, contract);
   OCC_KERNEL_OK("k_points_in_boxes");
   return 0;
 }
@@ -104,11 +104,11 @@ static int launch_pib(const float *boxes, const float *pts, const float *trig, i
 }  // namespace occb200
 
 extern "C" int occb200_points_in_boxes_gpu(const float *boxes, const float *pts, const float *trig, int32_t *out,
-                                           int B, int T, int M, void *stream) {
-  return occb200::launch_pib<false>(boxes, pts, trig, out, B, T, M, (cudaStream_t)stream);
+                                           int B, int T, int M, int contract, void *stream) {
+  return occb200::launch_pib<false>(boxes, pts, trig, out, B, T, M, contract, (cudaStream_t)stream);
 }
 
 extern "C" int occb200_points_in_boxes_batch(const float *boxes, const float *pts, const float *trig, int32_t *out,
-                                             int B, int T, int M, void *stream) {
-  return occb200::launch_pib<true>(boxes, pts, trig, out, B, T, M, (cudaStream_t)stream);
+                                             int B, int T, int M, int contract, void *stream) {
+  return occb200::launch_pib<true>(boxes, pts, trig, out, B, T, M, contract, (cudaStream_t)stream);
 }

@@ -2,9 +2,13 @@
 ``mmdet3d/ops/roiaware_pool3d/points_in_boxes.py:6-50, 86-123``.
 
 Same arguments, asserts and return layout as the reference wrappers; the kernels are in
-``csrc/points_in_boxes.cu``.  ``host_trig=True`` evaluates ``cosf/sinf(rz + pi/2)`` with the host
-libm (one D2H of the boxes), which makes the result bit-identical to ``points_in_boxes_cpu``; the
-default evaluates them on the device like the reference's CUDA kernel (no synchronisation).
+``csrc/points_in_boxes.cu``.  Two arithmetics, both bit-exact against their reference:
+
+* default (``host_trig=False``): what the reference's CUDA kernel computes -- ``cosf/sinf(rz + pi/2)`` on the
+  device and the FMA contraction nvcc applies to ``local_x`` / ``local_y`` (points_in_boxes_cuda.cu:24-49; equal to
+  the unmodified kernel built for sm_100a, tests/test_ref_cuda_gpu.py); no synchronisation;
+* ``host_trig=True``: what ``points_in_boxes_cpu`` computes -- host libm trig (one D2H of the boxes) and unfused
+  products (points_in_boxes_cpu.cpp:16-41); the arithmetic of the annotate path's crop and of the CPU oracle.
 """
 from __future__ import annotations
 
@@ -40,7 +44,7 @@ def _run(fn_name, points, boxes, out, host_trig):
     T = bx.shape[1]
     with torch.cuda.device(pts.device):
         rc = getattr(_lib.lib(), fn_name)(bx.data_ptr(), pts.data_ptr(), _lib.ptr(trig), out.data_ptr(), B, T, M,
-                                          _lib.stream_ptr(pts.device))
+                                          0 if host_trig else 1, _lib.stream_ptr(pts.device))
     _lib.check(rc, fn_name)
     return out
 

@@ -190,9 +190,11 @@ def test_work_overflow_is_reported():
 
 
 def test_cuda_arith_flag_matches_torch_cuda_division():
-    """Flag bit 5 evaluates the two scalar divisions of the path the way torch evaluates them on CUDA tensors
-    (x * (1 / vs)): dims and occupied voxels equal a torch-CUDA evaluation of occ_annotate.py:414-416 / :425 on
-    the oracle's own kept points."""
+    """Flag bit 5 evaluates the scalar divisions of the path the way torch evaluates them on CUDA tensors
+    (x * (1 / vs)) and the in-box test the way the reference's CUDA kernel does (device trig, FMA contraction;
+    pinned bit-exactly in tests/test_ref_cuda_gpu.py).  dims equal a torch-CUDA evaluation of
+    occ_annotate.py:414-416; the occupied voxels equal a torch-CUDA evaluation of :425 on the oracle's kept points
+    except where a point sits within an ulp of a box face (the two in-box arithmetics differ there: < 1e-4)."""
     import torch
 
     from objectcentricocccompletion_b200 import occ_annotate, synth
@@ -202,6 +204,7 @@ def test_cuda_arith_flag_matches_torch_cuda_division():
     base = oracle.annotate_batch(batch, threads=8)
     got = _cuda(batch, flags=occ_annotate.FLAG_CUDA_ARITH)
     dbg = [oracle.annotate_tracklet_debug(batch, t) for t in range(len(batch.tracklets))]
+    nvox = nbad = 0
     for t, (g, e) in enumerate(zip(got, base)):
         if e["occ"] is None:
             continue
@@ -216,7 +219,9 @@ def test_cuda_arith_flag_matches_torch_cuda_division():
         q = q[keep]
         occ = torch.zeros(tuple(int(v) for v in dims), dtype=torch.bool, device="cuda")
         occ[q[:, 0], q[:, 1], q[:, 2]] = True
-        assert ((g["occ"] == 1) == occ.cpu().numpy()).all()
+        nvox += occ.numel()
+        nbad += int(((g["occ"] == 1) != occ.cpu().numpy()).sum())
+    assert nvox > 0 and nbad <= 1e-4 * nvox, (nbad, nvox)
 
 
 def test_fast_path_margins():
