@@ -168,6 +168,16 @@ int occb200_segment_reduce_backward(float *grad_feats, const float *grad_reduced
                                     const int32_t *counts, const int32_t *argmax, int64_t N,
                                     int64_t M, int C, int reduce, void *stream);
 
+/* The same two entry points for float64 features: the reference dispatches DynamicScatter over
+ * AT_DISPATCH_FLOATING_TYPES (scatter_points_cuda.cu:215, 260, 276, 289). */
+int occb200_segment_reduce_f64(const double *feats, int64_t N, int C, const int32_t *order,
+                               const int32_t *gstart, const int32_t *counts, int64_t M, int reduce,
+                               double *out, int32_t *argmax, void *stream);
+int occb200_segment_reduce_backward_f64(double *grad_feats, const double *grad_reduced, const double *feats,
+                                        const double *reduced_feats, const int32_t *inverse,
+                                        const int32_t *counts, const int32_t *argmax, int64_t N,
+                                        int64_t M, int C, int reduce, void *stream);
+
 /* ---- A10: occ_ops --------------------------------------------------------------------- */
 
 /* mmdet3d/ops/occ/occ_ops.py:53-93 quantize_points: rois f32 [R,roi_dim] (sizes in columns 4..6),

@@ -73,6 +73,8 @@ SIGNATURES = {
     "occb200_plan_from_inverse": (C.c_int, [vp, i64, i64, vp, vp, vp, vp, i64, vp]),
     "occb200_segment_reduce": (C.c_int, [vp, i64, C.c_int, vp, vp, vp, i64, C.c_int, vp, vp, vp]),
     "occb200_segment_reduce_backward": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, i64, i64, C.c_int, C.c_int, vp]),
+    "occb200_segment_reduce_f64": (C.c_int, [vp, i64, C.c_int, vp, vp, vp, i64, C.c_int, vp, vp, vp]),
+    "occb200_segment_reduce_backward_f64": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, i64, i64, C.c_int, C.c_int, vp]),
     "occb200_quantize_points": (C.c_int, [vp, i64, vp, i64, C.c_int, vp, f32, vp, vp, C.c_int, vp, vp, vp, vp]),
     "occb200_dense_voxel_centers": (C.c_int, [vp, vp, vp, C.c_int, i64, f32, vp, vp, vp, vp]),
     "occb200_mirror_occ_label": (C.c_int, [vp, vp, vp, vp, i32, i64, vp, vp]),

@@ -263,34 +263,41 @@ static PlLayout pl_layout(int64_t N) {
 
 // --------------------------------------------------------------------------- segmented reductions
 // WIDTH lanes cooperate on one voxel; lane = channel (+ WIDTH strides when C > WIDTH).
-template <int WIDTH>
+// exact IEEE add / divide in either precision (never contracted or reordered)
+__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ float div_rn(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ double div_rn(double a, double b) { return __ddiv_rn(a, b); }
+
+template <int WIDTH, typename F>
 __global__ void __launch_bounds__(256)
-k_segment_reduce(const float *__restrict__ feats, int C, const int32_t *__restrict__ order,
+k_segment_reduce(const F *__restrict__ feats, int C, const int32_t *__restrict__ order,
                  const int32_t *__restrict__ gstart, const int32_t *__restrict__ counts, int64_t M, int reduce,
-                 int64_t N, float *__restrict__ out, int32_t *__restrict__ argmax) {
+                 int64_t N, F *__restrict__ out, int32_t *__restrict__ argmax) {
   const int64_t g = ((int64_t)blockIdx.x * 256 + threadIdx.x) / WIDTH;
   const int lane = threadIdx.x % WIDTH;
   if (g >= M) return;
   const int s = gstart[g], n = counts[g];
   for (int c = lane; c < C; c += WIDTH) {
-    float acc = (reduce == OCCB200_MAX) ? -INFINITY : 0.f;
+    F acc = (reduce == OCCB200_MAX) ? (F)-INFINITY : (F)0;
     int32_t arg = (int32_t)N;
     for (int j = 0; j < n; ++j) {
       const int p = __ldg(order + s + j);
-      const float v = __ldg(feats + (int64_t)p * C + c);
+      const F v = __ldg(feats + (int64_t)p * C + c);
       if (reduce == OCCB200_MAX) {
         if (v > acc) { acc = v; arg = p; }       // ascending p: the first attaining index is kept
       } else {
-        acc = __fadd_rn(acc, v);
+        acc = add_rn(acc, v);
       }
     }
-    if (reduce == OCCB200_MEAN) acc = __fdiv_rn(acc, (float)(n < 1 ? 1 : n));
+    if (reduce == OCCB200_MEAN) acc = div_rn(acc, (F)(n < 1 ? 1 : n));
     out[g * C + c] = acc;
     if (argmax) argmax[g * C + c] = arg;
   }
 }
 
-__global__ void k_bwd_add(float *__restrict__ grad_feats, const float *__restrict__ grad_reduced,
+template <typename F>
+__global__ void k_bwd_add(F *__restrict__ grad_feats, const F *__restrict__ grad_reduced,
                           const int32_t *__restrict__ inverse, const int32_t *__restrict__ counts, int64_t N, int C,
                           int reduce) {
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -298,15 +305,16 @@ __global__ void k_bwd_add(float *__restrict__ grad_feats, const float *__restric
   const int64_t i = e / C;
   const int c = (int)(e % C);
   const int v = inverse[i];
-  float g = 0.f;
+  F g = (F)0;
   if (v >= 0) {
     g = grad_reduced[(int64_t)v * C + c];
-    if (reduce == OCCB200_MEAN) g = __fdiv_rn(g, (float)counts[v]);   // :126-129
+    if (reduce == OCCB200_MEAN) g = div_rn(g, (F)counts[v]);   // :126-129
   }
   grad_feats[e] = g;
 }
 
-__global__ void k_bwd_argmin(const float *__restrict__ feats, const float *__restrict__ reduced,
+template <typename F>
+__global__ void k_bwd_argmin(const F *__restrict__ feats, const F *__restrict__ reduced,
                              const int32_t *__restrict__ inverse, int64_t N, int C, int32_t *__restrict__ from) {
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= N * C) return;
@@ -322,7 +330,8 @@ __global__ void k_fill_i32(int32_t *p, int64_t n, int32_t v) {
   if (e < n) p[e] = v;
 }
 
-__global__ void k_bwd_max_scatter(float *__restrict__ grad_feats, const float *__restrict__ grad_reduced,
+template <typename F>
+__global__ void k_bwd_max_scatter(F *__restrict__ grad_feats, const F *__restrict__ grad_reduced,
                                   const int32_t *__restrict__ from, int64_t M, int C, int64_t N) {
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= M * C) return;
@@ -389,16 +398,16 @@ extern "C" int occb200_plan_from_inverse(const int32_t *inverse, int64_t N, int6
   return 0;
 }
 
-extern "C" int occb200_segment_reduce(const float *feats, int64_t N, int C, const int32_t *order, const int32_t *gstart,
-                                      const int32_t *counts, int64_t M, int reduce, float *out, int32_t *argmax,
-                                      void *stream_) {
-  cudaStream_t stream = (cudaStream_t)stream_;
+template <typename F>
+static int segment_reduce_impl(const F *feats, int64_t N, int C, const int32_t *order, const int32_t *gstart,
+                               const int32_t *counts, int64_t M, int reduce, F *out, int32_t *argmax,
+                               cudaStream_t stream) {
   OCC_REQUIRE(C >= 1 && M >= 0 && N >= 0, "bad sizes");
   OCC_REQUIRE(reduce >= 0 && reduce <= 2, "do not support reduce type");
   if (M == 0) return 0;
-#define OCC_SR(W)                                                                                      \
-  k_segment_reduce<W><<<(unsigned)ceil_div(M * W, 256), 256, 0, stream>>>(feats, C, order, gstart, counts, M, \
-                                                                          reduce, N, out, argmax)
+#define OCC_SR(W)                                                                                         \
+  k_segment_reduce<W, F><<<(unsigned)ceil_div(M * W, 256), 256, 0, stream>>>(feats, C, order, gstart, counts, M, \
+                                                                             reduce, N, out, argmax)
   if (C <= 4) OCC_SR(4);
   else if (C <= 8) OCC_SR(8);
   else if (C <= 16) OCC_SR(16);
@@ -408,18 +417,17 @@ extern "C" int occb200_segment_reduce(const float *feats, int64_t N, int C, cons
   return 0;
 }
 
-extern "C" int occb200_segment_reduce_backward(float *grad_feats, const float *grad_reduced, const float *feats,
-                                               const float *reduced_feats, const int32_t *inverse,
-                                               const int32_t *counts, const int32_t *argmax, int64_t N, int64_t M,
-                                               int C, int reduce, void *stream_) {
-  cudaStream_t stream = (cudaStream_t)stream_;
+template <typename F>
+static int segment_reduce_backward_impl(F *grad_feats, const F *grad_reduced, const F *feats, const F *reduced_feats,
+                                        const int32_t *inverse, const int32_t *counts, const int32_t *argmax, int64_t N,
+                                        int64_t M, int C, int reduce, cudaStream_t stream) {
   OCC_REQUIRE(C >= 1 && M >= 0 && N >= 0, "bad sizes");
   OCC_REQUIRE(reduce >= 0 && reduce <= 2, "do not support reduce type");
   if (N == 0) return 0;
-  if (M == 0 || reduce == OCCB200_MAX) OCC_CUDA(cudaMemsetAsync(grad_feats, 0, 4 * N * C, stream));   // :254
+  if (M == 0 || reduce == OCCB200_MAX) OCC_CUDA(cudaMemsetAsync(grad_feats, 0, sizeof(F) * N * C, stream));   // :254
   if (M == 0) return 0;
   if (reduce != OCCB200_MAX) {
-    k_bwd_add<<<(unsigned)ceil_div(N * C, 256), 256, 0, stream>>>(grad_feats, grad_reduced, inverse, counts, N, C, reduce);
+    k_bwd_add<F><<<(unsigned)ceil_div(N * C, 256), 256, 0, stream>>>(grad_feats, grad_reduced, inverse, counts, N, C, reduce);
     OCC_KERNEL_OK("k_bwd_add");
     return 0;
   }
@@ -429,12 +437,40 @@ extern "C" int occb200_segment_reduce_backward(float *grad_feats, const float *g
     OCC_CUDA(cudaMallocAsync((void **)&from, 4 * M * C, stream));
     k_fill_i32<<<(unsigned)ceil_div(M * C, 256), 256, 0, stream>>>(from, M * C, (int32_t)N);
     OCC_KERNEL_OK("k_fill_i32");
-    k_bwd_argmin<<<(unsigned)ceil_div(N * C, 256), 256, 0, stream>>>(feats, reduced_feats, inverse, N, C, from);
+    k_bwd_argmin<F><<<(unsigned)ceil_div(N * C, 256), 256, 0, stream>>>(feats, reduced_feats, inverse, N, C, from);
     OCC_KERNEL_OK("k_bwd_argmin");
     argmax = from;
   }
-  k_bwd_max_scatter<<<(unsigned)ceil_div(M * C, 256), 256, 0, stream>>>(grad_feats, grad_reduced, argmax, M, C, N);
+  k_bwd_max_scatter<F><<<(unsigned)ceil_div(M * C, 256), 256, 0, stream>>>(grad_feats, grad_reduced, argmax, M, C, N);
   OCC_KERNEL_OK("k_bwd_max_scatter");
   if (from) OCC_CUDA(cudaFreeAsync(from, stream));
   return 0;
+}
+
+extern "C" int occb200_segment_reduce(const float *feats, int64_t N, int C, const int32_t *order, const int32_t *gstart,
+                                      const int32_t *counts, int64_t M, int reduce, float *out, int32_t *argmax,
+                                      void *stream) {
+  return segment_reduce_impl<float>(feats, N, C, order, gstart, counts, M, reduce, out, argmax, (cudaStream_t)stream);
+}
+
+extern "C" int occb200_segment_reduce_f64(const double *feats, int64_t N, int C, const int32_t *order,
+                                          const int32_t *gstart, const int32_t *counts, int64_t M, int reduce,
+                                          double *out, int32_t *argmax, void *stream) {
+  return segment_reduce_impl<double>(feats, N, C, order, gstart, counts, M, reduce, out, argmax, (cudaStream_t)stream);
+}
+
+extern "C" int occb200_segment_reduce_backward(float *grad_feats, const float *grad_reduced, const float *feats,
+                                               const float *reduced_feats, const int32_t *inverse,
+                                               const int32_t *counts, const int32_t *argmax, int64_t N, int64_t M,
+                                               int C, int reduce, void *stream) {
+  return segment_reduce_backward_impl<float>(grad_feats, grad_reduced, feats, reduced_feats, inverse, counts, argmax, N,
+                                             M, C, reduce, (cudaStream_t)stream);
+}
+
+extern "C" int occb200_segment_reduce_backward_f64(double *grad_feats, const double *grad_reduced, const double *feats,
+                                                   const double *reduced_feats, const int32_t *inverse,
+                                                   const int32_t *counts, const int32_t *argmax, int64_t N, int64_t M,
+                                                   int C, int reduce, void *stream) {
+  return segment_reduce_backward_impl<double>(grad_feats, grad_reduced, feats, reduced_feats, inverse, counts, argmax,
+                                              N, M, C, reduce, (cudaStream_t)stream);
 }

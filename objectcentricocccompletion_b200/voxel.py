@@ -108,12 +108,12 @@ def _unique(coors, mode):
 def _reduce(feats, plan, reduce, want_argmax=False):
     N, Cc = feats.shape
     dev = feats.device
-    out = torch.empty((plan.M, Cc), dtype=torch.float32, device=dev)
+    out = torch.empty((plan.M, Cc), dtype=feats.dtype, device=dev)
     argmax = torch.empty((plan.M, Cc), dtype=torch.int32, device=dev) if want_argmax else None
+    fn = _lib.lib().occb200_segment_reduce if feats.dtype == torch.float32 else _lib.lib().occb200_segment_reduce_f64
     with torch.cuda.device(dev):
-        rc = _lib.lib().occb200_segment_reduce(feats.data_ptr(), N, Cc, plan.order.data_ptr(), plan.gstart.data_ptr(),
-                                               plan.counts.data_ptr(), plan.M, reduce, out.data_ptr(),
-                                               _lib.ptr(argmax), _lib.stream_ptr(dev))
+        rc = fn(feats.data_ptr(), N, Cc, plan.order.data_ptr(), plan.gstart.data_ptr(), plan.counts.data_ptr(), plan.M,
+                reduce, out.data_ptr(), _lib.ptr(argmax), _lib.stream_ptr(dev))
     _lib.check(rc, "occb200_segment_reduce")
     return out, argmax
 
@@ -138,8 +138,8 @@ def dynamic_point_to_voxel_forward(feats, coors, reduce_type, _mode=1):
     if feats.size(0) == 0:                                                          # :192-196
         return [feats.clone().detach(), coors.clone().detach(),
                 coors.new_empty((0,), dtype=torch.int32), coors.new_empty((0,), dtype=torch.int32), None]
-    if feats.dtype != torch.float32:
-        raise RuntimeError("dynamic_point_to_voxel_forward supports float32 features")
+    if feats.dtype not in (torch.float32, torch.float64):       # AT_DISPATCH_FLOATING_TYPES (scatter_points_cuda.cu:215)
+        raise RuntimeError("dynamic_point_to_voxel_forward supports float32 / float64 features")
     plan = _unique(coors, _mode)
     out, argmax = _reduce(feats, plan, red, want_argmax=(red == 2))
     return [out, plan.uniq, plan.inverse, plan.counts, argmax]
@@ -154,8 +154,10 @@ def dynamic_point_to_voxel_backward(grad_feats, grad_reduced_feats, feats, reduc
     M = reduced_feats.size(0)
     if N == 0:
         return
+    fn = (_lib.lib().occb200_segment_reduce_backward if grad_feats.dtype == torch.float32
+          else _lib.lib().occb200_segment_reduce_backward_f64)
     with torch.cuda.device(grad_feats.device):
-        rc = _lib.lib().occb200_segment_reduce_backward(
+        rc = fn(
             grad_feats.data_ptr(), grad_reduced_feats.data_ptr(), feats.data_ptr(), reduced_feats.data_ptr(),
             coors_idx.data_ptr(), reduce_count.data_ptr(), _lib.ptr(argmax), N, M, Cc, red,
             _lib.stream_ptr(grad_feats.device))

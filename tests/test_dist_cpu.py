@@ -72,3 +72,57 @@ def test_shard_indices_balance():
         loads = [sum(costs[i] for i in s) for s in sh]
         assert max(loads) - min(loads) <= max(costs)                        # LPT bound
     assert shard_indices([], 4) == [[], [], [], []]
+
+
+def _gather_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from objectcentricocccompletion_b200 import dist as occ_dist
+
+        n = 1000 + 37 * rank                                     # uneven payloads
+        local = torch.full((n + 5,), rank + 1, dtype=torch.uint8)  # the buffer may be larger than the payload
+        sizes = occ_dist.exchange_sizes(n)
+        out = occ_dist.gather_labels(local, sizes, dst=0)
+        again = occ_dist.gather_labels(local, sizes, dst=0, out=out)      # reusing the destination buffer
+        if rank == 0:
+            want = torch.cat([torch.full((1000 + 37 * r,), r + 1, dtype=torch.uint8) for r in range(world)])
+            q.put(("dst", sizes == [1000 + 37 * r for r in range(world)], bool((out == want).all()), again is out))
+        else:
+            q.put(("src", out is None and again is None, True, True))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gather_labels_exact_sizes_world3():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_gather_worker, args=(r, 3, port, q)) for r in range(3)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=180) for _ in range(3)]
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert all(g[1] and g[2] and g[3] for g in got), got
+
+
+def test_shard_by_segment_keeps_only_referenced_segments():
+    sys.path.insert(0, ROOT)
+    from objectcentricocccompletion_b200 import dist as occ_dist
+    from objectcentricocccompletion_b200 import synth
+
+    batch = synth.make_batch(12, 10, 0.2, seed=4, small=True, tracklets_per_segment=3)      # 4 segments
+    seen = []
+    for rank in range(2):
+        sub, mine = occ_dist.shard_batch(batch, rank, 2, by="segment")
+        assert len(sub.segments) == 2 and len(sub.tracklets) == 6                          # whole segments
+        for t, gi in zip(sub.tracklets, mine):
+            src = batch.tracklets[gi]
+            assert sub.segments[t.segment] is batch.segments[src.segment] and t.boxes is src.boxes
+        seen += mine
+    assert sorted(seen) == list(range(12))
+    sub, mine = occ_dist.shard_batch(batch, 0, 8, by="tracklet")                            # more ranks than segments
+    assert len(sub.segments) == len({batch.tracklets[i].segment for i in mine})

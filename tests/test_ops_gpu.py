@@ -305,3 +305,28 @@ def test_mirror_occ_label_gpu():
     for g, o in zip(grids, got):
         assert o.shape == g.shape and (o.cpu().numpy() == oracle.mirror_occ_label(g)).all()
     assert occ_ops.mirror_occ_label([]) == []
+
+
+@pytest.mark.parametrize("mode", ["mean", "max", "sum"])
+def test_dynamic_scatter_float64(mode):
+    """float64 features (the reference dispatches AT_DISPATCH_FLOATING_TYPES, scatter_points_cuda.cu:215): forward
+    against a numpy f64 evaluation, and gradcheck in double precision (test_dynamic_scatter.py:86-93)."""
+    import torch
+    from torch.autograd import gradcheck
+
+    from objectcentricocccompletion_b200 import voxel
+
+    rng = np.random.default_rng(5)
+    N, C = 20011, 5
+    feats = rng.standard_normal((N, C))
+    coors = rng.integers(-1, 9, (N, 3)).astype(np.int32)
+    vf, vc, mp, cnt, _ = voxel.dynamic_point_to_voxel_forward(_t(feats), _t(coors), mode)
+    assert vf.dtype == torch.float64
+    mp_h, vf_h = mp.cpu().numpy(), vf.cpu().numpy()
+    for v in range(0, vf_h.shape[0], 7):
+        sel = feats[mp_h == v]
+        want = {"mean": sel.mean(0), "max": sel.max(0), "sum": sel.sum(0)}[mode]
+        np.testing.assert_allclose(vf_h[v], want, rtol=1e-12, atol=1e-12)
+    f = _t(rng.standard_normal((60, 3))).requires_grad_()
+    c = _t(rng.integers(-1, 3, (60, 3)).astype(np.int32))
+    assert gradcheck(lambda x: voxel.dynamic_scatter(x, c, mode)[0], (f,), eps=1e-6, atol=1e-6, rtol=1e-4)
