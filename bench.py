@@ -317,6 +317,7 @@ def measure_resident(ctx, batch, warmup):
 
     torch = ctx.torch
     B, L = len(batch.tracklets[0]), len(batch.segments[0].inclinations)
+    pk = occ_annotate.pack_tracklets(batch)                  # first call: lazy imports, torch's CPU thread pool ...
     t0 = time.perf_counter()
     pk = occ_annotate.pack_tracklets(batch)
     pack_ms = (time.perf_counter() - t0) * 1e3

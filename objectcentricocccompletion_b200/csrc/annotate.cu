@@ -969,8 +969,9 @@ k_pyr_build(const occb200_sensor_t *__restrict__ sensors, const float *__restric
   const int ntr = (H + kTileR - 1) / kTileR, ntc = (W + kTileC - 1) / kTileC;
   const float *img = ri_pool + sn.ri_off;
   float *out = pyr + pyr_off[e];
-  float *out2 = pyr2 + 16 * pyr_off[e];            // fine level: 16 slots per coarse tile always suffice
-  const int nr2 = (H + kFineR - 1) / kFineR, nc2 = (W + kFineC - 1) / kFineC;
+  float *out2 = pyr2 + 16 * pyr_off[e];            // fine level: 16 slots per coarse tile; row pitch 4 * ntc tiles
+                                                   // (>= ceil(W / 8), a multiple of 4: rows are read with 16-byte loads)
+  const int nr2 = (H + kFineR - 1) / kFineR, nc2 = (W + kFineC - 1) / kFineC, pitch2 = 4 * ntc;
   constexpr int kU = 4;                            // tiles per warp in flight: 32 independent loads per lane
   // the image's tiles as one list, dealt to (row group, warp) in runs of kU: every warp is busy whatever the
   // image shape (a 200 x 600 image has only 19 tiles per tile row)
@@ -1010,7 +1011,7 @@ k_pyr_build(const occb200_sensor_t *__restrict__ sensors, const float *__restric
           m2 = fmaxf(m2, __shfl_xor_sync(0xffffffffu, m2, 1));
           m2 = fmaxf(m2, __shfl_xor_sync(0xffffffffu, m2, 2));
           const int r2 = tr * (kTileR / kFineR) + j, c2 = tp * (2 * kTileC / kFineC) + (lane >> 2);
-          if ((lane & 3) == 0 && p < npair && r2 < nr2 && c2 < nc2) out2[r2 * nc2 + c2] = m2;
+          if ((lane & 3) == 0 && p < npair && r2 < nr2 && c2 < nc2) out2[r2 * pitch2 + c2] = m2;
         }
         for (int o = 8; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));   // within 16 lanes
         const int tc = 2 * tp + (lane >> 4);       // lanes 0-15: first tile of the pair, 16-31: second
@@ -1047,7 +1048,7 @@ k_pyr_build(const occb200_sensor_t *__restrict__ sensors, const float *__restric
           m2 = fmaxf(m2, __shfl_xor_sync(0xffffffffu, m2, 2));
           m2 = fmaxf(m2, __shfl_xor_sync(0xffffffffu, m2, 4));
           const int r2 = tr * (kTileR / kFineR) + j, c2 = tc * (kTileC / kFineC) + (lane >> 3);
-          if ((lane & 7) == 0 && tile < ntile && r2 < nr2 && c2 < nc2) out2[r2 * nc2 + c2] = m2;
+          if ((lane & 7) == 0 && tile < ntile && r2 < nr2 && c2 < nc2) out2[r2 * pitch2 + c2] = m2;
         }
       }
       for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
@@ -1488,19 +1489,33 @@ k_brick_cull(const int2 *__restrict__ item_map, long long bricks_total, const un
     if (!(len > 0 && len < W / 2)) continue;
     // fine tiles covering rows [r0, r1] and columns [q_lo, q_hi] modulo W: segment 1 = tiles [ta, tb], segment 2
     // (wrapped past the seam) = tiles [0, tw]
-    const int nc2 = (W + kFineC - 1) / kFineC;
-    const float *pimg = pyr2 + 16 * pyr_off[p.sens];
+    const int pitch2 = 4 * ((W + kTileC - 1) / kTileC);
+    const float4 *pimg = reinterpret_cast<const float4 *>(pyr2 + 16 * pyr_off[p.sens]);
     int a0 = q_lo % W;
     a0 += (a0 < 0) ? W : 0;
     const int ta = a0 / kFineC, tb = (min(a0 + len, W) - 1) / kFineC;
     const int tw = (a0 + len > W) ? (a0 + len - W - 1) / kFineC : -1;
-    // every tile of the footprint, no early exit: the loads are independent of the running maximum, so they all
-    // go out back to back (a loop that stops at the first large tile pays one L2 round trip per iteration)
+    // every tile of the footprint, four tiles per 16-byte load (the scalar version spent its time in the load /
+    // store unit: ~25 sector requests per thread), no early exit: the loads are independent of the running maximum
     float mx = 0.f;
     for (int tr = r0 / kFineR; tr <= r1 / kFineR; ++tr) {
-      const float *prow = pimg + (int64_t)tr * nc2;
-      for (int tcx = ta; tcx <= tb; ++tcx) mx = fmaxf(mx, __ldg(prow + tcx));
-      for (int tcx = 0; tcx <= tw; ++tcx) mx = fmaxf(mx, __ldg(prow + tcx));
+      const float4 *prow = pimg + (tr * pitch2 >> 2);
+      for (int g = ta >> 2; g <= tb >> 2; ++g) {
+        const float4 v = __ldg(prow + g);
+        const int c = 4 * g;
+        mx = fmaxf(mx, (c >= ta && c <= tb) ? v.x : 0.f);
+        mx = fmaxf(mx, (c + 1 >= ta && c + 1 <= tb) ? v.y : 0.f);
+        mx = fmaxf(mx, (c + 2 >= ta && c + 2 <= tb) ? v.z : 0.f);
+        mx = fmaxf(mx, (c + 3 >= ta && c + 3 <= tb) ? v.w : 0.f);
+      }
+      for (int g = 0; g <= tw >> 2 && tw >= 0; ++g) {
+        const float4 v = __ldg(prow + g);
+        const int c = 4 * g;
+        mx = fmaxf(mx, (c <= tw) ? v.x : 0.f);
+        mx = fmaxf(mx, (c + 1 <= tw) ? v.y : 0.f);
+        mx = fmaxf(mx, (c + 2 <= tw) ? v.z : 0.f);
+        mx = fmaxf(mx, (c + 3 <= tw) ? v.w : 0.f);
+      }
     }
     if (mx < r_lo) {
       const int lb = (bx * bricks_of(h.dY) + by) * bricks_of(h.dZ) + bz;

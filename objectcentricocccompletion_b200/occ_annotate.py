@@ -122,17 +122,16 @@ _SMALL_FIELDS = ("trk_frame_off", "poses", "frame_sf", "frame_trk", "frame_pt_of
                  "label_off", "brick_off", "pyr_off", "table_off", "table_H")
 
 
-def _same_memory(flat, pieces) -> bool:
-    """``flat`` is exactly the concatenation of ``pieces`` (views into it, in order)."""
-    if flat is None or flat.ndim != 2 or not flat.flags.c_contiguous or flat.dtype != np.float32:
+def _same_memory(flat, pieces, n_rows) -> bool:
+    """``flat`` is the concatenation of ``pieces`` (views into it, in order): same start, same end, same rows."""
+    if flat is None or flat.ndim != 2 or not flat.flags.c_contiguous or flat.dtype != np.float32 or not pieces:
         return False
-    addr = flat.__array_interface__["data"][0]
-    for p_ in pieces:
-        if p_.dtype != np.float32 or p_.ndim != 2 or p_.shape[1] != flat.shape[1] or (len(p_) and (
-                not p_.flags.c_contiguous or p_.__array_interface__["data"][0] != addr)):
-            return False
-        addr += p_.nbytes
-    return addr == flat.__array_interface__["data"][0] + flat.nbytes
+    first, last = pieces[0], pieces[-1]
+    if n_rows != len(flat) or first.dtype != np.float32 or first.ndim != 2 or first.shape[1] != flat.shape[1]:
+        return False
+    a0 = flat.__array_interface__["data"][0]
+    return (first.__array_interface__["data"][0] == a0 and last.flags.c_contiguous
+            and last.__array_interface__["data"][0] + last.nbytes == a0 + flat.nbytes)
 
 
 def pack_tracklets(batch, pack_override: Optional[dict] = None) -> PackedTracklets:
@@ -195,7 +194,7 @@ def pack_tracklets(batch, pack_override: Optional[dict] = None) -> PackedTrackle
         lens.extend(n_t)
         if len(t.points) and stride is None:
             stride = int(t.points[0].shape[1])
-        if getattr(t, "flat", None) is not None and _same_memory(t.flat, t.points):
+        if getattr(t, "flat", None) is not None and _same_memory(t.flat, t.points, sum(n_t)):
             if len(t.flat):
                 pt_parts.append((row, t.flat))
             row += len(t.flat)

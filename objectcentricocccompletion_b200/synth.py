@@ -618,8 +618,15 @@ def make_batch(num_tracklets, num_frames, voxel_size=0.2, kind="vehicle", seed=0
     segments, tracklets, gidx = [], [], []
     for i in want:
         k = min(tps, num_tracklets - i * tps)
-        seg, boxes, points, flats = make_segment(segment_rng(seed, i), k, num_frames, kind=kind, extent=extent,
-                                                 small=small, occluder_prob=occluder_prob, fast=fast)
+        for attempt in range(16):      # a crowded draw may leave no room for the last tracks: redraw the segment
+            rng = segment_rng(seed, i) if attempt == 0 else np.random.default_rng([int(seed), int(i), attempt])
+            try:
+                seg, boxes, points, flats = make_segment(rng, k, num_frames, kind=kind, extent=extent, small=small,
+                                                         occluder_prob=occluder_prob, fast=fast)
+                break
+            except RuntimeError:
+                if attempt == 15:
+                    raise
         si = len(segments)
         segments.append(seg)
         for j, (b, p, fl) in enumerate(zip(boxes, points, flats)):
