@@ -338,6 +338,35 @@ int occb200_build_range_images(const float *points, int point_stride, const int6
                                const occb200_ri_desc_t *desc, int32_t n_images, const float *incl_pool,
                                float *ri_pool, int64_t ri_len, unsigned long long *n_bad, void *stream);
 
+/* ---- candidate selection from whole-frame clouds (occ_annotate.py:96-112 reads the full frame per tracklet-frame) ---- */
+
+/* One candidate sphere: a box alive in a frame.  32 bytes. */
+typedef struct occb200_cand_box {
+  float cx, cy, cz;   /* sphere centre (box centre), ego frame of the frame                               */
+  float r2;           /* squared radius: must contain the box (half diagonal + margin)                    */
+  int32_t tf;         /* tracklet-frame this sphere feeds (informational; the output order is [frame][box]) */
+  int32_t pad[3];
+} occb200_cand_box_t;
+
+/* Points per CTA chunk / warps per CTA of the selection kernel: the caller sizes `counts` with them. */
+int occb200_candidate_chunk(void);
+int occb200_candidate_warps(void);
+
+/*
+ * clouds f32 [*, stride]: the NF frame clouds of a segment back to back, frame f = rows [cloud_off[f], cloud_off[f+1]);
+ * boxes: the spheres of frame f = boxes[frame_box_off[f] .. frame_box_off[f+1]).  With nchunk_f =
+ * ceil(cloud size / occb200_candidate_chunk()) and W = occb200_candidate_warps(), the count of sphere k of frame f,
+ * chunk c, warp w lives at counts[cnt_off[f] + ((k * nchunk_f + c) * W + w)].
+ * Pass 1 (out_points == NULL) fills `counts`.  The caller takes the exclusive prefix sum over the whole array
+ * (int64, same indexing) and calls again with out_points: every sphere's hits are then written to
+ * out_points[prefix .. ) in cloud order, out_stride floats per point -- i.e. the candidate lists of the
+ * tracklet-frames, contiguous, in [frame][box] order.  max_cloud = the largest cloud (sizes the grid).
+ */
+int occb200_select_candidates(const float *clouds, int stride, const int64_t *cloud_off, int32_t NF,
+                              int64_t max_cloud, const occb200_cand_box_t *boxes,
+                              const int64_t *frame_box_off, const int64_t *cnt_off, int32_t *counts,
+                              const int64_t *prefix, float *out_points, int out_stride, void *stream);
+
 /* HOST helper: fills poses[i] from boxes7 f32 [n,7] and torch-evaluated trig f32 [n,4]
  * (cos(-yaw), sin(-yaw), cos(yaw), sin(yaw)); cos_pib/sin_pib come from the host libm. */
 void occb200_host_pose_pack(const float *boxes7, const float *trig4, int64_t n, occb200_pose_t *poses);

@@ -47,6 +47,9 @@ SENSOR_DTYPE = np.dtype([("ri_off", "<i8"), ("incl_off", "<i8"), ("H", "<i4"), (
 assert POSE_DTYPE.itemsize == C.sizeof(Pose) == 64
 assert SENSOR_DTYPE.itemsize == C.sizeof(Sensor) == 80
 
+CAND_BOX_DTYPE = np.dtype([("cx", "<f4"), ("cy", "<f4"), ("cz", "<f4"), ("r2", "<f4"), ("tf", "<i4"), ("pad", "<i4", (3,))])
+assert CAND_BOX_DTYPE.itemsize == 32
+
 RI_DESC_DTYPE = np.dtype([("v2l", "<f8", (12,)), ("azc", "<f8"), ("incl_off", "<i8"), ("ri_off", "<i8"), ("H", "<i4"),
                           ("W", "<i4"), ("mono", "<i4"), ("pad", "<i4")])
 assert RI_DESC_DTYPE.itemsize == 136
@@ -78,6 +81,9 @@ SIGNATURES = {
     "occb200_quantize_points": (C.c_int, [vp, i64, vp, i64, C.c_int, vp, f32, vp, vp, C.c_int, vp, vp, vp, vp]),
     "occb200_dense_voxel_centers": (C.c_int, [vp, vp, vp, C.c_int, i64, f32, vp, vp, vp, vp]),
     "occb200_mirror_occ_label": (C.c_int, [vp, vp, vp, vp, i32, i64, vp, vp]),
+    "occb200_candidate_chunk": (C.c_int, []),
+    "occb200_candidate_warps": (C.c_int, []),
+    "occb200_select_candidates": (C.c_int, [vp, C.c_int, vp, i32, i64, vp, vp, vp, vp, vp, vp, C.c_int, vp]),
     "occb200_annotate_workspace_bytes": (i64, [i32, i64, i64, i64, i32, i64, i64, i64, i32]),
     "occb200_grid_bricks": (i64, [i32, i32, i32]),
     "occb200_pyramid_tiles": (i64, [i32, i32]),

@@ -1425,10 +1425,17 @@ k_brick_cull(const int2 *__restrict__ item_map, long long bricks_total, const un
              uint32_t *__restrict__ pair_mask) {
   const int s = blockIdx.y;
   const long long n_items = (long long)counter[8 + 2 * s];
-  for (long long gidx = (long long)blockIdx.x * blockDim.x + threadIdx.x; gidx < n_items * kPairsPerItem;
+  // thread -> (brick item, pair): a warp holds 32 CONSECUTIVE bricks (one tracklet, as a rule) and ONE pair, so the
+  // pair record is read at a warp-uniform address (one L1 wavefront per load instead of one per distinct record:
+  // with 16 pairs across the lanes the record loads alone kept the load / store unit busy for most of the kernel)
+  const long long n_groups = (n_items + 31) / 32;
+  for (long long gidx = (long long)blockIdx.x * blockDim.x + threadIdx.x; gidx < n_groups * 32 * kPairsPerItem;
        gidx += (long long)gridDim.x * blockDim.x) {
-    const long long item = gidx / kPairsPerItem;
-    const int k = s * kPairsPerItem + (int)(gidx - item * kPairsPerItem);
+    const long long grp = gidx / (32 * kPairsPerItem);
+    const int within = (int)(gidx - grp * (32 * kPairsPerItem));
+    const long long item = grp * 32 + (within & 31);
+    if (item >= n_items) continue;
+    const int k = s * kPairsPerItem + (within >> 5);
     const int2 m = __ldg(item_map + (long long)s * bricks_total + item);
     const TrkHot &h = hot[m.x];
     if (k >= h.nact) continue;
@@ -2049,7 +2056,7 @@ extern "C" int occb200_annotate_batch(const occb200_annotate_args_t *a, int64_t 
   }
   if (brick_cull && w.bricks > 0) {
     ProfScope ps(kProfBrickCull, stream);
-    const unsigned gx = (unsigned)std::min<int64_t>(ceil_div(w.bricks * kPairsPerItem, 256), (int64_t)kNumSMs * 16);
+    const unsigned gx = (unsigned)std::min<int64_t>(ceil_div((w.bricks + 31) / 32 * 32 * kPairsPerItem, 256), (int64_t)kNumSMs * 16);
     k_brick_cull<<<dim3(gx, (unsigned)w.n_slices), 256, 0, stream>>>(w.item_map, (long long)w.bricks, w.counter, w.hot,
                                                                      w.pairs_c, w.lut_pool, a->pyr_off, w.pyr2,
                                                                      w.mask_words, w.pair_mask);

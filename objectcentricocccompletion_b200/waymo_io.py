@@ -23,7 +23,7 @@ from __future__ import annotations
 import os
 import pickle
 from dataclasses import dataclass
-from typing import Dict, List, Optional, Sequence
+from typing import Tuple, Dict, List, Optional, Sequence
 
 import numpy as np
 
@@ -76,20 +76,29 @@ def _needs_work(path: str, overwrite: bool) -> bool:
 
 
 def build_segment_batch(records: Sequence[TrackletRecord], ts2idx: Dict, data_root: str, split: str,
-                        voxel_size: float, candidate_margin: float = 0.5) -> Optional[TrackletBatch]:
+                        voxel_size: float, candidate_margin: float = 0.5, device_select: Optional[bool] = None,
+                        device=None) -> Tuple[Optional[TrackletBatch], List[int]]:
     """All tracklets of ONE segment -> a TrackletBatch sharing that segment's frames (each frame's point cloud and
     range images are read once per segment, like ``cache_segment_pcs``, occ_annotate.py:312).
-    Returns None if a raw frame file is missing (the reference aborts the tracklet, :503-510)."""
+
+    A tracklet that touches a timestamp whose raw frame file is missing is dropped -- the reference aborts exactly
+    those tracklets (:503-510), not the segment.  Returns (batch or None if nothing is left, indices of the kept
+    records).  ``device_select`` (default: when CUDA is available) picks each tracklet-frame's candidate points
+    from the whole-frame clouds on the GPU (candidates.select_candidates: every cloud is read once); otherwise a
+    numpy sphere test per (tracklet, frame)."""
     kitti_root = os.path.join(data_root, "kitti_format")
     raw_root = os.path.join(data_root, "waymo_raw", split)
+    all_ts = sorted({ts for r in records for ts in r.ts_list})
+    missing = {ts for ts in all_ts if not os.path.isfile(os.path.join(raw_root, f"{ts2idx[ts]}.pkl"))}
+    kept = [i for i, r in enumerate(records) if not (set(r.ts_list) & missing)]
+    records = [records[i] for i in kept]
+    if not records:
+        return None, []
     all_ts = sorted({ts for r in records for ts in r.ts_list})
     frame_of = {ts: i for i, ts in enumerate(all_ts)}
     clouds, extr, incl, ris = [], [], None, None
     for ts in all_ts:
         idx = ts2idx[ts]
-        raw_path = os.path.join(raw_root, f"{idx}.pkl")
-        if not os.path.isfile(raw_path):
-            return None
         fd = load_raw_frame(raw_root, idx)
         clouds.append(read_velodyne_bin(os.path.join(kitti_root, split, "velodyne", f"{idx}.bin")))
         extr.append(np.stack([np.asarray(fd[f"{n}_LIDAR_EXTRINSIC"], np.float32) for n in LiDAR_NAME_LIST], 0))
@@ -104,18 +113,30 @@ def build_segment_batch(records: Sequence[TrackletRecord], ts2idx: Dict, data_ro
                     raise ValueError("beam inclinations change inside a segment: split it into per-table segments")
                 ris[c].append(imgs[c])
     seg = Segment(extrinsics=np.stack(extr, 0), inclinations=incl, range_images=[np.stack(r, 0) for r in ris])
+    boxes = [np.asarray(r.boxes, np.float32).reshape(-1, 7) for r in records]
+    frames = [np.array([frame_of[ts] for ts in r.ts_list], np.int32) for r in records]
+    if device_select is None:
+        import torch
+
+        device_select = torch.cuda.is_available()
     trks = []
-    for r in records:
-        boxes = np.asarray(r.boxes, np.float32).reshape(-1, 7)
-        pts = []
-        for b, ts in zip(boxes, r.ts_list):
-            pc = clouds[frame_of[ts]]
-            ctr = b[:3] + np.array([0, 0, 0.5 * b[5]], np.float32)
-            rad = 0.5 * float(np.linalg.norm(b[3:6])) + candidate_margin
-            pts.append(np.ascontiguousarray(pc[np.linalg.norm(pc[:, :3] - ctr, axis=1) <= rad]))
-        trks.append(Tracklet(boxes=boxes, points=pts, segment=0,
-                             frame_ids=np.array([frame_of[ts] for ts in r.ts_list], np.int32)))
-    return TrackletBatch(segments=[seg], tracklets=trks, voxel_size=float(voxel_size))
+    if device_select:
+        from .candidates import select_candidates, split_candidates
+
+        pts, cnt = select_candidates(clouds, boxes, frames, margin=candidate_margin, device=device)
+        for b, f, (flat, per_frame) in zip(boxes, frames, split_candidates(pts, cnt, [len(b) for b in boxes])):
+            trks.append(Tracklet(boxes=b, points=per_frame, segment=0, frame_ids=f, flat=flat))
+    else:
+        for b7, f in zip(boxes, frames):
+            pts = []
+            for b, fi in zip(b7, f):
+                pc = clouds[int(fi)]
+                ctr = b[:3] + np.array([0, 0, 0.5 * b[5]], np.float32)
+                rad = np.float32(0.5) * np.linalg.norm(b[3:6]).astype(np.float32) + np.float32(candidate_margin)
+                d = pc[:, :3] - ctr
+                pts.append(np.ascontiguousarray(pc[(d * d).sum(1) <= rad * rad]))
+            trks.append(Tracklet(boxes=b7, points=pts, segment=0, frame_ids=f))
+    return TrackletBatch(segments=[seg], tracklets=trks, voxel_size=float(voxel_size)), kept
 
 
 def save_tracklet_records(path: str, records: Sequence[TrackletRecord]) -> None:
@@ -142,10 +163,15 @@ def segments_of_rank(segment_names: Sequence[str], rank: int, world: int) -> Lis
 
 
 def annotate_from_disk(records: Sequence[TrackletRecord], data_root: str, out_dir: str, split: str = "training",
-                       voxel_size: float = 0.2, overwrite: bool = False, annotate_fn=annotate_batch) -> List[Optional[str]]:
+                       voxel_size: float = 0.2, overwrite: bool = False, annotate_fn=None, save_mean_var: bool = False,
+                       device=None, device_select: Optional[bool] = None) -> List[Optional[str]]:
     """The job of ``OccAnnotator.annotate_segment`` (occ_annotate.py:649-671) on a converted Waymo directory:
-    group by segment, skip finished / short tracklets (:335-345), annotate each segment's batch, write npz files.
+    group by segment, skip finished / short tracklets (:335-345), annotate each segment's batch, write npz files
+    (``save_mean_var``: the ``--save-mean-var`` grids beside the labels, :627-645).
     Returns the written (or kept) path per record, None where the reference writes nothing."""
+    if annotate_fn is None:
+        def annotate_fn(batch):
+            return annotate_batch(batch, device=device, save_mean_var=save_mean_var)
     ts2idx = load_idx2timestamp(os.path.join(data_root, "kitti_format"))
     result: List[Optional[str]] = [None] * len(records)
     by_seg: Dict[str, List[int]] = {}
@@ -161,10 +187,12 @@ def annotate_from_disk(records: Sequence[TrackletRecord], data_root: str, out_di
                 todo.append(i)
         if not todo:
             continue
-        batch = build_segment_batch([records[i] for i in todo], ts2idx, data_root, split, voxel_size)
+        batch, kept = build_segment_batch([records[i] for i in todo], ts2idx, data_root, split, voxel_size,
+                                          device_select=device_select, device=device)
         if batch is None:
             continue
-        for i, res in zip(todo, annotate_fn(batch)):
+        for k, res in zip(kept, annotate_fn(batch)):
+            i = todo[k]
             if res["occ"] is None:
                 continue
             path = out_name(out_dir, split, seg_name, records[i].id)
