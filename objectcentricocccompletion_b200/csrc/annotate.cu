@@ -424,11 +424,9 @@ __device__ __forceinline__ FramePose load_frame_pose(const occb200_pose_t &ps, b
 #define OCC_PPT 4
 #endif
 constexpr int kPtsPerThread = OCC_PPT;          // independent point loads in flight per thread
-#ifndef OCC_CROP_CHUNK
-#define OCC_CROP_CHUNK 2048
-#endif
-constexpr int kCropChunk = OCC_CROP_CHUNK;      // candidate points per crop CTA
-// First pass (redo_list == NULL): CTA c owns the candidate points [c * kCropChunk, (c+1) * kCropChunk) of the flat
+constexpr int kCropChunkMin = kFrameThreads * kPtsPerThread;   // candidate points per crop CTA: a multiple of one
+constexpr int kCropChunkMax = 8 * kCropChunkMin;               // iteration of the point loop, chosen per call
+// First pass (redo_list == NULL): CTA c owns the candidate points [c * chunk, (c+1) * chunk) of the flat
 // point array, whatever frames they belong to -- every CTA has the same amount of work (frames of a close object
 // carry several times the points of a far one; one CTA per frame left the longest frame as the kernel's tail).
 // Warp 0 finds the first frame of the chunk with a 32-way search of frame_pt_off (3 dependent loads for 32 768
@@ -439,7 +437,7 @@ constexpr int kCropChunk = OCC_CROP_CHUNK;      // candidate points per crop CTA
 // Second pass (redo_list != NULL): a small grid strides over the frames of the tracklets whose optimistic grid was
 // wrong -- usually none -- whole frames, with the true grid from grids[].
 __global__ void __launch_bounds__(kFrameThreads, OCC_FMINB)
-k_crop_voxelize(int64_t F, int64_t P, const occb200_pose_t *__restrict__ poses, const float *__restrict__ points,
+k_crop_voxelize(int64_t F, int64_t P, int chunk, const occb200_pose_t *__restrict__ poses, const float *__restrict__ points,
                 int stride, const int64_t *__restrict__ frame_pt_off, const int64_t *__restrict__ trk_frame_off,
                 const int64_t *__restrict__ label_off, const int32_t *__restrict__ frame_trk,
                 int32_t *__restrict__ frame_kept, int32_t *__restrict__ trk_flags, const TrkGrid *__restrict__ grids,
@@ -464,8 +462,8 @@ k_crop_voxelize(int64_t F, int64_t P, const occb200_pose_t *__restrict__ poses, 
       p0 = frame_pt_off[fa];
       p1 = frame_pt_off[fa + 1];
     } else {
-      p0 = (int64_t)wi * kCropChunk;
-      p1 = min(p0 + (int64_t)kCropChunk, P);
+      p0 = (int64_t)wi * chunk;
+      p1 = min(p0 + (int64_t)chunk, P);
       __syncthreads();
       if (warp == 0) {                              // largest f with frame_pt_off[f] <= p0 (p0 < P = frame_pt_off[F])
         int64_t lo = 0, hi = F;
@@ -482,6 +480,7 @@ k_crop_voxelize(int64_t F, int64_t P, const occb200_pose_t *__restrict__ poses, 
       __syncthreads();
       fa = s_first;
     }
+    int t_grid = -1;                                // tracklet whose grid s_grid holds
     while (fa < F && frame_pt_off[fa] < p1) {       // one run = consecutive frames of ONE tracklet
       __syncthreads();                              // the previous run's shared state is no longer read
       const int t = frame_trk[fa];
@@ -495,7 +494,8 @@ k_crop_voxelize(int64_t F, int64_t P, const occb200_pose_t *__restrict__ poses, 
       const int nfr = (int)(fb - fa);
       if (redo_pass) {
         if (threadIdx.x == 0) s_grid = grids[t];
-      } else {
+      } else if (t != t_grid) {                     // a chunk rarely leaves its tracklet: the grid is derived once
+        t_grid = t;
         float sz[3] = {-INFINITY, -INFINITY, -INFINITY};
         for (int64_t f = f0 + threadIdx.x; f < f1; f += kFrameThreads)
           if (frame_pt_off[f + 1] > frame_pt_off[f])   // a frame without candidates cannot be a kept frame
@@ -1994,8 +1994,11 @@ extern "C" int occb200_annotate_batch(const occb200_annotate_args_t *a, int64_t 
   }
   if (a->F > 0 && a->n_points > 0) {
     ProfScope ps(kProfCrop, stream);
-    k_crop_voxelize<<<(unsigned)ceil_div(a->n_points, kCropChunk), kFrameThreads, 4 * smem_words, stream>>>(
-        a->F, a->n_points, a->poses, a->points, a->point_stride, a->frame_pt_off, a->trk_frame_off, a->label_off, a->frame_trk,
+    // about one CTA per resident slot (148 SMs x OCC_FMINB): a second, partly filled wave would be the kernel's tail
+    const int crop_chunk = (int)std::min<int64_t>(
+        kCropChunkMax, align_up(std::max<int64_t>(ceil_div(a->n_points, (int64_t)kNumSMs * OCC_FMINB), 1), kCropChunkMin));
+    k_crop_voxelize<<<(unsigned)ceil_div(a->n_points, crop_chunk), kFrameThreads, 4 * smem_words, stream>>>(
+        a->F, a->n_points, crop_chunk, a->poses, a->points, a->point_stride, a->frame_pt_off, a->trk_frame_off, a->label_off, a->frame_trk,
         w.frame_kept, w.trk_flags, w.grids, w.bits, vsf, inv_vs, nullptr, nullptr, smem_words);
     OCC_KERNEL_OK("k_crop_voxelize");
   }
@@ -2015,7 +2018,7 @@ extern "C" int occb200_annotate_batch(const occb200_annotate_args_t *a, int64_t 
         rs = side->stream;
       }
       k_crop_voxelize<<<(unsigned)std::min<int64_t>(a->F, kNumSMs * 2), kFrameThreads, 4 * smem_words, rs>>>(
-          a->F, a->n_points, a->poses, a->points, a->point_stride, a->frame_pt_off, a->trk_frame_off, a->label_off, a->frame_trk,
+          a->F, a->n_points, 0, a->poses, a->points, a->point_stride, a->frame_pt_off, a->trk_frame_off, a->label_off, a->frame_trk,
           w.frame_kept, w.trk_flags, w.grids, w.bits, vsf, inv_vs, w.redo_list, w.counter + 2, smem_words);
       OCC_KERNEL_OK("k_crop_voxelize(redo)");
       if (fast) OCC_CUDA(cudaEventRecord(side->join, side->stream));
