@@ -165,6 +165,26 @@ def workload_config(name, batch, T=None):
             "frames": B, "lidars": L, "voxel_size": batch.voxel_size}
 
 
+def full_config(name, T, B, L, voxel_size, world, args):
+    """The config both arms print (the reference arm echoes the CUDA arm's keys so that the two lines describe the
+    same workload key for key)."""
+    cfg = {"workload": WORKLOADS[name], "tracklets_per_step": int(T), "frames": int(B), "lidars": int(L),
+           "voxel_size": float(voxel_size)}
+    if name == "c5":
+        cfg.update({"segments": (int(T) + JOB_PER_SEGMENT - 1) // JOB_PER_SEGMENT,
+                    "sharding": "by segment, LPT (dist.shard_indices)", "batch_segments": args.batch_segments,
+                    "final_gather": "inside the timed step (uint8 labels, device to device)",
+                    "l2": "not flushed: every rank's inputs per step exceed L2 many times over",
+                    "launch": "kernel by kernel" if args.no_graph else "cuda graph replay per batch"})
+    else:
+        cfg.update({"l2": "flushed (256 MiB write) between timed steps",
+                    "visibility": "f64" if args.force_f64 else "default",
+                    "labels": "uint8 on the device (int32 at the file boundary)",
+                    "launch": "kernel by kernel" if args.no_graph else "cuda graph replay",
+                    "parallelism": "one batch of this shape per GPU" if world > 1 else "1 GPU"})
+    return cfg
+
+
 # ------------------------------------------------------------------------------------------------
 def cpu_port(batch, threads, min_seconds=8.0, max_reps=3):
     """Time the CPU oracle port on the whole batch with `threads` OpenMP threads (packing excluded)."""
@@ -228,11 +248,11 @@ def run_reference(args):
     ws = workload_stats(res, B, L)
     T = len(batch.tracklets)
     val = T / dt
-    cfg = workload_config(name, batch, T_cfg)
+    cfg = full_config(name, T_cfg, B, L, batch.voxel_size, args.gpus, args)
     line = {"impl": "reference", "metric": "tracklets_per_s", "value": val, "unit": "tracklets/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3 * (T_cfg / T), "higher_is_better": True,
             "scaling": "weak" if name != "c5" else "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": cfg, "voxel_steps_per_s": ws["steps"] / dt,
+            "config": cfg, "ok_tracklets_in_sample": ws["ok"], "voxel_steps_per_s": ws["steps"] / dt,
             "cpu_baseline": {"value": val, "unit": "tracklets/s", "cores": threads, "kind": "port",
                              "sample": sample + f", {steps} steps, OpenMP over tracklets"},
             "e2e": {"value": val, "unit": "tracklets/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -448,6 +468,7 @@ def run_job(ctx, n_tracklets, steps, warmup, peak, peak_src, with_e2e=True, pari
     nseg = (n_tracklets + JOB_PER_SEGMENT - 1) // JOB_PER_SEGMENT
     seg_cost = [float(min(JOB_PER_SEGMENT, n_tracklets - i * JOB_PER_SEGMENT)) for i in range(nseg)]
     mine = occ_dist.shard_indices(seg_cost, world)[rank]
+    synth.set_threads(max(1, (os.cpu_count() or 1) // world))
     t0 = time.perf_counter()
     full = synth.make_batch(n_tracklets, 40, 0.2, "vehicle", 0, tracklets_per_segment=JOB_PER_SEGMENT,
                             only_segments=mine)
@@ -627,12 +648,7 @@ def main():
             line = {"metric": "tracklets_per_s", "value": rec["value"], "unit": "tracklets/s", "n_gpus": world,
                     "steps": args.steps, "warmup": args.warmup, "ms_per_step": rec["ms_per_step"], "higher_is_better": True,
                     "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                    "config": {"workload": WORKLOADS["c5"], "tracklets_per_step": rec["tracklets"], "frames": 40, "lidars": 5,
-                               "voxel_size": 0.2, "segments": rec["segments"],
-                               "sharding": "by segment, LPT (dist.shard_indices)", "batch_segments": rec["batch_segments"],
-                               "final_gather": "inside the timed step (uint8 labels, device to device)",
-                               "l2": "not flushed: every rank's inputs per step exceed L2 many times over",
-                               "launch": "cuda graph replay per batch" if ctx.use_graph else "kernel by kernel"},
+                    "config": full_config("c5", rec["tracklets"], 40, 5, 0.2, world, args),
                     "voxel_steps_per_s": rec["voxel_steps_per_s"], "executed_steps_per_s": rec["executed_steps_per_s"],
                     "e2e": rec.get("e2e"), "gpu_launches": launches,
                     "roofline": {"bound": "hbm", "kernel": "k_brick_cull + k_visibility (the ray-cast)", "unit": "GB/s",
@@ -726,12 +742,7 @@ def main():
                "sample": f"full {name} batch ({T} tracklets), best of {reps}, OpenMP over tracklets, "
                          f"C port of the reference path; labels vs GPU: {mism} mismatches (asserted)",
                "voxel_steps_per_s": ws["steps"] / dt}
-    cfg = workload_config(name, batch)
-    cfg.update({"ok_tracklets": ws["ok"], "l2": "flushed (256 MiB write) between timed steps",
-                "visibility": "f64" if args.force_f64 else "default",
-                "labels": "uint8 on the device (int32 at the file boundary)",
-                "launch": "cuda graph replay" if ctx.use_graph else "kernel by kernel",
-                "parallelism": "one batch of this shape per GPU" if world > 1 else "1 GPU"})
+    cfg = full_config(name, T, m["B"], m["L"], batch.voxel_size, world, args)
     line = {
         "metric": "tracklets_per_s", "value": T_all / sec, "unit": "tracklets/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
@@ -739,6 +750,7 @@ def main():
         "voxel_steps_per_s": steps_all / sec, "executed_steps_per_s": exec_all / sec,
         "voxel_steps_per_step": ws["steps"], "executed_steps_per_step": ws["executed"],
         "f64_rechecks_per_step": m["n_recheck"], "unknown_voxels_per_step": ws["U"], "voxels_per_step": ws["V"],
+        "ok_tracklets": ws["ok"],
         "e2e": {"value": T_all / sec_e2e, "unit": "tracklets/s", "h2d_bytes_per_step": host.nbytes(),
                 "d2h_bytes_per_step": sum(h.numel() * h.element_size() for h in out_host.values()),
                 "ms_per_step": sec_e2e * 1e3, "pack_ms": m["pack_ms"], "api_one_shot_ms": api_ms},

@@ -7,6 +7,7 @@
  * compiled with -ffp-contract=off, so both generators produce the same bits (tests/test_synth_fast.py).
  */
 #include <math.h>
+#include <omp.h>
 #include <stdint.h>
 #include <string.h>
 
@@ -154,3 +155,6 @@ void synth_repeat(const double *base, double *dst, int64_t n, int B) {
 #pragma omp parallel for schedule(static)
   for (int b = 0; b < B; ++b) memcpy(dst + (int64_t)b * n, base, (size_t)n * sizeof(double));
 }
+
+/* torchrun exports OMP_NUM_THREADS=1 to every rank: the generator takes its share of the host cores explicitly */
+void synth_set_threads(int n) { omp_set_num_threads(n > 0 ? n : 1); }

@@ -368,8 +368,17 @@ def fast_lib():
             L.synth_f64_to_f32.restype = None
             L.synth_repeat.argtypes = [vp, vp, C.c_int64, C.c_int]
             L.synth_repeat.restype = None
+            L.synth_set_threads.argtypes = [C.c_int]
+            L.synth_set_threads.restype = None
             _SYNTH_LIB = L
     return _SYNTH_LIB or None
+
+
+def set_threads(n: int) -> None:
+    """OpenMP threads of the C pixel loops (torchrun pins OMP_NUM_THREADS=1 for every rank)."""
+    L = fast_lib()
+    if L is not None:
+        L.synth_set_threads(int(n))
 
 
 class _FastRenderer:
