@@ -1720,12 +1720,16 @@ __device__ __forceinline__ unsigned run_pairs(const VisArgs &a, int t, const Trk
 //   lane; otherwise the undecided voxels are dealt one per lane (dense lanes).
 // Labels are written afterwards by k_labels from the occupancy and free bitsets.
 __global__ void __launch_bounds__(32 * kFastWarps, OCC_MINB) k_visibility(const VisArgs a) {
-  // Work assignment is STATIC: the per-slice lists are walked as one sequence (slice 0 first), warp w of the grid
-  // takes items w, w + W, w + 2W, ...  (A global ticket per item was measured at 2.6 us per atomicAdd with 4 736
-  // warps on the counter -- 37 % of the kernel; neighbouring warps now also get neighbouring bricks of one
-  // tracklet, which share their pair records in L1.)
+  // Work assignment: the per-slice lists are walked as one sequence (slice 0 first) in rounds of W = 8 x gridDim
+  // items; CTA c owns items [c*8, c*8 + 8) of every round and its 8 warps draw them from a SHARED-MEMORY ticket, so
+  // a warp that finishes early takes the CTA's next item instead of idling (a static item per warp left the
+  // longest warp as the kernel's tail on small batches; a global ticket per item was measured at 2.6 us per
+  // atomicAdd with 4 736 warps on one counter).  Neighbouring warps get neighbouring bricks of one tracklet, which
+  // share their pair records and pixel windows in L1.
   __shared__ long long s_base[kMaxSlices + 1];
+  __shared__ unsigned s_ticket;
   if (threadIdx.x < a.n_slices) s_base[threadIdx.x + 1] = (long long)a.counter[8 + 2 * threadIdx.x];
+  if (threadIdx.x == 0) s_ticket = 0u;
   __syncthreads();
   if (threadIdx.x == 0) {
     s_base[0] = 0;
@@ -1734,9 +1738,18 @@ __global__ void __launch_bounds__(32 * kFastWarps, OCC_MINB) k_visibility(const 
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const long long n_items = s_base[a.n_slices];
-  const long long n_warps = (long long)gridDim.x * kFastWarps;
+  const long long round_items = (long long)gridDim.x * kFastWarps;
   int s = 0;
-  for (long long g = (long long)blockIdx.x * kFastWarps + (threadIdx.x >> 5); g < n_items; g += n_warps) {
+  for (;;) {
+    unsigned tk = 0u;
+    if (lane == 0) tk = atomicAdd(&s_ticket, 1u);
+    tk = __shfl_sync(0xffffffffu, tk, 0);
+    const long long g = (long long)(tk / kFastWarps) * round_items + (long long)blockIdx.x * kFastWarps + (tk % kFastWarps);
+    if (g >= n_items) {
+      if ((long long)(tk / kFastWarps) * round_items + (long long)blockIdx.x * kFastWarps >= n_items) break;   // round is past the end
+      continue;                                                  // this slot of the last round is empty
+    }
+    s = 0;
     while (g >= s_base[s + 1]) ++s;
     const long long item = g - s_base[s];
     const int2 *items = a.item_map + (long long)s * a.bricks_total;
