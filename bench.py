@@ -155,7 +155,7 @@ def workload_stats(res, B, L):
                 ok=len(ok))
 
 
-KERNEL_KINDS = ("k_crop_voxelize", "k_tracklet_setup+redo", "k_scan_chunks", "k_brick_cull", "k_visibility",
+KERNEL_KINDS = ("k_crop_voxelize", "k_tracklet_setup (f64 path) / side: redo crop pass", "k_scan_chunks", "k_brick_cull", "k_visibility",
                 "side:k_pyr_build+k_table_setup", "k_visibility_recheck", "k_pair_build", "k_labels")
 
 

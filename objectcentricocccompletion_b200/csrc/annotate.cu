@@ -61,8 +61,6 @@ constexpr int kLutPerRow = 64;           // lookup-table cells reserved per incl
 constexpr int kTileR = 8, kTileC = 32;   // range-image max-pyramid tile (rows x columns): pair-level cull
 constexpr int kFineR = 2, kFineC = 8;    // second pyramid level: brick-level cull; 16 fine tiles per coarse tile
 constexpr int kBrick = 4;                // brick edge in voxels: 64 voxels = 2 per lane of one warp
-constexpr int kMinChunk = 8, kMaxChunk = 32;   // bricks per work item of k_visibility (one CTA: the 8 warps share the
-                                               // slice's pair records in shared memory)
 #ifndef OCC_FT
 #define OCC_FT 256
 #endif
@@ -157,7 +155,7 @@ struct Workspace {
   // ---- zeroed by ONE memset at the start of every call
   char *zero_begin;
   unsigned long long *counter;   // [0] f64-path ticket, [1] recheck-queue length, [2] redo frames,
-                                 // [8 + 2s] brick items of slice s, [9 + 2s] work items (brick chunks) of slice s
+                                 // [8 + 2s] brick items of slice s
   int32_t *trk_flags;    // [T] flags of the crop kernel (bit0 kept a point, bit1 index error)
   int32_t *frame_kept;   // [F] 1: the frame has an in-box point (set by the crop CTAs that see one)
   uint32_t *bits;        // occupancy bitsets, linear voxel order, tracklet t at label_off[t]/32 + t
@@ -175,9 +173,6 @@ struct Workspace {
   PairHot *pairs_c;      // [F*L] the non-culled pairs of each tracklet, compacted at trk_frame_off[t] * L
   TrkHot *hot;           // [T]
   int2 *item_map;        // [n_slices * bricks] brick items of slice s at s * bricks: (tracklet, bx | by << 10 | bz << 20)
-  int4 *sitems;          // [n_slices * sitem_cap] work items of k_visibility, slice s at s * sitem_cap:
-                         // (tracklet, slice, first brick, bricks) -- up to kMaxChunk consecutive bricks of one tracklet
-  int64_t sitem_cap;
   int64_t bricks;        // brick_off[T]
   int32_t mask_words;    // ceil(max_pairs / 32)
   int32_t n_slices;      // ceil(max_pairs / kPairsPerItem)
@@ -222,8 +217,6 @@ static int64_t ws_layout(int32_t T, int64_t F, int64_t total, int64_t SF, int32_
   int64_t o_py = take(4 * pyr_tiles);
   int64_t o_py2 = take(4 * 16 * pyr_tiles);
   int64_t o_im = take(8 * (int64_t)n_slices * std::max<int64_t>(bricks, 1));
-  const int64_t sitem_cap = bricks / kMinChunk + T + 1;
-  int64_t o_si = take(16 * (int64_t)n_slices * sitem_cap);
   (void)SF;
   if (w) {
     w->grids = (TrkGrid *)(base + o_grid);
@@ -247,8 +240,6 @@ static int64_t ws_layout(int32_t T, int64_t F, int64_t total, int64_t SF, int32_
     w->pairs_c = (PairHot *)(base + o_pc);
     w->hot = (TrkHot *)(base + o_na);
     w->item_map = (int2 *)(base + o_im);
-    w->sitems = (int4 *)(base + o_si);
-    w->sitem_cap = sitem_cap;
     w->bricks = bricks;
     w->mask_words = mask_words;
     w->n_slices = n_slices;
@@ -638,18 +629,15 @@ k_frame_points(const occb200_pose_t *__restrict__ poses, const float *__restrict
 
 // One warp per tracklet: the grid the crop kernel assumed (size = max over the frames with candidate points) against
 // the true one (max over KEPT frames, occ_annotate.py:111-112, :132-133, box_mode="max"); writes grids[t], dims,
-// sizes, the first status, and zeroes the per-tracklet counters of the call.
-__global__ void __launch_bounds__(256)
-k_tracklet_setup(int T, const int64_t *__restrict__ trk_frame_off, const occb200_pose_t *__restrict__ poses,
-                 const int64_t *__restrict__ frame_pt_off, const int32_t *__restrict__ frame_kept,
-                 const int64_t *__restrict__ label_off, float vsf, float inv_vs, int chunk,
-                 TrkGrid *__restrict__ grids, uint32_t *__restrict__ bits, int32_t *__restrict__ trk_flags,
-                 int32_t *__restrict__ redo_list, unsigned long long *__restrict__ redo_count,
-                 int32_t *__restrict__ dims_out, float *__restrict__ sizes_out, int32_t *__restrict__ status_out,
-                 int64_t *__restrict__ n_unknown, int64_t *__restrict__ n_steps) {
-  const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);   // one warp per tracklet
-  const int lane = threadIdx.x & 31;
-  if (t >= T) return;
+// sizes, the first status, and zeroes the per-tracklet counters of the call.  Returns the tracklet's grid (every lane).
+__device__ __forceinline__ TrkGrid
+tracklet_setup_warp(int t, int lane, const int64_t *__restrict__ trk_frame_off, const occb200_pose_t *__restrict__ poses,
+                    const int64_t *__restrict__ frame_pt_off, const int32_t *__restrict__ frame_kept,
+                    const int64_t *__restrict__ label_off, float vsf, float inv_vs, int chunk,
+                    TrkGrid *__restrict__ grids, uint32_t *__restrict__ bits, int32_t *__restrict__ trk_flags,
+                    int32_t *__restrict__ redo_list, unsigned long long *__restrict__ redo_count,
+                    int32_t *__restrict__ dims_out, float *__restrict__ sizes_out, int32_t *__restrict__ status_out,
+                    int64_t *__restrict__ n_unknown, int64_t *__restrict__ n_steps) {
   const int64_t f0 = trk_frame_off[t], f1 = trk_frame_off[t + 1];
   float sz[3] = {-INFINITY, -INFINITY, -INFINITY}, sz_all[3] = {-INFINITY, -INFINITY, -INFINITY};
   int kept = 0;
@@ -701,15 +689,32 @@ k_tracklet_setup(int T, const int64_t *__restrict__ trk_frame_off, const occb200
       }
     }
   }
-  if (lane != 0) return;
-  grids[t] = g;
-  for (int k = 0; k < 3; ++k) {
-    dims_out[3 * t + k] = g.dims[k];
-    sizes_out[3 * t + k] = (g.status == OCCB200_OK) ? sz[k] : 0.f;
+  if (lane == 0) {
+    grids[t] = g;
+    for (int k = 0; k < 3; ++k) {
+      dims_out[3 * t + k] = g.dims[k];
+      sizes_out[3 * t + k] = (g.status == OCCB200_OK) ? sz[k] : 0.f;
+    }
+    status_out[t] = g.status;                    // refined by k_pair_build / k_labels (flags)
+    n_unknown[t] = 0;
+    if (n_steps) n_steps[t] = 0;
   }
-  status_out[t] = g.status;                    // refined by k_pair_build / k_labels (flags)
-  n_unknown[t] = 0;
-  if (n_steps) n_steps[t] = 0;
+  return g;
+}
+
+// The set-up as a kernel of its own: the all-f64 path (flag bit 0); the fast path runs it as k_pair_build's prologue.
+__global__ void __launch_bounds__(256)
+k_tracklet_setup(int T, const int64_t *__restrict__ trk_frame_off, const occb200_pose_t *__restrict__ poses,
+                 const int64_t *__restrict__ frame_pt_off, const int32_t *__restrict__ frame_kept,
+                 const int64_t *__restrict__ label_off, float vsf, float inv_vs, int chunk,
+                 TrkGrid *__restrict__ grids, uint32_t *__restrict__ bits, int32_t *__restrict__ trk_flags,
+                 int32_t *__restrict__ redo_list, unsigned long long *__restrict__ redo_count,
+                 int32_t *__restrict__ dims_out, float *__restrict__ sizes_out, int32_t *__restrict__ status_out,
+                 int64_t *__restrict__ n_unknown, int64_t *__restrict__ n_steps) {
+  const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);   // one warp per tracklet
+  if (t >= T) return;
+  tracklet_setup_warp(t, threadIdx.x & 31, trk_frame_off, poses, frame_pt_off, frame_kept, label_off, vsf, inv_vs, chunk,
+                      grids, bits, trk_flags, redo_list, redo_count, dims_out, sizes_out, status_out, n_unknown, n_steps);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1260,27 +1265,47 @@ __device__ __forceinline__ int bricks_of(int n) { return (n + kBrick - 1) / kBri
 // thread 0 fixes the final status and writes the tracklet's hot record; all threads then emit the work items:
 // one per (slice of kPairsPerItem pairs, brick), appended to the slice's own list (the kernels walk the lists
 // slice by slice, so the pairs that free most voxels are tested first, on every brick of the batch).
+struct SetupArgs {               // what k_pair_build's set-up prologue needs (see tracklet_setup_warp)
+  const int64_t *frame_pt_off;
+  const int32_t *frame_kept;
+  const int64_t *label_off;
+  float vsf, inv_vs;
+  uint32_t *bits;
+  int32_t *redo_list;
+  unsigned long long *redo_count;
+  int32_t *dims_out;
+  float *sizes_out;
+  int64_t *n_unknown;
+  int64_t *n_steps;
+};
+
 __global__ void __launch_bounds__(256)
-k_pair_build(int T, int L, const int64_t *__restrict__ trk_frame_off, const int64_t *__restrict__ brick_off,
-             const TrkGrid *__restrict__ grids, const int32_t *__restrict__ trk_flags,
+k_pair_build(int T, int L, const SetupArgs su, const int64_t *__restrict__ trk_frame_off,
+             const int64_t *__restrict__ brick_off, TrkGrid *__restrict__ grids, int32_t *__restrict__ trk_flags,
              const occb200_pose_t *__restrict__ poses, const int32_t *__restrict__ frame_sf,
              const occb200_sensor_t *__restrict__ sensors, const TabCoef *__restrict__ tabcoef,
              const LutCell *__restrict__ lut_pool, double vs, const int64_t *__restrict__ pyr_off,
              const float *__restrict__ pyr, int cull_on, PairHot *__restrict__ pairs_c, TrkHot *__restrict__ hot,
-             int2 *__restrict__ item_map, long long bricks_total, int n_slices, int4 *__restrict__ sitems,
-             long long sitem_cap, int chunk, unsigned long long *__restrict__ counter,
-             int32_t *__restrict__ status_out) {
-  __shared__ long long s_i0[kMaxSlices], s_j0[kMaxSlices];
+             int2 *__restrict__ item_map, long long bricks_total, int n_slices,
+             unsigned long long *__restrict__ counter, int32_t *__restrict__ status_out) {
+  __shared__ long long s_i0[kMaxSlices];
   __shared__ int s_cnt[8];
-  __shared__ int s_status;
+  __shared__ TrkGrid s_g;
   const int t = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const TrkGrid g = grids[t];
+  if (warp == 0) {                                  // the tracklet's set-up (true grid, redo list, first status)
+    const TrkGrid g0 = tracklet_setup_warp(t, lane, trk_frame_off, poses, su.frame_pt_off, su.frame_kept, su.label_off,
+                                           su.vsf, su.inv_vs, 32, grids, su.bits, trk_flags, su.redo_list, su.redo_count,
+                                           su.dims_out, su.sizes_out, status_out, su.n_unknown, su.n_steps);
+    if (lane == 0) s_g = g0;
+  }
+  __syncthreads();
+  const TrkGrid g = s_g;
   // the flags of a tracklet whose grid was right the first time are final; those of a corrected one are still
   // being rewritten by the redo pass (side stream) -- it is treated as OK here and k_labels folds its flags in
   int status = g.status;
   if (status == OCCB200_OK && !g.redo) {
-    const int fl = trk_flags[t];
+    const int fl = g.flags;
     if (fl & 2) status = OCCB200_INDEX_ERROR;
     else if (!(fl & 1)) status = OCCB200_EMPTY_AFTER_FILTER;
   }
@@ -1333,18 +1358,9 @@ k_pair_build(int T, int L, const int64_t *__restrict__ trk_frame_off, const int6
     hot[t] = h;
     status_out[t] = status;
   }
-  const int nchunk = (int)((nbricks + chunk - 1) / chunk);
-  for (int s = threadIdx.x; s < nslice; s += blockDim.x) {
+  for (int s = threadIdx.x; s < nslice; s += blockDim.x)
     s_i0[s] = (long long)atomicAdd(counter + 8 + 2 * s, (unsigned long long)nbricks);
-    s_j0[s] = (long long)atomicAdd(counter + 9 + 2 * s, (unsigned long long)nchunk);
-  }
   __syncthreads();
-  for (int i = threadIdx.x; i < nchunk * nslice; i += blockDim.x) {
-    const int s = i / nchunk, c = i - s * nchunk;
-    const long long slot = s_j0[s] + c;
-    if (slot < sitem_cap)                            // always true: sitem_cap >= bricks / kMinChunk + T
-      sitems[(long long)s * sitem_cap + slot] = make_int4(t, s, c * chunk, (int)min((long long)chunk, nbricks - (long long)c * chunk));
-  }
   const int nyz = nby * nbz;
   for (long long i = threadIdx.x; i < nbricks * nslice; i += blockDim.x) {
     const int s = (int)(i / nbricks);
@@ -2015,29 +2031,23 @@ extern "C" int occb200_annotate_batch(const occb200_annotate_args_t *a, int64_t 
         w.frame_kept, w.trk_flags, w.grids, w.bits, vsf, inv_vs, nullptr, nullptr, smem_words);
     OCC_KERNEL_OK("k_crop_voxelize");
   }
-  {
-    ProfScope ps(kProfSetup, stream);
-    k_tracklet_setup<<<(unsigned)ceil_div(a->T, 8), 256, 0, stream>>>(
-        a->T, a->trk_frame_off, a->poses, a->frame_pt_off, w.frame_kept, a->label_off, vsf, inv_vs, chunk, w.grids,
-        w.bits, w.trk_flags, w.redo_list, w.counter + 2, a->dims, a->sizes, a->status, a->n_unknown, a->n_steps);
-    OCC_KERNEL_OK("k_tracklet_setup");
-    if (a->F > 0) {   // frames of corrected tracklets only (device-side list, usually short); in the fast path
-                      // this runs on the side stream, next to k_pair_build, and joins before the ray-cast
-      cudaStream_t rs = stream;
-      if (fast) {
-        OCC_CUDA(cudaStreamWaitEvent(stream, side->join, 0));      // the side stream is idle from here on
-        OCC_CUDA(cudaEventRecord(side->fork, stream));
-        OCC_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
-        rs = side->stream;
-      }
-      k_crop_voxelize<<<(unsigned)std::min<int64_t>(a->F, kNumSMs * 2), kFrameThreads, 4 * smem_words, rs>>>(
-          a->F, a->n_points, 0, a->poses, a->points, a->point_stride, a->frame_pt_off, a->trk_frame_off, a->label_off, a->frame_trk,
-          w.frame_kept, w.trk_flags, w.grids, w.bits, vsf, inv_vs, w.redo_list, w.counter + 2, smem_words);
-      OCC_KERNEL_OK("k_crop_voxelize(redo)");
-      if (fast) OCC_CUDA(cudaEventRecord(side->join, side->stream));
-    }
-  }
+  // the redo pass: frames of corrected tracklets only (device-side list, usually short)
+  auto launch_redo = [&](cudaStream_t rs) -> int {
+    k_crop_voxelize<<<(unsigned)std::min<int64_t>(a->F, kNumSMs * 2), kFrameThreads, 4 * smem_words, rs>>>(
+        a->F, a->n_points, 0, a->poses, a->points, a->point_stride, a->frame_pt_off, a->trk_frame_off, a->label_off, a->frame_trk,
+        w.frame_kept, w.trk_flags, w.grids, w.bits, vsf, inv_vs, w.redo_list, w.counter + 2, smem_words);
+    OCC_KERNEL_OK("k_crop_voxelize(redo)");
+    return 0;
+  };
   if (f64_only) {
+    {
+      ProfScope ps(kProfSetup, stream);
+      k_tracklet_setup<<<(unsigned)ceil_div(a->T, 8), 256, 0, stream>>>(
+          a->T, a->trk_frame_off, a->poses, a->frame_pt_off, w.frame_kept, a->label_off, vsf, inv_vs, chunk, w.grids,
+          w.bits, w.trk_flags, w.redo_list, w.counter + 2, a->dims, a->sizes, a->status, a->n_unknown, a->n_steps);
+      OCC_KERNEL_OK("k_tracklet_setup");
+      if (a->F > 0 && launch_redo(stream)) return 1;
+    }
     {
       ProfScope ps(kProfScan, stream);
       k_scan_chunks<<<1, 1024, 0, stream>>>(a->T, w.grids, w.chunk_off);
@@ -2053,22 +2063,33 @@ extern "C" int occb200_annotate_batch(const occb200_annotate_args_t *a, int64_t 
     OCC_KERNEL_OK("k_visibility_f64");
     return 0;
   }
-  if (!fast) {                                      // no tracklet-frames at all: statuses are final, nothing to label
+  if (!fast) {                                      // no tracklet-frames at all: only the statuses are due
+    k_tracklet_setup<<<(unsigned)ceil_div(a->T, 8), 256, 0, stream>>>(
+        a->T, a->trk_frame_off, a->poses, a->frame_pt_off, w.frame_kept, a->label_off, vsf, inv_vs, chunk, w.grids,
+        w.bits, w.trk_flags, w.redo_list, w.counter + 2, a->dims, a->sizes, a->status, a->n_unknown, a->n_steps);
+    OCC_KERNEL_OK("k_tracklet_setup");
     return 0;
   }
-  // bricks per work item of k_visibility: large chunks amortise the staging of the pair records, small ones keep
-  // every SM busy on a small batch (about half of the nominal pairs survive the pair cull)
-  const int64_t est_items = w.bricks * std::max<int64_t>(1, std::min<int64_t>(w.n_slices, (a->max_pairs / 2 + kPairsPerItem - 1) / kPairsPerItem));
-  const int vis_chunk = est_items / 32 >= (int64_t)kNumSMs * OCC_MINB * 4 ? 32
-                        : est_items / 16 >= (int64_t)kNumSMs * OCC_MINB * 2 ? 16 : kMinChunk;
+  OCC_CUDA(cudaStreamWaitEvent(stream, side->join, 0));          // tables and pyramid are ready
   {
+    // the tracklet set-up runs as the prologue of each tracklet's CTA (one launch and one dependency level fewer)
     ProfScope ps(kProfPairBuild, stream);
-    k_pair_build<<<(unsigned)a->T, 256, 0, stream>>>(a->T, a->L, a->trk_frame_off, a->brick_off, w.grids, w.trk_flags,
+    SetupArgs su;
+    su.frame_pt_off = a->frame_pt_off; su.frame_kept = w.frame_kept; su.label_off = a->label_off;
+    su.vsf = vsf; su.inv_vs = inv_vs; su.bits = w.bits; su.redo_list = w.redo_list; su.redo_count = w.counter + 2;
+    su.dims_out = a->dims; su.sizes_out = a->sizes; su.n_unknown = a->n_unknown; su.n_steps = a->n_steps;
+    k_pair_build<<<(unsigned)a->T, 256, 0, stream>>>(a->T, a->L, su, a->trk_frame_off, a->brick_off, w.grids, w.trk_flags,
                                                      a->poses, a->frame_sf, a->sensors, w.tabcoef, w.lut_pool,
                                                      a->voxel_size, a->pyr_off, w.pyr, cull ? 1 : 0, w.pairs_c, w.hot,
-                                                     w.item_map, (long long)w.bricks, w.n_slices, w.sitems,
-                                                     (long long)w.sitem_cap, vis_chunk, w.counter, a->status);
+                                                     w.item_map, (long long)w.bricks, w.n_slices, w.counter, a->status);
     OCC_KERNEL_OK("k_pair_build");
+  }
+  {   // the redo pass runs on the side stream, next to k_brick_cull, and joins before the ray-cast
+    OCC_CUDA(cudaEventRecord(side->fork, stream));
+    OCC_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
+    ProfScope ps(kProfSetup, side->stream);
+    if (launch_redo(side->stream)) return 1;
+    OCC_CUDA(cudaEventRecord(side->join, side->stream));
   }
   if (brick_cull && w.bricks > 0) {
     ProfScope ps(kProfBrickCull, stream);
