@@ -562,14 +562,15 @@ k_crop_voxelize(int64_t F, int64_t P, int chunk, const occb200_pose_t *__restric
             const uint32_t cur = use_smem ? s_bits[word] : __ldg(gbits + word);
             if (cur & bit) word = -1;
           }
-          // warp-level dedup of what is left: lanes on the same bitset word merge their bits, one atomic per word
-          if (__any_sync(0xffffffffu, word >= 0)) {
+          if (use_smem) {
+            // shared-memory bitset: a plain atomic per NEW bit (the look above has removed most points; a warp-level
+            // match_any dedup in front of it cost ~80 instructions per point -- its loop runs once per distinct word)
+            if (word >= 0) atomicOr(&s_bits[word], bit);
+          } else if (__any_sync(0xffffffffu, word >= 0)) {
+            // global bitset (grids beyond the shared-memory limit): lanes on the same word merge their bits first
             const unsigned peers = __match_any_sync(0xffffffffu, word);
             const uint32_t merged = __reduce_or_sync(peers, word >= 0 ? bit : 0u);
-            if (word >= 0 && lane == __ffs(peers) - 1) {
-              if (use_smem) atomicOr(&s_bits[word], merged);
-              else atomicOr(&gbits[word], merged);
-            }
+            if (word >= 0 && lane == __ffs(peers) - 1) atomicOr(&gbits[word], merged);
           }
         }
       }
@@ -870,29 +871,33 @@ __device__ __forceinline__ double u_of_angle(double a) {
   return s / (fabs(s) + c);
 }
 
-// One CTA per DISTINCT table (the frames of a segment share one table per LiDAR): boundaries, cell geometry,
-// lookup cells.
+// kTabSplit CTAs per DISTINCT table (the frames of a segment share one table per LiDAR): every CTA derives the
+// boundaries and the cell geometry (a few hundred values), CTA y writes the lookup cells k = y*256 + tid (+ stride):
+// one binary search per thread instead of sixteen in sequence.
+constexpr int kTabSplit = 16;
 __global__ void __launch_bounds__(256)
 k_table_setup(int n_tables, const int64_t *__restrict__ table_off, const int32_t *__restrict__ table_H,
               const float *__restrict__ incl_pool, TabCoef *__restrict__ tabcoef, float *__restrict__ ub_pool,
               LutCell *__restrict__ lut_pool) {
   __shared__ float s_min[256];
   __shared__ TabCoef s_tc;
+  extern __shared__ float s_ub[];                 // H - 1 boundaries (this CTA's private copy)
   const int e = blockIdx.x;
   if (e >= n_tables) return;
   const int H = table_H[e];
   const int64_t off = table_off[e];
   const float *tab = incl_pool + off;
-  float *ub = ub_pool + off;                      // H - 1 boundaries
   LutCell *lut = lut_pool + off * kLutPerRow;
-  const bool candidate = H >= 2 && H < 65535 && off < (1ll << 24);
+  (void)ub_pool;
+  const bool candidate = H >= 2 && H < 8192 && off < (1ll << 24);
   float local_min = INFINITY;
   if (candidate)
     for (int h = threadIdx.x; h < H - 1; h += blockDim.x) {
       const double m = 0.5 * ((double)tab[h] + (double)tab[h + 1]);
-      ub[h] = (float)u_of_angle(m);
+      s_ub[h] = (float)u_of_angle(m);
     }
   __syncthreads();
+  const float *ub = s_ub;
   if (candidate) {
     for (int h = threadIdx.x; h < H - 2; h += blockDim.x) local_min = fminf(local_min, ub[h] - ub[h + 1]);
     // the table must stay inside (-90, 90) degrees for u() to be monotone, and descend (tab[h] > tab[h+1]: a
@@ -926,13 +931,13 @@ k_table_setup(int n_tables, const int64_t *__restrict__ table_off, const int32_t
       }
     }
     s_tc = tc;
-    tabcoef[off] = tc;
+    if (blockIdx.y == 0) tabcoef[off] = tc;
   }
   __syncthreads();
   const TabCoef tc = s_tc;
   if (!tc.ok) return;
   const double w = (double)tc.w, inv_w = (double)tc.inv_w, c0 = (double)tc.cell0m;
-  for (int k = threadIdx.x; k < tc.ncell; k += blockDim.x) {
+  for (int k = blockIdx.y * blockDim.x + threadIdx.x; k < tc.ncell; k += gridDim.y * blockDim.x) {
     const double uk = ((double)k - c0) / inv_w;
     int lo = 0, hi = H - 1;                       // count of ub_h > uk (ub descending)
     while (lo < hi) {
@@ -2015,8 +2020,8 @@ extern "C" int occb200_annotate_batch(const occb200_annotate_args_t *a, int64_t 
       OCC_KERNEL_OK("k_pyr_build");
     }
     if (a->n_tables > 0) {
-      k_table_setup<<<(unsigned)a->n_tables, 256, 0, side->stream>>>(a->n_tables, a->table_off, a->table_H,
-                                                                     a->incl_pool, w.tabcoef, w.ub_pool, w.lut_pool);
+      k_table_setup<<<dim3((unsigned)a->n_tables, kTabSplit), 256, 4 * 8192, side->stream>>>(
+          a->n_tables, a->table_off, a->table_H, a->incl_pool, w.tabcoef, w.ub_pool, w.lut_pool);
       OCC_KERNEL_OK("k_table_setup");
     }
     OCC_CUDA(cudaEventRecord(side->join, side->stream));
