@@ -75,6 +75,9 @@ def parse(argv=None):
     ap.add_argument("--also", default="c1,c3,c4,c5", help="N=1: sub-records to add to the line (comma list, 'none')")
     ap.add_argument("--batch-segments", type=int, default=8, help="c5 job: segments per device call")
     ap.add_argument("--job-tracklets", type=int, default=JOB_TRACKLETS, help="c5 job size (tests use a small one)")
+    ap.add_argument("--ri-upload", default="pull", choices=["pull", "host", "whole"],
+                    help="e2e leg: how the range images reach the device (pull: the device fetches the windows it "
+                         "can read from pinned host memory; host: the host gathers them; whole: every image)")
     return ap.parse_args(argv)
 
 
@@ -341,7 +344,7 @@ def measure_resident(ctx, batch, warmup):
     t0 = time.perf_counter()
     pk = occ_annotate.pack_tracklets(batch)
     pack_ms = (time.perf_counter() - t0) * 1e3
-    host = occ_annotate.HostBuffers(pk, pin=True)
+    host = occ_annotate.HostBuffers(pk, pin=True, windows=ctx.args.ri_upload)
     d = occ_annotate.DeviceTracklets(pk, ctx.dev, labels="u8")
     d.upload(host)
     d.run(ctx.flags)
@@ -487,7 +490,7 @@ def run_job(ctx, n_tracklets, steps, warmup, peak, peak_src, with_e2e=True, pari
     labels_u8 = torch.zeros(max(n_local, 1), dtype=torch.uint8, device=dev)
     devs, hosts, off = [], [], 0
     for pk in pks:
-        hosts.append(occ_annotate.HostBuffers(pk, pin=with_e2e))
+        hosts.append(occ_annotate.HostBuffers(pk, pin=with_e2e, windows=ctx.args.ri_upload if with_e2e else True))
         devs.append(occ_annotate.DeviceTracklets(pk, dev, labels="u8",
                                                  labels_u8=labels_u8[off: off + max(pk.total_slots, 1)]))
         off += pk.total_slots
@@ -544,6 +547,9 @@ def run_job(ctx, n_tracklets, steps, warmup, peak, peak_src, with_e2e=True, pari
         streams = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
 
         def e2e_run(n):
+            for d in devs:
+                d.pulled.zero_()
+            torch.cuda.synchronize()
             start = torch.cuda.Event(enable_timing=True)
             start.record()
             for st in streams:
@@ -551,6 +557,8 @@ def run_job(ctx, n_tracklets, steps, warmup, peak, peak_src, with_e2e=True, pari
             k = 0
             for _ in range(n):
                 for d, h, o in zip(devs, hosts, outs):
+                    if h.ri_mode == "host" and k >= len(devs):      # (each batch has its own staging buffer)
+                        h.gather_windows()
                     with torch.cuda.stream(streams[k % 2]):
                         d.upload(h)
                         d.replay(ctx.flags) if ctx.use_graph else d.run(ctx.flags)
@@ -569,7 +577,7 @@ def run_job(ctx, n_tracklets, steps, warmup, peak, peak_src, with_e2e=True, pari
         ctx.barrier()
         ms_e2e = e2e_run(steps)
         ctx.barrier()
-        h2d = sum(h.nbytes() for h in hosts)
+        h2d = sum(h.nbytes() for h in hosts) + sum(d.pulled_bytes() for d in devs) // max(steps, 1)
         d2h = sum(b.numel() * b.element_size() for o in outs for b in o.values())
     # ---- reduce over ranks
     t = torch.tensor([ms, ms_compute, ms_gather, ms_e2e], dtype=torch.float64, device=dev)
@@ -686,16 +694,25 @@ def main():
         d2.capture(ctx.flags)
     out_host2 = {k: torch.empty_like(h).pin_memory() for k, h in out_host.items()}
     pipes = [(torch.cuda.Stream(dev), d, out_host), (torch.cuda.Stream(dev), d2, out_host2)]
+    staged = [torch.cuda.Event(), torch.cuda.Event()]
 
     def e2e_run(n):
+        for _, dd, _ in pipes:
+            dd.pulled.zero_()
+        torch.cuda.synchronize()
         start = torch.cuda.Event(enable_timing=True)
         start.record()
         for st, _, _ in pipes:
             st.wait_event(start)
         for i in range(n):
             st, dd, oh = pipes[i % 2]
+            if host.ri_mode == "host":                  # the host's share of the step: re-read the window blocks
+                if i >= 1:
+                    staged[(i - 1) % 2].synchronize()   # (one staging buffer: the previous upload must have left it)
+                host.gather_windows()
             with torch.cuda.stream(st):
                 dd.upload(host)
+                staged[i % 2].record(st)
                 dd.replay(ctx.flags) if ctx.use_graph else dd.run(ctx.flags)
                 for k, h in oh.items():
                     h.copy_(getattr(dd, k), non_blocking=True)
@@ -711,7 +728,11 @@ def main():
     ctx.barrier()
     ms_e2e = e2e_run(args.steps)
     ctx.barrier()
+    pulled_per_step = sum(dd.pulled_bytes() for _, dd, _ in pipes) / max(args.steps, 1)
     assert all(bool((out_host2[k] == out_host[k]).all()) for k in out_host), "pipelined e2e results differ"
+    # the e2e outputs against the resident run's (whole-pipeline parity of the upload mode in use)
+    res_e2e = d.results()
+    assert count_mismatches(res_e2e, res) == 0, "e2e labels differ from the resident run"
     # the public one-shot call, for scale: pack + allocate + upload from pageable memory + run + download
     t0 = time.perf_counter()
     occ.annotate_batch(batch, flags=ctx.flags)
@@ -751,9 +772,12 @@ def main():
         "voxel_steps_per_step": ws["steps"], "executed_steps_per_step": ws["executed"],
         "f64_rechecks_per_step": m["n_recheck"], "unknown_voxels_per_step": ws["U"], "voxels_per_step": ws["V"],
         "ok_tracklets": ws["ok"],
-        "e2e": {"value": T_all / sec_e2e, "unit": "tracklets/s", "h2d_bytes_per_step": host.nbytes(),
+        "e2e": {"value": T_all / sec_e2e, "unit": "tracklets/s", "h2d_bytes_per_step": int(host.nbytes() + pulled_per_step),
                 "d2h_bytes_per_step": sum(h.numel() * h.element_size() for h in out_host.values()),
-                "ms_per_step": sec_e2e * 1e3, "pack_ms": m["pack_ms"], "api_one_shot_ms": api_ms},
+                "ms_per_step": sec_e2e * 1e3, "pack_ms": m["pack_ms"], "api_one_shot_ms": api_ms,
+                "range_images": {"upload": host.ri_mode, "bytes_per_step": int(pulled_per_step) if host.ri_mode == "pull"
+                                 else int(host.nbytes() - host.small.numel() - sum(t.numel() for _, t in host.pt_parts)),
+                                 "whole_images_bytes": int(4 * pk.ri_len)}},
         "gpu_launches": int(launches),
         "roofline": roofline_record(ws, kms, args.steps, peak, peak_src, ncu_traffic() if name == "c2" else None),
         "cpu_baseline": cpu, "clocks": clocks,

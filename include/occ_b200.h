@@ -367,6 +367,53 @@ int occb200_select_candidates(const float *clouds, int stride, const int64_t *cl
                               const int64_t *frame_box_off, const int64_t *cnt_off, int32_t *counts,
                               const int64_t *prefix, float *out_points, int out_stride, void *stream);
 
+/* ---- windowed upload of the range images (occ_annotate.py:502-533 loads every whole image; the visibility test
+ *      reads a small window of each) ---------------------------------------------------------------------------- */
+
+/* HOST helper.  mask (ceil(ri_len / 16) bytes, zeroed by the caller) receives 1 for every 64-byte block -- floats
+ * [16k, 16k + 16) of ri_pool -- that the visibility test (occ_annotate.py:141-201, 541-547) of any voxel of any
+ * tracklet of the batch can read: per (tracklet-frame, LiDAR) a conservative pixel window derived from the box
+ * (max size over the tracklet's frames), the pose and the sensor entry.  All pointers are HOST arrays in the
+ * layout of occb200_annotate_args_t.  Uploading only the marked blocks (occb200_host_gather_blocks +
+ * occb200_scatter_blocks) into a zero-initialised ri_pool gives the same labels, dims and statuses as uploading
+ * every image; n_steps may differ (the culls see zeros outside the windows). */
+int occb200_host_ri_window_blocks(int32_t T, int32_t L, const int64_t *trk_frame_off, const occb200_pose_t *poses,
+                                  const int32_t *frame_sf, const occb200_sensor_t *sensors, int64_t SF,
+                                  const float *incl_pool, double voxel_size, int64_t ri_len, uint8_t *mask);
+
+/* HOST helper.  staging[16 i .. 16 i + 16) = block block_idx[i] of the pool, read from the source arrays: part j
+ * holds floats [part_off[j], part_off[j] + part_len[j]) of the pool at part_ptr[j].  block_idx ascending;
+ * part_off ascending multiples of 16; floats past a part's end are zero-filled. */
+int occb200_host_gather_blocks(const uint32_t *block_idx, int64_t n_blocks, const int64_t *part_off,
+                               const int64_t *part_len, const float *const *part_ptr, int32_t n_parts,
+                               float *staging);
+
+/* DEVICE.  ri_pool[16 block_idx[i] + j] = blocks[16 i + j], j < 16 (clipped at ri_len): scatters the uploaded
+ * blocks to their place in the dense pool.  blocks and ri_pool 16-byte aligned.  Asynchronous on `stream`. */
+int occb200_scatter_blocks(const float *blocks, const uint32_t *block_idx, int64_t n_blocks, float *ri_pool,
+                           int64_t ri_len, void *stream);
+
+/* The same upload with no host work.  occb200_window_mask_words(ri_len) uint32 of device scratch hold one bit per
+ * 32-byte block (8 floats) of the pool.  occb200_pull_windows marks, ON THE DEVICE, the blocks the visibility test
+ * of the batch can read -- per (tracklet-frame, LiDAR, sub-box of <= 0.8 m of the tracklet's centre box) the pixel
+ * footprint bracketed from the sub-box's 8 corners -- and reads exactly those blocks from `ri_host`: the PINNED
+ * HOST array holding the range images in the layout of ri_pool (a kernel may read pinned host memory under unified
+ * addressing; the traffic crosses PCIe once, without a staging copy), storing them at the same offsets of ri_pool
+ * (device, zero-initialised by the caller once).  `args` supplies the DEVICE metadata of occb200_annotate_batch
+ * (T, L, F, SF, trk_frame_off, poses, frame_sf, sensors, incl_pool, voxel_size); trk_smax f32 [T,3] (device) = the
+ * max box size over all frames of each tracklet.  ri_len % 8 == 0.  *pulled_blocks (device, optional, zeroed by
+ * the caller) accumulates the 32-byte blocks read.  Asynchronous on `stream`. */
+int64_t occb200_window_mask_words(int64_t ri_len);
+/* HOST test hook: the footprint code of occb200_pull_windows compiled for the CPU; mask8 (ri_len / 8 bytes, zeroed by
+ * the caller) receives 1 per marked 32-byte block.  All pointers HOST. */
+int occb200_host_window_mark(int32_t T, int32_t L, const int64_t *trk_frame_off, const occb200_pose_t *poses,
+                             const int32_t *frame_sf, const occb200_sensor_t *sensors, int64_t SF,
+                             const float *incl_pool, const float *trk_smax, double voxel_size, int64_t ri_len,
+                             uint8_t *mask8);
+int occb200_pull_windows(const occb200_annotate_args_t *args, const float *trk_smax, const float *ri_host,
+                         float *ri_pool, int64_t ri_len, uint32_t *mask, unsigned long long *pulled_blocks,
+                         void *stream);
+
 /* HOST helper: fills poses[i] from boxes7 f32 [n,7] and torch-evaluated trig f32 [n,4]
  * (cos(-yaw), sin(-yaw), cos(yaw), sin(yaw)); cos_pib/sin_pib come from the host libm. */
 void occb200_host_pose_pack(const float *boxes7, const float *trig4, int64_t n, occb200_pose_t *poses);

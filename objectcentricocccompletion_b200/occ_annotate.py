@@ -94,6 +94,7 @@ class PackedTracklets:
     ri_len: int
     pt_parts: list                 # [(row offset, f32 [n, stride] array)]
     ri_parts: list                 # [(float offset, f32 [nb, H, W] array)]
+    trk_smax: Optional[np.ndarray] = None    # f32 [T,3] max box size over all frames (the grid's upper bound)
 
     @property
     def total_slots(self) -> int:
@@ -119,7 +120,7 @@ class PackedTracklets:
 
 
 _SMALL_FIELDS = ("trk_frame_off", "poses", "frame_sf", "frame_trk", "frame_pt_off", "sensors", "incl_pool",
-                 "label_off", "brick_off", "pyr_off", "table_off", "table_H")
+                 "label_off", "brick_off", "pyr_off", "table_off", "table_H", "trk_smax")
 
 
 def _same_memory(flat, pieces, n_rows) -> bool:
@@ -132,6 +133,22 @@ def _same_memory(flat, pieces, n_rows) -> bool:
     a0 = flat.__array_interface__["data"][0]
     return (first.__array_interface__["data"][0] == a0 and last.flags.c_contiguous
             and last.__array_interface__["data"][0] + last.nbytes == a0 + flat.nbytes)
+
+
+RI_BLOCK = 16      # floats per block of the windowed range-image upload (csrc/ri_windows.cu)
+
+
+def window_blocks(pk: "PackedTracklets") -> np.ndarray:
+    """The blocks of ``ri_pool`` any visibility test of the batch can read (``occb200_host_ri_window_blocks``)."""
+    nblk = (pk.ri_len + RI_BLOCK - 1) // RI_BLOCK
+    mask = np.zeros(max(nblk, 1), np.uint8)
+    if pk.T and pk.F and nblk:
+        rc = _lib.lib().occb200_host_ri_window_blocks(
+            pk.T, pk.L, pk.trk_frame_off.ctypes.data, pk.poses.ctypes.data, pk.frame_sf.ctypes.data,
+            pk.sensors.ctypes.data, pk.sensors.shape[0], pk.incl_pool.ctypes.data, float(pk.voxel_size),
+            pk.ri_len, mask.ctypes.data)
+        _lib.check(rc, "occb200_host_ri_window_blocks")
+    return np.flatnonzero(mask[:nblk]).astype(np.uint32)
 
 
 def pack_tracklets(batch, pack_override: Optional[dict] = None) -> PackedTracklets:
@@ -172,7 +189,7 @@ def pack_tracklets(batch, pack_override: Optional[dict] = None) -> PackedTrackle
             table_H.append(H)
             ri_parts.append((ri_off, img))
             incl_off += H
-            ri_off += nb * H * W
+            ri_off += -(-(nb * H * W) // RI_BLOCK) * RI_BLOCK      # parts start on block boundaries
     L_ = _lib.lib()
     sn = sensors.reshape(-1)
     tiles = np.zeros(sn.size + 1, np.int64)
@@ -225,9 +242,11 @@ def pack_tracklets(batch, pack_override: Optional[dict] = None) -> PackedTrackle
     # form (torch-CUDA arithmetic, flag bit 5) may round one voxel higher, so the slot takes the larger of the two
     vsf = np.float32(batch.voxel_size)
     caps = np.zeros((T, 3), np.int64)
+    smax = np.zeros((T, 3), np.float32)
     if F:
         nz = nfr > 0
         mx = np.maximum.reduceat(boxes[:, 3:6], trk_frame_off[:-1][nz], axis=0)
+        smax[nz] = mx
         d = np.maximum(np.ceil(mx / vsf), np.ceil(mx * (np.float32(1.0) / vsf))).astype(np.int64)
         caps[nz] = np.maximum(d, 0)
     label_off = np.concatenate([[0], np.cumsum(caps.prod(1))]).astype(np.int64)
@@ -238,7 +257,7 @@ def pack_tracklets(batch, pack_override: Optional[dict] = None) -> PackedTrackle
         incl_pool=np.concatenate(incl_parts) if incl_parts else np.zeros(0, np.float32), label_off=label_off,
         brick_off=brick_off, pyr_off=tiles, table_off=np.asarray(table_off, np.int64),
         table_H=np.asarray(table_H, np.int32), max_pairs=int(nfr.max()) * L if T else 0, point_stride=stride,
-        n_points=int(frame_pt_off[-1]), ri_len=int(ri_off), pt_parts=pt_parts, ri_parts=ri_parts)
+        n_points=int(frame_pt_off[-1]), ri_len=int(ri_off), pt_parts=pt_parts, ri_parts=ri_parts, trk_smax=smax)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -250,23 +269,96 @@ def _as_bytes(a: np.ndarray) -> torch.Tensor:
 
 
 class HostBuffers:
-    """Pinned host copies of a PackedTracklets' arrays, ready for asynchronous H2D: one buffer per small field and
-    one per part of the two pools (a loader that reads into pinned memory would hand these over directly)."""
+    """Host side of the H2D copies of a PackedTracklets.
 
-    def __init__(self, pk: PackedTracklets, pin: bool = True):
+    The small fields travel as ONE buffer.  The range images -- 104 MB per segment, of which the visibility test
+    reads a small window per (tracklet-frame, LiDAR) -- go up in one of three ways (``ri_mode``):
+
+    ``"pull"``  (``windows`` and ``pin``) the images sit in ONE pinned pool in the device layout (where a loader that
+                reads into pinned memory would put them); the device marks the blocks the batch can read and pulls
+                exactly those over PCIe (``occb200_pull_windows``).  No host work per step.
+    ``"host"``  (``windows``, pageable memory) the host derives the windows (``occb200_host_ri_window_blocks``),
+                gathers the blocks from the source arrays into a staging buffer, and the device scatters them.
+    ``"whole"`` every image is copied whole, as the reference loads them (occ_annotate.py:502-533).
+
+    ``pin=True`` also puts the candidate points into one pinned buffer; ``pin=False`` (one-shot calls) uploads
+    everything from where it lies."""
+
+    def __init__(self, pk: PackedTracklets, pin: bool = True, windows=True):
         self.pk = pk
+        self.pin = pin
+        if windows in ("pull", "host", "whole"):
+            assert windows != "pull" or pin, "the device can only pull from pinned memory"
+            self.ri_mode = windows
+        else:
+            self.ri_mode = ("pull" if pin else "host") if windows else "whole"
+        if not (pk.ri_len and pk.F):
+            self.ri_mode = "whole"
 
         def host(a):
             t = _as_bytes(a)
             return t.pin_memory() if (pin and t.numel()) else t
 
-        self.bufs = {name: host(getattr(pk, name)) for name in _SMALL_FIELDS}
-        self.pt_parts = [(off * pk.point_stride * 4, host(a)) for off, a in pk.pt_parts]
-        self.ri_parts = [(off * 4, host(a)) for off, a in pk.ri_parts]
+        # small fields: one buffer, 256-byte aligned slots (one copy instead of a dozen)
+        self.small_off, off = _small_layout(pk)
+        small = torch.zeros(off, dtype=torch.uint8)
+        for name in _SMALL_FIELDS:
+            src = _as_bytes(getattr(pk, name))
+            small[self.small_off[name]: self.small_off[name] + src.numel()] = src
+        self.small = small.pin_memory() if pin else small
+        if pin and pk.n_points:
+            pool = torch.empty(4 * pk.n_points * pk.point_stride, dtype=torch.uint8).pin_memory()
+            for o, a in pk.pt_parts:
+                b = _as_bytes(a)
+                pool[o * pk.point_stride * 4: o * pk.point_stride * 4 + b.numel()] = b
+            self.pt_parts = [(0, pool)]
+        else:
+            self.pt_parts = [(o * pk.point_stride * 4, _as_bytes(a)) for o, a in pk.pt_parts]
+        self.ri_parts, self.ri_staging, self.ri_idx, self.ri_blocks, self.ri_pinned = [], None, None, None, None
+        if self.ri_mode == "pull":
+            pool = torch.zeros(pk.ri_len, dtype=torch.float32).pin_memory()
+            for o, a in pk.ri_parts:
+                pool[o: o + a.size] = torch.from_numpy(np.ascontiguousarray(a, np.float32).reshape(-1))
+            self.ri_pinned = pool
+        elif self.ri_mode == "host":
+            self.ri_blocks = window_blocks(pk)
+            n = int(self.ri_blocks.size)
+            self.ri_idx = host(self.ri_blocks)
+            self.ri_staging = torch.empty(max(n, 1) * RI_BLOCK, dtype=torch.float32)
+            if pin:
+                self.ri_staging = self.ri_staging.pin_memory()
+            srcs = [np.ascontiguousarray(a, np.float32) for _, a in pk.ri_parts]
+            self._src = srcs                                       # keeps the source arrays alive
+            self._part_off = np.asarray([o for o, _ in pk.ri_parts], np.int64)
+            self._part_len = np.asarray([a.size for a in srcs], np.int64)
+            self._part_ptr = np.asarray([a.ctypes.data for a in srcs], np.uint64)
+            self.gather_windows()
+        else:
+            self.ri_parts = [(o * 4, host(a)) for o, a in pk.ri_parts]
+
+    def gather_windows(self):
+        """"host" mode: copy the window blocks from the source range images into the staging buffer (OpenMP)."""
+        n = int(self.ri_blocks.size)
+        rc = _lib.lib().occb200_host_gather_blocks(self.ri_blocks.ctypes.data, n, self._part_off.ctypes.data,
+                                                   self._part_len.ctypes.data, self._part_ptr.ctypes.data,
+                                                   len(self._src), self.ri_staging.data_ptr())
+        _lib.check(rc, "occb200_host_gather_blocks")
 
     def nbytes(self) -> int:
-        return (sum(t.numel() for t in self.bufs.values()) + sum(t.numel() for _, t in self.pt_parts)
-                + sum(t.numel() for _, t in self.ri_parts))
+        """Bytes one ``DeviceTracklets.upload`` copies with cudaMemcpy ("pull" mode: plus what the device pulls,
+        ``DeviceTracklets.pulled_bytes()``)."""
+        ri = sum(t.numel() for _, t in self.ri_parts)
+        if self.ri_mode == "host":
+            ri = 4 * RI_BLOCK * int(self.ri_blocks.size) + self.ri_idx.numel()
+        return self.small.numel() + sum(t.numel() for _, t in self.pt_parts) + ri
+
+
+def _small_layout(pk: PackedTracklets):
+    offs, off = {}, 0
+    for name in _SMALL_FIELDS:
+        offs[name] = off
+        off += -(-max(getattr(pk, name).nbytes, 16) // 256) * 256
+    return offs, off
 
 
 class DeviceTracklets:
@@ -281,10 +373,13 @@ class DeviceTracklets:
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.pk = pk
         dev = self.device
-        self.bufs = {name: torch.empty(max(getattr(pk, name).nbytes, 16), dtype=torch.uint8, device=dev)
-                     for name in _SMALL_FIELDS}
+        self.small_off, off = _small_layout(pk)       # the same slots as HostBuffers.small
+        self.small = torch.empty(off, dtype=torch.uint8, device=dev)
+        self.bufs = {name: self.small[self.small_off[name]:] for name in _SMALL_FIELDS}
         self.bufs["points"] = torch.empty(max(4 * pk.n_points * pk.point_stride, 16), dtype=torch.uint8, device=dev)
-        self.bufs["ri_pool"] = torch.empty(max(4 * pk.ri_len, 16), dtype=torch.uint8, device=dev)
+        # a windowed upload fills only the blocks the batch can read: everything else reads as "no return"
+        self.bufs["ri_pool"] = torch.zeros(max(4 * pk.ri_len, 16), dtype=torch.uint8, device=dev)
+        self.pulled = torch.zeros(1, dtype=torch.int64, device=dev)      # 32-byte blocks pulled so far ("pull" mode)
         T, total = pk.T, pk.total_slots
         self.labels = torch.zeros(max(total, 1), dtype=torch.int32, device=dev) if labels in ("i32", "both") else None
         if labels_u8 is not None:
@@ -305,17 +400,58 @@ class DeviceTracklets:
 
     def upload(self, host: HostBuffers):
         """Asynchronous H2D of every input on the current stream; returns the bytes copied."""
-        n = 0
-        for name in _SMALL_FIELDS:
-            src = host.bufs[name]
-            if src.numel():
-                self.bufs[name][: src.numel()].copy_(src, non_blocking=True)
-                n += src.numel()
+        self.small.copy_(host.small, non_blocking=True)
+        n = host.small.numel()
         for dst, parts in ((self.bufs["points"], host.pt_parts), (self.bufs["ri_pool"], host.ri_parts)):
             for off, src in parts:
                 dst[off: off + src.numel()].copy_(src, non_blocking=True)
                 n += src.numel()
+        if host.ri_mode == "host":
+            n += self._upload_blocks(host.ri_staging, host.ri_idx, int(host.ri_blocks.size))
+        elif host.ri_mode == "pull":
+            self._pull(host.ri_pinned)
         return n
+
+    def _upload_blocks(self, staging: torch.Tensor, idx: torch.Tensor, nblk: int) -> int:
+        """"host" mode: H2D of the gathered blocks and their indices + the scatter into the dense pool."""
+        if not nblk:
+            return 0
+        if "ri_blocks" not in self.bufs or self.bufs["ri_idx"].numel() < 4 * nblk:
+            self.bufs["ri_blocks"] = torch.empty(4 * RI_BLOCK * nblk, dtype=torch.uint8, device=self.device)
+            self.bufs["ri_idx"] = torch.empty(4 * nblk, dtype=torch.uint8, device=self.device)
+        sb = staging.view(torch.uint8)[: 4 * RI_BLOCK * nblk]
+        self.bufs["ri_blocks"][: sb.numel()].copy_(sb, non_blocking=True)
+        self.bufs["ri_idx"][: idx.numel()].copy_(idx, non_blocking=True)
+        with torch.cuda.device(self.device):
+            rc = _lib.lib().occb200_scatter_blocks(self.bufs["ri_blocks"].data_ptr(), self.bufs["ri_idx"].data_ptr(),
+                                                   nblk, self.bufs["ri_pool"].data_ptr(), self.pk.ri_len,
+                                                   _lib.stream_ptr(self.device))
+        _lib.check(rc, "occb200_scatter_blocks")
+        return sb.numel() + idx.numel()
+
+    def _pull(self, ri_pinned: torch.Tensor):
+        """"pull" mode: the device marks the blocks it can read and fetches them from the pinned host pool."""
+        L_ = _lib.lib()
+        if "ri_mask" not in self.bufs:
+            self.bufs["ri_mask"] = torch.empty(4 * L_.occb200_window_mask_words(self.pk.ri_len), dtype=torch.uint8,
+                                               device=self.device)
+        assert ri_pinned.is_pinned() and ri_pinned.numel() == self.pk.ri_len
+        a = self.args(0)
+        with torch.cuda.device(self.device):
+            rc = L_.occb200_pull_windows(C.byref(a), self.bufs["trk_smax"].data_ptr(), ri_pinned.data_ptr(),
+                                         self.bufs["ri_pool"].data_ptr(), self.pk.ri_len,
+                                         self.bufs["ri_mask"].data_ptr(), self.pulled.data_ptr(),
+                                         _lib.stream_ptr(self.device))
+        _lib.check(rc, "occb200_pull_windows")
+
+    def pulled_bytes(self) -> int:
+        """Bytes the device has pulled from pinned host memory so far (synchronises)."""
+        return 32 * int(self.pulled.item())
+
+    def window_mask(self) -> np.ndarray:
+        """bool per 32-byte block of ri_pool: the blocks the last ``_pull`` marked (tests; synchronises)."""
+        m = self.bufs["ri_mask"].cpu().numpy().view(np.uint32)
+        return np.unpackbits(m.view(np.uint8), bitorder="little").astype(bool)[: self.pk.ri_len // 8]
 
     def args(self, flags: int = 0) -> _lib.AnnotateArgs:
         pk, b = self.pk, self.bufs
@@ -475,7 +611,7 @@ class DeviceTracklets:
 
 
 def annotate_batch(batch, flags: int = 0, pack_override: Optional[dict] = None, device=None,
-                   save_mean_var: bool = False) -> List[dict]:
+                   save_mean_var: bool = False, windows: bool = True) -> List[dict]:
     """Annotate every tracklet of ``batch``: the batched equivalent of ``OccAnnotator.annotate_trk``.
 
     Returns one dict per tracklet: ``status`` (``ok`` or the reason the reference produces no file),
@@ -483,7 +619,7 @@ def annotate_batch(batch, flags: int = 0, pack_override: Optional[dict] = None, 
     ``size``, ``n_unknown`` (U) and ``n_steps`` (visibility tests evaluated).
     """
     pk = pack_tracklets(batch, pack_override)
-    host = HostBuffers(pk, pin=False)       # one-shot call: the arrays are uploaded from where they lie
+    host = HostBuffers(pk, pin=False, windows=windows)       # one-shot call: uploaded from where the arrays lie
     dev = DeviceTracklets(pk, device)
     dev.upload(host)
     dev.run(flags)

@@ -129,12 +129,18 @@ def test_pack_matches_oracle_pack():
     ok = oracle.PackedBatch(b)
     assert (pk.trk_frame_off == ok.trk_frame_off).all() and (pk.frame_pt_off == ok.pt_off).all()
     assert (pk.label_off == ok.label_off).all() and (pk.frame_sf == ok.frame_sf).all()
-    for f in ("ri_off", "incl_off", "H", "W", "v2l", "azc"):
+    for f in ("incl_off", "H", "W", "v2l", "azc"):
         assert (pk.sensors[f] == ok.sensors[f]).all(), f
     assert (pk.poses["box"] == ok.boxes).all()
     assert (np.stack([pk.poses[k] for k in ("cos_m", "sin_m", "cos_p", "sin_p")], 1) == ok.trig).all()
     assert (pk.sensors["incl_mono"] == -1).all()          # flipped ascending tables are descending
-    assert (pk.incl_pool == ok.incl_pool).all() and (pk.ri_pool == ok.ri_pool).all()
+    assert (pk.incl_pool == ok.incl_pool).all()
+    # the product pool pads every (segment, LiDAR) part to a multiple of 16 floats (windowed upload): same images
+    mine, theirs = pk.ri_pool, ok.ri_pool
+    for a, b_ in zip(pk.sensors.reshape(-1), ok.sensors.reshape(-1)):
+        n = int(a["H"]) * int(a["W"])
+        assert (mine[a["ri_off"]: a["ri_off"] + n] == theirs[b_["ri_off"]: b_["ri_off"] + n]).all()
+    assert pk.ri_len % 16 == 0 and (pk.trk_smax >= pk.poses["box"][pk.trk_frame_off[:-1], 3:6]).all()
 
 
 def test_ops_fail_loudly_without_cuda():
