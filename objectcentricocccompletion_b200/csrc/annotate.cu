@@ -61,6 +61,12 @@ constexpr int kLutPerRow = 64;           // lookup-table cells reserved per incl
 constexpr int kTileR = 8, kTileC = 32;   // range-image max-pyramid tile (rows x columns): pair-level cull
 constexpr int kFineR = 2, kFineC = 8;    // second pyramid level: brick-level cull; 16 fine tiles per coarse tile
 constexpr int kBrick = 4;                // brick edge in voxels: 64 voxels = 2 per lane of one warp
+#ifndef OCC_DYN
+#define OCC_DYN 1
+#endif
+#ifndef OCC_SMEMPAIRS
+#define OCC_SMEMPAIRS 1
+#endif
 #ifndef OCC_FT
 #define OCC_FT 256
 #endif
@@ -154,7 +160,7 @@ struct Workspace {
   int64_t *chunk_off;    // [T+1] (f64 path)
   // ---- zeroed by ONE memset at the start of every call
   char *zero_begin;
-  unsigned long long *counter;   // [0] f64-path ticket, [1] recheck-queue length, [2] redo frames,
+  unsigned long long *counter;   // [0] f64-path ticket, [1] recheck-queue length, [2] redo frames, [3] visibility ticket,
                                  // [8 + 2s] brick items of slice s
   int32_t *trk_flags;    // [T] flags of the crop kernel (bit0 kept a point, bit1 index error)
   int32_t *frame_kept;   // [F] 1: the frame has an in-box point (set by the crop CTAs that see one)
@@ -1676,16 +1682,20 @@ template <int VPL>
 __device__ __forceinline__ unsigned run_pairs(const VisArgs &a, int t, const TrkHot &h, int bx, int by, int bz, int lb,
                                               unsigned live, int k0, unsigned todo, const float (&dx)[VPL],
                                               const float (&dy)[VPL], const float (&dz)[VPL], const int (&vj)[VPL],
-                                              unsigned &steps) {
+                                              unsigned &steps, const PairHot *__restrict__ staged) {
   const int lane = threadIdx.x & 31;
-  const PairHot *tp = a.pairs + h.pairs_base + k0;
   unsigned found = 0u;
   while (live) {
     if (!__any_sync(0xffffffffu, todo != 0u)) break;           // every voxel of the item is settled
     const int kk = __ffs(live) - 1;
     live &= live - 1u;
+#if OCC_SMEMPAIRS
+    const PairHot &pc = staged[kk];                            // the warp's own shared-memory copy (broadcast reads)
+#else
+    const PairHot *tp = a.pairs + h.pairs_base + k0;
     const PairHot pc = load128(tp + kk);
     if (live) asm volatile("prefetch.global.L1 [%0];" ::"l"(tp + (__ffs(live) - 1)));   // next record: one 128-byte line
+#endif
     const int2 *lut = reinterpret_cast<const int2 *>(a.lut_pool) + pc.lut_off;
     const float *ri_img = a.ri_pool + pc.ri_off;
     // materialise the bases as 64-bit registers: per-test addresses are then ONE imad.wide each
@@ -1748,6 +1758,32 @@ __global__ void __launch_bounds__(32 * kFastWarps, OCC_MINB) k_visibility(const 
   // atomicAdd with 4 736 warps on one counter).  Neighbouring warps get neighbouring bricks of one tracklet, which
   // share their pair records and pixel windows in L1.
   __shared__ long long s_base[kMaxSlices + 1];
+#if OCC_SMEMPAIRS
+  __shared__ __align__(16) PairHot s_pairs[kFastWarps][kPairsPerItem];
+#endif
+#if OCC_DYN
+  if (threadIdx.x < a.n_slices) s_base[threadIdx.x + 1] = (long long)a.counter[8 + 2 * threadIdx.x];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    s_base[0] = 0;
+    for (int s = 0; s < a.n_slices; ++s) s_base[s + 1] += s_base[s];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const long long n_items = s_base[a.n_slices];
+  // Work assignment: the per-slice lists are walked as one sequence (slice 0, the heavy items, first).  A warp's
+  // first item is static (its global warp index: no atomic while every warp of the grid starts at once); every
+  // later one is a ticket from a global counter, requested BEFORE the current item is processed so that the
+  // atomic's round trip hides behind it.  (Static rounds left the slowest CTA as the kernel's tail: SMs were
+  // active 70 % of the kernel's duration.)
+  const long long n_static = (long long)gridDim.x * kFastWarps;
+  long long g = (long long)blockIdx.x * kFastWarps + (threadIdx.x >> 5);
+  int s = 0;
+  for (;;) {
+    if (g >= n_items) break;
+    unsigned long long nxt = 0;
+    if (lane == 0) nxt = atomicAdd(a.counter + 3, 1ull);
+#else
   __shared__ unsigned s_ticket;
   if (threadIdx.x < a.n_slices) s_base[threadIdx.x + 1] = (long long)a.counter[8 + 2 * threadIdx.x];
   if (threadIdx.x == 0) s_ticket = 0u;
@@ -1770,11 +1806,12 @@ __global__ void __launch_bounds__(32 * kFastWarps, OCC_MINB) k_visibility(const 
       if ((long long)(tk / kFastWarps) * round_items + (long long)blockIdx.x * kFastWarps >= n_items) break;   // round is past the end
       continue;                                                  // this slot of the last round is empty
     }
+#endif
     s = 0;
     while (g >= s_base[s + 1]) ++s;
     const long long item = g - s_base[s];
     const int2 *items = a.item_map + (long long)s * a.bricks_total;
-    {
+    do {
       const int2 m = __ldg(items + item);
       const int t = m.x;
       const int bx = m.y & 1023, by = (m.y >> 10) & 1023, bz = (m.y >> 20) & 1023;
@@ -1785,7 +1822,7 @@ __global__ void __launch_bounds__(32 * kFastWarps, OCC_MINB) k_visibility(const 
       const long long gb = h.brick_base + lb;
       const unsigned mw = __ldg(a.pair_mask + gb * a.mask_words + (k0 >> 5));
       const unsigned live = ~(mw >> (k0 & 31)) & (npair >= 32 ? 0xffffffffu : ((1u << npair) - 1u));
-      if (!live) continue;
+      if (!live) break;
       // the brick's voxels: j = 32 v + lane -> (j >> 4, (j >> 2) & 3, j & 3); undecided = inside the grid, holds no
       // point, not yet proven free
       unsigned und[2];
@@ -1802,8 +1839,25 @@ __global__ void __launch_bounds__(32 * kFastWarps, OCC_MINB) k_visibility(const 
         und[v] = __ballot_sync(0xffffffffu, need) & ~fw;
       }
       const int n0 = __popc(und[0]), n = n0 + __popc(und[1]);
-      if (n == 0) continue;
+      if (n == 0) break;
       unsigned steps = 0;
+#if OCC_SMEMPAIRS
+      // the slice's pair records (<= kPairsPerItem x 128 bytes, contiguous) into the warp's own shared-memory slot:
+      // four independent 16-byte loads per lane, all records at once, instead of one dependent 128-byte warp-uniform
+      // load per loop iteration
+      PairHot *staged = s_pairs[threadIdx.x >> 5];
+      {
+        const float4 *src = reinterpret_cast<const float4 *>(a.pairs + h.pairs_base + k0);
+        float4 *dst = reinterpret_cast<float4 *>(staged);
+        __syncwarp();                                            // the previous item's reads are done
+#pragma unroll
+        for (int q = 0; q < kPairsPerItem * 8 / 32; ++q)
+          if (q * 32 + lane < npair * 8) dst[q * 32 + lane] = __ldg(src + q * 32 + lane);
+        __syncwarp();
+      }
+#else
+      const PairHot *staged = nullptr;
+#endif
       if (n > 32) {                                              // two voxels per lane, natural mapping
         float dx[2], dy[2], dz[2];
         int vj[2];
@@ -1817,7 +1871,7 @@ __global__ void __launch_bounds__(32 * kFastWarps, OCC_MINB) k_visibility(const 
           dz[v] = (float)(kBrick * bz + (j & 3)) - h.cen[2];
           todo |= ((und[v] >> lane) & 1u) << v;
         }
-        const unsigned found = run_pairs<2>(a, t, h, bx, by, bz, lb, live, k0, todo, dx, dy, dz, vj, steps);
+        const unsigned found = run_pairs<2>(a, t, h, bx, by, bz, lb, live, k0, todo, dx, dy, dz, vj, steps, staged);
 #pragma unroll
         for (int v = 0; v < 2; ++v) {
           const unsigned fw = __ballot_sync(0xffffffffu, (found >> v) & 1u);
@@ -1835,14 +1889,17 @@ __global__ void __launch_bounds__(32 * kFastWarps, OCC_MINB) k_visibility(const 
         dx[0] = (float)(kBrick * bx + (vj[0] >> 4)) - h.cen[0];
         dy[0] = (float)(kBrick * by + ((vj[0] >> 2) & 3)) - h.cen[1];
         dz[0] = (float)(kBrick * bz + (vj[0] & 3)) - h.cen[2];
-        const unsigned found = run_pairs<1>(a, t, h, bx, by, bz, lb, live, k0, mine ? 1u : 0u, dx, dy, dz, vj, steps);
+        const unsigned found = run_pairs<1>(a, t, h, bx, by, bz, lb, live, k0, mine ? 1u : 0u, dx, dy, dz, vj, steps, staged);
         if (found) atomicOr(a.free_brick + 2 * gb + (vj[0] >> 5), 1u << (vj[0] & 31));
       }
       if (a.n_steps) {
         for (int o = 16; o > 0; o >>= 1) steps += __shfl_xor_sync(0xffffffffu, steps, o);
         if (lane == 0 && steps) atomicAdd((unsigned long long *)&a.n_steps[t], (unsigned long long)steps);
       }
-    }
+    } while (0);
+#if OCC_DYN
+    g = n_static + (long long)__shfl_sync(0xffffffffu, nxt, 0);
+#endif
   }
 }
 
