@@ -132,7 +132,7 @@ class ClockSampler:
 def ncu_traffic():
     """DRAM bytes per step of the ray-cast kernels from the COMMITTED ncu capture (profiles/): a static record of
     the build that was profiled, not a measurement of this run."""
-    p = os.path.join(ROOT, "profiles", "vis_fast_ncu.json")
+    p = os.path.join(ROOT, "profiles", "raycast_ncu.json")
     try:
         m = json.load(open(p))["metrics"]
         scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
@@ -327,7 +327,7 @@ def roofline_record(ws, kms, n_steps, peak, peak_src, traffic=None):
     achieved = ws["vis_bytes"] / (vis_ms / 1e3) / 1e9 if vis_ms > 0 else 0.0
     return {"bound": "hbm", "kernel": "k_brick_cull + k_visibility (the ray-cast)", "achieved": achieved, "peak": peak,
             "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-            "traffic_source": ("profiles/vis_fast_ncu.json (static: the committed ncu capture, not this run)"
+            "traffic_source": ("profiles/raycast_ncu.json (static: the committed ncu capture, not this run)"
                                if traffic else None),
             "peak_source": peak_src, "algorithmic_bytes_per_launch": ws["vis_bytes"], "kernel_ms": vis_ms,
             "kernel_share_of_step": vis_ms / step_ms if step_ms else None,

@@ -1,9 +1,10 @@
 #!/usr/bin/env python
-"""Summarise an ncu report (``ncu --set full`` capture of the ray-cast launches) into the small JSON kept under
-``profiles/``: per launch the duration, DRAM bytes, issue utilisation and the top stall reasons; at the top level
-the per-step sums that ``bench.py`` reads for ``roofline.traffic``.
+"""Summarise an ncu report (``ncu --set full``) into the small JSON kept under ``profiles/``: per launch the
+duration, DRAM bytes, issue utilisation, occupancy, local-memory traffic and the top stall reasons; at the top
+level the sums over the launches whose kernel name matches ``--sum`` (default: the ray-cast kernels, which
+``bench.py`` reads for ``roofline.traffic``).
 
-    python tools/ncu_summary.py gpurun_out/vis.ncu-rep profiles/vis_fast_ncu.json "capture command line"
+    python tools/ncu_summary.py gpurun_out/step.ncu-rep profiles/r2_step_ncu.json "capture command line" [--sum regex]
 """
 import csv
 import io
@@ -29,7 +30,14 @@ SCALE = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-3, "us"
 
 
 def main():
-    rep, out, capture = sys.argv[1], sys.argv[2], (sys.argv[3] if len(sys.argv) > 3 else "")
+    import re
+    argv = list(sys.argv)
+    pat = "k_brick_cull|k_visibility\\("
+    if "--sum" in argv:
+        i = argv.index("--sum")
+        pat = argv[i + 1]
+        del argv[i:i + 2]
+    rep, out, capture = argv[1], argv[2], (argv[3] if len(argv) > 3 else "")
     txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(io.StringIO(txt)))
     names, units = rows[0], rows[1]
@@ -44,12 +52,14 @@ def main():
                   for k, v in rec.items() if k.startswith("smsp__average_warps_issue_stalled_")
                   and k.endswith("_per_issue_active.ratio") and v not in ("", None)}
         top = dict(sorted(stalls.items(), key=lambda kv: -kv[1])[:6])
-        launches.append({"kernel": rec.get("Kernel Name", "")[:80], "metrics": m, "stall_cycles_per_issue": top})
-        for k in total:
-            if k in m:
-                total[k] += float(m[k]["value"]) * SCALE.get(m[k]["unit"], 1.0)
+        name = rec.get("Kernel Name", "")
+        launches.append({"kernel": name[:80], "metrics": m, "stall_cycles_per_issue": top})
+        if re.search(pat, name):
+            for k in total:
+                if k in m:
+                    total[k] += float(m[k]["value"]) * SCALE.get(m[k]["unit"], 1.0)
     doc = {
-        "kernel": "k_visibility_fast (phase 1 + phase 2 launches of one step)",
+        "kernel": "launches matching /%s/ (sums below)" % pat,
         "capture": capture,
         "metrics": {
             "gpu__time_duration.sum": {"unit": "us", "value": "%.3f" % total["gpu__time_duration.sum"]},
