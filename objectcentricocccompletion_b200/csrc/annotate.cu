@@ -61,11 +61,17 @@ constexpr int kLutPerRow = 64;           // lookup-table cells reserved per incl
 constexpr int kTileR = 8, kTileC = 32;   // range-image max-pyramid tile (rows x columns): pair-level cull
 constexpr int kFineR = 2, kFineC = 8;    // second pyramid level: brick-level cull; 16 fine tiles per coarse tile
 constexpr int kBrick = 4;                // brick edge in voxels: 64 voxels = 2 per lane of one warp
-#ifndef OCC_DYN
-#define OCC_DYN 1
+#ifndef OCC_OVERLAP
+#define OCC_OVERLAP 0  // 1: cull of slices >= 1 on a second side stream next to the visibility pass over slice 0 (measured
+#endif                 // slower on C2, 94 vs 83 us for the ray-cast, and equal on 1 024 tracklets: kept for A/B only)
+#ifndef OCC_VISDEBUG
+#define OCC_VISDEBUG 0
 #endif
-#ifndef OCC_SMEMPAIRS
-#define OCC_SMEMPAIRS 1
+#ifndef OCC_PP1
+#define OCC_PP1 2      // pairs per loop iteration of the one-voxel-per-lane path
+#endif
+#ifndef OCC_PP2
+#define OCC_PP2 2      // ... of the two-voxels-per-lane path
 #endif
 #ifndef OCC_FT
 #define OCC_FT 256
@@ -160,7 +166,7 @@ struct Workspace {
   int64_t *chunk_off;    // [T+1] (f64 path)
   // ---- zeroed by ONE memset at the start of every call
   char *zero_begin;
-  unsigned long long *counter;   // [0] f64-path ticket, [1] recheck-queue length, [2] redo frames, [3] visibility ticket,
+  unsigned long long *counter;   // [0] f64-path ticket, [1] recheck-queue length, [2] redo frames, [3], [4] visibility tickets,
                                  // [8 + 2s] brick items of slice s
   int32_t *trk_flags;    // [T] flags of the crop kernel (bit0 kept a point, bit1 index error)
   int32_t *frame_kept;   // [F] 1: the frame has an in-box point (set by the crop CTAs that see one)
@@ -261,8 +267,8 @@ static int64_t ws_layout(int32_t T, int64_t F, int64_t total, int64_t SF, int32_
 // a side stream concurrently with the crop/voxelise chain and joins before k_pair_build (fork/join with
 // events; capturable in a CUDA graph).
 struct SideStream {
-  cudaStream_t stream = nullptr;
-  cudaEvent_t fork = nullptr, join = nullptr;
+  cudaStream_t stream = nullptr, stream2 = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr, fork2 = nullptr, join2 = nullptr;
 };
 static SideStream g_side[64];
 static std::mutex g_side_mu;
@@ -277,6 +283,9 @@ static int side_stream(SideStream **out) {
     OCC_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
     OCC_CUDA(cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming));
     OCC_CUDA(cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming));
+    OCC_CUDA(cudaStreamCreateWithFlags(&s.stream2, cudaStreamNonBlocking));
+    OCC_CUDA(cudaEventCreateWithFlags(&s.fork2, cudaEventDisableTiming));
+    OCC_CUDA(cudaEventCreateWithFlags(&s.join2, cudaEventDisableTiming));
   }
   *out = &s;
   return 0;
@@ -1446,11 +1455,11 @@ __device__ __forceinline__ float u_of_sin(float s) {
 // All quantities below are conservative bounds with generous padding, so the approximate reciprocal / square root
 // / arctangent (<= 2 ulp, <= 2e-6 rad) are used throughout: their error is orders of magnitude below the padding.
 __global__ void __launch_bounds__(256)
-k_brick_cull(const int2 *__restrict__ item_map, long long bricks_total, const unsigned long long *__restrict__ counter,
+k_brick_cull(int s_first, const int2 *__restrict__ item_map, long long bricks_total, const unsigned long long *__restrict__ counter,
              const TrkHot *__restrict__ hot, const PairHot *__restrict__ pairs, const LutCell *__restrict__ lut_pool,
              const int64_t *__restrict__ pyr_off, const float *__restrict__ pyr2, int mask_words,
              uint32_t *__restrict__ pair_mask) {
-  const int s = blockIdx.y;
+  const int s = s_first + blockIdx.y;
   const long long n_items = (long long)counter[8 + 2 * s];
   // thread -> (brick item, pair): a warp holds 32 CONSECUTIVE bricks (one tracklet, as a rule) and ONE pair, so the
   // pair record is read at a warp-uniform address (one L1 wavefront per load instead of one per distinct record:
@@ -1652,7 +1661,8 @@ __device__ __noinline__ bool exact_from_ids(int t, int f, int q, int L, double v
 struct VisArgs {                 // what the visibility kernel needs (passed by value: one constant-bank block)
   int L;
   int mask_words;
-  int n_slices;
+  int s_lo, s_hi;                // slices of pairs this launch walks
+  int ticket;                    // which ticket counter it draws from (counter[3 + ticket])
   int pad;
   long long bricks_total;
   long long queue_cap;
@@ -1678,62 +1688,75 @@ struct VisArgs {                 // what the visibility kernel needs (passed by 
 
 // The pair loop of one work item: VPL voxels per lane (lattice offsets d*, brick-local ids vj, -1 = none).
 // Returns the bits of the voxels proven free (bit v = this lane's voxel v).
-template <int VPL>
+template <int VPL, int PP, bool MIXED>
 __device__ __forceinline__ unsigned run_pairs(const VisArgs &a, int t, const TrkHot &h, int bx, int by, int bz, int lb,
                                               unsigned live, int k0, unsigned todo, const float (&dx)[VPL],
                                               const float (&dy)[VPL], const float (&dz)[VPL], const int (&vj)[VPL],
-                                              unsigned &steps, const PairHot *__restrict__ staged) {
+                                              unsigned &steps, const PairHot *__restrict__ staged, unsigned &iters) {
+  // PP pairs per loop iteration: their VPL x PP tests are independent dependent-load chains (record -> lookup cell
+  // -> pixel) that overlap; a voxel freed by the first pair of an iteration still pays the second one's test.
   const int lane = threadIdx.x & 31;
   unsigned found = 0u;
   while (live) {
     if (!__any_sync(0xffffffffu, todo != 0u)) break;           // every voxel of the item is settled
-    const int kk = __ffs(live) - 1;
-    live &= live - 1u;
-#if OCC_SMEMPAIRS
-    const PairHot &pc = staged[kk];                            // the warp's own shared-memory copy (broadcast reads)
-#else
-    const PairHot *tp = a.pairs + h.pairs_base + k0;
-    const PairHot pc = load128(tp + kk);
-    if (live) asm volatile("prefetch.global.L1 [%0];" ::"l"(tp + (__ffs(live) - 1)));   // next record: one 128-byte line
-#endif
-    const int2 *lut = reinterpret_cast<const int2 *>(a.lut_pool) + pc.lut_off;
-    const float *ri_img = a.ri_pool + pc.ri_off;
-    // materialise the bases as 64-bit registers: per-test addresses are then ONE imad.wide each
-    asm volatile("" : "+l"(lut), "+l"(ri_img));
-    // all VPL tests are evaluated unconditionally (no divergence, their dependent chains interleave);
-    // results of voxels this lane does not need are discarded
-    int res[VPL];
-    if (pc.wide) {
+    ++iters;
+    int res[PP][VPL];
+    const PairHot *pcs[PP];
+    bool has[PP];
 #pragma unroll
-      for (int v = 0; v < VPL; ++v) res[v] = fast_test<true>(pc, dx[v], dy[v], dz[v], lut, ri_img);
-    } else {
-#pragma unroll
-      for (int v = 0; v < VPL; ++v) res[v] = fast_test<false>(pc, dx[v], dy[v], dz[v], lut, ri_img);
+    for (int p = 0; p < PP; ++p) {
+      has[p] = live != 0u;
+      const int kk = has[p] ? __ffs(live) - 1 : 0;
+      live &= live - 1u;                                         // (0 stays 0)
+      pcs[p] = staged + kk;
     }
 #pragma unroll
-    for (int v = 0; v < VPL; ++v) {
-      const bool need = (todo >> v) & 1u;
-      res[v] = need ? ((pc.eps >= 0.f) ? res[v] : 1) : 0;
-      steps += need ? 1u : 0u;
-      if (res[v] == 2) {
-        found |= 1u << v;
-        todo &= ~(1u << v);
+    for (int p = 0; p < PP; ++p) {
+      // (an absent second pair repeats record 0: straight-line code, its results are dropped below)
+      const PairHot &pc = *pcs[p];                               // the warp's own shared-memory copy (broadcast reads)
+      const int2 *lut = reinterpret_cast<const int2 *>(a.lut_pool) + pc.lut_off;
+      const float *ri_img = a.ri_pool + pc.ri_off;
+      // materialise the bases as 64-bit registers: per-test addresses are then ONE imad.wide each
+      asm volatile("" : "+l"(lut), "+l"(ri_img));
+      // all VPL tests are evaluated unconditionally (no divergence, their dependent chains interleave);
+      // results of voxels this lane does not need are discarded
+      if (MIXED && pc.wide) {                                      // (a branch here keeps the pairs' chains apart)
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) res[p][v] = fast_test<true>(pc, dx[v], dy[v], dz[v], lut, ri_img);
+      } else {
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) res[p][v] = fast_test<false>(pc, dx[v], dy[v], dz[v], lut, ri_img);
       }
-      const unsigned umask = __ballot_sync(0xffffffffu, res[v] == 1);
-      if (umask) {                                             // queue the undecided tests (warp-aggregated)
-        unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(a.counter + 1, (unsigned long long)__popc(umask));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (res[v] == 1) {
-          const int j = vj[v];
-          const int f = ((kBrick * bx + (j >> 4)) * h.dY + kBrick * by + ((j >> 2) & 3)) * h.dZ + kBrick * bz + (j & 3);
-          const unsigned long long slot = base + __popc(umask & ((1u << lane) - 1u));
-          if (slot < (unsigned long long)a.queue_cap) {
-            a.queue[slot] = make_int4(t, f, pc.q, lb * 64 + j);
-          } else if (exact_from_ids(t, f, pc.q, a.L, a.vs, a.grids, a.trk_frame_off, a.poses, a.frame_sf, a.sensors,
-                                    a.incl_pool, a.ri_pool)) {     // queue full: decide right here
-            found |= 1u << v;
-            todo &= ~(1u << v);
+    }
+#pragma unroll
+    for (int p = 0; p < PP; ++p) {
+      if (!has[p]) continue;
+      const PairHot &pc = *pcs[p];
+#pragma unroll
+      for (int v = 0; v < VPL; ++v) {
+        const bool need = (todo >> v) & 1u;
+        const int r = need ? ((pc.eps >= 0.f) ? res[p][v] : 1) : 0;
+        steps += need ? 1u : 0u;
+        if (r == 2) {
+          found |= 1u << v;
+          todo &= ~(1u << v);
+        }
+        const unsigned umask = __ballot_sync(0xffffffffu, r == 1);
+        if (umask) {                                             // queue the undecided tests (warp-aggregated)
+          unsigned long long base = 0;
+          if (lane == 0) base = atomicAdd(a.counter + 1, (unsigned long long)__popc(umask));
+          base = __shfl_sync(0xffffffffu, base, 0);
+          if (r == 1) {
+            const int j = vj[v];
+            const int f = ((kBrick * bx + (j >> 4)) * h.dY + kBrick * by + ((j >> 2) & 3)) * h.dZ + kBrick * bz + (j & 3);
+            const unsigned long long slot = base + __popc(umask & ((1u << lane) - 1u));
+            if (slot < (unsigned long long)a.queue_cap) {
+              a.queue[slot] = make_int4(t, f, pc.q, lb * 64 + j);
+            } else if (exact_from_ids(t, f, pc.q, a.L, a.vs, a.grids, a.trk_frame_off, a.poses, a.frame_sf, a.sensors,
+                                      a.incl_pool, a.ri_pool)) {     // queue full: decide right here
+              found |= 1u << v;
+              todo &= ~(1u << v);
+            }
           }
         }
       }
@@ -1750,27 +1773,26 @@ __device__ __forceinline__ unsigned run_pairs(const VisArgs &a, int t, const Trk
 //   slices never test a voxel an earlier one has freed.  A brick with more than 32 undecided voxels runs two per
 //   lane; otherwise the undecided voxels are dealt one per lane (dense lanes).
 // Labels are written afterwards by k_labels from the occupancy and free bitsets.
-__global__ void __launch_bounds__(32 * kFastWarps, OCC_MINB) k_visibility(const VisArgs a) {
-  // Work assignment: the per-slice lists are walked as one sequence (slice 0 first) in rounds of W = 8 x gridDim
-  // items; CTA c owns items [c*8, c*8 + 8) of every round and its 8 warps draw them from a SHARED-MEMORY ticket, so
-  // a warp that finishes early takes the CTA's next item instead of idling (a static item per warp left the
-  // longest warp as the kernel's tail on small batches; a global ticket per item was measured at 2.6 us per
-  // atomicAdd with 4 736 warps on one counter).  Neighbouring warps get neighbouring bricks of one tracklet, which
-  // share their pair records and pixel windows in L1.
-  __shared__ long long s_base[kMaxSlices + 1];
-#if OCC_SMEMPAIRS
-  __shared__ __align__(16) PairHot s_pairs[kFastWarps][kPairsPerItem];
+#if OCC_VISDEBUG
+__device__ long long g_visdbg[8 * 148 * 8 * 8];    // per warp: t_start, t_end, items, iterations, longest item (cycles, its iterations), smid
 #endif
-#if OCC_DYN
-  if (threadIdx.x < a.n_slices) s_base[threadIdx.x + 1] = (long long)a.counter[8 + 2 * threadIdx.x];
+__global__ void __launch_bounds__(32 * kFastWarps, OCC_MINB) k_visibility(const VisArgs a) {
+#if OCC_VISDEBUG
+  const long long dbg_t0 = clock64();
+  long long dbg_items = 0, dbg_iters = 0, dbg_max = 0, dbg_max_it = 0;
+#endif
+  __shared__ long long s_base[kMaxSlices + 1];
+  __shared__ __align__(16) PairHot s_pairs[kFastWarps][kPairsPerItem];
+  const int ns = a.s_hi - a.s_lo;                  // this launch walks the lists of slices [s_lo, s_hi)
+  if (threadIdx.x < ns) s_base[threadIdx.x + 1] = (long long)a.counter[8 + 2 * (a.s_lo + threadIdx.x)];
   __syncthreads();
   if (threadIdx.x == 0) {
     s_base[0] = 0;
-    for (int s = 0; s < a.n_slices; ++s) s_base[s + 1] += s_base[s];
+    for (int s = 0; s < ns; ++s) s_base[s + 1] += s_base[s];
   }
   __syncthreads();
   const int lane = threadIdx.x & 31;
-  const long long n_items = s_base[a.n_slices];
+  const long long n_items = s_base[ns];
   // Work assignment: the per-slice lists are walked as one sequence (slice 0, the heavy items, first).  A warp's
   // first item is static (its global warp index: no atomic while every warp of the grid starts at once); every
   // later one is a ticket from a global counter, requested BEFORE the current item is processed so that the
@@ -1782,34 +1804,15 @@ __global__ void __launch_bounds__(32 * kFastWarps, OCC_MINB) k_visibility(const 
   for (;;) {
     if (g >= n_items) break;
     unsigned long long nxt = 0;
-    if (lane == 0) nxt = atomicAdd(a.counter + 3, 1ull);
-#else
-  __shared__ unsigned s_ticket;
-  if (threadIdx.x < a.n_slices) s_base[threadIdx.x + 1] = (long long)a.counter[8 + 2 * threadIdx.x];
-  if (threadIdx.x == 0) s_ticket = 0u;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    s_base[0] = 0;
-    for (int s = 0; s < a.n_slices; ++s) s_base[s + 1] += s_base[s];
-  }
-  __syncthreads();
-  const int lane = threadIdx.x & 31;
-  const long long n_items = s_base[a.n_slices];
-  const long long round_items = (long long)gridDim.x * kFastWarps;
-  int s = 0;
-  for (;;) {
-    unsigned tk = 0u;
-    if (lane == 0) tk = atomicAdd(&s_ticket, 1u);
-    tk = __shfl_sync(0xffffffffu, tk, 0);
-    const long long g = (long long)(tk / kFastWarps) * round_items + (long long)blockIdx.x * kFastWarps + (tk % kFastWarps);
-    if (g >= n_items) {
-      if ((long long)(tk / kFastWarps) * round_items + (long long)blockIdx.x * kFastWarps >= n_items) break;   // round is past the end
-      continue;                                                  // this slot of the last round is empty
-    }
-#endif
+    if (lane == 0) nxt = atomicAdd(a.counter + 3 + a.ticket, 1ull);
     s = 0;
     while (g >= s_base[s + 1]) ++s;
     const long long item = g - s_base[s];
+    s += a.s_lo;
+#if OCC_VISDEBUG
+    const long long dbg_ti = clock64();
+    unsigned dbg_steps_lane = 0;
+#endif
     const int2 *items = a.item_map + (long long)s * a.bricks_total;
     do {
       const int2 m = __ldg(items + item);
@@ -1840,8 +1843,7 @@ __global__ void __launch_bounds__(32 * kFastWarps, OCC_MINB) k_visibility(const 
       }
       const int n0 = __popc(und[0]), n = n0 + __popc(und[1]);
       if (n == 0) break;
-      unsigned steps = 0;
-#if OCC_SMEMPAIRS
+      unsigned steps = 0, iters = 0;
       // the slice's pair records (<= kPairsPerItem x 128 bytes, contiguous) into the warp's own shared-memory slot:
       // four independent 16-byte loads per lane, all records at once, instead of one dependent 128-byte warp-uniform
       // load per loop iteration
@@ -1855,9 +1857,9 @@ __global__ void __launch_bounds__(32 * kFastWarps, OCC_MINB) k_visibility(const 
           if (q * 32 + lane < npair * 8) dst[q * 32 + lane] = __ldg(src + q * 32 + lane);
         __syncwarp();
       }
-#else
-      const PairHot *staged = nullptr;
-#endif
+      // pairs through which the object spans more than +-45 degrees of azimuth (an object next to the sensor) need
+      // the full-quadrant arctangent: an item that holds one takes the branching loop, one pair per iteration
+      const bool any_wide = __any_sync(0xffffffffu, lane < npair && staged[lane].wide != 0);
       if (n > 32) {                                              // two voxels per lane, natural mapping
         float dx[2], dy[2], dz[2];
         int vj[2];
@@ -1871,7 +1873,9 @@ __global__ void __launch_bounds__(32 * kFastWarps, OCC_MINB) k_visibility(const 
           dz[v] = (float)(kBrick * bz + (j & 3)) - h.cen[2];
           todo |= ((und[v] >> lane) & 1u) << v;
         }
-        const unsigned found = run_pairs<2>(a, t, h, bx, by, bz, lb, live, k0, todo, dx, dy, dz, vj, steps, staged);
+        const unsigned found = any_wide
+            ? run_pairs<2, 1, true>(a, t, h, bx, by, bz, lb, live, k0, todo, dx, dy, dz, vj, steps, staged, iters)
+            : run_pairs<2, OCC_PP2, false>(a, t, h, bx, by, bz, lb, live, k0, todo, dx, dy, dz, vj, steps, staged, iters);
 #pragma unroll
         for (int v = 0; v < 2; ++v) {
           const unsigned fw = __ballot_sync(0xffffffffu, (found >> v) & 1u);
@@ -1889,19 +1893,43 @@ __global__ void __launch_bounds__(32 * kFastWarps, OCC_MINB) k_visibility(const 
         dx[0] = (float)(kBrick * bx + (vj[0] >> 4)) - h.cen[0];
         dy[0] = (float)(kBrick * by + ((vj[0] >> 2) & 3)) - h.cen[1];
         dz[0] = (float)(kBrick * bz + (vj[0] & 3)) - h.cen[2];
-        const unsigned found = run_pairs<1>(a, t, h, bx, by, bz, lb, live, k0, mine ? 1u : 0u, dx, dy, dz, vj, steps, staged);
+        const unsigned found = any_wide
+            ? run_pairs<1, 1, true>(a, t, h, bx, by, bz, lb, live, k0, mine ? 1u : 0u, dx, dy, dz, vj, steps, staged, iters)
+            : run_pairs<1, OCC_PP1, false>(a, t, h, bx, by, bz, lb, live, k0, mine ? 1u : 0u, dx, dy, dz, vj, steps, staged, iters);
         if (found) atomicOr(a.free_brick + 2 * gb + (vj[0] >> 5), 1u << (vj[0] & 31));
       }
       if (a.n_steps) {
         for (int o = 16; o > 0; o >>= 1) steps += __shfl_xor_sync(0xffffffffu, steps, o);
         if (lane == 0 && steps) atomicAdd((unsigned long long *)&a.n_steps[t], (unsigned long long)steps);
       }
-    } while (0);
-#if OCC_DYN
-    g = n_static + (long long)__shfl_sync(0xffffffffu, nxt, 0);
+#if OCC_VISDEBUG
+      dbg_iters += iters;
 #endif
+    } while (0);
+#if OCC_VISDEBUG
+    {
+      const long long dt = clock64() - dbg_ti;
+      ++dbg_items;
+      if (dt > dbg_max) { dbg_max = dt; dbg_max_it = s; }
+    }
+#endif
+    g = n_static + (long long)__shfl_sync(0xffffffffu, nxt, 0);
   }
+#if OCC_VISDEBUG
+  if (lane == 0 && a.ticket == 0) {
+    const long long w = (long long)blockIdx.x * kFastWarps + (threadIdx.x >> 5);
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    long long *d = g_visdbg + 8 * w;
+    d[0] = dbg_t0; d[1] = clock64(); d[2] = dbg_items; d[3] = dbg_iters; d[4] = dbg_max; d[5] = dbg_max_it; d[6] = smid;
+  }
+#endif
 }
+#if OCC_VISDEBUG
+extern "C" int occb200_debug_visibility(long long *out_host, int n) {
+  return cudaMemcpyFromSymbol(out_host, g_visdbg, sizeof(long long) * n) == cudaSuccess ? 0 : 1;
+}
+#endif
 
 __global__ void __launch_bounds__(256)
 k_visibility_recheck(int L, const int64_t *__restrict__ trk_frame_off, const occb200_pose_t *__restrict__ poses,
@@ -2153,30 +2181,51 @@ extern "C" int occb200_annotate_batch(const occb200_annotate_args_t *a, int64_t 
     if (launch_redo(side->stream)) return 1;
     OCC_CUDA(cudaEventRecord(side->join, side->stream));
   }
-  if (brick_cull && w.bricks > 0) {
-    ProfScope ps(kProfBrickCull, stream);
-    const unsigned gx = (unsigned)std::min<int64_t>(ceil_div((w.bricks + 31) / 32 * 32 * kPairsPerItem, 256), (int64_t)kNumSMs * 16);
-    k_brick_cull<<<dim3(gx, (unsigned)w.n_slices), 256, 0, stream>>>(w.item_map, (long long)w.bricks, w.counter, w.hot,
-                                                                     w.pairs_c, w.lut_pool, a->pyr_off, w.pyr2,
-                                                                     w.mask_words, w.pair_mask);
-    OCC_KERNEL_OK("k_brick_cull");
-  }
-  OCC_CUDA(cudaStreamWaitEvent(stream, side->join, 0));   // redo pass done: bits and flags final
-  // flag bit 3 (tests): the kernels see a 64-entry recheck queue, so the decide-in-place path runs
+  // The ray-cast: brick cull + visibility.  With more than one slice of pairs the two kernels are split by slice
+  // and overlapped: the cull of slices >= 1 (latency-bound: one short dependent chain per thread) runs on a second
+  // side stream next to the visibility pass over slice 0 (issue-bound), which only needs slice 0's mask bits.
   const long long queue_cap_used = (a->flags & 8) ? std::min<long long>(64, (long long)w.queue_cap) : (long long)w.queue_cap;
-  {
+  const bool split = OCC_OVERLAP && brick_cull && w.bricks > 0 && w.n_slices > 1;
+  auto launch_cull = [&](int s0, int s1, cudaStream_t cs) -> int {
+    const unsigned gx = (unsigned)std::min<int64_t>(ceil_div((w.bricks + 31) / 32 * 32 * kPairsPerItem, 256), (int64_t)kNumSMs * 16);
+    k_brick_cull<<<dim3(gx, (unsigned)(s1 - s0)), 256, 0, cs>>>(s0, w.item_map, (long long)w.bricks, w.counter, w.hot,
+                                                                 w.pairs_c, w.lut_pool, a->pyr_off, w.pyr2, w.mask_words,
+                                                                 w.pair_mask);
+    OCC_KERNEL_OK("k_brick_cull");
+    return 0;
+  };
+  auto launch_vis = [&](int s0, int s1, int ticket) -> int {
     VisArgs va;
-    va.L = a->L; va.mask_words = w.mask_words; va.n_slices = w.n_slices; va.pad = 0;
+    va.L = a->L; va.mask_words = w.mask_words; va.s_lo = s0; va.s_hi = s1; va.ticket = ticket; va.pad = 0;
     va.bricks_total = (long long)w.bricks; va.queue_cap = queue_cap_used; va.vs = a->voxel_size;
     va.trk_frame_off = a->trk_frame_off; va.poses = a->poses; va.frame_sf = a->frame_sf; va.sensors = a->sensors;
     va.incl_pool = a->incl_pool; va.ri_pool = a->ri_pool; va.grids = w.grids; va.counter = w.counter;
     va.bits = w.bits; va.free_brick = w.free_brick; va.pair_mask = w.pair_mask; va.item_map = w.item_map;
     va.hot = w.hot; va.pairs = w.pairs_c; va.lut_pool = w.lut_pool; va.queue = w.queue; va.n_steps = a->n_steps;
-    const int grid = (int)std::min<int64_t>(ceil_div(std::max<int64_t>(w.bricks * w.n_slices, 1), kFastWarps),
+    const int grid = (int)std::min<int64_t>(ceil_div(std::max<int64_t>(w.bricks * (s1 - s0), 1), kFastWarps),
                                             (int64_t)kNumSMs * OCC_MINB);
-    ProfScope ps(kProfVisibility, stream);
     k_visibility<<<grid, 32 * kFastWarps, 0, stream>>>(va);
     OCC_KERNEL_OK("k_visibility");
+    return 0;
+  };
+  if (split) {
+    OCC_CUDA(cudaEventRecord(side->fork2, stream));           // after k_pair_build
+    OCC_CUDA(cudaStreamWaitEvent(side->stream2, side->fork2, 0));
+    if (launch_cull(1, w.n_slices, side->stream2)) return 1;
+    OCC_CUDA(cudaEventRecord(side->join2, side->stream2));
+  }
+  if (brick_cull && w.bricks > 0) {
+    ProfScope ps(kProfBrickCull, stream);
+    if (launch_cull(0, split ? 1 : w.n_slices, stream)) return 1;
+  }
+  OCC_CUDA(cudaStreamWaitEvent(stream, side->join, 0));   // redo pass done: bits and flags final
+  {
+    ProfScope ps(kProfVisibility, stream);                  // (split: slice 0, the wait for the other culls, the rest)
+    if (launch_vis(0, split ? 1 : w.n_slices, 0)) return 1;
+    if (split) {
+      OCC_CUDA(cudaStreamWaitEvent(stream, side->join2, 0));
+      if (launch_vis(1, w.n_slices, 1)) return 1;
+    }
   }
   {
     ProfScope ps(kProfRecheck, stream);
