@@ -734,9 +734,11 @@ def main():
     res_e2e = d.results()
     assert count_mismatches(res_e2e, res) == 0, "e2e labels differ from the resident run"
     # the public one-shot call, for scale: pack + allocate + upload from pageable memory + run + download
-    t0 = time.perf_counter()
-    occ.annotate_batch(batch, flags=ctx.flags)
-    api_ms = (time.perf_counter() - t0) * 1e3
+    api_ms = float("inf")
+    for _ in range(3):                               # best of 3: the first call also pays allocator warm-up
+        t0 = time.perf_counter()
+        occ.annotate_batch(batch, flags=ctx.flags)
+        api_ms = min(api_ms, (time.perf_counter() - t0) * 1e3)
     clocks = sampler.stop() if rank == 0 else None
 
     t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)

@@ -36,16 +36,28 @@ __global__ void k_minmax(const CT *__restrict__ coors, int64_t N, int K, long lo
       lo[k] = v < lo[k] ? v : lo[k];
       hi[k] = v > hi[k] ? v : hi[k];
     }
+  // warp -> CTA -> ONE atomic pair per column and CTA (per-warp atomics on the 2K result words serialised: 59 us for
+  // 650 k rows, the longest kernel of a DynamicScatter call)
+  __shared__ long long s_lo[8][kMaxK], s_hi[8][kMaxK];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int k = 0; k < K; ++k) {
     for (int o = 16; o > 0; o >>= 1) {
       const long long a = __shfl_xor_sync(0xffffffffu, lo[k], o), b = __shfl_xor_sync(0xffffffffu, hi[k], o);
       lo[k] = a < lo[k] ? a : lo[k];
       hi[k] = b > hi[k] ? b : hi[k];
     }
-    if ((threadIdx.x & 31) == 0) {
-      atomicMin(&mm[2 * k], lo[k]);
-      atomicMax(&mm[2 * k + 1], hi[k]);
+    if (lane == 0) { s_lo[warp][k] = lo[k]; s_hi[warp][k] = hi[k]; }
+  }
+  __syncthreads();
+  if (threadIdx.x < K) {
+    const int k = threadIdx.x;
+    long long a = s_lo[0][k], b = s_hi[0][k];
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) {
+      a = s_lo[w][k] < a ? s_lo[w][k] : a;
+      b = s_hi[w][k] > b ? s_hi[w][k] : b;
     }
+    atomicMin(&mm[2 * k], a);
+    atomicMax(&mm[2 * k + 1], b);
   }
 }
 
@@ -162,7 +174,7 @@ static int unique_impl(const CT *coors, int64_t N, int K, int mode, CT *uniq, in
   long long *mm = (long long *)(ws + l.mm);
   k_minmax_init<<<1, 32, 0, stream>>>(mm);
   OCC_KERNEL_OK("k_minmax_init");
-  const int mm_grid = (int)std::min<int64_t>(ceil_div(N, 256), kNumSMs * 8);
+  const int mm_grid = (int)std::min<int64_t>(ceil_div(N, 256 * 4), kNumSMs * 4);
   k_minmax<CT><<<mm_grid, 256, 0, stream>>>(coors, N, K, mm);
   OCC_KERNEL_OK("k_minmax");
   long long h_mm[2 * kMaxK + 1];
