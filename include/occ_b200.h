@@ -370,16 +370,23 @@ int occb200_select_candidates(const float *clouds, int stride, const int64_t *cl
 /* ---- windowed upload of the range images (occ_annotate.py:502-533 loads every whole image; the visibility test
  *      reads a small window of each) ---------------------------------------------------------------------------- */
 
-/* HOST helper.  mask (ceil(ri_len / 16) bytes, zeroed by the caller) receives 1 for every 64-byte block -- floats
- * [16k, 16k + 16) of ri_pool -- that the visibility test (occ_annotate.py:141-201, 541-547) of any voxel of any
- * tracklet of the batch can read: per (tracklet-frame, LiDAR) a conservative pixel window derived from the box
- * (max size over the tracklet's frames), the pose and the sensor entry.  All pointers are HOST arrays in the
- * layout of occb200_annotate_args_t.  Uploading only the marked blocks (occb200_host_gather_blocks +
- * occb200_scatter_blocks) into a zero-initialised ri_pool gives the same labels, dims and statuses as uploading
- * every image; n_steps may differ (the culls see zeros outside the windows). */
-int occb200_host_ri_window_blocks(int32_t T, int32_t L, const int64_t *trk_frame_off, const occb200_pose_t *poses,
-                                  const int32_t *frame_sf, const occb200_sensor_t *sensors, int64_t SF,
-                                  const float *incl_pool, double voxel_size, int64_t ri_len, uint8_t *mask);
+/* HOST helper.  mask8 (ceil(ri_len / 8) bytes, zeroed by the caller) receives 1 for every 32-byte block -- floats
+ * [8k, 8k + 8) of ri_pool -- that the visibility test (occ_annotate.py:141-201, 541-547) of any voxel of any tracklet
+ * of the batch can read: per (tracklet-frame, LiDAR, sub-box of the tracklet's centre box) the pixel footprint
+ * bracketed from the sub-box's 8 corners.  trk_smax f32 [T,3] = the max box size over all frames of each tracklet;
+ * sub_edge = sub-box edge in metres (<= 0: 0.8 m, what occb200_pull_windows uses on the device; 1e9: one box per
+ * tracklet-frame, 12 % more bytes for 1/40 of the work).  All pointers are HOST arrays in the layout of
+ * occb200_annotate_args_t.  Uploading only the marked blocks (occb200_host_mask_to_blocks + occb200_host_gather_blocks
+ * + occb200_scatter_blocks) into a zero-initialised ri_pool gives the same labels, dims and statuses as uploading every
+ * image; n_steps may differ (the culls see zeros outside the windows). */
+int occb200_host_window_mark(int32_t T, int32_t L, const int64_t *trk_frame_off, const occb200_pose_t *poses,
+                             const int32_t *frame_sf, const occb200_sensor_t *sensors, int64_t SF,
+                             const float *incl_pool, const float *trk_smax, double voxel_size, int64_t ri_len,
+                             uint8_t *mask8, float sub_edge);
+
+/* HOST helper.  The ascending list of 16-float blocks (64 bytes) that hold a marked 8-float block; returns their
+ * number.  out has room for ceil(n8 / 2) entries. */
+int64_t occb200_host_mask_to_blocks(const uint8_t *mask8, int64_t n8, uint32_t *out);
 
 /* HOST helper.  staging[16 i .. 16 i + 16) = block block_idx[i] of the pool, read from the source arrays: part j
  * holds floats [part_off[j], part_off[j] + part_len[j]) of the pool at part_ptr[j].  block_idx ascending;
@@ -404,12 +411,6 @@ int occb200_scatter_blocks(const float *blocks, const uint32_t *block_idx, int64
  * max box size over all frames of each tracklet.  ri_len % 8 == 0.  *pulled_blocks (device, optional, zeroed by
  * the caller) accumulates the 32-byte blocks read.  Asynchronous on `stream`. */
 int64_t occb200_window_mask_words(int64_t ri_len);
-/* HOST test hook: the footprint code of occb200_pull_windows compiled for the CPU; mask8 (ri_len / 8 bytes, zeroed by
- * the caller) receives 1 per marked 32-byte block.  All pointers HOST. */
-int occb200_host_window_mark(int32_t T, int32_t L, const int64_t *trk_frame_off, const occb200_pose_t *poses,
-                             const int32_t *frame_sf, const occb200_sensor_t *sensors, int64_t SF,
-                             const float *incl_pool, const float *trk_smax, double voxel_size, int64_t ri_len,
-                             uint8_t *mask8);
 int occb200_pull_windows(const occb200_annotate_args_t *args, const float *trk_smax, const float *ri_host,
                          float *ri_pool, int64_t ri_len, uint32_t *mask, unsigned long long *pulled_blocks,
                          void *stream);

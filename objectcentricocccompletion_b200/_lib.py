@@ -91,11 +91,11 @@ SIGNATURES = {
     "occb200_annotate_queue_stats": (C.c_int, [C.POINTER(AnnotateArgs), i64, vp, vp]),
     "occb200_annotate_point_voxels": (C.c_int, [C.POINTER(AnnotateArgs), i64, vp, vp, vp]),
     "occb200_host_pose_pack": (None, [vp, vp, i64, vp]),
-    "occb200_host_ri_window_blocks": (C.c_int, [i32, i32, vp, vp, vp, vp, i64, vp, f64, i64, vp]),
+    "occb200_host_mask_to_blocks": (i64, [vp, i64, vp]),
     "occb200_host_gather_blocks": (C.c_int, [vp, i64, vp, vp, vp, i32, vp]),
     "occb200_scatter_blocks": (C.c_int, [vp, vp, i64, vp, i64, vp]),
     "occb200_window_mask_words": (i64, [i64]),
-    "occb200_host_window_mark": (C.c_int, [i32, i32, vp, vp, vp, vp, i64, vp, vp, f64, i64, vp]),
+    "occb200_host_window_mark": (C.c_int, [i32, i32, vp, vp, vp, vp, i64, vp, vp, f64, i64, vp, f32]),
     "occb200_pull_windows": (C.c_int, [C.POINTER(AnnotateArgs), vp, vp, vp, i64, vp, vp, vp]),
     "occb200_build_range_images": (C.c_int, [vp, C.c_int, vp, i64, vp, i32, vp, vp, i64, vp, vp]),
     "occb200_point_cloud_to_range_image_idx": (C.c_int, [vp, C.c_int, i64, vp, vp, vp, C.c_int, C.c_int, vp, vp, vp]),

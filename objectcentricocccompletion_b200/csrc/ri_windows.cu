@@ -4,18 +4,30 @@
 // frame, 104 MB for the 40 frames of one segment) and reads, per tracklet, a window of a few hundred pixels of
 // each: the pixels the voxel centres of the tracklet's grid project to (:141-201, :541-547).  On the B200 path
 // the host -> device copy of those images was the whole end-to-end step (134 MB over PCIe against 0.18 ms of
-// kernels).  Here the host derives, per (tracklet-frame, LiDAR), a conservative pixel window from the box alone,
-// marks the 64-byte blocks (16 floats of the flat pool) it touches, gathers exactly those blocks from the source
-// arrays into one staging buffer, and a kernel scatters them to their place in the (dense, zero-initialised)
-// device pool.  The kernels of annotate.cu are unchanged: they index the dense pool.
+// kernels).  Two ways to move only the windows, both filling the same dense, zero-initialised device pool (the
+// kernels of annotate.cu are unchanged: they index the dense pool):
 //
-// Why the labels cannot change.  Every pixel the exact test of a real voxel centre can read lies inside its
-// pair's window (derivation at host_ri_window_blocks).  What lies outside the windows keeps its previous content
-// (zeros, or an earlier upload of the same pool): only the max-pyramid and the discarded tests of padding lanes
-// ever look at it.  A pyramid tile that holds such pixels can only make a cull LESS likely than the truth
-// restricted to the window requires -- or more likely, but then every in-window pixel is below the cull's bound
-// and the culled tests would all have failed.  (n_steps, the count of evaluated tests, may differ from a
-// whole-image upload for that reason; labels, dims and statuses cannot.)
+//   pull  (occb200_pull_windows)  the range images stay in PINNED host memory in the pool's layout; the device
+//         marks the 32-byte blocks the batch can read (k_window_mark: footprints of <= 0.8 m sub-boxes of each
+//         tracklet's centre box) and reads exactly those over PCIe (k_window_pull: unified addressing).  No host
+//         work per step, no staging copy.
+//   host  (occb200_host_window_mark + occb200_host_gather_blocks + occb200_scatter_blocks)  for images in pageable
+//         memory: the host marks the blocks with the same footprint code (one box per tracklet-frame), gathers
+//         them from the source arrays into one staging buffer, the device scatters them to their place.
+//
+// The centre box.  In the box frame every voxel centre is idx*vs + min_bound + vs/2 with 0 <= idx < dims =
+// ceil(size / vs) and min_bound = (-sx/2, -sy/2, 0) (occ_annotate.py:414-423, 467-471), size <= S = the max of the box
+// size over ALL frames of the tracklet (the true size is the max over the frames that keep a point, :111-112,
+// :132-133).  So the centres lie in  [-S/2, S/2 + vs] x [-S/2, S/2 + vs] x [0, Sz + vs]  (+ 1 cm).  The chain box frame
+// -> ego -> sensor (:490-499, :161-164) is affine, so a (sub-)box maps to a parallelepiped whose corner extremes
+// bracket range, height and azimuth (sub_footprint below).
+//
+// Why the labels cannot change.  Every pixel the exact test of a real voxel centre can read lies inside a marked
+// block.  What lies outside keeps its previous content (zeros, or an earlier upload of the same pool): only the
+// max-pyramid and the discarded tests of padding lanes ever look at it.  A pyramid tile that holds such pixels can
+// only make a cull LESS likely than the truth restricted to the window requires -- or more likely, but then every
+// in-window pixel is below the cull's bound and the culled tests would all have failed.  (n_steps, the count of
+// evaluated tests, may differ from a whole-image upload for that reason; labels, dims and statuses cannot.)
 #include <math.h>
 #include <string.h>
 
@@ -26,22 +38,6 @@
 namespace occb200 {
 
 constexpr int kBlk = 16;      // floats per block: 64 bytes = two sectors
-
-// argmin_h |x - tab[h]| for a strictly descending table (first index on ties): occ_annotate.py:168-173
-static int host_row_desc(const float *tab, int H, double x) {
-  int lo = 0, hi = H;
-  while (lo < hi) {
-    const int mid = (lo + hi) >> 1;
-    if ((double)tab[mid] > x) lo = mid + 1; else hi = mid;
-  }
-  if (lo >= H) return H - 1;
-  if (lo == 0) return 0;
-  return (fabs(x - (double)tab[lo]) < fabs(x - (double)tab[lo - 1])) ? lo : lo - 1;
-}
-
-static inline void mark_flat(uint8_t *mask, int64_t a, int64_t b) {   // floats [a, b] of the pool
-  for (int64_t k = a / kBlk; k <= b / kBlk; ++k) mask[k] = 1;
-}
 
 __global__ void __launch_bounds__(256)
 k_scatter_blocks(const float4 *__restrict__ blocks, const uint32_t *__restrict__ block_idx, long long n_blocks,
@@ -67,12 +63,12 @@ k_scatter_blocks(const float4 *__restrict__ blocks, const uint32_t *__restrict__
 // pinned host copy of the range images (unified addressing: a kernel may read pinned host memory over PCIe).
 // No host geometry, no host gather, no staging buffer: the host only keeps the images where the loader put them.
 //
-// k_window_mark   one thread per (tracklet-frame, LiDAR, sub-box): the tracklet's centre box (see
-//                 occb200_host_ri_window_blocks) is cut into sub-boxes of <= kSubEdge metres; each sub-box maps to a
+// k_window_mark   one thread per (tracklet-frame, LiDAR, sub-box): the tracklet's centre box (file header) is cut
+//                 into sub-boxes of <= kSubEdge metres; each sub-box maps to a
 //                 convex body in the sensor frame whose pixel footprint is bracketed from its 8 corners exactly as
 //                 k_brick_cull does for a brick (annotate.cu): range r_lo <= |p| <= r_hi, z extremes at corners,
 //                 sin(inc) = z / |p|, azimuth half-width from cross / dot sums.  The union of the sub-box footprints
-//                 hugs the object's outline (a single ball around the whole box marked 2.5x the pixels).  f32 with
+//                 hugs the object's outline (one ball around the whole box marks 2x the pixels).  f32 with
 //                 generous padding: 1e-4 rad, 1 mm + 1e-5 d, one row, two columns; any doubt marks whole rows /
 //                 the whole image.  Sets one bit per 32-byte block (8 floats) of the pool.
 // k_window_pull   one warp per 32 mask bits (1 KB of the pool): the marked blocks are read from the host pool with
@@ -122,7 +118,7 @@ struct SubGrid {
   int nsub;
 };
 
-__host__ __device__ inline SubGrid sub_grid(const float *__restrict__ smax3, float vs) {
+__host__ __device__ inline SubGrid sub_grid(const float *__restrict__ smax3, float vs, float edge = kSubEdge) {
   SubGrid g;
   const float m = 0.01f;
   g.lo[0] = -0.5f * smax3[0] - m; g.lo[1] = -0.5f * smax3[1] - m; g.lo[2] = -m;
@@ -131,7 +127,7 @@ __host__ __device__ inline SubGrid sub_grid(const float *__restrict__ smax3, flo
   for (int k = 0; k < 3; ++k)
     if (!(g.ext[k] > 0.f && g.ext[k] < 1e4f)) g.sane = false;
   for (int k = 0; k < 3; ++k) {
-    const int c = (int)ceilf(g.ext[k] / kSubEdge);
+    const int c = (int)ceilf(g.ext[k] / edge);
     g.n[k] = g.sane ? (c < 1 ? 1 : (c > 64 ? 64 : c)) : 1;     // absurd sizes: one item per pair marks the whole image
   }
   g.nsub = g.n[0] * g.n[1] * g.n[2];
@@ -288,98 +284,14 @@ k_window_pull(const uint32_t *__restrict__ mask, long long n_words, const float 
 
 using namespace occb200;
 
-// HOST.  Marks mask[k] = 1 for every block k (floats [16k, 16k + 16) of ri_pool) that the visibility test of any
-// tracklet of the batch can read.  mask has ceil(ri_len / 16) bytes; the caller zeroes it.
-//
-// Window of one (tracklet-frame, LiDAR).  In the box frame every voxel centre is idx*vs + min_bound + vs/2 with
-// 0 <= idx < dims = ceil(size / vs) and min_bound = (-sx/2, -sy/2, 0) (occ_annotate.py:414-423, 467-471), size <=
-// S = the max of the box size over ALL frames of the tracklet (the true size is the max over the frames that keep
-// a point, :111-112, :132-133).  So the centres lie in the box  [-S/2, S/2 + vs] x [-S/2, S/2 + vs] x [0, Sz + vs]
-// (+ 1 cm), hence in the ball around its centre with its half diagonal R.  The chain box frame -> ego -> sensor
-// (:490-499, :161-164) is rigid (up to the f32 inverse: R * 1.001 + 1 mm), so seen from the sensor at distance d,
-// horizontal distance rho, every centre has
-//     inclination in inc_c +- asin(R / d),     azimuth in az_c +- asin(R / rho)
-// and the reference's row (nearest table entry, :168-173) and column (:176-191) rules are monotone in those angles:
-// the window is the image of the interval ends, padded by one row and two columns, modulo W.  d <= 1.02 R or a
-// table that does not descend: every row; rho <= 1.02 R or a window wider than the image: every column.
-extern "C" int occb200_host_ri_window_blocks(int32_t T, int32_t L, const int64_t *trk_frame_off,
-                                             const occb200_pose_t *poses, const int32_t *frame_sf,
-                                             const occb200_sensor_t *sensors, int64_t SF, const float *incl_pool,
-                                             double voxel_size, int64_t ri_len, uint8_t *mask) {
-  OCC_REQUIRE(T >= 0 && L >= 1 && ri_len >= 0 && voxel_size > 0, "bad arguments");
-  const double kPi = 3.14159265358979323846;
-  int bad = 0;
-#pragma omp parallel for schedule(dynamic, 4)
-  for (int t = 0; t < T; ++t) {
-    const int64_t f0 = trk_frame_off[t], f1 = trk_frame_off[t + 1];
-    double S[3] = {0, 0, 0};
-    for (int64_t f = f0; f < f1; ++f)
-      for (int k = 0; k < 3; ++k) S[k] = std::max(S[k], (double)poses[f].box[3 + k]);
-    if (!(S[0] < 1e6 && S[1] < 1e6 && S[2] < 1e6)) S[0] = S[1] = S[2] = 1e6;      // NaN / absurd: whole images
-    const double m = 0.01, vs = voxel_size;
-    const double lo[3] = {-0.5 * S[0] - m, -0.5 * S[1] - m, -m};
-    const double hi[3] = {0.5 * S[0] + vs + m, 0.5 * S[1] + vs + m, S[2] + vs + m};
-    double cb[3], Rb = 0;
-    for (int k = 0; k < 3; ++k) {
-      cb[k] = 0.5 * (lo[k] + hi[k]);
-      Rb += 0.25 * (hi[k] - lo[k]) * (hi[k] - lo[k]);
-    }
-    const double R = sqrt(Rb) * 1.001 + 1e-3;
-    for (int64_t f = f0; f < f1; ++f) {
-      const occb200_pose_t &ps = poses[f];
-      const double c = (double)ps.cos_p, s = (double)ps.sin_p;
-      const double ex = cb[0] * c + cb[1] * s + (double)ps.box[0];
-      const double ey = -cb[0] * s + cb[1] * c + (double)ps.box[1];
-      const double ez = cb[2] + (double)ps.box[2];
-      const int64_t sf = frame_sf[f];
-      if (sf < 0 || sf >= SF) { bad = 1; continue; }
-      for (int l = 0; l < L; ++l) {
-        const occb200_sensor_t &sn = sensors[sf * L + l];
-        const int H = sn.H, W = sn.W;
-        if (H < 1 || W < 1) continue;
-        const int64_t img = sn.ri_off;
-        if (img < 0 || img + (int64_t)H * W > ri_len) { bad = 1; continue; }
-        const float *v = sn.v2l;
-        const double px = v[0] * ex + v[1] * ey + v[2] * ez + v[3];
-        const double py = v[4] * ex + v[5] * ey + v[6] * ez + v[7];
-        const double pz = v[8] * ex + v[9] * ey + v[10] * ez + v[11];
-        const double rho = sqrt(px * px + py * py), d = sqrt(rho * rho + pz * pz);
-        int r0 = 0, r1 = H - 1;
-        if (d > 1.02 * R && sn.incl_mono == -1 && isfinite(d)) {
-          const double delta = asin(R / d) + 1e-6, inc_c = atan2(pz, rho);
-          const float *tab = incl_pool + sn.incl_off;
-          r0 = std::max(host_row_desc(tab, H, std::min(inc_c + delta, 0.5 * kPi)) - 1, 0);
-          r1 = std::min(host_row_desc(tab, H, std::max(inc_c - delta, -0.5 * kPi)) + 1, H - 1);
-        }
-        long long c_lo = 0, c_hi = W - 1;
-        if (rho > 1.02 * R && isfinite(rho)) {
-          const double daz = asin(R / rho) + 1e-6;
-          const double az = atan2(py, px) + (double)sn.azc;
-          // colf = (W - 0.5) - (az + pi) / (2 pi) W (:187-189); the reference's wrap by float32(2 pi) moves it by
-          // 3e-8 W pixels at most: far inside the two-column padding
-          const double kc = (double)W / (2.0 * kPi);
-          const double cf_lo = ((double)W - 0.5) - (az + daz + kPi) * kc;
-          const double cf_hi = ((double)W - 0.5) - (az - daz + kPi) * kc;
-          if (cf_hi - cf_lo + 6.0 < (double)W) {
-            c_lo = (long long)floor(cf_lo) - 2;
-            c_hi = (long long)ceil(cf_hi) + 2;
-          }
-        }
-        if (c_hi - c_lo + 1 >= W) {                 // whole rows
-          mark_flat(mask, img + (int64_t)r0 * W, img + (int64_t)r1 * W + W - 1);
-          continue;
-        }
-        const long long a0 = ((c_lo % W) + W) % W, len = c_hi - c_lo + 1;
-        for (int r = r0; r <= r1; ++r) {
-          const int64_t row = img + (int64_t)r * W;
-          mark_flat(mask, row + a0, row + std::min<long long>(a0 + len, W) - 1);
-          if (a0 + len > W) mark_flat(mask, row, row + (a0 + len - W) - 1);
-        }
-      }
-    }
-  }
-  OCC_REQUIRE(!bad, "frame_sf or ri_off out of range");
-  return 0;
+// HOST.  Compacts an 8-float block mask into the ascending list of 16-float blocks (64 bytes, the unit of the gather /
+// scatter pair) that hold a marked block; returns their number.  out has room for ceil(n8 / 2) entries.
+extern "C" int64_t occb200_host_mask_to_blocks(const uint8_t *mask8, int64_t n8, uint32_t *out) {
+  int64_t n = 0;
+  for (int64_t k = 0; k + 1 < n8; k += 2)
+    if (mask8[k] | mask8[k + 1]) out[n++] = (uint32_t)(k >> 1);
+  if ((n8 & 1) && mask8[n8 - 1]) out[n++] = (uint32_t)(n8 >> 1);
+  return n;
 }
 
 // HOST.  Copies the listed blocks from the source arrays to staging[16 * i ..]: block k of the pool lies in part
@@ -461,17 +373,20 @@ extern "C" int occb200_pull_windows(const occb200_annotate_args_t *a, const floa
   return 0;
 }
 
-// HOST test hook: the footprint code of k_window_mark compiled for the CPU.  mask8[k] = 1 for every 8-float block
-// the device-side path would mark (up to the last-ulp differences of the host's libm, far inside the padding).
+// HOST: the footprint code of k_window_mark compiled for the CPU.  mask8[k] = 1 for every 8-float block some
+// tracklet of the batch can read.  sub_edge <= 0: the device path's sub-boxes (the CPU tests compare the two, equal
+// up to the last-ulp differences of the host's libm, far inside the padding); a large value: one box per
+// tracklet-frame -- what the "host" upload mode uses (12 % more bytes than 0.8 m sub-boxes for 1/40 of the work).
 extern "C" int occb200_host_window_mark(int32_t T, int32_t L, const int64_t *trk_frame_off, const occb200_pose_t *poses,
                                         const int32_t *frame_sf, const occb200_sensor_t *sensors, int64_t SF,
                                         const float *incl_pool, const float *trk_smax, double voxel_size,
-                                        int64_t ri_len, uint8_t *mask8) {
+                                        int64_t ri_len, uint8_t *mask8, float sub_edge) {
   OCC_REQUIRE(T >= 0 && L >= 1 && ri_len >= 0, "bad arguments");
+  const float edge = sub_edge > 0.f ? sub_edge : kSubEdge;
 #pragma omp parallel for schedule(dynamic, 1)
   for (int t = 0; t < T; ++t) {
     const int64_t f0 = trk_frame_off[t], f1 = trk_frame_off[t + 1];
-    const SubGrid g = sub_grid(trk_smax + 3 * t, (float)voxel_size);
+    const SubGrid g = sub_grid(trk_smax + 3 * t, (float)voxel_size, edge);
     for (int64_t f = f0; f < f1; ++f) {
       const int64_t sf = frame_sf[f];
       if (sf < 0 || sf >= SF) continue;

@@ -138,17 +138,26 @@ def _same_memory(flat, pieces, n_rows) -> bool:
 RI_BLOCK = 16      # floats per block of the windowed range-image upload (csrc/ri_windows.cu)
 
 
-def window_blocks(pk: "PackedTracklets") -> np.ndarray:
-    """The blocks of ``ri_pool`` any visibility test of the batch can read (``occb200_host_ri_window_blocks``)."""
-    nblk = (pk.ri_len + RI_BLOCK - 1) // RI_BLOCK
-    mask = np.zeros(max(nblk, 1), np.uint8)
-    if pk.T and pk.F and nblk:
-        rc = _lib.lib().occb200_host_ri_window_blocks(
+def window_mask(pk: "PackedTracklets", sub_edge: float = 1e9) -> np.ndarray:
+    """u8 per 8-float block of ``ri_pool``: 1 where a visibility test of the batch can read
+    (``occb200_host_window_mark``: corner-bracketed footprints; ``sub_edge`` <= 0: the device path's 0.8 m sub-boxes)."""
+    n8 = (pk.ri_len + 7) // 8
+    mask = np.zeros(max(n8, 1), np.uint8)
+    if pk.T and pk.F and n8:
+        rc = _lib.lib().occb200_host_window_mark(
             pk.T, pk.L, pk.trk_frame_off.ctypes.data, pk.poses.ctypes.data, pk.frame_sf.ctypes.data,
-            pk.sensors.ctypes.data, pk.sensors.shape[0], pk.incl_pool.ctypes.data, float(pk.voxel_size),
-            pk.ri_len, mask.ctypes.data)
-        _lib.check(rc, "occb200_host_ri_window_blocks")
-    return np.flatnonzero(mask[:nblk]).astype(np.uint32)
+            pk.sensors.ctypes.data, pk.sensors.shape[0], pk.incl_pool.ctypes.data, pk.trk_smax.ctypes.data,
+            float(pk.voxel_size), pk.ri_len, mask.ctypes.data, float(sub_edge))
+        _lib.check(rc, "occb200_host_window_mark")
+    return mask[:n8]
+
+
+def window_blocks(pk: "PackedTracklets") -> np.ndarray:
+    """The 16-float blocks of ``ri_pool`` the "host" upload mode copies (ascending u32)."""
+    mask = window_mask(pk)
+    out = np.empty((mask.size + 1) // 2 + 1, np.uint32)
+    n = _lib.lib().occb200_host_mask_to_blocks(mask.ctypes.data, mask.size, out.ctypes.data)
+    return out[:n].copy()
 
 
 def pack_tracklets(batch, pack_override: Optional[dict] = None) -> PackedTracklets:

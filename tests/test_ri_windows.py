@@ -75,16 +75,9 @@ def test_windows_cover_close_and_overhead_objects():
     _check_cover(batch)
 
 
-def device_style_mask(pk):
+def device_style_mask(pk, sub_edge=0.0):
     """The 8-float block mask of the device-side path, from the host build of the same footprint code."""
-    from objectcentricocccompletion_b200 import _lib
-    mask8 = np.zeros(pk.ri_len // 8 + 1, np.uint8)
-    rc = _lib.lib().occb200_host_window_mark(pk.T, pk.L, pk.trk_frame_off.ctypes.data, pk.poses.ctypes.data,
-                                             pk.frame_sf.ctypes.data, pk.sensors.ctypes.data, pk.sensors.shape[0],
-                                             pk.incl_pool.ctypes.data, pk.trk_smax.ctypes.data, float(pk.voxel_size),
-                                             pk.ri_len, mask8.ctypes.data)
-    assert rc == 0
-    return mask8[: pk.ri_len // 8].astype(bool)
+    return occ_annotate.window_mask(pk, sub_edge).astype(bool)
 
 
 @pytest.mark.parametrize("kind,vs,drag", [("vehicle", 0.2, 1.0), ("large", 0.1, 1.0), ("vehicle", 0.2, 0.02)])
@@ -97,9 +90,10 @@ def test_subbox_footprints_cover_every_pixel_the_reference_reads(kind, vs, drag)
     mask = device_style_mask(pk)
     assert check_cover(batch, pk, mask, 8) > 0
     if drag == 1.0:
-        ball = np.zeros(pk.ri_len // 16, bool)
-        ball[occ_annotate.window_blocks(pk)] = True
-        assert mask.sum() * 8 < ball.sum() * 16                # tighter than one ball per tracklet-frame
+        one = np.zeros(pk.ri_len // 16, bool)
+        one[occ_annotate.window_blocks(pk)] = True
+        assert mask.sum() * 8 <= one.sum() * 16                # sub-boxes are at least as tight as one box
+        assert one.sum() * 16 < 0.6 * pk.ri_len                # and one box is already a fraction of the images
 
 
 def test_gather_blocks_reproduces_the_pool():
