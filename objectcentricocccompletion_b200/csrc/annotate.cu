@@ -51,8 +51,13 @@ constexpr int kFastWarps = 8;       // fast kernel: independent warps per CTA
 #ifndef OCC_PPI
 #define OCC_PPI 16
 #endif
+#ifndef OCC_TAILSPLIT
+#define OCC_TAILSPLIT 2
+#endif
 constexpr int kPairsPerItem = OCC_PPI;   // (frame, LiDAR) pairs one work item covers for its brick; divides 32
 static_assert(32 % OCC_PPI == 0, "a slice of pairs must sit inside one 32-bit mask word");
+constexpr int kTailSplit = OCC_TAILSPLIT; // tickets per item in the last round of k_visibility; divides kPairsPerItem
+static_assert(OCC_PPI % OCC_TAILSPLIT == 0, "the tail split must divide the pairs of an item");
 constexpr int kMaxSlices = 256;          // => at most 4096 pairs (frames x LiDARs) per tracklet on the fast path
 constexpr float kAtanNarrow = 1.0e-6f;   // bound on |atan_poly(t) - atan(t)|, |t| <= 1 (derivation at atan_narrow)
 constexpr float kAtanWide = 2.0e-6f;     // bound on |atan2_fast - atan2| (derivation at atan2_fast)
@@ -173,6 +178,7 @@ struct Workspace {
   uint32_t *bits;        // occupancy bitsets, linear voxel order, tracklet t at label_off[t]/32 + t
   int64_t bits_words;
   uint32_t *free_brick;  // [2 * bricks] voxels proven free, BRICK order: bit j = lx*16 + ly*4 + lz of word pair 2*brick
+  uint32_t *unk_brick;   // [2 * bricks] voxels inside the grid that hold no point, same order (k_brick_unknown; not zeroed)
   uint32_t *pair_mask;   // [mask_words * bricks] bit k: pair k of the tracklet cannot free any voxel of the brick
   TabCoef *tabcoef;      // [incl_len] (entries at table offsets only)
   char *zero_end;
@@ -229,6 +235,7 @@ static int64_t ws_layout(int32_t T, int64_t F, int64_t total, int64_t SF, int32_
   int64_t o_py = take(4 * pyr_tiles);
   int64_t o_py2 = take(4 * 16 * pyr_tiles);
   int64_t o_im = take(8 * (int64_t)n_slices * std::max<int64_t>(bricks, 1));
+  int64_t o_ub2 = take(8 * std::max<int64_t>(bricks, 1));
   (void)SF;
   if (w) {
     w->grids = (TrkGrid *)(base + o_grid);
@@ -241,6 +248,7 @@ static int64_t ws_layout(int32_t T, int64_t F, int64_t total, int64_t SF, int32_
     w->bits = (uint32_t *)(base + o_bits);
     w->bits_words = words;
     w->free_brick = (uint32_t *)(base + o_fb);
+    w->unk_brick = (uint32_t *)(base + o_ub2);
     w->pair_mask = (uint32_t *)(base + o_pm);
     w->tabcoef = (TabCoef *)(base + o_tc);
     w->zero_end = base + o_zend;
@@ -1454,7 +1462,14 @@ __device__ __forceinline__ float u_of_sin(float s) {
 
 // All quantities below are conservative bounds with generous padding, so the approximate reciprocal / square root
 // / arctangent (<= 2 ulp, <= 2e-6 rad) are used throughout: their error is orders of magnitude below the padding.
-__global__ void __launch_bounds__(256)
+#ifndef OCC_CULL_MINB
+#define OCC_CULL_MINB 6
+#endif
+#ifndef OCC_CULL_UNROLL
+#define OCC_CULL_UNROLL 1
+#endif
+constexpr int kCullUnroll = OCC_CULL_UNROLL;
+__global__ void __launch_bounds__(256, OCC_CULL_MINB)
 k_brick_cull(int s_first, const int2 *__restrict__ item_map, long long bricks_total, const unsigned long long *__restrict__ counter,
              const TrkHot *__restrict__ hot, const PairHot *__restrict__ pairs, const LutCell *__restrict__ lut_pool,
              const int64_t *__restrict__ pyr_off, const float *__restrict__ pyr2, int mask_words,
@@ -1543,6 +1558,7 @@ k_brick_cull(int s_first, const int2 *__restrict__ item_map, long long bricks_to
     float mx = 0.f;
     for (int tr = r0 / kFineR; tr <= r1 / kFineR; ++tr) {
       const float4 *prow = pimg + (tr * pitch2 >> 2);
+#pragma unroll kCullUnroll
       for (int g = ta >> 2; g <= tb >> 2; ++g) {
         const float4 v = __ldg(prow + g);
         const int c = 4 * g;
@@ -1677,6 +1693,7 @@ struct VisArgs {                 // what the visibility kernel needs (passed by 
   unsigned long long *counter;
   const uint32_t *bits;
   uint32_t *free_brick;
+  const uint32_t *unk_brick;
   const uint32_t *pair_mask;
   const int2 *item_map;
   const TrkHot *hot;
@@ -1773,6 +1790,36 @@ __device__ __forceinline__ unsigned run_pairs(const VisArgs &a, int t, const Trk
 //   slices never test a voxel an earlier one has freed.  A brick with more than 32 undecided voxels runs two per
 //   lane; otherwise the undecided voxels are dealt one per lane (dense lanes).
 // Labels are written afterwards by k_labels from the occupancy and free bitsets.
+// One warp per brick of the slice-0 list (every brick of every tracklet that has a surviving pair): the brick's
+// voxels that lie inside the grid and hold no point, as two words in brick order -- what every work item of the
+// brick starts from (an item then needs two 8-byte loads instead of 64 bit extractions from the linear bitset).
+// Runs after the redo crop pass (the occupancy bits are final), next to k_brick_cull.
+__global__ void __launch_bounds__(256)
+k_brick_unknown(const int2 *__restrict__ item_map, const unsigned long long *__restrict__ counter,
+                const TrkHot *__restrict__ hot, const uint32_t *__restrict__ bits, uint32_t *__restrict__ unk_brick) {
+  const long long n_items = (long long)counter[8];
+  const int lane = threadIdx.x & 31;
+  for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n_items;
+       i += ((long long)gridDim.x * blockDim.x) >> 5) {
+    const int2 m = __ldg(item_map + i);
+    const TrkHot &h = hot[m.x];
+    const int bx = m.y & 1023, by = (m.y >> 10) & 1023, bz = (m.y >> 20) & 1023;
+    const int lb = (bx * ((h.dY + kBrick - 1) / kBrick) + by) * ((h.dZ + kBrick - 1) / kBrick) + bz;
+#pragma unroll
+    for (int v = 0; v < 2; ++v) {
+      const int j = 32 * v + lane;
+      const int x = kBrick * bx + (j >> 4), y = kBrick * by + ((j >> 2) & 3), z = kBrick * bz + (j & 3);
+      bool need = x < h.dX && y < h.dY && z < h.dZ;
+      if (need) {
+        const int f = (x * h.dY + y) * h.dZ + z;
+        need = !((__ldg(bits + h.bits_off + (f >> 5)) >> (f & 31)) & 1u);
+      }
+      const unsigned w = __ballot_sync(0xffffffffu, need);
+      if (lane == 0) unk_brick[2 * (h.brick_base + lb) + v] = w;
+    }
+  }
+}
+
 #if OCC_VISDEBUG
 __device__ long long g_visdbg[8 * 148 * 8 * 8];    // per warp: t_start, t_end, items, iterations, longest item (cycles, its iterations), smid
 #endif
@@ -1780,6 +1827,8 @@ __global__ void __launch_bounds__(32 * kFastWarps, OCC_MINB) k_visibility(const 
 #if OCC_VISDEBUG
   const long long dbg_t0 = clock64();
   long long dbg_items = 0, dbg_iters = 0, dbg_max = 0, dbg_max_it = 0;
+  unsigned long long dbg_g0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_g0));
 #endif
   __shared__ long long s_base[kMaxSlices + 1];
   __shared__ __align__(16) PairHot s_pairs[kFastWarps][kPairsPerItem];
@@ -1798,16 +1847,32 @@ __global__ void __launch_bounds__(32 * kFastWarps, OCC_MINB) k_visibility(const 
   // later one is a ticket from a global counter, requested BEFORE the current item is processed so that the
   // atomic's round trip hides behind it.  (Static rounds left the slowest CTA as the kernel's tail: SMs were
   // active 70 % of the kernel's duration.)
+  // The items of the LAST round (as many as there are warps) are cut into kTailSplit tickets of kPairsPerItem /
+  // kTailSplit pairs each: whatever a warp starts when the tickets run out is then a quarter of an item, and the
+  // kernel's drain is as long as 4 pairs instead of 16 (measured on C2: every warp busy until 24 us, the last one
+  // until 51 us -- one 16-pair item of a never-freed brick).  The parts of an item run on different warps at the
+  // same time; they only lose the early exit between them, and late items rarely free anything.
   const long long n_static = (long long)gridDim.x * kFastWarps;
+  const long long n_split = min(n_items, n_static);
+  const long long n_whole = n_items - n_split;
+  const long long n_tickets = n_whole + n_split * kTailSplit;
   long long g = (long long)blockIdx.x * kFastWarps + (threadIdx.x >> 5);
   int s = 0;
   for (;;) {
-    if (g >= n_items) break;
+    if (g >= n_tickets) break;
     unsigned long long nxt = 0;
     if (lane == 0) nxt = atomicAdd(a.counter + 3 + a.ticket, 1ull);
+    long long gi = g;
+    unsigned part_mask = 0xffffffffu;                          // which pairs of the slice this ticket covers
+    if (g >= n_whole) {
+      const long long r = g - n_whole;
+      gi = n_whole + r / kTailSplit;
+      constexpr int kPart = kPairsPerItem / kTailSplit;
+      part_mask = ((1u << kPart) - 1u) << ((int)(r % kTailSplit) * kPart);
+    }
     s = 0;
-    while (g >= s_base[s + 1]) ++s;
-    const long long item = g - s_base[s];
+    while (gi >= s_base[s + 1]) ++s;
+    const long long item = gi - s_base[s];
     s += a.s_lo;
 #if OCC_VISDEBUG
     const long long dbg_ti = clock64();
@@ -1824,22 +1889,17 @@ __global__ void __launch_bounds__(32 * kFastWarps, OCC_MINB) k_visibility(const 
       const int lb = (bx * ((h.dY + kBrick - 1) / kBrick) + by) * ((h.dZ + kBrick - 1) / kBrick) + bz;
       const long long gb = h.brick_base + lb;
       const unsigned mw = __ldg(a.pair_mask + gb * a.mask_words + (k0 >> 5));
-      const unsigned live = ~(mw >> (k0 & 31)) & (npair >= 32 ? 0xffffffffu : ((1u << npair) - 1u));
+      const unsigned live = ~(mw >> (k0 & 31)) & (npair >= 32 ? 0xffffffffu : ((1u << npair) - 1u)) & part_mask;
       if (!live) break;
-      // the brick's voxels: j = 32 v + lane -> (j >> 4, (j >> 2) & 3, j & 3); undecided = inside the grid, holds no
-      // point, not yet proven free
+      // undecided = inside the grid, holds no point (k_brick_unknown), not yet proven free; voxel j = 32 v + lane of
+      // the brick sits at (j >> 4, (j >> 2) & 3, j & 3)
       unsigned und[2];
-#pragma unroll
-      for (int v = 0; v < 2; ++v) {
-        const int j = 32 * v + lane;
-        const int x = kBrick * bx + (j >> 4), y = kBrick * by + ((j >> 2) & 3), z = kBrick * bz + (j & 3);
-        bool need = x < h.dX && y < h.dY && z < h.dZ;
-        if (need) {
-          const int f = (x * h.dY + y) * h.dZ + z;
-          need = !((__ldg(a.bits + h.bits_off + (f >> 5)) >> (f & 31)) & 1u);
-        }
-        const unsigned fw = *(volatile const uint32_t *)(a.free_brick + 2 * gb + v);
-        und[v] = __ballot_sync(0xffffffffu, need) & ~fw;
+      {
+        const uint2 unk = __ldg(reinterpret_cast<const uint2 *>(a.unk_brick + 2 * gb));
+        const unsigned f0 = *(volatile const uint32_t *)(a.free_brick + 2 * gb);
+        const unsigned f1 = *(volatile const uint32_t *)(a.free_brick + 2 * gb + 1);
+        und[0] = unk.x & ~f0;
+        und[1] = unk.y & ~f1;
       }
       const int n0 = __popc(und[0]), n = n0 + __popc(und[1]);
       if (n == 0) break;
@@ -1921,7 +1981,10 @@ __global__ void __launch_bounds__(32 * kFastWarps, OCC_MINB) k_visibility(const 
     unsigned smid;
     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
     long long *d = g_visdbg + 8 * w;
-    d[0] = dbg_t0; d[1] = clock64(); d[2] = dbg_items; d[3] = dbg_iters; d[4] = dbg_max; d[5] = dbg_max_it; d[6] = smid;
+    unsigned long long dbg_g1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_g1));
+    d[0] = clock64() - dbg_t0; d[1] = (long long)dbg_g1; d[2] = dbg_items; d[3] = dbg_iters; d[4] = dbg_max; d[5] = dbg_max_it; d[6] = smid;
+    d[7] = (long long)dbg_g0;
   }
 #endif
 }
@@ -2179,6 +2242,11 @@ extern "C" int occb200_annotate_batch(const occb200_annotate_args_t *a, int64_t 
     OCC_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
     ProfScope ps(kProfSetup, side->stream);
     if (launch_redo(side->stream)) return 1;
+    if (w.bricks > 0) {
+      k_brick_unknown<<<(unsigned)std::min<int64_t>(ceil_div(w.bricks, 8), (int64_t)kNumSMs * 8), 256, 0, side->stream>>>(
+          w.item_map, w.counter, w.hot, w.bits, w.unk_brick);
+      OCC_KERNEL_OK("k_brick_unknown");
+    }
     OCC_CUDA(cudaEventRecord(side->join, side->stream));
   }
   // The ray-cast: brick cull + visibility.  With more than one slice of pairs the two kernels are split by slice
@@ -2200,7 +2268,7 @@ extern "C" int occb200_annotate_batch(const occb200_annotate_args_t *a, int64_t 
     va.bricks_total = (long long)w.bricks; va.queue_cap = queue_cap_used; va.vs = a->voxel_size;
     va.trk_frame_off = a->trk_frame_off; va.poses = a->poses; va.frame_sf = a->frame_sf; va.sensors = a->sensors;
     va.incl_pool = a->incl_pool; va.ri_pool = a->ri_pool; va.grids = w.grids; va.counter = w.counter;
-    va.bits = w.bits; va.free_brick = w.free_brick; va.pair_mask = w.pair_mask; va.item_map = w.item_map;
+    va.bits = w.bits; va.free_brick = w.free_brick; va.unk_brick = w.unk_brick; va.pair_mask = w.pair_mask; va.item_map = w.item_map;
     va.hot = w.hot; va.pairs = w.pairs_c; va.lut_pool = w.lut_pool; va.queue = w.queue; va.n_steps = a->n_steps;
     const int grid = (int)std::min<int64_t>(ceil_div(std::max<int64_t>(w.bricks * (s1 - s0), 1), kFastWarps),
                                             (int64_t)kNumSMs * OCC_MINB);

@@ -25,19 +25,15 @@ buf = np.zeros(n, np.int64)
 assert L.occb200_debug_visibility(C.c_void_p(buf.ctypes.data), n) == 0
 w = buf.reshape(-1, 8)
 w = w[w[:, 1] > 0]
-t0 = w[:, 0].min()
-start, end = w[:, 0] - t0, w[:, 1] - t0
-print("warps", len(w), "kernel span cycles", end.max(), "mean end", end.mean(), "median end", np.median(end))
-print("start: min/median/max", start.min(), np.median(start), start.max())
-print("items/warp mean", w[:, 2].mean(), "max", w[:, 2].max(), " iterations/warp mean", w[:, 3].mean(), "max", w[:, 3].max(), "total", w[:, 3].sum())
-busy = end - start
-print("busy cycles/warp mean", busy.mean(), "max", busy.max(), " cycles per iteration (mean busy/mean iters)", busy.mean() / max(w[:, 3].mean(), 1))
-print("longest single item cycles: mean", w[:, 4].mean(), "max", w[:, 4].max(), "slice of the max", np.bincount(w[:, 5].astype(int)).tolist())
-q = np.quantile(end, [0.1, 0.25, 0.5, 0.75, 0.9, 0.99, 1.0])
-print("end-time quantiles", q.astype(int).tolist())
-late = w[end > 0.8 * end.max()]
-print("warps ending in the last 20% of the span:", len(late), " their iterations mean", late[:, 3].mean(), "items", late[:, 2].mean(),
-      "longest item mean", late[:, 4].mean())
-sm = w[:, 6]
-per_sm_end = np.array([end[sm == s].max() for s in np.unique(sm)])
-print("per-SM last end: min", per_sm_end.min(), "mean", per_sm_end.mean(), "max", per_sm_end.max())
+g0 = w[:, 7].min()
+start, end = (w[:, 7] - g0) / 1e3, (w[:, 1] - g0) / 1e3            # microseconds on the global timer
+busy_cyc = w[:, 0]
+print("warps", len(w), "kernel span us", round(end.max(), 2))
+print("start us: quantiles 0/10/50/90/100", np.quantile(start, [0, .1, .5, .9, 1]).round(2).tolist())
+print("end   us: quantiles 0/10/25/50/75/90/100", np.quantile(end, [0, .1, .25, .5, .75, .9, 1]).round(2).tolist())
+print("items/warp mean", w[:, 2].mean().round(2), "max", w[:, 2].max(), " iterations/warp mean", w[:, 3].mean().round(2), "max", w[:, 3].max(), "total", w[:, 3].sum())
+print("busy cycles/warp mean", busy_cyc.mean().round(0), "max", busy_cyc.max(), " cycles per iteration", (busy_cyc.mean() / max(w[:, 3].mean(), 1)).round(0))
+print("longest single item cycles: mean", w[:, 4].mean().round(0), "max", w[:, 4].max())
+# how many warps are still running at time t
+for t in np.linspace(0, end.max(), 13):
+    print("  t=%6.2f us  running warps %5d" % (t, int(((start <= t) & (end > t)).sum())))
