@@ -197,6 +197,13 @@ int occb200_dense_voxel_centers(const float *sizes, const int32_t *dims, const i
                                 int R, int64_t total, float voxel_size, const float *scale_wlh,
                                 const float *offset_wlh, float *centers, void *stream);
 
+/* The dense observation grids of sample_observation (mmdet3d/models/roi_heads/bbox_heads/occ_ae_head.py:100-127) for
+ * all R ROIs in one launch: coors int64 [N,3] (occb200_quantize_points), roi_idx int64 [N] (an index outside [0, R)
+ * matches no ROI), dims int32 [R,3] and off int64 [R+1] as for occb200_dense_voxel_centers; labels int64 [off[R]]
+ * (zero-filled by the caller) receives 1 at (c0*Y + c1)*Z + c2 of the point's ROI where 0 <= c < dims. */
+int occb200_observed_labels(const int64_t *coors, const int64_t *roi_idx, int64_t N, const int32_t *dims,
+                            const int64_t *off, int64_t R, int64_t *labels, void *stream);
+
 /* MirrorOccLabel (mmdet3d/datasets/pipelines/occ_pinelines.py:82-126) on the label layout of
  * occb200_annotate_batch: out[label_off[t] + f] = labels[...] with every unknown (0) voxel replaced by the label
  * of its mirror image across the x mid-plane, read from the unmodified grid.  status may be NULL; tracklets with

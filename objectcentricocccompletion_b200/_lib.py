@@ -80,6 +80,7 @@ SIGNATURES = {
     "occb200_segment_reduce_backward_f64": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, i64, i64, C.c_int, C.c_int, vp]),
     "occb200_quantize_points": (C.c_int, [vp, i64, vp, i64, C.c_int, vp, f32, vp, vp, C.c_int, vp, vp, vp, vp]),
     "occb200_dense_voxel_centers": (C.c_int, [vp, vp, vp, C.c_int, i64, f32, vp, vp, vp, vp]),
+    "occb200_observed_labels": (C.c_int, [vp, vp, i64, vp, vp, i64, vp, vp]),
     "occb200_mirror_occ_label": (C.c_int, [vp, vp, vp, vp, i32, i64, vp, vp]),
     "occb200_candidate_chunk": (C.c_int, []),
     "occb200_candidate_warps": (C.c_int, []),

@@ -86,9 +86,36 @@ __global__ void k_mirror_occ_label(const int32_t *__restrict__ labels, const int
   }
 }
 
+// sample_observation (mmdet3d/models/roi_heads/bbox_heads/occ_ae_head.py:100-127): the dense "observed" grid of
+// every ROI in one launch.  Point i belongs to ROI roi_idx[i] (an index outside [0, R) matches no ROI, as in the
+// reference's `pts_roi_inds == i` masks); its quantised coordinate marks voxel (c0 * Y + c1) * Z + c2 of that ROI's
+// grid iff 0 <= c < dims (:108-111: points on the boundary are dropped).
+__global__ void k_observed_labels(const int64_t *__restrict__ coors, const int64_t *__restrict__ roi_idx, int64_t N,
+                                  const int32_t *__restrict__ dims, const int64_t *__restrict__ off, int64_t R,
+                                  int64_t *__restrict__ labels) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const int64_t r = roi_idx[i];
+  if (r < 0 || r >= R) return;
+  const int64_t c0 = coors[3 * i], c1 = coors[3 * i + 1], c2 = coors[3 * i + 2];
+  const int64_t X = dims[3 * r], Y = dims[3 * r + 1], Z = dims[3 * r + 2];
+  if (c0 < 0 || c1 < 0 || c2 < 0 || c0 >= X || c1 >= Y || c2 >= Z) return;
+  labels[off[r] + (c0 * Y + c1) * Z + c2] = 1;                  // every writer stores 1
+}
+
 }  // namespace occb200
 
 using namespace occb200;
+
+extern "C" int occb200_observed_labels(const int64_t *coors, const int64_t *roi_idx, int64_t N, const int32_t *dims,
+                                       const int64_t *off, int64_t R, int64_t *labels, void *stream) {
+  OCC_REQUIRE(N >= 0 && R >= 0, "bad sizes");
+  if (N == 0 || R == 0) return 0;
+  OCC_REQUIRE(coors && roi_idx && dims && off && labels, "NULL argument");
+  k_observed_labels<<<(unsigned)ceil_div(N, 256), 256, 0, (cudaStream_t)stream>>>(coors, roi_idx, N, dims, off, R, labels);
+  OCC_KERNEL_OK("k_observed_labels");
+  return 0;
+}
 
 extern "C" int occb200_mirror_occ_label(const int32_t *labels, const int64_t *label_off, const int32_t *dims,
                                         const int32_t *status, int32_t T, int64_t max_voxels, int32_t *out,
