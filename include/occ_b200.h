@@ -422,6 +422,19 @@ int occb200_pull_windows(const occb200_annotate_args_t *args, const float *trk_s
                          float *ri_pool, int64_t ri_len, uint32_t *mask, unsigned long long *pulled_blocks,
                          void *stream);
 
+/* ---- (f)3: dynamic_point_pool_mixed (mmdet3d/ops/dynamic_point_pool_op.py:63-113; the extension's kernel is not in
+ *      the reference tree: PARITY UNPINNED, semantics from the extractor's own assertions, see csrc/point_pool.cu) ---- */
+
+/* rois f32 [R,7]; ROI r scans the points perm[roi_lo[r] .. roi_hi[r]) (the caller sorts the points by batch index:
+ * perm = that order, [lo, hi) = the run with the ROI's index); pts f32 [P,3]; extra_wlh HOST f32[3]; max_range = the
+ * longest run (sizes the grid).  Pass 1 (out_feats == NULL): counts[r] += hits (caller-zeroed).  Pass 2: every hit is
+ * written at base[r] + atomicAdd(cursor[r]) (cursor caller-zeroed): out_pidx / out_roi int64, out_feats f32 [.,13] =
+ * xyz, ROI-local xyz, offsets to the six faces, is_in_margin.  Hits of a ROI arrive in arbitrary order. */
+int occb200_point_pool(const float *rois, const int64_t *roi_lo, const int64_t *roi_hi, int64_t R, const float *pts,
+                       const int64_t *perm, int64_t max_range, const float *extra_wlh, int32_t *counts,
+                       const int64_t *base, int32_t *cursor, int64_t *out_pidx, int64_t *out_roi, float *out_feats,
+                       void *stream);
+
 /* HOST helper: fills poses[i] from boxes7 f32 [n,7] and torch-evaluated trig f32 [n,4]
  * (cos(-yaw), sin(-yaw), cos(yaw), sin(yaw)); cos_pib/sin_pib come from the host libm. */
 void occb200_host_pose_pack(const float *boxes7, const float *trig4, int64_t n, occb200_pose_t *poses);

@@ -91,6 +91,7 @@ SIGNATURES = {
     "occb200_annotate_batch": (C.c_int, [C.POINTER(AnnotateArgs), i64, vp]),
     "occb200_annotate_queue_stats": (C.c_int, [C.POINTER(AnnotateArgs), i64, vp, vp]),
     "occb200_annotate_point_voxels": (C.c_int, [C.POINTER(AnnotateArgs), i64, vp, vp, vp]),
+    "occb200_point_pool": (C.c_int, [vp, vp, vp, i64, vp, vp, i64, vp, vp, vp, vp, vp, vp, vp, vp]),
     "occb200_host_pose_pack": (None, [vp, vp, i64, vp]),
     "occb200_host_mask_to_blocks": (i64, [vp, i64, vp]),
     "occb200_host_gather_blocks": (C.c_int, [vp, i64, vp, vp, vp, i32, vp]),

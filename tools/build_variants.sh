@@ -6,7 +6,7 @@ cd "$(dirname "$0")/../objectcentricocccompletion_b200/csrc"
 make -s -j8
 mkdir -p _build/variants
 FLAGS="-O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -fmad=false -prec-div=true -prec-sqrt=true -Xcompiler -fPIC,-O2,-Wall,-fno-fast-math,-fopenmp -I../../include -I. --expt-relaxed-constexpr"
-OTHERS="_build/lib.o _build/points_in_boxes.o _build/voxelize.o _build/scatter.o _build/occ_ops.o _build/range_image.o _build/candidates.o _build/ri_windows.o"
+OTHERS="_build/lib.o _build/points_in_boxes.o _build/voxelize.o _build/scatter.o _build/occ_ops.o _build/range_image.o _build/candidates.o _build/ri_windows.o _build/point_pool.o"
 for v in "$@"; do
   name="${v%%:*}"; defs="${v#*:}"
   nvcc $FLAGS $defs -Xptxas -v -c annotate.cu -o _build/variants/annotate_$name.o 2> _build/variants/$name.ptxas.log
