@@ -1745,31 +1745,41 @@ __device__ __forceinline__ unsigned run_pairs(const VisArgs &a, int t, const Trk
         for (int v = 0; v < VPL; ++v) res[p][v] = fast_test<false>(pc, dx[v], dy[v], dz[v], lut, ri_img);
       }
     }
+    unsigned und = 0u;                                           // bit p * VPL + v: that test is undecided
 #pragma unroll
     for (int p = 0; p < PP; ++p) {
       if (!has[p]) continue;
-      const PairHot &pc = *pcs[p];
+      const bool fast_ok = pcs[p]->eps >= 0.f;                    // eps < 0: no fast path through this pair
+      steps += __popc(todo);
 #pragma unroll
-      for (int v = 0; v < VPL; ++v) {
-        const bool need = (todo >> v) & 1u;
-        const int r = need ? ((pc.eps >= 0.f) ? res[p][v] : 1) : 0;
-        steps += need ? 1u : 0u;
-        if (r == 2) {
-          found |= 1u << v;
-          todo &= ~(1u << v);
-        }
-        const unsigned umask = __ballot_sync(0xffffffffu, r == 1);
-        if (umask) {                                             // queue the undecided tests (warp-aggregated)
+      for (int v = 0; v < VPL; ++v) {                              // (branch-free: selects only)
+        const unsigned need = (todo >> v) & 1u;
+        const unsigned fr = (fast_ok && res[p][v] == 2) ? need : 0u;
+        const unsigned ud = (!fast_ok || res[p][v] == 1) ? need : 0u;
+        found |= fr << v;
+        todo &= ~(fr << v);
+        und |= ud << (p * VPL + v);
+      }
+    }
+    if (__any_sync(0xffffffffu, und != 0u)) {                  // rare: queue the undecided tests (warp-aggregated)
+#pragma unroll
+      for (int p = 0; p < PP; ++p) {
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+          const bool mine = (und >> (p * VPL + v)) & 1u;
+          const unsigned umask = __ballot_sync(0xffffffffu, mine);
+          if (!umask) continue;
           unsigned long long base = 0;
           if (lane == 0) base = atomicAdd(a.counter + 1, (unsigned long long)__popc(umask));
           base = __shfl_sync(0xffffffffu, base, 0);
-          if (r == 1) {
+          if (mine) {
             const int j = vj[v];
+            const int q = pcs[p]->q;
             const int f = ((kBrick * bx + (j >> 4)) * h.dY + kBrick * by + ((j >> 2) & 3)) * h.dZ + kBrick * bz + (j & 3);
             const unsigned long long slot = base + __popc(umask & ((1u << lane) - 1u));
             if (slot < (unsigned long long)a.queue_cap) {
-              a.queue[slot] = make_int4(t, f, pc.q, lb * 64 + j);
-            } else if (exact_from_ids(t, f, pc.q, a.L, a.vs, a.grids, a.trk_frame_off, a.poses, a.frame_sf, a.sensors,
+              a.queue[slot] = make_int4(t, f, q, lb * 64 + j);
+            } else if (exact_from_ids(t, f, q, a.L, a.vs, a.grids, a.trk_frame_off, a.poses, a.frame_sf, a.sensors,
                                       a.incl_pool, a.ri_pool)) {     // queue full: decide right here
               found |= 1u << v;
               todo &= ~(1u << v);
