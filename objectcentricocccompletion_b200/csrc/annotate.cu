@@ -73,7 +73,7 @@ constexpr int kBrick = 4;                // brick edge in voxels: 64 voxels = 2 
 #define OCC_VISDEBUG 0
 #endif
 #ifndef OCC_PP1
-#define OCC_PP1 2      // pairs per loop iteration of the one-voxel-per-lane path
+#define OCC_PP1 4      // pairs per loop iteration of the one-voxel-per-lane path (4 tests in flight per lane, like 2 x 2)
 #endif
 #ifndef OCC_PP2
 #define OCC_PP2 2      // ... of the two-voxels-per-lane path
@@ -140,7 +140,7 @@ struct __align__(16) PairHot {
   float e15z;       // row margin: m = e15z / r + 1.5e-6
   float nkcol;      // -W / (2 pi)
   float c0f;        // colf_rel = fma(phi, nkcol, c0f): column relative to cint
-  int32_t cint;
+  int32_t cint;     // first column (narrow pairs: + W where it is below W / 2, see fast_test)
   int32_t W;
   float ecolk, ecol;   // column margin: ecolk / rho + ecol
   float c1;         // range margin: m = r * 6.5e-7 + c1
@@ -1190,7 +1190,7 @@ make_pair(int64_t f, int c, int q, int L, const TrkGrid &g, const occb200_pose_t
   const double e15z = 1.5 * fmax(eps_xz, eps_y);
   const double d_min = d_c - R;
   bool ok = tc.ok && tc.H == H && sn.incl_mono == -1 && isfinite(eps_xz) && isfinite(eps_y) && se < (1ll << 31) &&
-            W >= 2 && W < (1 << 22) && d_min > 0.05;
+            W >= 16 && W < (1 << 22) && d_min > 0.05;          // (W >= 16: the narrow column wrap of fast_test)
   // the row test needs its margin below a fifth of a lookup cell (k_table_setup / fast_test)
   if (ok && !(e15z / d_min + 1.5e-6 < 0.2 * (double)tc.w)) ok = false;
   p.eps = ok ? (float)fmax(eps_xz, eps_y) : -1.f;
@@ -1202,7 +1202,7 @@ make_pair(int64_t f, int c, int q, int L, const TrkGrid &g, const occb200_pose_t
   p.e15z = (float)e15z;
   p.nkcol = (float)(-kcol);
   p.c0f = (float)(C0m - (double)cint);
-  p.cint = cint;
+  p.cint = (narrow && cint < W / 2) ? cint + W : cint;         // narrow: fast_test wraps with one unsigned minimum
   p.W = W;
   p.ecolk = (float)(1.5 * (eps_y + tmax * eps_xz) * kcol);
   p.ecol = (float)((katan + 3.0e-7) * kcol + c_col);
@@ -1466,7 +1466,7 @@ __device__ __forceinline__ float u_of_sin(float s) {
 #define OCC_CULL_MINB 6
 #endif
 #ifndef OCC_CULL_UNROLL
-#define OCC_CULL_UNROLL 1
+#define OCC_CULL_UNROLL 2
 #endif
 constexpr int kCullUnroll = OCC_CULL_UNROLL;
 __global__ void __launch_bounds__(256, OCC_CULL_MINB)
@@ -1549,33 +1549,38 @@ k_brick_cull(int s_first, const int2 *__restrict__ item_map, long long bricks_to
     // (wrapped past the seam) = tiles [0, tw]
     const int pitch2 = 4 * ((W + kTileC - 1) / kTileC);
     const float4 *pimg = reinterpret_cast<const float4 *>(pyr2 + 16 * pyr_off[p.sens]);
-    int a0 = q_lo % W;
-    a0 += (a0 < 0) ? W : 0;
+    if (!(q_lo > -W && q_lo < 3 * W)) continue;                   // (cannot happen for finite inputs: keep the pair)
+    int a0 = q_lo + ((q_lo < 0) ? W : 0);                         // q_lo modulo W without the integer division
+    a0 -= (a0 >= 2 * W) ? 2 * W : ((a0 >= W) ? W : 0);
     const int ta = a0 / kFineC, tb = (min(a0 + len, W) - 1) / kFineC;
     const int tw = (a0 + len > W) ? (a0 + len - W - 1) / kFineC : -1;
-    // every tile of the footprint, four tiles per 16-byte load (the scalar version spent its time in the load /
-    // store unit: ~25 sector requests per thread), no early exit: the loads are independent of the running maximum
+    // every tile of the footprint, four tiles per 16-byte load, no early exit (the loads are independent of the
+    // running maximum).  Columns outermost: which of a load's four tiles belong to the footprint depends on the
+    // column group only, so the row loop is load + 4 max and the mask is applied once per group.
+    const int tr0 = r0 / kFineR, tr1 = r1 / kFineR;
+    const int rstride = pitch2 >> 2;                              // float4 per tile row
     float mx = 0.f;
-    for (int tr = r0 / kFineR; tr <= r1 / kFineR; ++tr) {
-      const float4 *prow = pimg + (tr * pitch2 >> 2);
+    auto scan = [&](int g0, int g1, int lo, int hi) {             // column groups [g0, g1], tiles [lo, hi] count
+      for (int g = g0; g <= g1; ++g) {
+        const float4 *pcol = pimg + (tr0 * rstride + g);
+        float m0 = 0.f, m1 = 0.f, m2 = 0.f, m3 = 0.f;
 #pragma unroll kCullUnroll
-      for (int g = ta >> 2; g <= tb >> 2; ++g) {
-        const float4 v = __ldg(prow + g);
+        for (int tr = tr0; tr <= tr1; ++tr, pcol += rstride) {
+          const float4 v = __ldg(pcol);
+          m0 = fmaxf(m0, v.x);
+          m1 = fmaxf(m1, v.y);
+          m2 = fmaxf(m2, v.z);
+          m3 = fmaxf(m3, v.w);
+        }
         const int c = 4 * g;
-        mx = fmaxf(mx, (c >= ta && c <= tb) ? v.x : 0.f);
-        mx = fmaxf(mx, (c + 1 >= ta && c + 1 <= tb) ? v.y : 0.f);
-        mx = fmaxf(mx, (c + 2 >= ta && c + 2 <= tb) ? v.z : 0.f);
-        mx = fmaxf(mx, (c + 3 >= ta && c + 3 <= tb) ? v.w : 0.f);
+        mx = fmaxf(mx, (c >= lo && c <= hi) ? m0 : 0.f);
+        mx = fmaxf(mx, (c + 1 >= lo && c + 1 <= hi) ? m1 : 0.f);
+        mx = fmaxf(mx, (c + 2 >= lo && c + 2 <= hi) ? m2 : 0.f);
+        mx = fmaxf(mx, (c + 3 >= lo && c + 3 <= hi) ? m3 : 0.f);
       }
-      for (int g = 0; g <= tw >> 2 && tw >= 0; ++g) {
-        const float4 v = __ldg(prow + g);
-        const int c = 4 * g;
-        mx = fmaxf(mx, (c <= tw) ? v.x : 0.f);
-        mx = fmaxf(mx, (c + 1 <= tw) ? v.y : 0.f);
-        mx = fmaxf(mx, (c + 2 <= tw) ? v.z : 0.f);
-        mx = fmaxf(mx, (c + 3 <= tw) ? v.w : 0.f);
-      }
-    }
+    };
+    scan(ta >> 2, tb >> 2, ta, tb);
+    if (tw >= 0) scan(0, tw >> 2, 0, tw);
     if (mx < r_lo) {
       const int lb = (bx * bricks_of(h.dY) + by) * bricks_of(h.dZ) + bz;
       atomicOr(pair_mask + (h.brick_base + lb) * mask_words + (k >> 5), 1u << (k & 31));
@@ -1625,13 +1630,22 @@ __device__ __forceinline__ int fast_test(const PairHot &p, float dx, float dy, f
   const float cb = colf + kMagic;                             // |colf| <= W / 2 + 1 < 2^22
   const float cr = cb - kMagic;                               // == rintf(colf)
   const bool ok_col = fabsf(colf - cr) + fmaf(p.ecolk, inv_rho, p.ecol) < 0.5f;
-  int col = magic_int(cb) + p.cint;
-  col += (col < 0) ? p.W : 0;                                 // fmod(round(colf), W) (:191) and
-  col -= (col >= p.W) ? p.W : 0;                              // negative index wrap (:543)
-  col = min((unsigned)col, (unsigned)(p.W - 1));
+  unsigned col;
+  if (WIDE) {
+    int c = magic_int(cb) + p.cint;                           // cint in [0, W), |colf| <= W / 2 + 1
+    c += (c < 0) ? p.W : 0;                                   // fmod(round(colf), W) (:191) and
+    c -= (c >= p.W) ? p.W : 0;                                // negative index wrap (:543)
+    col = (unsigned)c;
+  } else {
+    // narrow pairs: |colf| <= W / 8 + 1 and make_pair stores cint + W where cint < W / 2, so the sum lies in
+    // (0, 2 W): ONE unsigned minimum does the wrap (col - W wraps around to a huge number when col < W)
+    col = (unsigned)(magic_int(cb) + p.cint);
+    col = min(col, col - (unsigned)p.W);
+  }
+  col = min(col, (unsigned)(p.W - 1));                        // (only a NaN position gets here out of range)
 
   // ---- range
-  const float ri = __ldg(ri_img + (min(row, p.last) * (unsigned)p.W + (unsigned)col));
+  const float ri = __ldg(ri_img + (min(row, p.last) * (unsigned)p.W + col));
   const float r = r2 * inv_r;
   const float dd = ri - r;
   const bool ok_rng = fabsf(dd) > fmaf(r, 6.5e-7f, p.c1);     // ri == 0 (no return): dd = -r, certainly not free
