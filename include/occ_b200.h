@@ -289,6 +289,13 @@ typedef struct occb200_annotate_args {
                                      the unit of work and of culling in the ray-cast                        */
   int64_t bricks;                 /* brick_off[T], from the host copy                                        */
   int64_t n_points;               /* frame_pt_off[F], from the host copy: the crop kernel's grid             */
+  /* ---- ABI v7 ---- */
+  const uint8_t *ri_tile_live;    /* optional [pyr_tiles]: one byte per 8x32-pixel pyramid tile (image e at
+                                     pyr_off[e], tile (tr, tc) at tr * ceil(W/32) + tc), 0 = no visibility test of
+                                     the batch can read a pixel of the tile (as marked by occb200_pull_windows with
+                                     the windowed upload): the max-pyramid skips those tiles instead of reading
+                                     the whole 2.6 MB per frame the reference loads (occ_annotate.py:502-533).
+                                     NULL = every tile is read                                               */
 } occb200_annotate_args_t;
 
 int64_t occb200_annotate_workspace_bytes(int32_t T, int64_t F, int64_t total_label_slots, int64_t SF,
@@ -420,7 +427,9 @@ int occb200_scatter_blocks(const float *blocks, const uint32_t *block_idx, int64
 int64_t occb200_window_mask_words(int64_t ri_len);
 int occb200_pull_windows(const occb200_annotate_args_t *args, const float *trk_smax, const float *ri_host,
                          float *ri_pool, int64_t ri_len, uint32_t *mask, unsigned long long *pulled_blocks,
-                         void *stream);
+                         uint8_t *tile_live, void *stream);
+/* tile_live (device, optional, args->pyr_tiles bytes; needs args->pyr_off): set to 1 for every pyramid tile that holds
+ * a marked block, 0 elsewhere -- what occb200_annotate_args_t.ri_tile_live takes for later calls on the same batch. */
 
 /* ---- (f)3: dynamic_point_pool_mixed (mmdet3d/ops/dynamic_point_pool_op.py:63-113; the extension's kernel is not in
  *      the reference tree: PARITY UNPINNED, semantics from the extractor's own assertions, see csrc/point_pool.cu) ---- */

@@ -17,7 +17,7 @@ LIB_PATH = os.environ.get("OCCB200_LIB", os.path.join(CSRC, "libocc_b200.so"))
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "occ_b200.h")
 
 vp, i32, i64, f32, f64 = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_double
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 
 class Pose(C.Structure):
@@ -37,7 +37,8 @@ class AnnotateArgs(C.Structure):
                 ("dims", vp), ("sizes", vp), ("status", vp), ("n_unknown", vp), ("n_steps", vp), ("workspace", vp),
                 ("workspace_bytes", i64), ("flags", i32), ("pad1", i32), ("max_label_slots", i64),
                 ("labels_u8", vp), ("frame_trk", vp), ("pyr_off", vp), ("table_off", vp), ("table_H", vp),
-                ("n_tables", i32), ("max_pairs", i32), ("brick_off", vp), ("bricks", i64), ("n_points", i64)]
+                ("n_tables", i32), ("max_pairs", i32), ("brick_off", vp), ("bricks", i64), ("n_points", i64),
+                ("ri_tile_live", vp)]
 
 
 POSE_DTYPE = np.dtype([("box", "<f4", (7,)), ("cos_pib", "<f4"), ("sin_pib", "<f4"), ("cos_m", "<f4"),
@@ -98,7 +99,7 @@ SIGNATURES = {
     "occb200_scatter_blocks": (C.c_int, [vp, vp, i64, vp, i64, vp]),
     "occb200_window_mask_words": (i64, [i64]),
     "occb200_host_window_mark": (C.c_int, [i32, i32, vp, vp, vp, vp, i64, vp, vp, f64, i64, vp, f32]),
-    "occb200_pull_windows": (C.c_int, [C.POINTER(AnnotateArgs), vp, vp, vp, i64, vp, vp, vp]),
+    "occb200_pull_windows": (C.c_int, [C.POINTER(AnnotateArgs), vp, vp, vp, i64, vp, vp, vp, vp]),
     "occb200_build_range_images": (C.c_int, [vp, C.c_int, vp, i64, vp, i32, vp, vp, i64, vp, vp]),
     "occb200_point_cloud_to_range_image_idx": (C.c_int, [vp, C.c_int, i64, vp, vp, vp, C.c_int, C.c_int, vp, vp, vp]),
 }

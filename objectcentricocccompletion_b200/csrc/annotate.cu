@@ -994,7 +994,11 @@ __device__ __forceinline__ int row_of_u(const LutCell *__restrict__ lut, float i
 constexpr int kPyrRowGroups = 8;
 __global__ void __launch_bounds__(256)
 k_pyr_build(const occb200_sensor_t *__restrict__ sensors, const float *__restrict__ ri_pool,
-            const int64_t *__restrict__ pyr_off, float *__restrict__ pyr, float *__restrict__ pyr2) {
+            const int64_t *__restrict__ pyr_off, float *__restrict__ pyr, float *__restrict__ pyr2,
+            const uint8_t *__restrict__ tile_live) {
+  // tile_live (optional, args.ri_tile_live): one byte per 8x32 tile, 0 = no visibility test of the batch can read a
+  // pixel of the tile.  Such tiles are skipped -- both levels were zeroed by the caller: their maxima count as 0,
+  // which is exact for every pixel a test can read (ri_windows.cu: "why the labels cannot change").
   const int e = blockIdx.x;                        // sensor entry; blockIdx.y = row group
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const occb200_sensor_t &sn = sensors[e];
@@ -1002,6 +1006,7 @@ k_pyr_build(const occb200_sensor_t *__restrict__ sensors, const float *__restric
   const int ntr = (H + kTileR - 1) / kTileR, ntc = (W + kTileC - 1) / kTileC;
   const float *img = ri_pool + sn.ri_off;
   float *out = pyr + pyr_off[e];
+  const uint8_t *live = tile_live ? tile_live + pyr_off[e] : nullptr;
   float *out2 = pyr2 + 16 * pyr_off[e];            // fine level: 16 slots per coarse tile; row pitch 4 * ntc tiles
                                                    // (>= ceil(W / 8), a multiple of 4: rows are read with 16-byte loads)
   const int nr2 = (H + kFineR - 1) / kFineR, nc2 = (W + kFineC - 1) / kFineC, pitch2 = 4 * ntc;
@@ -1017,6 +1022,17 @@ k_pyr_build(const occb200_sensor_t *__restrict__ sensors, const float *__restric
     constexpr int kP = 2;                          // tile pairs per warp in flight: 16 LDG.64 per lane
     for (int i0 = (blockIdx.y * 8 + warp) * kP; i0 < npair; i0 += kPyrRowGroups * 8 * kP) {
       float2 v[kP][kTileR];
+      bool on[kP];
+      bool any_on = false;
+#pragma unroll
+      for (int u = 0; u < kP; ++u) {               // (warp-uniform) a pair is read if one of its two tiles is live
+        const int p = i0 + u;
+        const int tr = p / npc, tp = p - tr * npc;
+        on[u] = p < npair;
+        if (live && on[u]) on[u] = live[tr * ntc + 2 * tp] || (2 * tp + 1 < ntc && live[tr * ntc + 2 * tp + 1]);
+        any_on = any_on || on[u];
+      }
+      if (!any_on) continue;
 #pragma unroll
       for (int u = 0; u < kP; ++u) {
         const int p = i0 + u;
@@ -1025,13 +1041,14 @@ k_pyr_build(const occb200_sensor_t *__restrict__ sensors, const float *__restric
 #pragma unroll
         for (int r = 0; r < kTileR; ++r) {
           const int row = tr * kTileR + r;
-          v[u][r] = (p < npair && col < W && row < H)
+          v[u][r] = (on[u] && col < W && row < H)
                         ? ld_stream2(reinterpret_cast<const float2 *>(img + (int64_t)row * W + col))
                         : make_float2(0.f, 0.f);
         }
       }
 #pragma unroll
       for (int u = 0; u < kP; ++u) {
+        if (!on[u]) continue;
         const int p = i0 + u;
         const int tr = p / npc, tp = p - tr * npc;
         float m = 0.f;
@@ -1055,6 +1072,14 @@ k_pyr_build(const occb200_sensor_t *__restrict__ sensors, const float *__restric
   }
   for (int i0 = (blockIdx.y * 8 + warp) * kU; i0 < ntile; i0 += kPyrRowGroups * 8 * kU) {
     float v[kU][kTileR];
+    bool on[kU];
+    bool any_on = false;
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      on[u] = i0 + u < ntile && (!live || live[i0 + u]);
+      any_on = any_on || on[u];
+    }
+    if (!any_on) continue;
 #pragma unroll
     for (int u = 0; u < kU; ++u) {
       const int tile = i0 + u;
@@ -1063,11 +1088,12 @@ k_pyr_build(const occb200_sensor_t *__restrict__ sensors, const float *__restric
 #pragma unroll
       for (int r = 0; r < kTileR; ++r) {           // range images are >= 0 (0 = no return)
         const int row = tr * kTileR + r;
-        v[u][r] = (tile < ntile && col < W && row < H) ? ld_stream(img + (int64_t)row * W + col) : 0.f;
+        v[u][r] = (on[u] && col < W && row < H) ? ld_stream(img + (int64_t)row * W + col) : 0.f;
       }
     }
 #pragma unroll
     for (int u = 0; u < kU; ++u) {
+      if (!on[u]) continue;
       float m = 0.f;
 #pragma unroll
       for (int r = 0; r < kTileR; ++r) m = fmaxf(m, v[u][r]);
@@ -1856,6 +1882,7 @@ __global__ void __launch_bounds__(32 * kFastWarps, OCC_MINB) k_visibility(const 
 #endif
   __shared__ long long s_base[kMaxSlices + 1];
   __shared__ __align__(16) PairHot s_pairs[kFastWarps][kPairsPerItem];
+  __shared__ unsigned char s_sel[kFastWarps][32];
   const int ns = a.s_hi - a.s_lo;                  // this launch walks the lists of slices [s_lo, s_hi)
   if (threadIdx.x < ns) s_base[threadIdx.x + 1] = (long long)a.counter[8 + 2 * (a.s_lo + threadIdx.x)];
   __syncthreads();
@@ -1967,13 +1994,16 @@ __global__ void __launch_bounds__(32 * kFastWarps, OCC_MINB) k_visibility(const 
         }
       } else {                                                   // one voxel per lane: lane i takes the i-th undecided
         const bool mine = lane < n;
-        const unsigned src = (lane < n0) ? und[0] : und[1];
-        const int rank = (lane < n0) ? lane : lane - n0;
-        const int pos = mine ? (int)__fns(src, 0, rank + 1) : 0;
+        // every undecided voxel writes its id to the slot of its rank (the warp's 32-byte list), lane i reads slot i
+        unsigned char *sel = s_sel[threadIdx.x >> 5];
+        const unsigned lt = (1u << lane) - 1u;
+        if ((und[0] >> lane) & 1u) sel[__popc(und[0] & lt)] = (unsigned char)lane;
+        if ((und[1] >> lane) & 1u) sel[n0 + __popc(und[1] & lt)] = (unsigned char)(32 + lane);
+        __syncwarp();
         float dx[1], dy[1], dz[1];
         int vj[1];
-        const int j = (mine ? pos : 0) + ((lane < n0) ? 0 : 32);
-        vj[0] = j & 63;
+        vj[0] = mine ? (int)sel[lane] : 0;
+        __syncwarp();                                            // (the next item rewrites the list)
         dx[0] = (float)(kBrick * bx + (vj[0] >> 4)) - h.cen[0];
         dy[0] = (float)(kBrick * by + ((vj[0] >> 2) & 3)) - h.cen[1];
         dz[0] = (float)(kBrick * bz + (vj[0] & 3)) - h.cen[2];
@@ -2187,8 +2217,12 @@ extern "C" int occb200_annotate_batch(const occb200_annotate_args_t *a, int64_t 
     ProfScope ps(kProfSide, side->stream);
     const int64_t n_sens = a->SF * a->L;
     if (cull) {
+      if (a->ri_tile_live) {                                 // dead tiles are skipped: both levels start from zero
+        OCC_CUDA(cudaMemsetAsync(w.pyr, 0, 4 * (size_t)a->pyr_tiles, side->stream));
+        OCC_CUDA(cudaMemsetAsync(w.pyr2, 0, 4 * 16 * (size_t)a->pyr_tiles, side->stream));
+      }
       k_pyr_build<<<dim3((unsigned)n_sens, kPyrRowGroups), 256, 0, side->stream>>>(a->sensors, a->ri_pool, a->pyr_off,
-                                                                                   w.pyr, w.pyr2);
+                                                                                   w.pyr, w.pyr2, a->ri_tile_live);
       OCC_KERNEL_OK("k_pyr_build");
     }
     if (a->n_tables > 0) {

@@ -19,7 +19,7 @@ void set_error(const char *fmt, ...) {
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 }  // namespace occb200
 
-extern "C" int occb200_abi_version(void) { return 6; }
+extern "C" int occb200_abi_version(void) { return 7; }
 extern "C" void occb200_struct_sizes(int64_t *out4) {
   out4[0] = (int64_t)sizeof(occb200_pose_t);
   out4[1] = (int64_t)sizeof(occb200_sensor_t);

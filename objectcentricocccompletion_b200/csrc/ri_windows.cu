@@ -89,6 +89,8 @@ struct WinArgs {
   const float *trk_smax;   // [T,3] max box size over ALL frames of the tracklet (the grid's upper bound)
   float vs;
   uint32_t *mask;
+  const int64_t *pyr_off;  // [SF*L+1] pyramid tiles before each image (optional, with tile_live)
+  uint8_t *tile_live;      // [pyr_tiles] set to 1 for every 8x32 tile that holds a marked pixel (optional)
 };
 
 __device__ __forceinline__ void mark_blocks(uint32_t *__restrict__ mask, long long a, long long b) {   // floats [a, b]
@@ -229,6 +231,25 @@ __host__ __device__ inline void mark_footprint(const Footprint &fp, long long im
   }
 }
 
+// The pyramid tiles (8 rows x 32 columns, annotate.cu's kTileR x kTileC) a footprint touches: every marked block lies
+// in a live tile, so a tile that stays 0 holds no pixel a visibility test can read.
+__device__ __forceinline__ void mark_tiles(const Footprint &fp, int H, int W, uint8_t *__restrict__ live) {
+  const int ntc = (W + 31) / 32;
+  const int tr0 = fp.r0 / 8, tr1 = min(fp.r1, H - 1) / 8;
+  auto cols = [&](long long c0, long long c1) {                  // columns [c0, c1] inside [0, W)
+    for (int tr = tr0; tr <= tr1; ++tr)
+      for (int tc = (int)(c0 / 32); tc <= (int)(c1 / 32); ++tc)
+        live[tr * ntc + tc] = 1;                                   // (plain stores: no load to wait for; every writer stores 1)
+  };
+  if (fp.all_cols || fp.c_hi - fp.c_lo + 1 >= W) {
+    cols(0, W - 1);
+    return;
+  }
+  const long long a0 = ((fp.c_lo % W) + W) % W, len = fp.c_hi - fp.c_lo + 1;
+  cols(a0, (a0 + len < W ? a0 + len : W) - 1);
+  if (a0 + len > W) cols(0, a0 + len - W - 1);
+}
+
 __global__ void __launch_bounds__(256) k_window_mark(const WinArgs a) {
   const int t = blockIdx.y;
   const int64_t f0 = a.trk_frame_off[t], f1 = a.trk_frame_off[t + 1];
@@ -248,6 +269,7 @@ __global__ void __launch_bounds__(256) k_window_mark(const WinArgs a) {
     const Footprint fp = sub_footprint(g, sub, a.poses[f0 + i], sn, a.incl_pool + sn.incl_off);
     uint32_t *mask = a.mask;
     mark_footprint(fp, img, sn.W, [mask](long long x, long long y) { mark_blocks(mask, x, y); });
+    if (a.tile_live) mark_tiles(fp, sn.H, sn.W, a.tile_live + a.pyr_off[sf * a.L + l]);
   }
 }
 
@@ -351,7 +373,7 @@ extern "C" int64_t occb200_window_mask_words(int64_t ri_len) {
 // caller-zeroed) accumulates the number of 32-byte blocks read over PCIe.  Asynchronous on `stream`.
 extern "C" int occb200_pull_windows(const occb200_annotate_args_t *a, const float *trk_smax, const float *ri_host,
                                     float *ri_pool, int64_t ri_len, uint32_t *mask,
-                                    unsigned long long *pulled_blocks, void *stream_) {
+                                    unsigned long long *pulled_blocks, uint8_t *tile_live, void *stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   OCC_REQUIRE(a != nullptr && ri_len >= 0, "bad arguments");
   if (a->T == 0 || a->F == 0 || ri_len == 0) return 0;
@@ -360,10 +382,13 @@ extern "C" int occb200_pull_windows(const occb200_annotate_args_t *a, const floa
   OCC_REQUIRE(ri_len % kPullBlk == 0, "ri_len must be a multiple of 8 floats (pad the pool)");
   const int64_t n_words = occb200_window_mask_words(ri_len);
   OCC_CUDA(cudaMemsetAsync(mask, 0, 4 * (size_t)n_words, stream));
+  OCC_REQUIRE(tile_live == nullptr || (a->pyr_off != nullptr && a->pyr_tiles > 0), "tile_live needs pyr_off / pyr_tiles");
+  if (tile_live) OCC_CUDA(cudaMemsetAsync(tile_live, 0, (size_t)a->pyr_tiles, stream));
   WinArgs w;
   w.T = a->T; w.L = a->L; w.SF = a->SF; w.ri_len = ri_len;
   w.trk_frame_off = a->trk_frame_off; w.poses = a->poses; w.frame_sf = a->frame_sf; w.sensors = a->sensors;
   w.incl_pool = a->incl_pool; w.trk_smax = trk_smax; w.vs = (float)a->voxel_size; w.mask = mask;
+  w.pyr_off = a->pyr_off; w.tile_live = tile_live;
   const unsigned gx = (unsigned)std::max<int64_t>(1, std::min<int64_t>(32, ceil_div((int64_t)kNumSMs * 16, a->T)));
   k_window_mark<<<dim3(gx, (unsigned)a->T), 256, 0, stream>>>(w);
   OCC_KERNEL_OK("k_window_mark");

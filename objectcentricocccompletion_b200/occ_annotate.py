@@ -406,6 +406,9 @@ class DeviceTracklets:
         ws = _lib.lib().occb200_annotate_workspace_bytes(T, pk.F, total, pk.sensors.shape[0], pk.L, pk.incl_pool.size,
                                                          self.pyr_tiles, int(pk.brick_off[-1]), pk.max_pairs)
         self.workspace = torch.empty(max(ws, 16), dtype=torch.uint8, device=dev)
+        # pull mode: the device also marks the pyramid tiles the batch can read (OCCB200_NO_TILE_LIVE=1: A/B knob)
+        self.use_tile_live = os.environ.get("OCCB200_NO_TILE_LIVE", "0") != "1"
+        self.tile_live = None          # set by a pulled upload, consumed by args()
 
     def upload(self, host: HostBuffers):
         """Asynchronous H2D of every input on the current stream; returns the bytes copied."""
@@ -419,6 +422,9 @@ class DeviceTracklets:
             n += self._upload_blocks(host.ri_staging, host.ri_idx, int(host.ri_blocks.size))
         elif host.ri_mode == "pull":
             self._pull(host.ri_pinned)
+        if host.ri_mode != "pull" and self.tile_live is not None:
+            self.tile_live = None          # the flags of an earlier pull say nothing about this upload,
+            self._graphs = {}              # and a captured graph still points at them: capture again
         return n
 
     def _upload_blocks(self, staging: torch.Tensor, idx: torch.Tensor, nblk: int) -> int:
@@ -445,13 +451,19 @@ class DeviceTracklets:
             self.bufs["ri_mask"] = torch.empty(4 * L_.occb200_window_mask_words(self.pk.ri_len), dtype=torch.uint8,
                                                device=self.device)
         assert ri_pinned.is_pinned() and ri_pinned.numel() == self.pk.ri_len
+        if self.pyr_tiles and "ri_tile_live" not in self.bufs:
+            self.bufs["ri_tile_live"] = torch.zeros(self.pyr_tiles, dtype=torch.uint8, device=self.device)
+        live = self.bufs.get("ri_tile_live") if self.use_tile_live else None
         a = self.args(0)
         with torch.cuda.device(self.device):
             rc = L_.occb200_pull_windows(C.byref(a), self.bufs["trk_smax"].data_ptr(), ri_pinned.data_ptr(),
                                          self.bufs["ri_pool"].data_ptr(), self.pk.ri_len,
                                          self.bufs["ri_mask"].data_ptr(), self.pulled.data_ptr(),
+                                         live.data_ptr() if live is not None else None,
                                          _lib.stream_ptr(self.device))
         _lib.check(rc, "occb200_pull_windows")
+        # the pyramid of later calls on this batch skips the tiles no test can read (args.ri_tile_live)
+        self.tile_live = live
 
     def pulled_bytes(self) -> int:
         """Bytes the device has pulled from pinned host memory so far (synchronises)."""
@@ -492,6 +504,7 @@ class DeviceTracklets:
         a.brick_off = b["brick_off"].data_ptr()
         a.bricks = int(pk.brick_off[-1])
         a.n_points = int(pk.n_points)
+        a.ri_tile_live = self.tile_live.data_ptr() if self.tile_live is not None else None
         a.dims = self.dims.data_ptr()
         a.sizes = self.sizes.data_ptr()
         a.status = self.status.data_ptr()

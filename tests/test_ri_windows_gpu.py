@@ -76,3 +76,49 @@ def test_pull_full_size_c2():
         if y["occ"] is not None:
             assert (x["occ"] == y["occ"]).all() and x["n_unknown"] == y["n_unknown"]
     assert dev.pulled_bytes() < pk.ri_len
+
+
+def test_tile_flags_cover_the_marked_blocks_and_keep_the_labels():
+    """args.ri_tile_live (ABI v7): every block the pull marks lies in a pyramid tile flagged live, a good part of the
+    tiles is dead (the pyramid skips them), and labels / dims / statuses are the same with and without the flags."""
+    import torch
+
+    from objectcentricocccompletion_b200 import occ_annotate, synth
+
+    batch = synth.make_batch(6, 14, 0.2, seed=4)
+    pk = occ_annotate.pack_tracklets(batch)
+    host = occ_annotate.HostBuffers(pk, pin=True, windows=True)
+    out = {}
+    for use in (True, False):
+        dev = occ_annotate.DeviceTracklets(pk)
+        dev.use_tile_live = use
+        dev.upload(host)
+        assert (dev.tile_live is not None) == use
+        for flags in (0, occ_annotate.FLAG_NO_BRICK_CULL):
+            dev.run(flags)
+            torch.cuda.synchronize()
+            out[use, flags] = dev.results()
+        if use:
+            live = dev.tile_live.cpu().numpy().astype(bool)
+            mask = dev.window_mask()
+    for flags in (0, occ_annotate.FLAG_NO_BRICK_CULL):
+        for x, y in zip(out[True, flags], out[False, flags]):
+            assert x["status"] == y["status"] and (x["dims"] == y["dims"]).all()
+            if y["occ"] is not None:
+                assert (x["occ"] == y["occ"]).all()
+    assert 0 < live.mean() < 0.7, live.mean()
+    # every pixel the reference's visibility test reads lies in a live tile (the blocks of the mask are 8 floats of the
+    # flat pool and may reach into a neighbouring tile; only the pixels a test can read matter)
+    from tests.test_ri_windows import check_cover
+
+    pix = np.zeros(pk.ri_len, bool)
+    sens = pk.sensors.reshape(-1)
+    for e in range(sens.size):
+        H, W = int(sens["H"][e]), int(sens["W"][e])
+        ntr, ntc = (H + 7) // 8, (W + 31) // 32
+        lv = live[int(pk.pyr_off[e]): int(pk.pyr_off[e]) + ntr * ntc].reshape(ntr, ntc)
+        img = np.repeat(np.repeat(lv, 8, 0), 32, 1)[:H, :W]
+        o = int(sens["ri_off"][e])
+        pix[o: o + H * W] |= img.reshape(-1)
+    assert check_cover(batch, pk, pix, 1) > 0
+    assert mask.any()
