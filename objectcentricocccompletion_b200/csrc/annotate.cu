@@ -82,7 +82,7 @@ constexpr int kBrick = 4;                // brick edge in voxels: 64 voxels = 2 
 #define OCC_FT 256
 #endif
 #ifndef OCC_FMINB
-#define OCC_FMINB 6
+#define OCC_FMINB 4
 #endif
 constexpr int kFrameThreads = OCC_FT;
 constexpr int kMaxGroup = 8;             // tracklet-frames one crop CTA handles at most
@@ -387,8 +387,8 @@ struct FramePose {     // what the crop needs of one tracklet-frame, in shared m
 
 // One in-box point -> bit index in the tracklet's occupancy bitset, or -1; flags |= 1 kept, |= 2 index error,
 // |= 4 the frame has an in-box point.
-__device__ __forceinline__ int64_t voxel_of_point(const FramePose &fp, const TrkGrid &g, float vsf, float inv_vs,
-                                                  float x, float y, float z, int &flags) {
+__device__ __forceinline__ int voxel_of_point(const FramePose &fp, const TrkGrid &g, float vsf, float inv_vs,
+                                              float x, float y, float z, int &flags) {
   if (!pt_in_box(fp.bt, x, y, z)) return -1;
   flags |= 4;
   // local = (p + (-origin)) @ [[c,-s,0],[s,c,0],[0,0,1]]  (:117-122, lidar_box3d.py:165-184):
@@ -412,7 +412,7 @@ __device__ __forceinline__ int64_t voxel_of_point(const FramePose &fp, const Trk
     flags |= 2;                                 // IndexError in the reference
     return -1;
   }
-  return ((int64_t)qx * g.dims[1] + (int64_t)qy) * g.dims[2] + (int64_t)qz;
+  return ((int)qx * g.dims[1] + (int)qy) * g.dims[2] + (int)qz;      // < V < 2^31 (grid_from_size)
 }
 
 // cuda_arith (flag bit 5): the in-box test as the reference's CUDA kernel evaluates it (device cosf / sinf, nvcc's
@@ -460,6 +460,7 @@ k_crop_voxelize(int64_t F, int64_t P, int chunk, const occb200_pose_t *__restric
   extern __shared__ uint32_t s_bits[];            // smem_words words
   __shared__ FramePose s_fp[kMaxGroup];
   __shared__ int64_t s_off[kMaxGroup + 1];
+  __shared__ __align__(16) int s_rel[kMaxGroup];      // first point of each frame of the run, relative to the run's first point in the chunk
   __shared__ int s_kept[kMaxGroup];
   __shared__ float s_red[kFrameThreads / 32][3];
   __shared__ TrkGrid s_grid;
@@ -534,6 +535,11 @@ k_crop_voxelize(int64_t F, int64_t P, int chunk, const occb200_pose_t *__restric
         s_off[threadIdx.x] = frame_pt_off[fa + threadIdx.x];
         s_kept[threadIdx.x] = 0;
       }
+      if (threadIdx.x < kMaxGroup) {                // 32-bit offsets for the per-point frame search (INT_MAX: no such frame)
+        const int64_t first = redo_pass ? frame_pt_off[fa] : max(frame_pt_off[fa], p0);
+        const int64_t rel = (threadIdx.x < nfr) ? frame_pt_off[fa + threadIdx.x] - first : (int64_t)INT_MAX;
+        s_rel[threadIdx.x] = (int)min(max(rel, (int64_t)INT_MIN), (int64_t)INT_MAX);
+      }
       if (threadIdx.x == 0) {
         s_off[nfr] = frame_pt_off[fb];
         s_flags = 0;
@@ -553,24 +559,37 @@ k_crop_voxelize(int64_t F, int64_t P, int chunk, const occb200_pose_t *__restric
 
       const int64_t n0 = max(s_off[0], p0), n1 = min(s_off[nfr], p1);    // the run's points inside the chunk
       int flags = 0;
-      for (int64_t base = n0; base < n1; base += kFrameThreads * kPtsPerThread) {   // warp-uniform trip count
+      // the run is walked in pieces of < 2^30 points (one piece, as a rule) with 32-bit point numbers relative to n0
+      const float *prun = points + n0 * stride;
+      const int4 rel_a = *reinterpret_cast<const int4 *>(s_rel), rel_b = *reinterpret_cast<const int4 *>(s_rel + 4);
+      static_assert(kMaxGroup == 8, "the frame search reads eight offsets");
+      for (int64_t piece = 0; piece < n1 - n0; piece += (1 << 30)) {
+      const int npts = (int)min(n1 - n0 - piece, (int64_t)(1 << 30));
+      const int jr0 = (int)piece;                                         // (pieces beyond the first: redo pass only, where nfr == 1)
+      for (int base = 0; base < npts; base += kFrameThreads * kPtsPerThread) {   // warp-uniform trip count
         float px[kPtsPerThread], py[kPtsPerThread], pz[kPtsPerThread];
 #pragma unroll
         for (int u = 0; u < kPtsPerThread; ++u) {
-          const int64_t j = base + u * kFrameThreads + threadIdx.x;
-          const float *p = points + j * stride;
-          const bool ok = j < n1;
+          const int j = base + u * kFrameThreads + (int)threadIdx.x;
+          const float *p = prun + (piece + j) * stride;
+          const bool ok = j < npts;
           px[u] = ok ? ld_stream(p) : 0.f;
           py[u] = ok ? ld_stream(p + 1) : 0.f;
           pz[u] = ok ? ld_stream(p + 2) : 0.f;
         }
 #pragma unroll
         for (int u = 0; u < kPtsPerThread; ++u) {
-          const int64_t j = base + u * kFrameThreads + threadIdx.x;
-          int64_t idx = -1;
-          if (j < n1) {
-            int k = 0;                              // frame of point j inside the run
-            for (int i = 1; i < nfr; ++i) k += (j >= s_off[i]) ? 1 : 0;
+          const int j = base + u * kFrameThreads + (int)threadIdx.x;
+          int idx = -1;
+          if (j < npts) {
+            const int jr = jr0 + j;
+            // frame of the point inside the run: the number of frames that start at or before it
+            // (sign bit of rel - 1 - jr: set iff jr >= rel; both lie in [0, 2^31), no overflow)
+            const int nj = ~jr;
+            const unsigned k = ((unsigned)(rel_a.y + nj) >> 31) + ((unsigned)(rel_a.z + nj) >> 31) +
+                               ((unsigned)(rel_a.w + nj) >> 31) + ((unsigned)(rel_b.x + nj) >> 31) +
+                               ((unsigned)(rel_b.y + nj) >> 31) + ((unsigned)(rel_b.z + nj) >> 31) +
+                               ((unsigned)(rel_b.w + nj) >> 31);
             int fl = 0;
             idx = voxel_of_point(s_fp[k], g, vsf, inv_vs, px[u], py[u], pz[u], fl);
             if ((fl & 4) && !s_kept[k]) s_kept[k] = 1;      // benign race: every writer stores 1
@@ -579,7 +598,7 @@ k_crop_voxelize(int64_t F, int64_t P, int chunk, const occb200_pose_t *__restric
           int word = -1;
           uint32_t bit = 0u;
           if (idx >= 0) {
-            word = (int)(idx >> 5);
+            word = idx >> 5;
             bit = 1u << (idx & 31);
             // most points land in voxels that are already marked: look before touching an atomic
             const uint32_t cur = use_smem ? s_bits[word] : __ldg(gbits + word);
@@ -596,6 +615,7 @@ k_crop_voxelize(int64_t F, int64_t P, int chunk, const occb200_pose_t *__restric
             if (word >= 0 && lane == __ffs(peers) - 1) atomicOr(&gbits[word], merged);
           }
         }
+      }
       }
       if (flags) atomicOr(&s_flags, flags);
       __syncthreads();
