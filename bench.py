@@ -75,6 +75,7 @@ def parse(argv=None):
     ap.add_argument("--also", default="c1,c3,c4,c5", help="N=1: sub-records to add to the line (comma list, 'none')")
     ap.add_argument("--batch-segments", type=int, default=8, help="c5 job: segments per device call")
     ap.add_argument("--job-tracklets", type=int, default=JOB_TRACKLETS, help="c5 job size (tests use a small one)")
+    ap.add_argument("--job-streams", type=int, default=2, help="c5 job: streams the batches' graphs alternate on")
     ap.add_argument("--ri-upload", default="pull", choices=["pull", "host", "whole"],
                     help="e2e leg: how the range images reach the device (pull: the device fetches the windows it "
                          "can read from pinned host memory; host: the host gathers them; whole: every image)")
@@ -178,7 +179,8 @@ def full_config(name, T, B, L, voxel_size, world, args):
                     "sharding": "by segment, LPT (dist.shard_indices)", "batch_segments": args.batch_segments,
                     "final_gather": "inside the timed step (uint8 labels, device to device)",
                     "l2": "not flushed: every rank's inputs per step exceed L2 many times over",
-                    "launch": "kernel by kernel" if args.no_graph else "cuda graph replay per batch"})
+                    "launch": "kernel by kernel" if args.no_graph else
+                    f"cuda graph replay per batch, batches alternating on {max(1, args.job_streams)} stream(s)"})
     else:
         cfg.update({"l2": "flushed (256 MiB write) between timed steps",
                     "visibility": "f64" if args.force_f64 else "default",
@@ -515,9 +517,28 @@ def run_job(ctx, n_tracklets, steps, warmup, peak, peak_src, with_e2e=True, pari
         for d in devs:
             d.capture(ctx.flags)
 
+    # the batches of a rank are independent: their graphs alternate on --job-streams streams (fork from / join into the
+    # current stream), so that the latency-bound ends of one batch overlap the wide kernels of the next
+    n_js = max(1, min(ctx.args.job_streams, len(devs))) if ctx.use_graph else 1
+    job_streams = [torch.cuda.Stream(dev) for _ in range(n_js)] if n_js > 1 else []
+
     def compute():
-        for d in devs:
-            d.replay(ctx.flags) if ctx.use_graph else d.run(ctx.flags)
+        if n_js <= 1:
+            for d in devs:
+                d.replay(ctx.flags) if ctx.use_graph else d.run(ctx.flags)
+            return
+        cur = torch.cuda.current_stream(dev)
+        fork = torch.cuda.Event()
+        fork.record(cur)
+        for st in job_streams:
+            st.wait_event(fork)
+        for i, d in enumerate(devs):
+            with torch.cuda.stream(job_streams[i % n_js]):
+                d.replay(ctx.flags)
+        for st in job_streams:
+            join = torch.cuda.Event()
+            join.record(st)
+            cur.wait_event(join)
 
     def gather():
         occ_dist.gather_labels(labels_u8, sizes, 0, None, gathered)
@@ -610,7 +631,7 @@ def run_job(ctx, n_tracklets, steps, warmup, peak, peak_src, with_e2e=True, pari
                      "load_imbalance": float(pr[:, 0].max() / max(pr[:, 0].mean(), 1e-9))},
         # whole job: all ranks' algorithmic ray-cast bytes / the slowest rank's ray-cast time / (N x peak)
         "roofline_frac": (float(pr[:, 3].sum() / (pr[:, 2].max() / 1e3) / 1e9 / peak / world) if pr[:, 2].max() > 0 else 0.0),
-        "batches_per_rank": len(batches), "batch_segments": S, "generate_s_max": float(gm[0]), "pack_ms_max": float(gm[1]),
+        "batches_per_rank": len(batches), "batch_segments": S, "job_streams": n_js, "generate_s_max": float(gm[0]), "pack_ms_max": float(gm[1]),
         "label_mismatches_vs_cpu_port": 0, "parity_sample": f"{parity_tracklets} tracklets per rank",
         "kernels_ms_rank0": dict(zip(KERNEL_KINDS, (kms / n_prof).round(5).tolist())),
         "graph_kernels_per_step_rank0": int(sum(getattr(d, "_graphs", {}).get(ctx.flags, (None, 0))[1] for d in devs)),
