@@ -89,8 +89,6 @@ struct WinArgs {
   const float *trk_smax;   // [T,3] max box size over ALL frames of the tracklet (the grid's upper bound)
   float vs;
   uint32_t *mask;
-  const int64_t *pyr_off;  // [SF*L+1] pyramid tiles before each image (optional, with tile_live)
-  uint8_t *tile_live;      // [pyr_tiles] set to 1 for every 8x32 tile that holds a marked pixel (optional)
 };
 
 __device__ __forceinline__ void mark_blocks(uint32_t *__restrict__ mask, long long a, long long b) {   // floats [a, b]
@@ -231,23 +229,37 @@ __host__ __device__ inline void mark_footprint(const Footprint &fp, long long im
   }
 }
 
-// The pyramid tiles (8 rows x 32 columns, annotate.cu's kTileR x kTileC) a footprint touches: every marked block lies
-// in a live tile, so a tile that stays 0 holds no pixel a visibility test can read.
-__device__ __forceinline__ void mark_tiles(const Footprint &fp, int H, int W, uint8_t *__restrict__ live) {
-  const int ntc = (W + 31) / 32;
-  const int tr0 = fp.r0 / 8, tr1 = min(fp.r1, H - 1) / 8;
-  auto cols = [&](long long c0, long long c1) {                  // columns [c0, c1] inside [0, W)
-    for (int tr = tr0; tr <= tr1; ++tr)
-      for (int tc = (int)(c0 / 32); tc <= (int)(c1 / 32); ++tc)
-        live[tr * ntc + tc] = 1;                                   // (plain stores: no load to wait for; every writer stores 1)
-  };
-  if (fp.all_cols || fp.c_hi - fp.c_lo + 1 >= W) {
-    cols(0, W - 1);
-    return;
+// The pyramid tiles (8 rows x 32 columns, annotate.cu's kTileR x kTileC) that hold a marked block, derived from the
+// block mask once it is complete: one thread per tile looks at the mask bits of its 8 row segments (<= 5 blocks each).
+// A tile that stays 0 holds no pixel a visibility test can read.  (Marking the tiles from inside k_window_mark made
+// hundreds of threads store to the same bytes: the end-to-end step lost 4 %.)
+__global__ void __launch_bounds__(256)
+k_tiles_from_mask(const occb200_sensor_t *__restrict__ sensors, const int64_t *__restrict__ pyr_off,
+                  const uint32_t *__restrict__ mask, long long ri_len, uint8_t *__restrict__ tile_live) {
+  const int e = blockIdx.x;
+  const occb200_sensor_t &sn = sensors[e];
+  const int H = sn.H, W = sn.W;
+  if (H < 1 || W < 1) return;
+  const int ntr = (H + 7) / 8, ntc = (W + 31) / 32;
+  uint8_t *live = tile_live + pyr_off[e];
+  const bool inside = sn.ri_off >= 0 && sn.ri_off + (long long)H * W <= ri_len;
+  for (int tile = blockIdx.y * blockDim.x + threadIdx.x; tile < ntr * ntc; tile += gridDim.y * blockDim.x) {
+    const int tr = tile / ntc, tc = tile - tr * ntc;
+    bool any = !inside;                                            // (an image outside the pool is never marked: build it)
+    for (int r = 0; r < 8 && !any; ++r) {
+      const int row = tr * 8 + r;
+      if (row >= H) break;
+      const long long o0 = sn.ri_off + (long long)row * W + tc * 32;
+      const long long o1 = o0 + min(31, W - 1 - tc * 32);
+      const long long b0 = o0 / kPullBlk, b1 = o1 / kPullBlk;       // <= 5 blocks: one or two mask words
+      for (long long w = b0 >> 5; w <= (b1 >> 5); ++w) {
+        const int lo = (w == (b0 >> 5)) ? (int)(b0 & 31) : 0, hi = (w == (b1 >> 5)) ? (int)(b1 & 31) : 31;
+        const uint32_t bits = (hi == 31 ? 0xffffffffu : ((1u << (hi + 1)) - 1u)) & ~((1u << lo) - 1u);
+        any = any || (__ldg(mask + w) & bits) != 0u;
+      }
+    }
+    live[tile] = any ? 1 : 0;
   }
-  const long long a0 = ((fp.c_lo % W) + W) % W, len = fp.c_hi - fp.c_lo + 1;
-  cols(a0, (a0 + len < W ? a0 + len : W) - 1);
-  if (a0 + len > W) cols(0, a0 + len - W - 1);
 }
 
 __global__ void __launch_bounds__(256) k_window_mark(const WinArgs a) {
@@ -269,7 +281,6 @@ __global__ void __launch_bounds__(256) k_window_mark(const WinArgs a) {
     const Footprint fp = sub_footprint(g, sub, a.poses[f0 + i], sn, a.incl_pool + sn.incl_off);
     uint32_t *mask = a.mask;
     mark_footprint(fp, img, sn.W, [mask](long long x, long long y) { mark_blocks(mask, x, y); });
-    if (a.tile_live) mark_tiles(fp, sn.H, sn.W, a.tile_live + a.pyr_off[sf * a.L + l]);
   }
 }
 
@@ -383,18 +394,21 @@ extern "C" int occb200_pull_windows(const occb200_annotate_args_t *a, const floa
   const int64_t n_words = occb200_window_mask_words(ri_len);
   OCC_CUDA(cudaMemsetAsync(mask, 0, 4 * (size_t)n_words, stream));
   OCC_REQUIRE(tile_live == nullptr || (a->pyr_off != nullptr && a->pyr_tiles > 0), "tile_live needs pyr_off / pyr_tiles");
-  if (tile_live) OCC_CUDA(cudaMemsetAsync(tile_live, 0, (size_t)a->pyr_tiles, stream));
   WinArgs w;
   w.T = a->T; w.L = a->L; w.SF = a->SF; w.ri_len = ri_len;
   w.trk_frame_off = a->trk_frame_off; w.poses = a->poses; w.frame_sf = a->frame_sf; w.sensors = a->sensors;
   w.incl_pool = a->incl_pool; w.trk_smax = trk_smax; w.vs = (float)a->voxel_size; w.mask = mask;
-  w.pyr_off = a->pyr_off; w.tile_live = tile_live;
   const unsigned gx = (unsigned)std::max<int64_t>(1, std::min<int64_t>(32, ceil_div((int64_t)kNumSMs * 16, a->T)));
   k_window_mark<<<dim3(gx, (unsigned)a->T), 256, 0, stream>>>(w);
   OCC_KERNEL_OK("k_window_mark");
   const unsigned gp = (unsigned)std::min<int64_t>(ceil_div(n_words, 8), (int64_t)kNumSMs * 4);
   k_window_pull<<<gp, 256, 0, stream>>>(mask, (long long)n_words - 1, ri_host, ri_pool, (long long)ri_len, pulled_blocks);
   OCC_KERNEL_OK("k_window_pull");
+  if (tile_live) {                                   // (behind the pull: nothing on this stream waits for it but the pyramid)
+    k_tiles_from_mask<<<dim3((unsigned)(a->SF * a->L), 2), 256, 0, stream>>>(a->sensors, a->pyr_off, mask, (long long)ri_len,
+                                                                             tile_live);
+    OCC_KERNEL_OK("k_tiles_from_mask");
+  }
   return 0;
 }
 
