@@ -461,7 +461,7 @@ k_crop_voxelize(int64_t F, int64_t P, int chunk, const occb200_pose_t *__restric
   __shared__ FramePose s_fp[kMaxGroup];
   __shared__ int64_t s_off[kMaxGroup + 1];
   __shared__ __align__(16) int s_rel[kMaxGroup];      // first point of each frame of the run, relative to the run's first point in the chunk
-  __shared__ int s_kept[kMaxGroup];
+  __shared__ unsigned s_keptmask;                 // bit k: frame k of the run has an in-box point
   __shared__ float s_red[kFrameThreads / 32][3];
   __shared__ TrkGrid s_grid;
   __shared__ int s_flags;
@@ -533,7 +533,6 @@ k_crop_voxelize(int64_t F, int64_t P, int chunk, const occb200_pose_t *__restric
       if (threadIdx.x < nfr) {
         s_fp[threadIdx.x] = load_frame_pose(poses[fa + threadIdx.x], inv_vs != 0.f);
         s_off[threadIdx.x] = frame_pt_off[fa + threadIdx.x];
-        s_kept[threadIdx.x] = 0;
       }
       if (threadIdx.x < kMaxGroup) {                // 32-bit offsets for the per-point frame search (INT_MAX: no such frame)
         const int64_t first = redo_pass ? frame_pt_off[fa] : max(frame_pt_off[fa], p0);
@@ -543,6 +542,7 @@ k_crop_voxelize(int64_t F, int64_t P, int chunk, const occb200_pose_t *__restric
       if (threadIdx.x == 0) {
         s_off[nfr] = frame_pt_off[fb];
         s_flags = 0;
+        s_keptmask = 0u;
       }
       __syncthreads();
       const TrkGrid g = s_grid;
@@ -559,6 +559,7 @@ k_crop_voxelize(int64_t F, int64_t P, int chunk, const occb200_pose_t *__restric
 
       const int64_t n0 = max(s_off[0], p0), n1 = min(s_off[nfr], p1);    // the run's points inside the chunk
       int flags = 0;
+      unsigned kept = 0u;                                                 // frames of the run this thread saw an in-box point in
       // the run is walked in pieces of < 2^30 points (one piece, as a rule) with 32-bit point numbers relative to n0
       const float *prun = points + n0 * stride;
       const int4 rel_a = *reinterpret_cast<const int4 *>(s_rel), rel_b = *reinterpret_cast<const int4 *>(s_rel + 4);
@@ -592,7 +593,7 @@ k_crop_voxelize(int64_t F, int64_t P, int chunk, const occb200_pose_t *__restric
                                ((unsigned)(rel_b.w + nj) >> 31);
             int fl = 0;
             idx = voxel_of_point(s_fp[k], g, vsf, inv_vs, px[u], py[u], pz[u], fl);
-            if ((fl & 4) && !s_kept[k]) s_kept[k] = 1;      // benign race: every writer stores 1
+            kept |= (fl & 4) ? (1u << k) : 0u;
             flags |= fl & 3;
           }
           int word = -1;
@@ -618,6 +619,7 @@ k_crop_voxelize(int64_t F, int64_t P, int chunk, const occb200_pose_t *__restric
       }
       }
       if (flags) atomicOr(&s_flags, flags);
+      if (kept) atomicOr(&s_keptmask, kept);
       __syncthreads();
       if (use_smem)
         for (int w2 = threadIdx.x; w2 < words; w2 += kFrameThreads) {
@@ -625,7 +627,7 @@ k_crop_voxelize(int64_t F, int64_t P, int chunk, const occb200_pose_t *__restric
           if (v) atomicOr(&gbits[w2], v);
         }
       // a frame may be shared with the neighbouring chunks: frame_kept starts at 0 and is only ever set
-      if (threadIdx.x < nfr && !redo_pass && s_kept[threadIdx.x]) frame_kept[fa + threadIdx.x] = 1;
+      if (threadIdx.x < nfr && !redo_pass && ((s_keptmask >> threadIdx.x) & 1u)) frame_kept[fa + threadIdx.x] = 1;
       if (threadIdx.x == 0 && s_flags) atomicOr(&trk_flags[t], s_flags);
       fa = fb;
     }

@@ -35,3 +35,20 @@ track_input.crop_frame(pts[0], b.tracklets[0].boxes[:3], 0.5)
 pk = occ_annotate.pack_tracklets(b)
 d = occ_annotate.DeviceTracklets(pk); d.upload(occ_annotate.HostBuffers(pk)); d.capture(); d.replay()
 torch.cuda.synchronize(); print('sanitizer workload (round-1 additions) ok')
+# round-2 additions: the three upload modes (window marks, pull, tile flags, host gather + scatter), brick-cull
+# on / off, point pool, candidate selection from whole-frame clouds
+from objectcentricocccompletion_b200 import candidates, point_pool
+b = synth.make_batch(3, 12, 0.2, seed=2, small=True)
+pk = occ_annotate.pack_tracklets(b)
+for pin, win in ((True, True), (False, True), (True, False)):
+    d = occ_annotate.DeviceTracklets(pk, labels="both"); d.upload(occ_annotate.HostBuffers(pk, pin=pin, windows=win))
+    for fl in (0, occ_annotate.FLAG_NO_BRICK_CULL, occ_annotate.FLAG_TINY_QUEUE, occ_annotate.FLAG_CUDA_ARITH):
+        d.run(fl)
+    torch.cuda.synchronize()
+rois = torch.tensor([[0, 0, 0, 4, 2, 2, 0.3], [5, 5, 0, 4, 2, 2, 1.0]], device='cuda')
+pp = torch.randn(2000, 3, device='cuda') * 3
+point_pool.dynamic_point_pool_mixed(rois, torch.tensor([0, 1], device='cuda'), pp, torch.randint(0, 2, (2000,), device='cuda'),
+                                    [0.5, 0.5, 0.5], 64)
+clouds = [np.random.default_rng(0).normal(size=(5000, 3)).astype(np.float32) * 10 for _ in range(3)]
+candidates.select_candidates(clouds, [np.array([[0, 0, 0, 4, 2, 2, 0.1]] * 3, np.float32)], [np.arange(3)], 1.0)
+torch.cuda.synchronize(); print('sanitizer workload (round-2 additions) ok')
