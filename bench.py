@@ -229,7 +229,8 @@ def run_reference(args):
     """--impl reference: the CPU port on all host cores, same config/metric/unit; rank 0 only."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
-    from objectcentricocccompletion_b200 import synth     # host-only module: no CUDA library is loaded on this arm
+    os.environ["OCCB200_HOST_ONLY"] = "1"               # the package then loads no CUDA library: this arm is the CPU port only
+    from objectcentricocccompletion_b200 import synth
     from oracle import oracle
 
     name = args.workload or ("c2" if args.gpus == 1 else "c5")

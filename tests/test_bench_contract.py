@@ -30,3 +30,19 @@ def test_reference_arm_other_ranks_exit_quietly():
                           "--steps", "1", "--warmup", "0", "--gpus", "2"], capture_output=True, text=True, timeout=300,
                          cwd=ROOT, env=env)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_host_only_import_maps_no_cuda_library():
+    """bench.py's reference arm imports the synthetic generator with OCCB200_HOST_ONLY=1: the package must not load
+    libocc_b200.so then (the arm times the CPU port; the driver records which libraries a process mapped)."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import objectcentricocccompletion_b200.synth as s; "
+            "print('libocc_b200.so' in open('/proc/self/maps').read(), hasattr(s, 'make_batch'))")
+    env = dict(os.environ, OCCB200_HOST_ONLY="1")
+    out = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-500:]
+    assert out.stdout.split() == ["False", "True"], out.stdout
