@@ -409,6 +409,11 @@ int occb200_host_gather_blocks(const uint32_t *block_idx, int64_t n_blocks, cons
                                const int64_t *part_len, const float *const *part_ptr, int32_t n_parts,
                                float *staging);
 
+/* HOST.  dst[dst_off[i] ..) = src[i][0 .. bytes[i]) for n parts, copied in parallel (OpenMP): the one-shot API stages its
+ * pageable inputs (the per-tracklet candidate point arrays the reference holds as separate tensors,
+ * occ_annotate.py:96-138) in one pinned buffer with this before a single asynchronous H2D copy. */
+int occb200_host_copy_parts(const void *const *src, const int64_t *bytes, const int64_t *dst_off, int32_t n, void *dst);
+
 /* DEVICE.  ri_pool[16 block_idx[i] + j] = blocks[16 i + j], j < 16 (clipped at ri_len): scatters the uploaded
  * blocks to their place in the dense pool.  blocks and ri_pool 16-byte aligned.  Asynchronous on `stream`. */
 int occb200_scatter_blocks(const float *blocks, const uint32_t *block_idx, int64_t n_blocks, float *ri_pool,

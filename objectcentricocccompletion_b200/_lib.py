@@ -99,6 +99,7 @@ SIGNATURES = {
     "occb200_scatter_blocks": (C.c_int, [vp, vp, i64, vp, i64, vp]),
     "occb200_window_mask_words": (i64, [i64]),
     "occb200_host_window_mark": (C.c_int, [i32, i32, vp, vp, vp, vp, i64, vp, vp, f64, i64, vp, f32]),
+    "occb200_host_copy_parts": (C.c_int, [vp, vp, vp, i32, vp]),
     "occb200_pull_windows": (C.c_int, [C.POINTER(AnnotateArgs), vp, vp, vp, i64, vp, vp, vp, vp]),
     "occb200_build_range_images": (C.c_int, [vp, C.c_int, vp, i64, vp, i32, vp, vp, i64, vp, vp]),
     "occb200_point_cloud_to_range_image_idx": (C.c_int, [vp, C.c_int, i64, vp, vp, vp, C.c_int, C.c_int, vp, vp, vp]),

@@ -32,6 +32,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <vector>
 
 #include "common.cuh"
 
@@ -354,6 +355,31 @@ extern "C" int occb200_host_gather_blocks(const uint32_t *block_idx, int64_t n_b
     }
   }
   OCC_REQUIRE(!bad, "a block lies outside every source array");
+  return 0;
+}
+
+// HOST.  dst[dst_off[i] .. dst_off[i] + bytes[i]) = src[i][0 .. bytes[i]) for n parts, in parallel (OpenMP, pieces of
+// 256 KB): how the one-shot API moves its pageable inputs (candidate points of every tracklet, small fields) into
+// ONE pinned staging buffer -- a pageable cudaMemcpy of the same 55 MB took 7.4 ms of a 12 ms call.
+extern "C" int occb200_host_copy_parts(const void *const *src, const int64_t *bytes, const int64_t *dst_off, int32_t n,
+                                       void *dst) {
+  OCC_REQUIRE(n >= 0 && (n == 0 || (src && bytes && dst_off && dst)), "bad arguments");
+  const int64_t piece = 256 * 1024;
+  int64_t total = 0;
+  for (int32_t i = 0; i < n; ++i) {
+    OCC_REQUIRE(bytes[i] >= 0 && dst_off[i] >= 0, "negative size / offset");
+    total += ceil_div(bytes[i], piece);
+  }
+  // piece -> (part, offset) by a prefix walk per thread chunk
+  std::vector<int64_t> first(n + 1, 0);
+  for (int32_t i = 0; i < n; ++i) first[i + 1] = first[i] + ceil_div(bytes[i], piece);
+#pragma omp parallel for schedule(static)
+  for (int64_t q = 0; q < total; ++q) {
+    const int32_t i = (int32_t)(std::upper_bound(first.begin(), first.end(), q) - first.begin()) - 1;
+    const int64_t o = (q - first[i]) * piece;
+    const int64_t len = std::min<int64_t>(piece, bytes[i] - o);
+    memcpy((char *)dst + dst_off[i] + o, (const char *)src[i] + o, (size_t)len);
+  }
   return 0;
 }
 

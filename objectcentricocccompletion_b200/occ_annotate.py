@@ -277,6 +277,18 @@ def _as_bytes(a: np.ndarray) -> torch.Tensor:
     return torch.from_numpy(a.view(np.uint8).reshape(-1)) if a.size else torch.zeros(0, dtype=torch.uint8)
 
 
+_ARENA: dict = {}
+
+
+def _pinned_arena(nbytes: int) -> torch.Tensor:
+    """One process-wide pinned staging buffer for the one-shot API, grown geometrically and reused across calls (pinning
+    memory costs milliseconds; a fresh pageable staging buffer costs its page faults on every call)."""
+    buf = _ARENA.get("buf")
+    if buf is None or buf.numel() < nbytes:
+        _ARENA["buf"] = buf = torch.empty(int(max(nbytes, 1) * 1.25) + 4096, dtype=torch.uint8, pin_memory=True)
+    return buf
+
+
 class HostBuffers:
     """Host side of the H2D copies of a PackedTracklets.
 
@@ -290,11 +302,17 @@ class HostBuffers:
                 gathers the blocks from the source arrays into a staging buffer, and the device scatters them.
     ``"whole"`` every image is copied whole, as the reference loads them (occ_annotate.py:502-533).
 
-    ``pin=True`` also puts the candidate points into one pinned buffer; ``pin=False`` (one-shot calls) uploads
-    everything from where it lies."""
+    ``pin=True`` also puts the candidate points into one pinned buffer; ``pin=False`` uploads everything from where it
+    lies; ``pin="arena"`` (the one-shot ``annotate_batch``) stages small fields, points, window blocks and block list
+    in the process-wide pinned arena with parallel host copies (``occb200_host_copy_parts``): valid until the next
+    arena user, i.e. for one synchronous call."""
 
-    def __init__(self, pk: PackedTracklets, pin: bool = True, windows=True):
+    def __init__(self, pk: PackedTracklets, pin=True, windows=True):
         self.pk = pk
+        self.arena = pin == "arena"
+        if self.arena:
+            assert windows is True or windows == "host", "the arena stages the host-gathered windows"
+            pin = False
         self.pin = pin
         if windows in ("pull", "host", "whole"):
             assert windows != "pull" or pin, "the device can only pull from pinned memory"
@@ -341,9 +359,46 @@ class HostBuffers:
             self._part_off = np.asarray([o for o, _ in pk.ri_parts], np.int64)
             self._part_len = np.asarray([a.size for a in srcs], np.int64)
             self._part_ptr = np.asarray([a.ctypes.data for a in srcs], np.uint64)
+            if self.arena:
+                self._stage_in_arena()
             self.gather_windows()
         else:
             self.ri_parts = [(o * 4, host(a)) for o, a in pk.ri_parts]
+            if self.arena:
+                self._stage_in_arena()
+
+    def _stage_in_arena(self):
+        """Move small fields, points, block list and the window staging area into the pinned arena (one buffer)."""
+        pk = self.pk
+
+        def up(n):
+            return -(-n // 256) * 256
+
+        n_small, n_pts = self.small.numel(), 4 * pk.n_points * pk.point_stride
+        n_idx = self.ri_idx.numel() if self.ri_idx is not None else 0
+        n_stage = 4 * self.ri_staging.numel() if self.ri_staging is not None else 0
+        o_small, o_pts = 0, up(n_small)
+        o_idx = o_pts + up(n_pts)
+        o_stage = o_idx + up(n_idx)
+        buf = _pinned_arena(o_stage + up(n_stage))
+        srcs, sizes, offs, keep = [], [], [], []
+        for off, t in [(o_small, self.small)] + [(o_pts + o, t) for o, t in self.pt_parts] + \
+                ([(o_idx, self.ri_idx)] if n_idx else []):
+            if t.numel():
+                keep.append(t)
+                srcs.append(t.data_ptr()); sizes.append(t.numel()); offs.append(off)
+        if srcs:
+            a_src = np.asarray(srcs, np.uint64)
+            a_sz, a_off = np.asarray(sizes, np.int64), np.asarray(offs, np.int64)
+            rc = _lib.lib().occb200_host_copy_parts(a_src.ctypes.data, a_sz.ctypes.data, a_off.ctypes.data, len(srcs),
+                                                    buf.data_ptr())
+            _lib.check(rc, "occb200_host_copy_parts")
+        self.small = buf[o_small: o_small + n_small]
+        self.pt_parts = [(0, buf[o_pts: o_pts + n_pts])] if n_pts else []
+        if n_idx:
+            self.ri_idx = buf[o_idx: o_idx + n_idx]
+        if n_stage:
+            self.ri_staging = buf[o_stage: o_stage + n_stage].view(torch.float32)
 
     def gather_windows(self):
         """"host" mode: copy the window blocks from the source range images into the staging buffer (OpenMP)."""
@@ -641,7 +696,8 @@ def annotate_batch(batch, flags: int = 0, pack_override: Optional[dict] = None, 
     ``size``, ``n_unknown`` (U) and ``n_steps`` (visibility tests evaluated).
     """
     pk = pack_tracklets(batch, pack_override)
-    host = HostBuffers(pk, pin=False, windows=windows)       # one-shot call: uploaded from where the arrays lie
+    # one-shot call: the pageable inputs are staged in the process-wide pinned arena (windows gathered by the host)
+    host = HostBuffers(pk, pin="arena" if windows is True and pk.ri_len and pk.F else False, windows=windows)
     dev = DeviceTracklets(pk, device)
     dev.upload(host)
     dev.run(flags)

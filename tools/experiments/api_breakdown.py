@@ -10,6 +10,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspa
 from objectcentricocccompletion_b200 import occ_annotate, synth  # noqa: E402
 
 name = sys.argv[1] if len(sys.argv) > 1 else "c2"
+MODE = {"arena": "arena", "pageable": False}[sys.argv[2] if len(sys.argv) > 2 else "arena"]
 batch = synth.config_batch(name, seed=0)
 for rep in range(4):
     t = [time.perf_counter()]
@@ -19,7 +20,7 @@ for rep in range(4):
         t.append(time.perf_counter())
 
     pk = occ_annotate.pack_tracklets(batch); lap()
-    host = occ_annotate.HostBuffers(pk, pin=False, windows=True); lap()
+    host = occ_annotate.HostBuffers(pk, pin=MODE, windows=True); lap()
     dev = occ_annotate.DeviceTracklets(pk); lap()
     dev.upload(host); lap()
     dev.run(0); lap()
