@@ -106,3 +106,26 @@ def test_gather_blocks_reproduces_the_pool():
     exp = pool.reshape(-1, occ_annotate.RI_BLOCK)[host.ri_blocks]
     assert (st[: host.ri_blocks.size] == exp).all()
     assert host.nbytes() < occ_annotate.HostBuffers(pk, pin=False, windows=False).nbytes()
+
+
+def test_host_copy_parts():
+    """occb200_host_copy_parts (host code of the library): parts of odd sizes, an empty one and one larger than a
+    copy piece land at their offsets; bytes between them are untouched."""
+    from objectcentricocccompletion_b200 import _lib
+
+    rng = np.random.default_rng(0)
+    sizes = [0, 1, 4097, 300_000, 700_001]
+    parts = [rng.integers(0, 256, n, dtype=np.uint8) for n in sizes]
+    offs, o = [], 16
+    for n in sizes:
+        offs.append(o)
+        o += n + 7
+    dst = np.full(o + 32, 0xAB, np.uint8)
+    src = np.asarray([p.ctypes.data for p in parts], np.uint64)
+    a_sz, a_off = np.asarray(sizes, np.int64), np.asarray(offs, np.int64)
+    rc = _lib.lib().occb200_host_copy_parts(src.ctypes.data, a_sz.ctypes.data, a_off.ctypes.data, len(parts), dst.ctypes.data)
+    assert rc == 0
+    exp = np.full_like(dst, 0xAB)
+    for p, off in zip(parts, offs):
+        exp[off: off + p.size] = p
+    assert (dst == exp).all()
