@@ -321,11 +321,44 @@ using namespace occb200;
 // HOST.  Compacts an 8-float block mask into the ascending list of 16-float blocks (64 bytes, the unit of the gather /
 // scatter pair) that hold a marked block; returns their number.  out has room for ceil(n8 / 2) entries.
 extern "C" int64_t occb200_host_mask_to_blocks(const uint8_t *mask8, int64_t n8, uint32_t *out) {
-  int64_t n = 0;
-  for (int64_t k = 0; k + 1 < n8; k += 2)
-    if (mask8[k] | mask8[k + 1]) out[n++] = (uint32_t)(k >> 1);
-  if ((n8 & 1) && mask8[n8 - 1]) out[n++] = (uint32_t)(n8 >> 1);
-  return n;
+  // two passes over chunks of 64 K mask bytes (OpenMP): count the pairs that hold a marked block, prefix, write.
+  // (The one-pass scalar loop was 2.6 ms of a 6.5 ms one-shot call for the 3.2 M mask bytes of one segment.)
+  const int64_t npair = (n8 + 1) / 2;                 // pair k = mask bytes 2k, 2k+1 (the last one may be half)
+  const int64_t chunk = 32768;                        // pairs per chunk
+  const int64_t nchunk = ceil_div(npair, chunk);
+  if (nchunk == 0) return 0;
+  std::vector<int64_t> cnt(nchunk + 1, 0);
+  auto marked = [&](int64_t k) -> bool { return mask8[2 * k] | ((2 * k + 1 < n8) ? mask8[2 * k + 1] : 0); };
+#pragma omp parallel for schedule(static)
+  for (int64_t c = 0; c < nchunk; ++c) {
+    const int64_t k0 = c * chunk, k1 = std::min(npair, k0 + chunk);
+    int64_t n = 0, k = k0;
+    for (; k + 4 <= k1 && 2 * (k + 4) <= n8; k += 4) {             // 8 mask bytes at a time: most words are all zero
+      uint64_t w;
+      memcpy(&w, mask8 + 2 * k, 8);
+      if (!w) continue;
+      for (int j = 0; j < 4; ++j) n += ((w >> (16 * j)) & 0xffffu) ? 1 : 0;
+    }
+    for (; k < k1; ++k) n += marked(k) ? 1 : 0;
+    cnt[c + 1] = n;
+  }
+  for (int64_t c = 0; c < nchunk; ++c) cnt[c + 1] += cnt[c];
+#pragma omp parallel for schedule(static)
+  for (int64_t c = 0; c < nchunk; ++c) {
+    const int64_t k0 = c * chunk, k1 = std::min(npair, k0 + chunk);
+    uint32_t *o = out + cnt[c];
+    int64_t k = k0;
+    for (; k + 4 <= k1 && 2 * (k + 4) <= n8; k += 4) {
+      uint64_t w;
+      memcpy(&w, mask8 + 2 * k, 8);
+      if (!w) continue;
+      for (int j = 0; j < 4; ++j)
+        if ((w >> (16 * j)) & 0xffffu) *o++ = (uint32_t)(k + j);
+    }
+    for (; k < k1; ++k)
+      if (marked(k)) *o++ = (uint32_t)k;
+  }
+  return cnt[nchunk];
 }
 
 // HOST.  Copies the listed blocks from the source arrays to staging[16 * i ..]: block k of the pool lies in part

@@ -129,3 +129,24 @@ def test_host_copy_parts():
     for p, off in zip(parts, offs):
         exp[off: off + p.size] = p
     assert (dst == exp).all()
+
+
+def test_mask_to_blocks_matches_numpy():
+    """occb200_host_mask_to_blocks (two-pass, OpenMP): the ascending list of 16-float blocks that hold a marked
+    8-float block, for odd lengths, empty / full / sparse masks and lengths around the chunk size."""
+    from objectcentricocccompletion_b200 import _lib
+
+    def blocks(m):
+        out = np.empty((m.size + 1) // 2 + 1, np.uint32)
+        n = _lib.lib().occb200_host_mask_to_blocks(m.ctypes.data, m.size, out.ctypes.data)
+        return out[:n].copy()
+
+    rng = np.random.default_rng(5)
+    for n, p in ((0, 0.5), (1, 1.0), (7, 0.5), (9, 1.0), (65535, 0.2), (65536, 0.01), (65537, 0.9), (200_003, 0.0),
+                 (1_000_001, 0.22)):
+        m = np.ascontiguousarray((rng.random(n) < p).astype(np.uint8))
+        k = (n + 1) // 2
+        pairs = np.concatenate([m, np.zeros(2 * k - n, np.uint8)]).reshape(k, 2)
+        exp = np.flatnonzero(pairs.any(1)).astype(np.uint32)
+        got = blocks(m)
+        assert got.size == exp.size and (got == exp).all(), (n, p)
