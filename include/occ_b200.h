@@ -137,6 +137,15 @@ int occb200_unique_rows(const void *coors, int coor_dtype, int64_t N, int K, int
                         int32_t *inverse, int32_t *counts, int32_t *order, int32_t *gstart,
                         void *workspace, int64_t workspace_bytes, int64_t *m_host, void *stream);
 
+/* The same with caller-provided bounds (modes 1 / 2): col_max HOST int64 [K] = the largest value a valid row may hold
+ * in each column (DynamicScatter knows its grid: round((range[3:] - range[:3]) / voxel_size) - 1, scatter_points.py:53-61;
+ * the batch column of mode 2 is bounded by the batch size instead).  The key widths then need no min/max pass over the
+ * rows and, in mode 1, no host round trip before the sort.  A row beyond a bound is detected on the device and the
+ * call falls back to the unbounded path: the result is always that of occb200_unique_rows.  col_max NULL = unbounded. */
+int occb200_unique_rows_bounded(const void *coors, int coor_dtype, int64_t N, int K, int mode, const int64_t *col_max,
+                                void *uniq, int32_t *inverse, int32_t *counts, int32_t *order, int32_t *gstart,
+                                void *workspace, int64_t workspace_bytes, int64_t *m_host, void *stream);
+
 /* Reduction plan (order, gstart, counts) from an existing inverse map int32 [N] with values in
  * [-1, M): what scatter_v2 needs when the caller passes unq_inv (sst_ops.py:159-160). No sync. */
 int64_t occb200_plan_workspace_bytes(int64_t N);

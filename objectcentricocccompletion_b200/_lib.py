@@ -73,6 +73,7 @@ SIGNATURES = {
     "occb200_hard_voxelize": (C.c_int, [vp, i64, C.c_int, vp, vp, C.c_int, C.c_int, vp, vp, vp, vp, i64, vp, vp]),
     "occb200_unique_workspace_bytes": (i64, [i64, C.c_int]),
     "occb200_unique_rows": (C.c_int, [vp, C.c_int, i64, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, i64, vp, vp]),
+    "occb200_unique_rows_bounded": (C.c_int, [vp, C.c_int, i64, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp, i64, vp, vp]),
     "occb200_plan_workspace_bytes": (i64, [i64]),
     "occb200_plan_from_inverse": (C.c_int, [vp, i64, i64, vp, vp, vp, vp, i64, vp]),
     "occb200_segment_reduce": (C.c_int, [vp, i64, C.c_int, vp, vp, vp, i64, C.c_int, vp, vp, vp]),

@@ -23,6 +23,8 @@ struct KeySpec {
   int mode;
   int flag_shift;          // modes 1/2: position of the "valid" flag bit
   long long batch_size;    // mode 2
+  long long vmax[kMaxK];   // bounded call: largest value a valid row may hold in the column (LLONG_MAX: unbounded)
+  unsigned long long *oob; // bounded call: set to 1 by a valid row beyond vmax (the caller then repeats the call unbounded)
 };
 
 template <typename CT>
@@ -77,6 +79,7 @@ __global__ void k_make_keys(const CT *__restrict__ coors, int64_t N, KeySpec sp,
   for (int k = 0; k < sp.K; ++k) {
     const long long v = (long long)r[k];
     if (sp.mode != 0 && k >= first && v < 0) valid = false;
+    if (v > sp.vmax[k] && sp.oob) *sp.oob = 1ull;                 // (only valid rows matter, but any overflow would corrupt a key)
     key |= (uint64_t)(v - sp.bias[k]) << sp.shift[k];
   }
   if (sp.mode == 1) {
@@ -168,25 +171,42 @@ static int bit_length(unsigned long long v) {
 }
 
 template <typename CT>
-static int unique_impl(const CT *coors, int64_t N, int K, int mode, CT *uniq, int32_t *inverse, int32_t *counts,
-                       int32_t *order, int32_t *gstart, char *ws, const UqLayout &l, int64_t *m_host,
+static int unique_impl(const CT *coors, int64_t N, int K, int mode, const int64_t *col_max, CT *uniq, int32_t *inverse,
+                       int32_t *counts, int32_t *order, int32_t *gstart, char *ws, const UqLayout &l, int64_t *m_host,
                        cudaStream_t stream) {
   long long *mm = (long long *)(ws + l.mm);
-  k_minmax_init<<<1, 32, 0, stream>>>(mm);
-  OCC_KERNEL_OK("k_minmax_init");
-  const int mm_grid = (int)std::min<int64_t>(ceil_div(N, 256 * 4), kNumSMs * 4);
-  k_minmax<CT><<<mm_grid, 256, 0, stream>>>(coors, N, K, mm);
-  OCC_KERNEL_OK("k_minmax");
+  // Bounded call (modes 1 / 2, every bound >= 0): the caller knows the grid the coordinates come from, so the key
+  // widths need no min/max pass over the rows and (mode 1) no host round trip before the sort.  A row beyond a bound
+  // raises a device flag that is read with the group count; the call is then repeated unbounded.
+  const bool bounded = col_max != nullptr && mode != 0;
   long long h_mm[2 * kMaxK + 1];
-  OCC_CUDA(cudaMemcpyAsync(h_mm, mm, 8 * 2 * K, cudaMemcpyDeviceToHost, stream));
   CT last0 = 0;
+  if (!bounded) {
+    k_minmax_init<<<1, 32, 0, stream>>>(mm);
+    OCC_KERNEL_OK("k_minmax_init");
+    const int mm_grid = (int)std::min<int64_t>(ceil_div(N, 256 * 4), kNumSMs * 4);
+    k_minmax<CT><<<mm_grid, 256, 0, stream>>>(coors, N, K, mm);
+    OCC_KERNEL_OK("k_minmax");
+    OCC_CUDA(cudaMemcpyAsync(h_mm, mm, 8 * 2 * K, cudaMemcpyDeviceToHost, stream));
+  } else {
+    for (int k = 0; k < K; ++k) {
+      OCC_REQUIRE(col_max[k] >= 0, "col_max must be non-negative");
+      h_mm[2 * k] = 0;
+      h_mm[2 * k + 1] = (long long)col_max[k];
+    }
+    OCC_CUDA(cudaMemsetAsync(mm + 2 * kMaxK, 0, 8, stream));       // the out-of-bounds flag
+  }
   if (mode == 2) OCC_CUDA(cudaMemcpyAsync(&last0, coors + (N - 1) * K, sizeof(CT), cudaMemcpyDeviceToHost, stream));
-  OCC_CUDA(cudaStreamSynchronize(stream));
+  if (!bounded || mode == 2) OCC_CUDA(cudaStreamSynchronize(stream));
 
   KeySpec sp;
   sp.K = K;
   sp.mode = mode;
   sp.batch_size = (long long)last0 + 1;          // scatter_points.py:86
+  sp.oob = bounded ? (unsigned long long *)(mm + 2 * kMaxK) : nullptr;
+  for (int k = 0; k < kMaxK; ++k) sp.vmax[k] = LLONG_MAX;
+  if (bounded)
+    for (int k = (mode == 2 ? 1 : 0); k < K; ++k) sp.vmax[k] = (long long)col_max[k];   // (the batch column is bounded by batch_size)
   int bits[kMaxK];
   for (int k = 0; k < K; ++k) {
     long long lo = h_mm[2 * k], hi = h_mm[2 * k + 1];
@@ -230,8 +250,12 @@ static int unique_impl(const CT *coors, int64_t N, int K, int mode, CT *uniq, in
   k_emit<CT><<<grid, 256, 0, stream>>>(coors, K, keys_b, order, N, seg_start, kept, drop, uniq, inverse, counts, gstart);
   OCC_KERNEL_OK("k_emit");
   int32_t m32 = 0;
+  unsigned long long oob = 0;
   OCC_CUDA(cudaMemcpyAsync(&m32, kept + (N - 1), 4, cudaMemcpyDeviceToHost, stream));
+  if (bounded) OCC_CUDA(cudaMemcpyAsync(&oob, mm + 2 * kMaxK, 8, cudaMemcpyDeviceToHost, stream));
   OCC_CUDA(cudaStreamSynchronize(stream));
+  if (oob)                                         // a coordinate beyond the caller's bound: the keys are not trustworthy
+    return unique_impl<CT>(coors, N, K, mode, nullptr, uniq, inverse, counts, order, gstart, ws, l, m_host, stream);
   *m_host = m32;
   return 0;
 }
@@ -361,9 +385,22 @@ extern "C" int64_t occb200_unique_workspace_bytes(int64_t N, int K) {
   return uq_layout(N).bytes;
 }
 
+extern "C" int occb200_unique_rows_bounded(const void *coors, int coor_dtype, int64_t N, int K, int mode,
+                                           const int64_t *col_max, void *uniq, int32_t *inverse, int32_t *counts,
+                                           int32_t *order, int32_t *gstart, void *workspace, int64_t workspace_bytes,
+                                           int64_t *m_host, void *stream_);
+
 extern "C" int occb200_unique_rows(const void *coors, int coor_dtype, int64_t N, int K, int mode, void *uniq,
                                    int32_t *inverse, int32_t *counts, int32_t *order, int32_t *gstart,
                                    void *workspace, int64_t workspace_bytes, int64_t *m_host, void *stream_) {
+  return occb200_unique_rows_bounded(coors, coor_dtype, N, K, mode, nullptr, uniq, inverse, counts, order, gstart,
+                                     workspace, workspace_bytes, m_host, stream_);
+}
+
+extern "C" int occb200_unique_rows_bounded(const void *coors, int coor_dtype, int64_t N, int K, int mode,
+                                           const int64_t *col_max, void *uniq, int32_t *inverse, int32_t *counts,
+                                           int32_t *order, int32_t *gstart, void *workspace, int64_t workspace_bytes,
+                                           int64_t *m_host, void *stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   OCC_REQUIRE(m_host != nullptr, "m_host is NULL");
   *m_host = 0;
@@ -376,9 +413,9 @@ extern "C" int occb200_unique_rows(const void *coors, int coor_dtype, int64_t N,
   const UqLayout l = uq_layout(N);
   OCC_REQUIRE(workspace != nullptr && workspace_bytes >= l.bytes, "workspace too small");
   if (coor_dtype == 0)
-    return unique_impl<int32_t>((const int32_t *)coors, N, K, mode, (int32_t *)uniq, inverse, counts, order, gstart,
-                                (char *)workspace, l, m_host, stream);
-  return unique_impl<int64_t>((const int64_t *)coors, N, K, mode, (int64_t *)uniq, inverse, counts, order, gstart,
+    return unique_impl<int32_t>((const int32_t *)coors, N, K, mode, col_max, (int32_t *)uniq, inverse, counts, order,
+                                gstart, (char *)workspace, l, m_host, stream);
+  return unique_impl<int64_t>((const int64_t *)coors, N, K, mode, col_max, (int64_t *)uniq, inverse, counts, order, gstart,
                               (char *)workspace, l, m_host, stream);
 }
 

@@ -77,7 +77,9 @@ class _Plan:
     __slots__ = ("uniq", "inverse", "counts", "order", "gstart", "M")
 
 
-def _unique(coors, mode):
+def _unique(coors, mode, col_max=None):
+    """``col_max`` (optional, modes 1 / 2): the largest valid value of each column, from the caller's grid -- the sort
+    keys are then laid out without a min/max pass over the rows (occb200_unique_rows_bounded)."""
     N, K = coors.shape
     dev = coors.device
     if coors.dtype == torch.int32:
@@ -95,10 +97,15 @@ def _unique(coors, mode):
     gstart = torch.empty(N, dtype=torch.int32, device=dev)
     ws = torch.empty(max(L.occb200_unique_workspace_bytes(N, K), 16), dtype=torch.uint8, device=dev)
     m = C.c_int64(0)
+    cm = None
+    if col_max is not None and mode != 0:
+        cm = np.ascontiguousarray(np.asarray(col_max, np.int64).reshape(-1))
+        assert cm.size == K
     with torch.cuda.device(dev):
-        rc = L.occb200_unique_rows(coors.data_ptr(), dt, N, K, mode, uniq.data_ptr(), p.inverse.data_ptr(),
-                                   counts.data_ptr(), p.order.data_ptr(), gstart.data_ptr(), ws.data_ptr(), ws.numel(),
-                                   C.addressof(m), _lib.stream_ptr(dev))
+        rc = L.occb200_unique_rows_bounded(coors.data_ptr(), dt, N, K, mode, cm.ctypes.data if cm is not None else None,
+                                           uniq.data_ptr(), p.inverse.data_ptr(), counts.data_ptr(),
+                                           p.order.data_ptr(), gstart.data_ptr(), ws.data_ptr(), ws.numel(),
+                                           C.addressof(m), _lib.stream_ptr(dev))
     _lib.check(rc, "occb200_unique_rows")
     p.M = int(m.value)
     p.uniq, p.counts, p.gstart = uniq[:p.M], counts[:p.M], gstart[:p.M]
@@ -124,7 +131,7 @@ def _convert_reduce_type(reduce_type):
     return _REDUCE[reduce_type]
 
 
-def dynamic_point_to_voxel_forward(feats, coors, reduce_type, _mode=1):
+def dynamic_point_to_voxel_forward(feats, coors, reduce_type, _mode=1, _col_max=None):
     """voxel_layer.dynamic_point_to_voxel_forward (voxelization.cpp:9, scatter_points_cuda.cu:183-234).
 
     Returns [voxel_feats, voxel_coors, point2voxel_map int32, voxel_points_count int32, argmax];
@@ -140,7 +147,7 @@ def dynamic_point_to_voxel_forward(feats, coors, reduce_type, _mode=1):
                 coors.new_empty((0,), dtype=torch.int32), coors.new_empty((0,), dtype=torch.int32), None]
     if feats.dtype not in (torch.float32, torch.float64):       # AT_DISPATCH_FLOATING_TYPES (scatter_points_cuda.cu:215)
         raise RuntimeError("dynamic_point_to_voxel_forward supports float32 / float64 features")
-    plan = _unique(coors, _mode)
+    plan = _unique(coors, _mode, _col_max)
     out, argmax = _reduce(feats, plan, red, want_argmax=(red == 2))
     return [out, plan.uniq, plan.inverse, plan.counts, argmax]
 
@@ -214,10 +221,10 @@ class Voxelization(nn.Module):
 class _dynamic_scatter(Function):
 
     @staticmethod
-    def forward(ctx, feats, coors, reduce_type='max', _mode=1):
+    def forward(ctx, feats, coors, reduce_type='max', _mode=1, _col_max=None):
         """feats [N,C], coors [N,ndim] int -> (voxel_feats [M,C], voxel_coors [M,ndim]) (scatter_points.py:11-34)."""
         voxel_feats, voxel_coors, point2voxel_map, voxel_points_count, argmax = dynamic_point_to_voxel_forward(
-            feats, coors, reduce_type, _mode)
+            feats, coors, reduce_type, _mode, _col_max)
         ctx.reduce_type = reduce_type
         ctx.has_argmax = argmax is not None
         saved = [feats, voxel_feats, point2voxel_map, voxel_points_count]
@@ -235,11 +242,11 @@ class _dynamic_scatter(Function):
         grad_feats = torch.zeros_like(feats)
         dynamic_point_to_voxel_backward(grad_feats, grad_voxel_feats.contiguous(), feats, voxel_feats,
                                         point2voxel_map, voxel_points_count, ctx.reduce_type, argmax)
-        return grad_feats, None, None, None
+        return grad_feats, None, None, None, None
 
 
 def dynamic_scatter(feats, coors, reduce_type='max'):
-    return _dynamic_scatter.apply(feats, coors, reduce_type, 1)
+    return _dynamic_scatter.apply(feats, coors, reduce_type, 1, None)
 
 
 class DynamicScatter(nn.Module):
@@ -255,10 +262,21 @@ class DynamicScatter(nn.Module):
         self.voxel_size = voxel_size
         self.point_cloud_range = point_cloud_range
         self.average_points = average_points
+        # the grid the coordinates come from (Voxelization with the same arguments, voxelize.py:93-98): bounds of the
+        # (z, y, x) columns for the sort keys; coordinates beyond them are detected and handled by the library
+        self._col_max = None
+        try:
+            pcr = np.asarray(point_cloud_range, np.float32).reshape(-1)
+            vs = np.asarray(voxel_size, np.float32).reshape(-1)
+            grid = np.round((pcr[3:6] - pcr[:3]) / vs[:3]).astype(np.int64)
+            if grid.size == 3 and (grid >= 1).all() and (grid < 2 ** 20).all():
+                self._col_max = [int(grid[2]) - 1, int(grid[1]) - 1, int(grid[0]) - 1]
+        except Exception:                                            # noqa: BLE001  (odd arguments: no bounds)
+            self._col_max = None
 
     def forward_single(self, points, coors):
         reduce = 'mean' if self.average_points else 'max'
-        return dynamic_scatter(points.contiguous(), coors.contiguous(), reduce)
+        return _dynamic_scatter.apply(points.contiguous(), coors.contiguous(), reduce, 1, self._col_max)
 
     def forward(self, points, coors):
         if coors.size(-1) == 3:
@@ -266,7 +284,8 @@ class DynamicScatter(nn.Module):
         reduce = 'mean' if self.average_points else 'max'
         if coors.size(0) == 0:
             raise IndexError("index -1 is out of bounds for dimension 0 with size 0")   # coors[-1, 0] in the reference
-        return _dynamic_scatter.apply(points.contiguous(), coors.contiguous(), reduce, 2)
+        cm = [0] + self._col_max if (self._col_max is not None and coors.size(-1) == 4) else None
+        return _dynamic_scatter.apply(points.contiguous(), coors.contiguous(), reduce, 2, cm)
 
     def __repr__(self):
         return (f"{self.__class__.__name__}(voxel_size={self.voxel_size}, point_cloud_range={self.point_cloud_range}"

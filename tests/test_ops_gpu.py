@@ -330,3 +330,29 @@ def test_dynamic_scatter_float64(mode):
     f = _t(rng.standard_normal((60, 3))).requires_grad_()
     c = _t(rng.integers(-1, 3, (60, 3)).astype(np.int32))
     assert gradcheck(lambda x: voxel.dynamic_scatter(x, c, mode)[0], (f,), eps=1e-6, atol=1e-6, rtol=1e-4)
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+def test_dynamic_scatter_bounded_keys_equal_unbounded(mode):
+    """occb200_unique_rows_bounded: with the grid's bounds the sort keys are laid out without the min/max pass; the
+    result equals the unbounded call, also when a row lies beyond a bound (device flag -> unbounded repeat)."""
+    import torch
+
+    from objectcentricocccompletion_b200.voxel import _dynamic_scatter
+
+    torch.manual_seed(3)
+    N = 150_000
+    grid = (40, 300, 280)                                  # (z, y, x)
+    cols = [torch.randint(-1, g, (N,), dtype=torch.int32, device='cuda') for g in grid]
+    if mode == 2:
+        cols = [torch.sort(torch.randint(0, 4, (N,), dtype=torch.int32, device='cuda')).values] + cols
+    coors = torch.stack(cols, 1).contiguous()
+    feats = torch.rand((N, 5), device='cuda')
+    cm = [g - 1 for g in grid] if mode == 1 else [0] + [g - 1 for g in grid]
+    for red in ('mean', 'max'):
+        a = _dynamic_scatter.apply(feats, coors, red, mode, None)
+        b = _dynamic_scatter.apply(feats, coors, red, mode, cm)
+        assert a[1].shape == b[1].shape and bool((a[1] == b[1]).all()) and bool((a[0] == b[0]).all())
+        tight = [max(c // 2, 0) for c in cm]               # rows beyond these bounds exist: the fallback path
+        c = _dynamic_scatter.apply(feats, coors, red, mode, tight)
+        assert a[1].shape == c[1].shape and bool((a[1] == c[1]).all()) and bool((a[0] == c[0]).all())
