@@ -67,8 +67,8 @@ __global__ void k_minmax_init(long long *mm) {
   if (threadIdx.x < kMaxK) { mm[2 * threadIdx.x] = LLONG_MAX; mm[2 * threadIdx.x + 1] = LLONG_MIN; }
 }
 
-template <typename CT>
-__global__ void k_make_keys(const CT *__restrict__ coors, int64_t N, KeySpec sp, uint64_t *__restrict__ keys,
+template <typename CT, typename KT>            // KT: uint32_t when the packed key fits 32 bits (less sort traffic), else uint64_t
+__global__ void k_make_keys(const CT *__restrict__ coors, int64_t N, KeySpec sp, KT *__restrict__ keys,
                             int32_t *__restrict__ idx) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
@@ -90,24 +90,25 @@ __global__ void k_make_keys(const CT *__restrict__ coors, int64_t N, KeySpec sp,
     else if (valid) key |= (1ull << sp.flag_shift);
     else key = (uint64_t)(b - sp.bias[0]) << sp.shift[0];         // the sample's (-1,-1,-1) group
   }
-  keys[i] = key;
+  keys[i] = (KT)key;
   idx[i] = (int32_t)i;
 }
 
 // heads of equal-key runs; which heads open a dropped group
-__global__ void k_heads(const uint64_t *__restrict__ keys, int64_t N, KeySpec sp, int32_t *__restrict__ seg_start,
+template <typename KT>
+__global__ void k_heads(const KT *__restrict__ keys, int64_t N, KeySpec sp, int32_t *__restrict__ seg_start,
                         int32_t *__restrict__ kept_head, uint8_t *__restrict__ drop_head) {
   const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= N) return;
-  const uint64_t k = keys[j];
-  const bool head = (j == 0) || k != keys[j - 1];
+  const uint64_t k = (uint64_t)keys[j];
+  const bool head = (j == 0) || keys[j] != keys[j - 1];
   bool drop = false;
   if (head) {
     if (sp.mode == 1) {
       drop = (j == 0);                                            // "first element is always (-1,-1,-1)" (:207)
     } else if (sp.mode == 2) {
       const int bs = sp.shift[0];
-      drop = ((long long)(k >> bs) == sp.batch_size) || (j == 0) || ((k >> bs) != (keys[j - 1] >> bs));   // first unique row of each sample
+      drop = ((long long)(k >> bs) == sp.batch_size) || (j == 0) || ((k >> bs) != ((uint64_t)keys[j - 1] >> bs));   // first unique row of each sample
     }
   }
   seg_start[j] = head ? (int32_t)j : 0;
@@ -115,8 +116,8 @@ __global__ void k_heads(const uint64_t *__restrict__ keys, int64_t N, KeySpec sp
   drop_head[j] = drop ? 1 : 0;
 }
 
-template <typename CT>
-__global__ void k_emit(const CT *__restrict__ coors, int K, const uint64_t *__restrict__ keys,
+template <typename CT, typename KT>
+__global__ void k_emit(const CT *__restrict__ coors, int K, const KT *__restrict__ keys,
                        const int32_t *__restrict__ idx, int64_t N, const int32_t *__restrict__ seg_start,
                        const int32_t *__restrict__ kept_scan, const uint8_t *__restrict__ drop_head,
                        CT *__restrict__ uniq, int32_t *__restrict__ inverse, int32_t *__restrict__ counts,
@@ -154,8 +155,12 @@ static UqLayout uq_layout(int64_t N) {
   l.idx_a = take(4 * n);
   l.seg_start = take(4 * n); l.kept = take(4 * n); l.drop = take(n);
   size_t s1 = 0, s2 = 0, s3 = 0;
+  size_t s1b = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, s1, (uint64_t *)nullptr, (uint64_t *)nullptr, (int32_t *)nullptr,
                                   (int32_t *)nullptr, (int)n);
+  cub::DeviceRadixSort::SortPairs(nullptr, s1b, (uint32_t *)nullptr, (uint32_t *)nullptr, (int32_t *)nullptr,
+                                  (int32_t *)nullptr, (int)n);
+  s1 = std::max(s1, s1b);
   cub::DeviceScan::InclusiveSum(nullptr, s2, (int32_t *)nullptr, (int32_t *)nullptr, (int)n);
   cub::DeviceScan::InclusiveScan(nullptr, s3, (int32_t *)nullptr, (int32_t *)nullptr, MaxOpI(), (int)n);
   l.cub_bytes = (int64_t)std::max(s1, std::max(s2, s3));
@@ -168,6 +173,33 @@ static int bit_length(unsigned long long v) {
   int b = 0;
   while (v) { ++b; v >>= 1; }
   return b;
+}
+
+// keys -> stable radix sort of (key, index) -> heads -> unique rows / inverse / counts / plan
+template <typename CT, typename KT>
+static int sort_and_emit(const CT *coors, int64_t N, int K, const KeySpec &sp, int end_bit, CT *uniq, int32_t *inverse,
+                         int32_t *counts, int32_t *order, int32_t *gstart, char *ws, const UqLayout &l,
+                         cudaStream_t stream) {
+  KT *keys_a = (KT *)(ws + l.keys_a), *keys_b = (KT *)(ws + l.keys_b);
+  int32_t *idx_a = (int32_t *)(ws + l.idx_a);
+  int32_t *seg_start = (int32_t *)(ws + l.seg_start), *kept = (int32_t *)(ws + l.kept);
+  uint8_t *drop = (uint8_t *)(ws + l.drop);
+  const unsigned grid = (unsigned)ceil_div(N, 256);
+  k_make_keys<CT, KT><<<grid, 256, 0, stream>>>(coors, N, sp, keys_a, idx_a);
+  OCC_KERNEL_OK("k_make_keys");
+  size_t cb = (size_t)l.cub_bytes;
+  OCC_CUDA(cub::DeviceRadixSort::SortPairs(ws + l.cub, cb, keys_a, keys_b, idx_a, order, (int)N, 0, end_bit, stream));
+  count_launch(3);
+  k_heads<KT><<<grid, 256, 0, stream>>>(keys_b, N, sp, seg_start, kept, drop);
+  OCC_KERNEL_OK("k_heads");
+  cb = (size_t)l.cub_bytes;
+  OCC_CUDA(cub::DeviceScan::InclusiveScan(ws + l.cub, cb, seg_start, seg_start, MaxOpI(), (int)N, stream));
+  cb = (size_t)l.cub_bytes;
+  OCC_CUDA(cub::DeviceScan::InclusiveSum(ws + l.cub, cb, kept, kept, (int)N, stream));
+  count_launch(4);
+  k_emit<CT, KT><<<grid, 256, 0, stream>>>(coors, K, keys_b, order, N, seg_start, kept, drop, uniq, inverse, counts, gstart);
+  OCC_KERNEL_OK("k_emit");
+  return 0;
 }
 
 template <typename CT>
@@ -230,25 +262,12 @@ static int unique_impl(const CT *coors, int64_t N, int K, int mode, const int64_
   OCC_REQUIRE(total <= 63, "coordinate ranges need more than 63 key bits");
   const int end_bit = std::max(total, 1);
 
-  uint64_t *keys_a = (uint64_t *)(ws + l.keys_a), *keys_b = (uint64_t *)(ws + l.keys_b);
-  int32_t *idx_a = (int32_t *)(ws + l.idx_a);
-  int32_t *seg_start = (int32_t *)(ws + l.seg_start), *kept = (int32_t *)(ws + l.kept);
-  uint8_t *drop = (uint8_t *)(ws + l.drop);
-  const unsigned grid = (unsigned)ceil_div(N, 256);
-  k_make_keys<CT><<<grid, 256, 0, stream>>>(coors, N, sp, keys_a, idx_a);
-  OCC_KERNEL_OK("k_make_keys");
-  size_t cb = (size_t)l.cub_bytes;
-  OCC_CUDA(cub::DeviceRadixSort::SortPairs(ws + l.cub, cb, keys_a, keys_b, idx_a, order, (int)N, 0, end_bit, stream));
-  count_launch(3);
-  k_heads<<<grid, 256, 0, stream>>>(keys_b, N, sp, seg_start, kept, drop);
-  OCC_KERNEL_OK("k_heads");
-  cb = (size_t)l.cub_bytes;
-  OCC_CUDA(cub::DeviceScan::InclusiveScan(ws + l.cub, cb, seg_start, seg_start, MaxOpI(), (int)N, stream));
-  cb = (size_t)l.cub_bytes;
-  OCC_CUDA(cub::DeviceScan::InclusiveSum(ws + l.cub, cb, kept, kept, (int)N, stream));
-  count_launch(4);
-  k_emit<CT><<<grid, 256, 0, stream>>>(coors, K, keys_b, order, N, seg_start, kept, drop, uniq, inverse, counts, gstart);
-  OCC_KERNEL_OK("k_emit");
+  int32_t *kept = (int32_t *)(ws + l.kept);
+  if (total <= 32) {
+    if (sort_and_emit<CT, uint32_t>(coors, N, K, sp, end_bit, uniq, inverse, counts, order, gstart, ws, l, stream)) return 1;
+  } else {
+    if (sort_and_emit<CT, uint64_t>(coors, N, K, sp, end_bit, uniq, inverse, counts, order, gstart, ws, l, stream)) return 1;
+  }
   int32_t m32 = 0;
   unsigned long long oob = 0;
   OCC_CUDA(cudaMemcpyAsync(&m32, kept + (N - 1), 4, cudaMemcpyDeviceToHost, stream));
