@@ -78,6 +78,9 @@ constexpr int kBrick = 4;                // brick edge in voxels: 64 voxels = 2 
 #ifndef OCC_PP2
 #define OCC_PP2 2      // ... of the two-voxels-per-lane path
 #endif
+#ifndef OCC_BULK_STAGE
+#define OCC_BULK_STAGE 0  // 1: k_visibility stages an item's pair records with ONE bulk copy (cp.async.bulk, the TMA engine's
+#endif                    // 1-D form) issued by lane 0 as soon as the tracklet record is known, instead of 4 LDG.128 + 4 STS.128 per lane
 #ifndef OCC_FT
 #define OCC_FT 256
 #endif
@@ -1892,6 +1895,22 @@ k_brick_unknown(const int2 *__restrict__ item_map, const unsigned long long *__r
   }
 }
 
+// 1-D bulk copy global -> shared (TMA engine) completing on an mbarrier, and the warp-wide wait for it.
+__device__ __forceinline__ void bulk_copy_g2s(void *dst_smem, const void *src, unsigned bytes, unsigned long long *bar) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem), b = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the slot's earlier generic-proxy reads come first
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(d), "l"(src), "r"(bytes), "r"(b) : "memory");
+}
+__device__ __forceinline__ void bulk_wait(unsigned long long *bar, unsigned phase) {
+  const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+  unsigned done = 0;
+  while (!done)
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(done) : "r"(b), "r"(phase) : "memory");
+}
+
 #if OCC_VISDEBUG
 __device__ long long g_visdbg[8 * 148 * 8 * 8];    // per warp: t_start, t_end, items, iterations, longest item (cycles, its iterations), smid
 #endif
@@ -1905,6 +1924,15 @@ __global__ void __launch_bounds__(32 * kFastWarps, OCC_MINB) k_visibility(const 
   __shared__ long long s_base[kMaxSlices + 1];
   __shared__ __align__(16) PairHot s_pairs[kFastWarps][kPairsPerItem];
   __shared__ unsigned char s_sel[kFastWarps][32];
+#if OCC_BULK_STAGE
+  __shared__ __align__(8) unsigned long long s_bar[kFastWarps];   // one mbarrier per warp: its staging copy
+  if ((threadIdx.x & 31) == 0) {
+    const unsigned b = (unsigned)__cvta_generic_to_shared(&s_bar[threadIdx.x >> 5]);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(b) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  unsigned bar_phase = 0;
+#endif
   const int ns = a.s_hi - a.s_lo;                  // this launch walks the lists of slices [s_lo, s_hi)
   if (threadIdx.x < ns) s_base[threadIdx.x + 1] = (long long)a.counter[8 + 2 * (a.s_lo + threadIdx.x)];
   __syncthreads();
@@ -1959,11 +1987,24 @@ __global__ void __launch_bounds__(32 * kFastWarps, OCC_MINB) k_visibility(const 
       const TrkHot h = load64(a.hot + t);
       const int k0 = s * kPairsPerItem;
       const int npair = min(h.nact - k0, kPairsPerItem);         // >= 1 by construction of the lists
+#if OCC_BULK_STAGE
+      // the slice's pair records start their way into the warp's slot now, behind the mask / bitset loads below
+      __syncwarp();                                              // the previous item's reads of the slot are done
+      if (lane == 0)
+        bulk_copy_g2s(s_pairs[threadIdx.x >> 5], a.pairs + h.pairs_base + k0, (unsigned)npair * (unsigned)sizeof(PairHot),
+                      &s_bar[threadIdx.x >> 5]);
+      const unsigned my_phase = bar_phase;
+      bar_phase ^= 1u;
+#endif
       const int lb = (bx * ((h.dY + kBrick - 1) / kBrick) + by) * ((h.dZ + kBrick - 1) / kBrick) + bz;
       const long long gb = h.brick_base + lb;
       const unsigned mw = __ldg(a.pair_mask + gb * a.mask_words + (k0 >> 5));
       const unsigned live = ~(mw >> (k0 & 31)) & (npair >= 32 ? 0xffffffffu : ((1u << npair) - 1u)) & part_mask;
+#if OCC_BULK_STAGE
+      if (!live) { bulk_wait(&s_bar[threadIdx.x >> 5], my_phase); break; }
+#else
       if (!live) break;
+#endif
       // undecided = inside the grid, holds no point (k_brick_unknown), not yet proven free; voxel j = 32 v + lane of
       // the brick sits at (j >> 4, (j >> 2) & 3, j & 3)
       unsigned und[2];
@@ -1975,12 +2016,19 @@ __global__ void __launch_bounds__(32 * kFastWarps, OCC_MINB) k_visibility(const 
         und[1] = unk.y & ~f1;
       }
       const int n0 = __popc(und[0]), n = n0 + __popc(und[1]);
+#if OCC_BULK_STAGE
+      if (n == 0) { bulk_wait(&s_bar[threadIdx.x >> 5], my_phase); break; }
+#else
       if (n == 0) break;
+#endif
       unsigned steps = 0, iters = 0;
       // the slice's pair records (<= kPairsPerItem x 128 bytes, contiguous) into the warp's own shared-memory slot:
       // four independent 16-byte loads per lane, all records at once, instead of one dependent 128-byte warp-uniform
       // load per loop iteration
       PairHot *staged = s_pairs[threadIdx.x >> 5];
+#if OCC_BULK_STAGE
+      bulk_wait(&s_bar[threadIdx.x >> 5], my_phase);
+#else
       {
         const float4 *src = reinterpret_cast<const float4 *>(a.pairs + h.pairs_base + k0);
         float4 *dst = reinterpret_cast<float4 *>(staged);
@@ -1990,6 +2038,7 @@ __global__ void __launch_bounds__(32 * kFastWarps, OCC_MINB) k_visibility(const 
           if (q * 32 + lane < npair * 8) dst[q * 32 + lane] = __ldg(src + q * 32 + lane);
         __syncwarp();
       }
+#endif
       // pairs through which the object spans more than +-45 degrees of azimuth (an object next to the sensor) need
       // the full-quadrant arctangent: an item that holds one takes the branching loop, one pair per iteration
       const bool any_wide = __any_sync(0xffffffffu, lane < npair && staged[lane].wide != 0);
