@@ -54,12 +54,18 @@ def main():
         top = dict(sorted(stalls.items(), key=lambda kv: -kv[1])[:6])
         name = rec.get("Kernel Name", "")
         launches.append({"kernel": name[:80], "metrics": m, "stall_cycles_per_issue": top})
-        if re.search(pat, name):
-            for k in total:
-                if k in m:
-                    total[k] += float(m[k]["value"]) * SCALE.get(m[k]["unit"], 1.0)
+    # the sums take ONE launch per distinct kernel name, the last one captured (a capture window may hold the same kernel
+    # of two consecutive steps; "per step" must not count it twice)
+    last = {}
+    for L in launches:
+        if re.search(pat, L["kernel"]):
+            last[L["kernel"].split("(")[0]] = L["metrics"]
+    for m in last.values():
+        for k in total:
+            if k in m:
+                total[k] += float(m[k]["value"]) * SCALE.get(m[k]["unit"], 1.0)
     doc = {
-        "kernel": "launches matching /%s/ (sums below)" % pat,
+        "kernel": "the last captured launch of every kernel matching /%s/ (sums below)" % pat,
         "capture": capture,
         "metrics": {
             "gpu__time_duration.sum": {"unit": "us", "value": "%.3f" % total["gpu__time_duration.sum"]},
