@@ -441,8 +441,11 @@ __device__ __forceinline__ FramePose load_frame_pose(const occb200_pose_t &ps, b
 #define OCC_PPT 4
 #endif
 constexpr int kPtsPerThread = OCC_PPT;          // independent point loads in flight per thread
-constexpr int kCropChunkMin = kFrameThreads * kPtsPerThread;   // candidate points per crop CTA: a multiple of one
-constexpr int kCropChunkMax = 8 * kCropChunkMin;               // iteration of the point loop, chosen per call
+#ifndef OCC_CROP_ALIGN
+#define OCC_CROP_ALIGN kFrameThreads   // (a whole iteration of the point loop, 1 024, left 16 % of the CTA slots of C2 empty)
+#endif
+constexpr int kCropChunkMin = OCC_CROP_ALIGN;                          // candidate points per crop CTA: a multiple of the CTA size,
+constexpr int kCropChunkMax = 8 * kFrameThreads * kPtsPerThread;       // chosen per call so that the grid fills one resident wave
 // First pass (redo_list == NULL): CTA c owns the candidate points [c * chunk, (c+1) * chunk) of the flat
 // point array, whatever frames they belong to -- every CTA has the same amount of work (frames of a close object
 // carry several times the points of a far one; one CTA per frame left the longest frame as the kernel's tail).
