@@ -4,14 +4,15 @@
 // OccAnnotator.annotate_trk :344-568 (normative step list: SURVEY.md Appendix A).
 //
 // Kernels (two streams with fork/join events, no host synchronisation; the whole call is capturable in a graph):
-//   main:  memset -> k_crop_voxelize -> k_tracklet_setup -> k_pair_build -> k_brick_cull -> k_visibility
-//          -> k_visibility_recheck -> k_labels
-//   side:  k_pyr_build (range-image max pyramid, two levels), k_table_setup (row lookup tables); later the
-//          re-voxelisation of the (rare) tracklets whose optimistic grid was wrong
+//   main:  memset -> k_crop_voxelize -> k_pair_build -> k_brick_cull -> k_visibility -> k_visibility_recheck -> k_labels
+//   side:  k_pyr_build (range-image max pyramid, two levels; tiles flagged dead in args.ri_tile_live are skipped),
+//          k_table_setup (row lookup tables); after k_pair_build: the re-voxelisation of the (rare) tracklets whose
+//          optimistic grid was wrong, then k_brick_unknown (per-brick masks of the voxels without a point)
 //
-//   k_crop_voxelize   one CTA per group of tracklet-frames: grid of the tracklet, in-box test, box frame,
-//                     quantise, bitset (A1/A2/A3)
-//   k_tracklet_setup  one warp per tracklet: box size = max over KEPT frames; rare re-voxelisation (A2/A3)
+//   k_crop_voxelize   one CTA per equal share of the flat candidate-point array: optimistic grid of the tracklet,
+//                     in-box test, box frame, quantise, bitset (A1/A2/A3)
+//   k_tracklet_setup  (f64-only path; the fast path runs it as the prologue of k_pair_build) one warp per tracklet:
+//                     box size = max over KEPT frames; rare re-voxelisation (A2/A3)
 //   k_table_setup     one CTA per DISTINCT inclination table: row boundaries + 8-byte lookup cells
 //   k_pyr_build       max of every 8x32 and 2x8 pixel tile of every range image
 //   k_pair_build      one CTA per tracklet, one thread per (frame, LiDAR): voxel-index -> sensor-frame affine map
