@@ -73,7 +73,8 @@ def parse(argv=None):
     ap.add_argument("--flags", type=int, default=0, help="extra occb200_annotate_args_t.flags bits (A/B measurements)")
     ap.add_argument("--no-graph", action="store_true", help="launch the kernels one by one instead of replaying a CUDA graph")
     ap.add_argument("--also", default="c1,c3,c4,c5", help="N=1: sub-records to add to the line (comma list, 'none')")
-    ap.add_argument("--batch-segments", type=int, default=8, help="c5 job: segments per device call")
+    ap.add_argument("--batch-segments", type=int, default=0,
+                    help="c5 job: segments per device call (0 = a rank's segments in equal batches of at most 16)")
     ap.add_argument("--job-tracklets", type=int, default=JOB_TRACKLETS, help="c5 job size (tests use a small one)")
     ap.add_argument("--job-streams", type=int, default=2, help="c5 job: streams the batches' graphs alternate on")
     ap.add_argument("--ri-upload", default="pull", choices=["pull", "host", "whole"],
@@ -176,7 +177,8 @@ def full_config(name, T, B, L, voxel_size, world, args):
            "voxel_size": float(voxel_size)}
     if name == "c5":
         cfg.update({"segments": (int(T) + JOB_PER_SEGMENT - 1) // JOB_PER_SEGMENT,
-                    "sharding": "by segment, LPT (dist.shard_indices)", "batch_segments": args.batch_segments,
+                    "sharding": "by segment, LPT (dist.shard_indices)",
+                    "batch_segments": args.batch_segments if args.batch_segments > 0 else "auto (equal batches of <= 16 segments per rank)",
                     "final_gather": "inside the timed step (uint8 labels, device to device)",
                     "l2": "not flushed: every rank's inputs per step exceed L2 many times over",
                     "launch": "kernel by kernel" if args.no_graph else
@@ -480,7 +482,10 @@ def run_job(ctx, n_tracklets, steps, warmup, peak, peak_src, with_e2e=True, pari
                             only_segments=mine)
     gen_s = time.perf_counter() - t0
     B, L = 40, len(full.segments[0].inclinations) if full.segments else 5
-    S = max(1, ctx.args.batch_segments)                       # batches of S segments
+    S = ctx.args.batch_segments                               # batches of S segments
+    if S <= 0:                                                # auto: as few batches of <= 16 segments as possible, equal sizes
+        nb = max(1, -(-len(full.segments) // 16))
+        S = max(1, -(-len(full.segments) // nb))
     batches = []
     for a in range(0, len(full.segments), S):
         trks = [synth.Tracklet(boxes=t.boxes, points=t.points, segment=t.segment - a, frame_ids=t.frame_ids,
